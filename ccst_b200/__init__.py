@@ -1,0 +1,23 @@
+"""ccst_b200 -- B200-native AdaIN style-transfer hot path of JeremyCJM/CCST.
+
+Operator surface (same names as the reference):
+
+    from ccst_b200 import (calc_mean_std, adaptive_instance_normalization,
+                           adaIN_StyleStat_ContentFeat, calc_sum, style_transfer)
+    from ccst_b200 import net            # net.vgg / net.decoder nn.Sequential definitions
+    from ccst_b200.overall import OverallStyleAccumulator
+
+Everything executes in libccst_b200.so (hand-written sm_100a CUDA behind a C
+ABI, `include/ccst_b200.h`); importing the package does not need a GPU, calling
+an operator without one raises.
+"""
+from .function import (EPS, WelfordState, adaIN_StyleStat_ContentFeat, adain_blend,
+                       adaptive_instance_normalization, calc_mean_std, calc_mean_std_vector,
+                       calc_sum)
+from .transfer import Engine, engine_for, style_transfer
+
+__all__ = [
+    "EPS", "WelfordState", "adaIN_StyleStat_ContentFeat", "adain_blend",
+    "adaptive_instance_normalization", "calc_mean_std", "calc_mean_std_vector", "calc_sum",
+    "Engine", "engine_for", "style_transfer",
+]

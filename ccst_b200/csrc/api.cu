@@ -1,0 +1,620 @@
+// C ABI of libccst_b200.so: handle, weight packing and the encoder / AdaIN / decoder pipelines.
+//
+// Pipelines follow vgg[:31] (net.py:38-69), decoder (net.py:6-36) and style_transfer
+// (CCST_OverallStyleTransfer.py:32-46).  Activations never leave the device arena between layers;
+// the only NCHW fp32 tensors are the caller's image / feature / output tensors.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "layers.h"
+
+namespace ccst {
+
+// ------------------------------------------------------------------ globals
+static thread_local char g_err[512] = "";
+int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int g_sm_count[64];
+static int g_cc_major[64];
+static bool g_dev_known[64];
+
+static int query_device(int dev) {
+  if (dev < 0 || dev >= 64) return CCST_EINVAL;
+  if (!g_dev_known[dev]) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("no usable CUDA device %d (libccst_b200 has no CPU fallback)", dev);
+      return CCST_ECUDA;
+    }
+    g_sm_count[dev] = prop.multiProcessorCount;
+    g_cc_major[dev] = prop.major;
+    g_dev_known[dev] = true;
+  }
+  return CCST_OK;
+}
+
+int require_sm100() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("no CUDA device available (libccst_b200 has no CPU fallback)");
+    return CCST_ECUDA;
+  }
+  if (int e = query_device(dev)) return e;
+  if (g_cc_major[dev] != 10) {
+    set_error("device %d has compute capability %d.x; libccst_b200 is built for sm_100a only", dev,
+              g_cc_major[dev]);
+    return CCST_EARCH;
+  }
+  return CCST_OK;
+}
+
+int sm_count() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && g_dev_known[dev]) return g_sm_count[dev];
+  return 148;
+}
+
+}  // namespace ccst
+
+using namespace ccst;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ handle
+namespace {
+
+struct ConvLayer {
+  int cin = 0, cout = 0;
+  int pad64 = 0;     // Cout rounded up to 64 (ffma weights / bias)
+  int pad_umma = 0;  // Cout, or 16 for the 3-channel last conv
+  float* w_ffma = nullptr;  // [9][cin][pad64]
+  bf16* w_umma = nullptr;   // [pad_umma][9*cin]
+  float* bias = nullptr;    // [pad64]
+};
+
+constexpr int kEncLayers = 8;  // conv1_2 .. conv4_1 (conv1_1 is the fused first conv)
+constexpr int kDecLayers = 9;
+constexpr int kMaxProf = 48;
+
+struct ProfSlot {
+  cudaEvent_t a = nullptr, b = nullptr;
+  double flops = 0, bytes = 0;
+  int kind = 0;
+};
+
+}  // namespace
+
+struct ccst_handle {
+  int device = 0;
+  bool enc_ready = false, dec_ready = false;
+  float* first_w27 = nullptr;
+  float* first_b64 = nullptr;
+  ConvLayer enc[kEncLayers];
+  ConvLayer dec[kDecLayers];
+  void* arena[2] = {nullptr, nullptr};
+  size_t arena_bytes[2] = {0, 0};
+  float2* raw = nullptr;
+  size_t raw_elems = 0;
+  bool fuse_pool = true;
+  bool profiling = false;
+  int prof_n = 0;
+  ProfSlot prof[kMaxProf];
+};
+
+namespace {
+
+struct ProfScope {
+  ccst_handle* h;
+  cudaStream_t st;
+  int slot = -1;
+  ProfScope(ccst_handle* h_, cudaStream_t st_, int kind, double flops, double bytes) : h(h_), st(st_) {
+    if (!h->profiling || h->prof_n >= kMaxProf) return;
+    slot = h->prof_n++;
+    ProfSlot& s = h->prof[slot];
+    if (!s.a) cudaEventCreate(&s.a), cudaEventCreate(&s.b);
+    s.kind = kind, s.flops = flops, s.bytes = bytes;
+    cudaEventRecord(s.a, st);
+  }
+  ~ProfScope() {
+    if (slot >= 0) cudaEventRecord(h->prof[slot].b, st);
+  }
+};
+
+void free_layer(ConvLayer& L) {
+  cudaFree(L.w_ffma);
+  cudaFree(L.w_umma);
+  cudaFree(L.bias);
+  L = ConvLayer();
+}
+
+// OIHW fp32 host weights -> device packs
+int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b) {
+  free_layer(L);
+  L.cin = cin, L.cout = cout;
+  L.pad64 = (cout + 63) / 64 * 64;
+  L.pad_umma = cout % 64 == 0 ? cout : 16;
+  CCST_CHECK_ARG(cout % 64 == 0 || cout <= 16, "unsupported Cout=%d", cout);
+  const int K = 9 * cin;
+  std::vector<float> wf((size_t)K * L.pad64, 0.f);
+  std::vector<bf16> wu((size_t)L.pad_umma * K);
+  std::vector<float> bp(L.pad64, 0.f);
+  for (size_t i = 0; i < wu.size(); ++i) wu[i] = __float2bfloat16(0.f);
+  for (int o = 0; o < cout; ++o) {
+    bp[o] = b[o];
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < 9; ++t) {
+        const float v = w[((size_t)o * cin + c) * 9 + t];
+        wf[((size_t)t * cin + c) * L.pad64 + o] = v;
+        wu[(size_t)o * K + (size_t)t * cin + c] = __float2bfloat16(v);
+      }
+  }
+  CCST_CUDA(cudaMalloc(&L.w_ffma, wf.size() * sizeof(float)));
+  CCST_CUDA(cudaMalloc(&L.w_umma, wu.size() * sizeof(bf16)));
+  CCST_CUDA(cudaMalloc(&L.bias, bp.size() * sizeof(float)));
+  CCST_CUDA(cudaMemcpy(L.w_ffma, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CCST_CUDA(cudaMemcpy(L.w_umma, wu.data(), wu.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  CCST_CUDA(cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return CCST_OK;
+}
+
+const int kEncCh[kEncLayers][2] = {{64, 64},   {64, 128},  {128, 128}, {128, 256},
+                                   {256, 256}, {256, 256}, {256, 256}, {256, 512}};
+const bool kEncPoolAfter[kEncLayers] = {true, false, true, false, false, false, true, false};
+const int kDecCh[kDecLayers][2] = {{512, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 128},
+                                   {128, 128}, {128, 64},  {64, 64},   {64, 3}};
+const bool kDecUpAfter[kDecLayers] = {true, false, false, false, true, false, true, false, false};
+
+size_t act_bytes(int N, int H, int W, int C, size_t esz) {
+  return (size_t)N * (H + 2) * (W + 2) * C * esz;
+}
+
+int ensure_arena(ccst_handle* h, size_t bytes) {
+  for (int i = 0; i < 2; ++i) {
+    if (h->arena_bytes[i] >= bytes) continue;
+    if (h->arena[i]) CCST_CUDA(cudaFree(h->arena[i]));
+    h->arena[i] = nullptr, h->arena_bytes[i] = 0;
+    CCST_CUDA(cudaMalloc(&h->arena[i], bytes));
+    h->arena_bytes[i] = bytes;
+  }
+  return CCST_OK;
+}
+
+int ensure_raw(ccst_handle* h, size_t elems) {
+  if (h->raw_elems >= elems) return CCST_OK;
+  if (h->raw) CCST_CUDA(cudaFree(h->raw));
+  h->raw = nullptr, h->raw_elems = 0;
+  CCST_CUDA(cudaMalloc(&h->raw, elems * sizeof(float2)));
+  h->raw_elems = elems;
+  return CCST_OK;
+}
+
+// largest activation of encoder (from an HxW image) and decoder (from an fh x fw feature map)
+size_t plan_bytes(int N, int H, int W, int fh, int fw, size_t esz, bool enc, bool dec) {
+  size_t m = 0;
+  auto upd = [&](int hh, int ww, int c) {
+    size_t b = act_bytes(N, hh, ww, c, esz);
+    if (b > m) m = b;
+  };
+  if (enc) {
+    int hh = H, ww = W;
+    upd(hh, ww, 64);
+    for (int i = 0; i < kEncLayers; ++i) {
+      upd(hh, ww, kEncCh[i][1]);
+      if (kEncPoolAfter[i]) {
+        hh = (hh + 1) / 2, ww = (ww + 1) / 2;
+        upd(hh, ww, kEncCh[i][1]);
+      }
+    }
+  }
+  if (dec) {
+    int hh = fh, ww = fw;
+    upd(hh, ww, 512);
+    for (int i = 0; i < kDecLayers - 1; ++i) {
+      if (kDecUpAfter[i]) hh *= 2, ww *= 2;
+      upd(hh, ww, kDecCh[i][1]);
+    }
+  }
+  return m;
+}
+
+template <typename T>
+struct Pipe {
+  ccst_handle* h;
+  cudaStream_t st;
+  int cur_slot = 0;
+  ActView<T> cur;
+
+  ActView<T> view(int slot, int N, int H, int W, int C) {
+    ActView<T> v;
+    v.p = reinterpret_cast<T*>(h->arena[slot]);
+    v.N = N, v.H = H, v.W = W, v.C = C;
+    return v;
+  }
+
+  int conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* out_nchw);
+
+  int first(const float* img, int N, int H, int W) {
+    cur_slot = 0;
+    cur = view(0, N, H, W, 64);
+    ProfScope ps(h, st, 0, 2.0 * 27 * 64 * (double)N * H * W,
+                 (double)N * H * W * (12.0 + 64.0 * sizeof(T)));
+    return launch_conv_first<T>(img, N, H, W, h->first_w27, h->first_b64, cur, st);
+  }
+
+  // conv (+ fused or separate pool / fused upsample); result becomes `cur`
+  int step(const ConvLayer& L, bool pool_after, bool up_after) {
+    const int N = cur.N, H = cur.H, W = cur.W;
+    const bool fused_pool = pool_after && h->fuse_pool && sizeof(T) == 2;
+    int oh = H, ow = W, epi = EPI_ACT;
+    if (up_after) oh = 2 * H, ow = 2 * W, epi = EPI_ACT_UP2;
+    if (fused_pool) oh = (H + 1) / 2, ow = (W + 1) / 2, epi = EPI_ACT_POOL;
+    ActView<T> out = view(cur_slot ^ 1, N, oh, ow, L.cout);
+    {
+      const double flops = 2.0 * 9 * L.cin * L.cout * (double)N * H * W;
+      const double bytes = (double)cur.elems() * sizeof(T) + (double)out.elems() * sizeof(T);
+      ProfScope ps(h, st, sizeof(T) == 2 ? 1 : 2, flops, bytes);
+      if (int e = conv(L, 1, epi, out, nullptr)) return e;
+    }
+    cur = out, cur_slot ^= 1;
+    if (pool_after && !fused_pool) {
+      ActView<T> po = view(cur_slot ^ 1, N, (H + 1) / 2, (W + 1) / 2, L.cout);
+      ProfScope ps(h, st, 3, 0, (double)(cur.elems() + po.elems()) * sizeof(T));
+      if (int e = launch_pool<T>(cur, po, st)) return e;
+      cur = po, cur_slot ^= 1;
+    }
+    return CCST_OK;
+  }
+
+  int encoder(const float* img, int N, int H, int W) {
+    if (int e = first(img, N, H, W)) return e;
+    for (int i = 0; i < kEncLayers; ++i)
+      if (int e = step(h->enc[i], kEncPoolAfter[i], false)) return e;
+    return CCST_OK;
+  }
+
+  int adain(const float* mu_s, const float* sigma_s, int64_t stride, float alpha) {
+    ActView<T> out = view(cur_slot ^ 1, cur.N, cur.H, cur.W, cur.C);
+    ProfScope ps(h, st, 4, 0, 2.0 * (double)cur.N * cur.H * cur.W * cur.C * sizeof(T));
+    if (int e = launch_adain_nhwc<T>(cur, out, mu_s, sigma_s, stride, alpha, 1e-5f, st)) return e;
+    cur = out, cur_slot ^= 1;
+    return CCST_OK;
+  }
+
+  int decoder(float* out_nchw) {
+    for (int i = 0; i < kDecLayers - 1; ++i)
+      if (int e = step(h->dec[i], false, kDecUpAfter[i])) return e;
+    const ConvLayer& L = h->dec[kDecLayers - 1];
+    const double flops = 2.0 * 9 * L.cin * L.cout * (double)cur.N * cur.H * cur.W;
+    const double bytes =
+        (double)cur.elems() * sizeof(T) + (double)cur.N * cur.H * cur.W * L.cout * 4.0;
+    ProfScope ps(h, st, sizeof(T) == 2 ? 1 : 2, flops, bytes);
+    return conv(L, 0, EPI_NCHW_F32, cur /*unused*/, out_nchw);
+  }
+};
+
+template <>
+int Pipe<float>::conv(const ConvLayer& L, int relu, int epi, ActView<float> out, float* out_nchw) {
+  return launch_conv_ffma(cur, L.w_ffma, L.bias, L.cout, L.pad64, relu, epi, out, out_nchw, st);
+}
+template <>
+int Pipe<bf16>::conv(const ConvLayer& L, int relu, int epi, ActView<bf16> out, float* out_nchw) {
+  return launch_conv_umma(cur, L.w_umma, L.bias, L.cout, L.pad_umma, relu, epi, out, out_nchw, st);
+}
+
+int check_common(ccst_handle* h, int precision) {
+  CCST_CHECK_ARG(h != nullptr, "null handle");
+  CCST_CHECK_ARG(precision == CCST_PREC_FP32 || precision == CCST_PREC_BF16, "bad precision %d",
+                 precision);
+  if (int e = require_sm100()) return e;
+  int dev = -1;
+  cudaGetDevice(&dev);
+  CCST_CHECK_ARG(dev == h->device, "handle belongs to device %d but current device is %d",
+                 h->device, dev);
+  h->prof_n = 0;
+  return CCST_OK;
+}
+
+template <typename T>
+int run_style_transfer(ccst_handle* h, const float* d_img, int N, int H, int W, const float* mu,
+                       const float* sg, int64_t stride, float alpha, float* d_out, cudaStream_t st) {
+  int fh, fw;
+  ccst_feature_hw(H, W, &fh, &fw);
+  if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T), true, true))) return e;
+  Pipe<T> p{h, st};
+  if (int e = p.encoder(d_img, N, H, W)) return e;
+  if (int e = p.adain(mu, sg, stride, alpha)) return e;
+  return p.decoder(d_out);
+}
+
+template <typename T>
+int run_encoder(ccst_handle* h, const float* d_img, int N, int H, int W, float* d_feat,
+                double* d_state, cudaStream_t st) {
+  int fh, fw;
+  ccst_feature_hw(H, W, &fh, &fw);
+  if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T), true, false))) return e;
+  Pipe<T> p{h, st};
+  if (int e = p.encoder(d_img, N, H, W)) return e;
+  if (d_feat) {
+    ProfScope ps(h, st, 5, 0, (double)N * fh * fw * 512 * (4.0 + sizeof(T)));
+    if (int e = launch_act_to_nchw<T>(p.cur, d_feat, st)) return e;
+  }
+  if (d_state) {
+    if (int e = ensure_raw(h, (size_t)N * 512)) return e;
+    ProfScope ps(h, st, 4, 0, (double)N * fh * fw * 512 * sizeof(T));
+    if (int e = launch_stats_nhwc<T>(p.cur, h->raw, st)) return e;
+    if (int e = merge_raw_into_state(h->raw, N, 512, (int64_t)fh * fw, d_state, st)) return e;
+  }
+  return CCST_OK;
+}
+
+template <typename T>
+int run_decoder(ccst_handle* h, const float* d_feat, int N, int fh, int fw, float* d_img,
+                cudaStream_t st) {
+  if (int e = ensure_arena(h, plan_bytes(N, 0, 0, fh, fw, sizeof(T), false, true))) return e;
+  Pipe<T> p{h, st};
+  p.cur_slot = 0;
+  p.cur = p.view(0, N, fh, fw, 512);
+  {
+    ProfScope ps(h, st, 5, 0, (double)N * fh * fw * 512 * (4.0 + sizeof(T)));
+    if (int e = launch_nchw_to_act<T>(d_feat, p.cur, st)) return e;
+  }
+  return p.decoder(d_img);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ exported functions
+extern "C" int ccst_abi_version(void) { return CCST_ABI_VERSION; }
+extern "C" const char* ccst_last_error(void) { return g_err; }
+extern "C" int64_t ccst_launch_count(void) { return g_launches; }
+
+extern "C" int ccst_check_device(int device) {
+  if (int e = query_device(device)) return e;
+  if (g_cc_major[device] != 10) {
+    set_error("device %d has compute capability %d.x; libccst_b200 is built for sm_100a only",
+              device, g_cc_major[device]);
+    return CCST_EARCH;
+  }
+  return CCST_OK;
+}
+
+extern "C" void ccst_feature_hw(int H, int W, int* fh, int* fw) {
+  int hh = H, ww = W;
+  for (int i = 0; i < 3; ++i) hh = (hh + 1) / 2, ww = (ww + 1) / 2;
+  if (fh) *fh = hh;
+  if (fw) *fw = ww;
+}
+
+extern "C" ccst_handle* ccst_create(int device) {
+  if (ccst_check_device(device) != CCST_OK) return nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    set_error("cudaSetDevice(%d) failed", device);
+    return nullptr;
+  }
+  ccst_handle* h = new ccst_handle();
+  h->device = device;
+  const char* fp = getenv("CCST_FUSE_POOL");
+  if (fp && fp[0] == '0') h->fuse_pool = false;
+  return h;
+}
+
+extern "C" void ccst_destroy(ccst_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->first_w27);
+  cudaFree(h->first_b64);
+  for (auto& L : h->enc) free_layer(L);
+  for (auto& L : h->dec) free_layer(L);
+  cudaFree(h->arena[0]);
+  cudaFree(h->arena[1]);
+  cudaFree(h->raw);
+  for (auto& s : h->prof) {
+    if (s.a) cudaEventDestroy(s.a);
+    if (s.b) cudaEventDestroy(s.b);
+  }
+  delete h;
+}
+
+extern "C" int ccst_set_encoder_weights(ccst_handle* h, const float* const* w,
+                                        const float* const* b) {
+  CCST_CHECK_ARG(h && w && b, "ccst_set_encoder_weights: null argument");
+  CCST_CUDA(cudaSetDevice(h->device));
+  for (int i = 0; i < 10; ++i)
+    CCST_CHECK_ARG(w[i] && b[i], "ccst_set_encoder_weights: null tensor %d", i);
+  // fold the 1x1 colour conv (net.py:39) into conv1_1 (net.py:41): a pointwise op commutes with
+  // reflection padding, so  conv3x3(pad(W1 x + b1)) = conv3x3'(pad(x)) with
+  //   W'[o][i][t] = sum_c W2[o][c][t] W1[c][i],   b'[o] = b2[o] + sum_{c,t} W2[o][c][t] b1[c]
+  const float *W1 = w[0], *b1 = b[0], *W2 = w[1], *b2 = b[1];
+  std::vector<float> w27(27 * 64), b64(64);
+  for (int o = 0; o < 64; ++o) {
+    double bacc = b2[o];
+    for (int t = 0; t < 9; ++t) {
+      for (int i = 0; i < 3; ++i) {
+        double acc = 0;
+        for (int c = 0; c < 3; ++c) acc += (double)W2[((size_t)o * 3 + c) * 9 + t] * W1[c * 3 + i];
+        w27[(size_t)(t * 3 + i) * 64 + o] = (float)acc;
+      }
+      for (int c = 0; c < 3; ++c) bacc += (double)W2[((size_t)o * 3 + c) * 9 + t] * b1[c];
+    }
+    b64[o] = (float)bacc;
+  }
+  if (!h->first_w27) CCST_CUDA(cudaMalloc(&h->first_w27, w27.size() * sizeof(float)));
+  if (!h->first_b64) CCST_CUDA(cudaMalloc(&h->first_b64, b64.size() * sizeof(float)));
+  CCST_CUDA(cudaMemcpy(h->first_w27, w27.data(), w27.size() * 4, cudaMemcpyHostToDevice));
+  CCST_CUDA(cudaMemcpy(h->first_b64, b64.data(), b64.size() * 4, cudaMemcpyHostToDevice));
+  for (int i = 0; i < kEncLayers; ++i)
+    if (int e = pack_layer(h->enc[i], kEncCh[i][0], kEncCh[i][1], w[2 + i], b[2 + i])) return e;
+  h->enc_ready = true;
+  return CCST_OK;
+}
+
+extern "C" int ccst_set_decoder_weights(ccst_handle* h, const float* const* w,
+                                        const float* const* b) {
+  CCST_CHECK_ARG(h && w && b, "ccst_set_decoder_weights: null argument");
+  CCST_CUDA(cudaSetDevice(h->device));
+  for (int i = 0; i < kDecLayers; ++i) {
+    CCST_CHECK_ARG(w[i] && b[i], "ccst_set_decoder_weights: null tensor %d", i);
+    if (int e = pack_layer(h->dec[i], kDecCh[i][0], kDecCh[i][1], w[i], b[i])) return e;
+  }
+  h->dec_ready = true;
+  return CCST_OK;
+}
+
+#define CCST_REQUIRE_STATE(cond, msg) \
+  do {                                \
+    if (!(cond)) {                    \
+      set_error(msg);                 \
+      return CCST_ESTATE;             \
+    }                                 \
+  } while (0)
+
+extern "C" int ccst_encoder_fwd(ccst_handle* h, const float* d_img, int N, int H, int W,
+                                float* d_feat, int precision, void* stream) {
+  if (int e = check_common(h, precision)) return e;
+  CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_fwd: encoder weights not set");
+  CCST_CHECK_ARG(d_img && d_feat && N >= 1 && H >= 8 && W >= 8, "ccst_encoder_fwd: bad argument");
+  return precision == CCST_PREC_BF16
+             ? run_encoder<bf16>(h, d_img, N, H, W, d_feat, nullptr, (cudaStream_t)stream)
+             : run_encoder<float>(h, d_img, N, H, W, d_feat, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N, int H, int W,
+                                       double* d_state, int precision, void* stream) {
+  if (int e = check_common(h, precision)) return e;
+  CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_accumulate: encoder weights not set");
+  CCST_CHECK_ARG(d_img && d_state && N >= 1 && H >= 8 && W >= 8,
+                 "ccst_encoder_accumulate: bad argument");
+  return precision == CCST_PREC_BF16
+             ? run_encoder<bf16>(h, d_img, N, H, W, nullptr, d_state, (cudaStream_t)stream)
+             : run_encoder<float>(h, d_img, N, H, W, nullptr, d_state, (cudaStream_t)stream);
+}
+
+extern "C" int ccst_decoder_fwd(ccst_handle* h, const float* d_feat, int N, int fh, int fw,
+                                float* d_img, int precision, void* stream) {
+  if (int e = check_common(h, precision)) return e;
+  CCST_REQUIRE_STATE(h->dec_ready, "ccst_decoder_fwd: decoder weights not set");
+  CCST_CHECK_ARG(d_feat && d_img && N >= 1 && fh >= 2 && fw >= 2, "ccst_decoder_fwd: bad argument");
+  return precision == CCST_PREC_BF16
+             ? run_decoder<bf16>(h, d_feat, N, fh, fw, d_img, (cudaStream_t)stream)
+             : run_decoder<float>(h, d_feat, N, fh, fw, d_img, (cudaStream_t)stream);
+}
+
+extern "C" int ccst_style_transfer(ccst_handle* h, const float* d_img, int N, int H, int W,
+                                   const float* d_mu_s, const float* d_sigma_s,
+                                   int64_t stat_batch_stride, float alpha, float* d_out,
+                                   int precision, void* stream) {
+  if (int e = check_common(h, precision)) return e;
+  CCST_REQUIRE_STATE(h->enc_ready && h->dec_ready, "ccst_style_transfer: weights not set");
+  CCST_CHECK_ARG(d_img && d_out && d_mu_s && d_sigma_s && N >= 1 && H >= 16 && W >= 16,
+                 "ccst_style_transfer: bad argument");
+  CCST_CHECK_ARG(stat_batch_stride == 0 || stat_batch_stride == 512,
+                 "ccst_style_transfer: stat_batch_stride must be 0 or 512");
+  CCST_CHECK_ARG(alpha >= 0.f && alpha <= 1.f, "ccst_style_transfer: alpha outside [0,1]");
+  return precision == CCST_PREC_BF16
+             ? run_style_transfer<bf16>(h, d_img, N, H, W, d_mu_s, d_sigma_s, stat_batch_stride,
+                                        alpha, d_out, (cudaStream_t)stream)
+             : run_style_transfer<float>(h, d_img, N, H, W, d_mu_s, d_sigma_s, stat_batch_stride,
+                                         alpha, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int ccst_profile_enable(ccst_handle* h, int on) {
+  CCST_CHECK_ARG(h != nullptr, "null handle");
+  h->profiling = on != 0;
+  h->prof_n = 0;
+  return CCST_OK;
+}
+
+extern "C" int ccst_profile_read(ccst_handle* h, int max, float* ms, double* flops, double* bytes,
+                                 int* kind) {
+  CCST_CHECK_ARG(h != nullptr, "null handle");
+  int n = h->prof_n < max ? h->prof_n : max;
+  for (int i = 0; i < n; ++i) {
+    ProfSlot& s = h->prof[i];
+    if (cudaEventSynchronize(s.b) != cudaSuccess) {
+      set_error("ccst_profile_read: event sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return CCST_ECUDA;
+    }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, s.a, s.b);
+    if (ms) ms[i] = t;
+    if (flops) flops[i] = s.flops;
+    if (bytes) bytes[i] = s.bytes;
+    if (kind) kind[i] = s.kind;
+  }
+  return n;
+}
+
+namespace {
+template <typename T>
+int debug_conv(ccst_handle* h, const float* d_in, int N, int H, int W, int Cin, int Cout,
+               const ConvLayer& L, int relu, int mode, float* d_out, cudaStream_t st) {
+  int oh = H, ow = W, epi = EPI_ACT;
+  if (mode == 1) oh = 2 * H, ow = 2 * W, epi = EPI_ACT_UP2;
+  if (mode == 2) oh = (H + 1) / 2, ow = (W + 1) / 2, epi = EPI_ACT_POOL;
+  if (mode == 3) epi = EPI_NCHW_F32;
+  T *bin = nullptr, *bout = nullptr, *btmp = nullptr;
+  CCST_CUDA(cudaMalloc(&bin, act_bytes(N, H, W, Cin, sizeof(T))));
+  ActView<T> vin{bin, N, H, W, Cin};
+  int rc = launch_nhwc_to_act<T>(d_in, vin, st);
+  ActView<T> vout{nullptr, N, oh, ow, L.cout};
+  if (rc == CCST_OK && mode != 3) {
+    if (cudaMalloc(&bout, act_bytes(N, oh, ow, L.cout, sizeof(T))) != cudaSuccess) rc = CCST_ECUDA;
+    vout.p = bout;
+  }
+  if (rc == CCST_OK) {
+    Pipe<T> p{h, st};
+    p.cur = vin;
+    if (mode == 2 && sizeof(T) == 4) {
+      // fp32 engine: conv then the stand-alone pool kernel
+      ActView<T> full{nullptr, N, H, W, L.cout};
+      if (cudaMalloc(&btmp, act_bytes(N, H, W, L.cout, sizeof(T))) != cudaSuccess) rc = CCST_ECUDA;
+      full.p = btmp;
+      if (rc == CCST_OK) rc = p.conv(L, relu, EPI_ACT, full, nullptr);
+      if (rc == CCST_OK) rc = launch_pool<T>(full, vout, st);
+    } else {
+      rc = p.conv(L, relu, epi, vout, d_out);
+    }
+  }
+  if (rc == CCST_OK && mode != 3) rc = launch_act_to_nhwc<T>(vout, d_out, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  if (rc == CCST_OK && se != cudaSuccess) {
+    set_error("ccst_debug_conv3x3: %s", cudaGetErrorString(se));
+    rc = CCST_ECUDA;
+  }
+  cudaFree(bin);
+  cudaFree(bout);
+  cudaFree(btmp);
+  return rc;
+}
+}  // namespace
+
+extern "C" int ccst_debug_conv3x3(ccst_handle* h, const float* d_in, int N, int H, int W, int Cin,
+                                  int Cout, const float* h_weight, const float* h_bias, int relu,
+                                  int mode, float* d_out, int precision, void* stream) {
+  if (int e = check_common(h, precision)) return e;
+  CCST_CHECK_ARG(d_in && d_out && h_weight && h_bias, "ccst_debug_conv3x3: null pointer");
+  CCST_CHECK_ARG(N >= 1 && H >= 2 && W >= 2 && Cin % 64 == 0 && mode >= 0 && mode <= 3,
+                 "ccst_debug_conv3x3: bad shape/mode");
+  CCST_CHECK_ARG(mode == 3 ? Cout <= 16 : Cout % 64 == 0, "ccst_debug_conv3x3: bad Cout");
+  CCST_CHECK_ARG(mode != 2 || relu, "ccst_debug_conv3x3: pool mode requires relu");
+  ConvLayer L;
+  int rc = pack_layer(L, Cin, Cout, h_weight, h_bias);
+  if (rc == CCST_OK)
+    rc = precision == CCST_PREC_BF16
+             ? debug_conv<bf16>(h, d_in, N, H, W, Cin, Cout, L, relu, mode, d_out,
+                                (cudaStream_t)stream)
+             : debug_conv<float>(h, d_in, N, H, W, Cin, Cout, L, relu, mode, d_out,
+                                 (cudaStream_t)stream);
+  free_layer(L);
+  return rc;
+}

@@ -1,0 +1,136 @@
+// Shared device/host helpers for libccst_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/ccst_b200.h"
+
+namespace ccst {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+extern int64_t g_launches;
+
+#define CCST_CHECK_ARG(cond, ...)      \
+  do {                                 \
+    if (!(cond)) {                     \
+      ccst::set_error(__VA_ARGS__);    \
+      return CCST_EINVAL;              \
+    }                                  \
+  } while (0)
+
+#define CCST_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ccst::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                \
+                      cudaGetErrorString(_e));                                            \
+      return CCST_ECUDA;                                                                  \
+    }                                                                                     \
+  } while (0)
+
+// counts the launch and surfaces launch-configuration errors immediately
+#define CCST_LAUNCHED()                                                                   \
+  do {                                                                                    \
+    ++ccst::g_launches;                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      ccst::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,            \
+                      cudaGetErrorString(_e));                                            \
+      return CCST_ECUDA;                                                                  \
+    }                                                                                     \
+  } while (0)
+
+int require_sm100();  // 0 or CCST_EARCH for the current device
+int sm_count();
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- Welford
+// (count, mean, M2) triple; `add` is the classic one-sample update, `merge` is
+// Chan et al.'s pairwise combination.  All fp32 unless the double variant.
+struct Wf {
+  float n, mean, m2;
+};
+
+__device__ __forceinline__ Wf wf_merge(Wf a, Wf b) {
+  float n = a.n + b.n;
+  if (n == 0.f) return a;
+  float d = b.mean - a.mean;
+  float f = __fdividef(b.n, n);
+  Wf r;
+  r.n = n;
+  r.mean = fmaf(d, f, a.mean);
+  r.m2 = a.m2 + b.m2 + d * d * a.n * f;
+  return r;
+}
+
+__device__ __forceinline__ Wf wf_warp_reduce(Wf v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    Wf o;
+    o.n = __shfl_xor_sync(0xffffffffu, v.n, off);
+    o.mean = __shfl_xor_sync(0xffffffffu, v.mean, off);
+    o.m2 = __shfl_xor_sync(0xffffffffu, v.m2, off);
+    v = wf_merge(v, o);
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------- activations layout
+// Internal activations are NHWC with a one-pixel reflection halo:
+//   buffer[n][y+1][x+1][c],  y in [-1,H], x in [-1,W],  halo(-1) = interior(1), halo(H) = interior(H-2)
+// so a 3x3 reflect-pad convolution reads plain shifted windows (TMA boxes) with no border logic.
+template <typename T>
+struct ActView {
+  T* p;
+  int N, H, W, C;  // interior size
+  __host__ __device__ size_t pitch_x() const { return (size_t)C; }
+  __host__ __device__ size_t pitch_y() const { return (size_t)(W + 2) * C; }
+  __host__ __device__ size_t pitch_n() const { return (size_t)(H + 2) * (W + 2) * C; }
+  __host__ __device__ size_t elems() const { return (size_t)N * pitch_n(); }
+  // pointer to pixel (n, y, x) with y,x in [-1, H] / [-1, W]
+  __device__ __forceinline__ T* px(int n, int y, int x) const {
+    return p + (size_t)n * pitch_n() + (size_t)(y + 1) * pitch_y() + (size_t)(x + 1) * C;
+  }
+};
+
+// Calls f(yy, xx) for (y, x) itself and for every halo position that mirrors it.
+template <typename F>
+__device__ __forceinline__ void for_each_halo_alias(int y, int x, int H, int W, F&& f) {
+  int ys[3], xs[3];
+  int ny = 0, nx = 0;
+  ys[ny++] = y;
+  if (y == 1) ys[ny++] = -1;
+  if (y == H - 2) ys[ny++] = H;
+  xs[nx++] = x;
+  if (x == 1) xs[nx++] = -1;
+  if (x == W - 2) xs[nx++] = W;
+  for (int i = 0; i < ny; ++i)
+    for (int j = 0; j < nx; ++j) f(ys[i], xs[j]);
+}
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+}  // namespace ccst

@@ -1,0 +1,538 @@
+// 3x3 reflect-pad convolution as a tcgen05 / TMEM implicit GEMM fed by TMA (sm_100a).
+//
+// Replaces the 17 `ReflectionPad2d(1) + Conv2d(3x3) (+ReLU)` stages of net.py:6-36 / :40-69 (all
+// convolutions except conv1_1, whose K = 27 is handled by conv_first), with the nearest x2
+// `Upsample` (net.py:10,23,30) and the ceil-mode `MaxPool2d` (net.py:46,53,66) fused into the store.
+//
+// GEMM view   D[M = pixels, N = Cout] = A[M, K = 9*Cin] * B[K, N]
+//   A  is never materialised: activations live in HBM as NHWC bf16 with a one-pixel reflection halo,
+//      so the A tile of filter tap (r,s) and channel chunk c0 for the output tile (n, y0..y0+7,
+//      x0..x0+15) is the plain TMA box {64 ch, 16 px, 8 rows, 1 img} at (c0, x0+s, y0+r, n).  The box
+//      lands in shared memory as 128 rows x 128 bytes with the 128-byte swizzle, which is exactly the
+//      K-major SWIZZLE_128B operand layout of tcgen05.mma.
+//   B  = weights packed [CoutPad][9*Cin] bf16 (K contiguous, k = tap*Cin + c), TMA box {64, BN}.
+//   D  accumulates in TMEM (fp32), two accumulator stages of BN columns so the epilogue of tile i
+//      overlaps the MMAs of tile i+1.
+//
+// Warp roles (256 threads, one CTA per SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer          warp 1 lane 0 : tcgen05.mma issuer
+//   warp 2        : TMEM alloc / dealloc  warps 4..7    : epilogue (TMEM -> regs -> bias/ReLU -> HBM)
+#include <cuda.h>
+
+#include "layers.h"
+
+namespace ccst {
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int kTileH = 8, kTileW = 16, kBlockM = kTileH * kTileW, kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kThreadsUmma = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int BN>
+struct UmmaCfg {
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  // B stage must keep every stage base 1024-byte aligned (SWIZZLE_128B atoms)
+  static constexpr int kBStride = (kBBytes + 1023) / 1024 * 1024;
+  static constexpr int kStageBytes = kABytes + kBStride;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct ConvParams {
+  int N, H, W, Cin;
+  int Cout, CoutPad;
+  int tiles_x, tiles_y, n_tiles, total_tiles;
+  int relu;
+  const float* bias;
+  ActView<bf16> out;
+  float* out_nchw;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must trap (reported as a CUDA error), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("ccst conv_umma: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag,
+             (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) |
+//   [32,46) SBO >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128, N = BN
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) /*D fp32*/ | (1u << 7) /*A bf16*/ | (1u << 10) /*B bf16*/ |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+struct TileCoord {
+  int n, y0, x0, nt;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+  TileCoord t;
+  t.nt = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  t.x0 = (m % p.tiles_x) * kTileW;
+  m /= p.tiles_x;
+  t.y0 = (m % p.tiles_y) * kTileH;
+  t.n = m / p.tiles_y;
+  return t;
+}
+
+// ------------------------------------------------------------------ epilogue stores
+__device__ __forceinline__ void store_act_chunk(const ConvParams& p, int n, int y, int x, int co,
+                                                const uint32_t (&pk)[16]) {
+  for_each_halo_alias(y, x, p.out.H, p.out.W, [&](int yy, int xx) {
+    uint4* dst = reinterpret_cast<uint4*>(p.out.px(n, yy, xx) + co);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  });
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreadsUmma, 1)
+    conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                     const __grid_constant__ CUtensorMap tmap_b, ConvParams p) {
+  using Cfg = UmmaCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte aligned stage bases
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto a_smem = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+  auto b_smem = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic alias of smem_base
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = p.Cin / kBlockK;
+  const int num_kb = 9 * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full_bar(s), 1);
+      mbar_init(tmem_empty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base =
+      *reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes +
+                                            8 * (2 * Cfg::kStages + 4));
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      for (int kc = 0; kc < kchunks; ++kc) {
+        for (int tap = 0; tap < 9; ++tap) {
+          const int r = tap / 3, s = tap - 3 * r;
+          mbar_wait(empty_bar(stage), phase ^ 1, 100 + stage);
+          mbar_expect_tx(full_bar(stage), kABytes + Cfg::kBBytes);
+          // padded coords: interior pixel (y, x) is stored at (y+1, x+1); tap (r,s) reads (y+r-1, x+s-1)
+          tma_load_4d(a_smem(stage), &tmap_a, full_bar(stage), kc * kBlockK, t.x0 + s, t.y0 + r, t.n);
+          tma_load_2d(b_smem(stage), &tmap_b, full_bar(stage), tap * p.Cin + kc * kBlockK,
+                      t.nt * BN);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc<BN>();
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tmem_empty_bar(as), aphase ^ 1, 200 + as);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase, 300 + stage);
+        tc_fence_after();
+        const uint64_t adesc = make_kmajor_sw128_desc(a_smem(stage));
+        const uint64_t bdesc = make_kmajor_sw128_desc(b_smem(stage));
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advancing 16 bf16 (32 bytes) along K inside the 128-byte swizzle atom = +2 in the
+          // 16-byte-granular start-address field
+          umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar(as));
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;    // accumulator row = pixel inside the tile
+    const int py = row / kTileW, px = row % kTileW;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int y = t.y0 + py, x = t.x0 + px;
+      const bool valid = (y < p.H) && (x < p.W);
+      mbar_wait(tmem_full_bar(as), aphase, 400 + as);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+      if (EPI == EPI_NCHW_F32) {
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            if (c < p.Cout) {
+              float v = __uint_as_float(r[c]) + __ldg(p.bias + c);
+              if (p.relu) v = fmaxf(v, 0.f);
+              p.out_nchw[(((size_t)t.n * p.Cout + c) * p.H + y) * p.W + x] = v;
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          const int co = t.nt * BN + ch * 32;
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co) + q);
+            v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
+            v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
+            v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (EPI == EPI_ACT_POOL) {
+            // 2x2 window = lanes {l, l^1, l^16, l^17} (tile rows are 16 lanes apart, 2 rows per
+            // warp); out-of-image pixels contribute 0, the identity for post-ReLU values.
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float m = valid ? v[j] : 0.f;
+              m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+              m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+              v[j] = m;
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          if (EPI == EPI_ACT) {
+            if (valid) store_act_chunk(p, t.n, y, x, co, pk);
+          } else if (EPI == EPI_ACT_UP2) {
+            if (valid) {
+#pragma unroll
+              for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) store_act_chunk(p, t.n, 2 * y + a, 2 * x + b, co, pk);
+            }
+          } else if (EPI == EPI_ACT_POOL) {
+            if (valid && !(lane & 1) && lane < 16) store_act_chunk(p, t.n, y >> 1, x >> 1, co, pk);
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete (wait::ld above)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int make_act_map(CUtensorMap* m, const ActView<bf16>& v) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return CCST_ECUDA;
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)(v.W + 2), (cuuint64_t)(v.H + 2),
+                              (cuuint64_t)v.N};
+  const cuuint64_t strides[3] = {(cuuint64_t)v.C * 2, (cuuint64_t)(v.W + 2) * v.C * 2,
+                                 (cuuint64_t)(v.H + 2) * (v.W + 2) * v.C * 2};
+  const cuuint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)v.p, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: CUresult %d", v.N, v.H, v.W,
+              v.C, (int)r);
+    return CCST_ECUDA;
+  }
+  return CCST_OK;
+}
+
+int make_weight_map(CUtensorMap* m, const bf16* wk, int K, int CoutPad, int BN) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return CCST_ECUDA;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)CoutPad};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {kBlockK, (cuuint32_t)BN};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wk, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weights K=%d Cout=%d) failed: CUresult %d", K, CoutPad,
+              (int)r);
+    return CCST_ECUDA;
+  }
+  return CCST_OK;
+}
+
+template <int BN, int EPI>
+int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, cudaStream_t st) {
+  using Cfg = UmmaCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CCST_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, EPI>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  conv_umma_kernel<BN, EPI><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, int epi,
+              cudaStream_t st) {
+  switch (epi) {
+    case EPI_ACT:
+      return launch_cfg<BN, EPI_ACT>(ma, mb, p, st);
+    case EPI_ACT_UP2:
+      return launch_cfg<BN, EPI_ACT_UP2>(ma, mb, p, st);
+    case EPI_ACT_POOL:
+      return launch_cfg<BN, EPI_ACT_POOL>(ma, mb, p, st);
+    default:
+      set_error("conv_umma: epilogue %d not available for BN=%d", epi, BN);
+      return CCST_EINVAL;
+  }
+}
+
+}  // namespace
+
+int launch_conv_umma(ActView<bf16> in, const bf16* wk, const float* bias, int Cout, int CoutPad,
+                     int relu, int epi, ActView<bf16> out, float* out_nchw, cudaStream_t st) {
+  CCST_CHECK_ARG(in.C % kBlockK == 0, "conv_umma: Cin=%d must be a multiple of 64", in.C);
+  int BN;
+  if (epi == EPI_NCHW_F32) {
+    CCST_CHECK_ARG(CoutPad == 16 && Cout <= 16, "conv_umma: NCHW epilogue expects CoutPad == 16");
+    BN = 16;
+  } else {
+    CCST_CHECK_ARG(CoutPad == Cout && Cout % 64 == 0, "conv_umma: Cout=%d must be a multiple of 64",
+                   Cout);
+    BN = Cout >= 256 ? 256 : Cout;  // 64, 128, 256
+    CCST_CHECK_ARG(BN == 64 || BN == 128 || BN == 256, "conv_umma: unsupported Cout=%d", Cout);
+  }
+  ConvParams p;
+  p.N = in.N, p.H = in.H, p.W = in.W, p.Cin = in.C;
+  p.Cout = Cout, p.CoutPad = CoutPad;
+  p.tiles_x = (in.W + kTileW - 1) / kTileW;
+  p.tiles_y = (in.H + kTileH - 1) / kTileH;
+  p.n_tiles = CoutPad / BN;
+  const int64_t total = (int64_t)in.N * p.tiles_x * p.tiles_y * p.n_tiles;
+  CCST_CHECK_ARG(total < (1ll << 31), "conv_umma: too many tiles");
+  p.total_tiles = (int)total;
+  p.relu = relu;
+  p.bias = bias;
+  p.out = out;
+  p.out_nchw = out_nchw;
+  CUtensorMap ma, mb;
+  if (int e = make_act_map(&ma, in)) return e;
+  if (int e = make_weight_map(&mb, wk, 9 * in.C, CoutPad, BN)) return e;
+  switch (BN) {
+    case 16:
+      return launch_cfg<16, EPI_NCHW_F32>(ma, mb, p, st);
+    case 64:
+      return launch_bn<64>(ma, mb, p, epi, st);
+    case 128:
+      return launch_bn<128>(ma, mb, p, epi, st);
+    default:
+      return launch_bn<256>(ma, mb, p, epi, st);
+  }
+}
+
+}  // namespace ccst

@@ -1,0 +1,614 @@
+// Bandwidth-side layers of the encoder/decoder and the fp32 validation convolution.
+//
+//  * conv_first      : conv1_1 with the 1x1 colour conv folded in (net.py:39-42), NCHW fp32 image in,
+//                      NHWC activation out (HBM-bound: K = 27)
+//  * conv_ffma       : fp32 implicit-GEMM 3x3 reflect-pad conv on CUDA cores -- the "fp32 mode"
+//                      whose output matches the reference within 1e-4 (net.py:6-69)
+//  * pool            : MaxPool2d(2,2,ceil_mode=True) (net.py:46,53,66)
+//  * adain_nhwc      : calc_mean_std + AdaIN + alpha blend on the arena layout
+//                      (function.py:26-33, CCST_OverallStyleTransfer.py:44-45)
+//  * stats_nhwc      : per-(n,c) Welford partials of relu4_1 for the overall-style loop
+//                      (mean_std_computation_effcientMem.py:103-131)
+//  * layout converters between the reference's NCHW fp32 tensors and the arena layout.
+#include "layers.h"
+
+namespace ccst {
+
+namespace {
+
+__host__ __device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+template <typename T, int VEC>
+struct Pack;  // VEC values of T moved as one vector
+template <>
+struct Pack<float, 4> {
+  float4 v;
+  __device__ __forceinline__ void set(int i, float f) { (&v.x)[i] = f; }
+  __device__ __forceinline__ float get(int i) const { return (&v.x)[i]; }
+};
+template <>
+struct Pack<__nv_bfloat16, 8> {
+  uint4 v;
+  __device__ __forceinline__ void set(int i, float f) {
+    reinterpret_cast<__nv_bfloat16*>(&v)[i] = __float2bfloat16_rn(f);
+  }
+  __device__ __forceinline__ float get(int i) const {
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&v)[i]);
+  }
+};
+template <typename T>
+struct VecOf {
+  static constexpr int value = 16 / sizeof(T);
+};
+
+// =====================================================================================
+// conv1_1 (+ folded 1x1): one CTA = 64 consecutive pixels of one image row, 4 threads per pixel
+// (16 output channels each).
+// =====================================================================================
+constexpr int kFirstTile = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ img, int N, int H,
+                                                         int W, const float* __restrict__ w27,
+                                                         const float* __restrict__ bias64,
+                                                         ActView<T> out) {
+  __shared__ __align__(16) float sw[27 * 64];
+  __shared__ float sb[64];
+  __shared__ float sin[3][3][kFirstTile + 2];  // [ci][row][col]
+  const int tiles_x = (W + kFirstTile - 1) / kFirstTile;
+  int b = blockIdx.x;
+  const int tx = b % tiles_x;
+  b /= tiles_x;
+  const int y = b % H;
+  const int n = b / H;
+  const int x0 = tx * kFirstTile;
+
+  for (int i = threadIdx.x; i < 27 * 64; i += 256) sw[i] = w27[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias64[threadIdx.x];
+  for (int i = threadIdx.x; i < 3 * 3 * (kFirstTile + 2); i += 256) {
+    int col = i % (kFirstTile + 2);
+    int row = (i / (kFirstTile + 2)) % 3;
+    int ci = i / (3 * (kFirstTile + 2));
+    int yy = reflect_idx(y + row - 1, H);
+    int xx = x0 + col - 1;
+    float v = 0.f;
+    if (xx <= W) {  // xx == W is the right halo of the last pixel
+      xx = reflect_idx(xx, W);
+      v = __ldg(img + (((size_t)n * 3 + ci) * H + yy) * W + xx);
+    }
+    sin[ci][row][col] = v;
+  }
+  __syncthreads();
+
+  const int p = threadIdx.x >> 2;        // pixel in tile
+  const int cg = (threadIdx.x & 3) * 16;  // first output channel
+  const int x = x0 + p;
+  if (x >= W) return;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = sb[cg + j];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float v = sin[ci][r][p + s];
+        const float4* w4 = reinterpret_cast<const float4*>(&sw[((r * 3 + s) * 3 + ci) * 64 + cg]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 w = w4[q];
+          acc[q * 4 + 0] = fmaf(v, w.x, acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(v, w.y, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(v, w.z, acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(v, w.w, acc[q * 4 + 3]);
+        }
+      }
+  constexpr int VEC = VecOf<T>::value;
+  Pack<T, VEC> pk[16 / VEC];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) pk[j / VEC].set(j % VEC, fmaxf(acc[j], 0.f));
+  for_each_halo_alias(y, x, H, W, [&](int yy, int xx) {
+    T* dst = out.px(n, yy, xx) + cg;
+#pragma unroll
+    for (int j = 0; j < 16 / VEC; ++j) reinterpret_cast<decltype(pk[0].v)*>(dst)[j] = pk[j].v;
+  });
+}
+
+// =====================================================================================
+// fp32 FFMA implicit GEMM: CTA tile = 8x16 pixels x 64 output channels, K chunk = 16 channels
+// (all 9 taps per chunk).  Thread = 8 consecutive pixels of one tile row x 4 output channels.
+// =====================================================================================
+constexpr int kFT_H = 8, kFT_W = 16, kFT_N = 64, kFT_K = 16;
+
+template <int EPI>
+__global__ void __launch_bounds__(256)
+    conv_ffma_kernel(ActView<float> in, const float* __restrict__ w, const float* __restrict__ bias,
+                     int Cout, int CoutPad, int relu, ActView<float> out,
+                     float* __restrict__ out_nchw) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_in = smem;                                          // [10][18][16]
+  float* s_w = smem + (kFT_H + 2) * (kFT_W + 2) * kFT_K;       // [9][16][64]
+  const int H = in.H, W = in.W, Cin = in.C;
+  const int tiles_x = (W + kFT_W - 1) / kFT_W, tiles_y = (H + kFT_H - 1) / kFT_H;
+  int b = blockIdx.x;
+  const int ntile = b % (CoutPad / kFT_N);
+  b /= (CoutPad / kFT_N);
+  const int tx = b % tiles_x;
+  b /= tiles_x;
+  const int ty = b % tiles_y;
+  const int n = b / tiles_y;
+  const int y0 = ty * kFT_H, x0 = tx * kFT_W, co0 = ntile * kFT_N;
+
+  const int t = threadIdx.x;
+  const int cq = (t & 15) * 4;      // output channel quad inside the tile
+  const int pg = t >> 4;            // pixel group 0..15
+  const int prow = pg >> 1;         // tile row
+  const int pcol = (pg & 1) * 8;    // first tile column
+  float acc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
+
+  for (int c0 = 0; c0 < Cin; c0 += kFT_K) {
+    __syncthreads();
+    // input halo tile: (10 x 18) pixels x 16 channels
+    for (int i = t; i < (kFT_H + 2) * (kFT_W + 2) * (kFT_K / 4); i += 256) {
+      const int c4 = i % (kFT_K / 4);
+      const int pix = i / (kFT_K / 4);
+      const int col = pix % (kFT_W + 2), row = pix / (kFT_W + 2);
+      const int yy = y0 - 1 + row, xx = x0 - 1 + col;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy <= H && xx <= W)
+        v = *reinterpret_cast<const float4*>(in.px(n, yy, xx) + c0 + c4 * 4);
+      *reinterpret_cast<float4*>(s_in + (size_t)pix * kFT_K + c4 * 4) = v;
+    }
+    // weights: [tap][ci][64]
+    for (int i = t; i < 9 * kFT_K * (kFT_N / 4); i += 256) {
+      const int q = i % (kFT_N / 4);
+      const int ci = (i / (kFT_N / 4)) % kFT_K;
+      const int tap = i / (kFT_N / 4 * kFT_K);
+      *reinterpret_cast<float4*>(s_w + ((size_t)tap * kFT_K + ci) * kFT_N + q * 4) =
+          *reinterpret_cast<const float4*>(w + ((size_t)tap * Cin + c0 + ci) * CoutPad + co0 + q * 4);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const float* ip = s_in + ((size_t)(prow + r) * (kFT_W + 2) + pcol + s) * kFT_K;
+        const float* wp = s_w + (size_t)(r * 3 + s) * kFT_K * kFT_N + cq;
+#pragma unroll
+        for (int c4 = 0; c4 < kFT_K / 4; ++c4) {
+          float4 wv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            wv[q] = *reinterpret_cast<const float4*>(wp + (size_t)(c4 * 4 + q) * kFT_N);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 iv = *reinterpret_cast<const float4*>(ip + (size_t)j * kFT_K + c4 * 4);
+            acc[j][0] = fmaf(iv.x, wv[0].x, acc[j][0]);
+            acc[j][1] = fmaf(iv.x, wv[0].y, acc[j][1]);
+            acc[j][2] = fmaf(iv.x, wv[0].z, acc[j][2]);
+            acc[j][3] = fmaf(iv.x, wv[0].w, acc[j][3]);
+            acc[j][0] = fmaf(iv.y, wv[1].x, acc[j][0]);
+            acc[j][1] = fmaf(iv.y, wv[1].y, acc[j][1]);
+            acc[j][2] = fmaf(iv.y, wv[1].z, acc[j][2]);
+            acc[j][3] = fmaf(iv.y, wv[1].w, acc[j][3]);
+            acc[j][0] = fmaf(iv.z, wv[2].x, acc[j][0]);
+            acc[j][1] = fmaf(iv.z, wv[2].y, acc[j][1]);
+            acc[j][2] = fmaf(iv.z, wv[2].z, acc[j][2]);
+            acc[j][3] = fmaf(iv.z, wv[2].w, acc[j][3]);
+            acc[j][0] = fmaf(iv.w, wv[3].x, acc[j][0]);
+            acc[j][1] = fmaf(iv.w, wv[3].y, acc[j][1]);
+            acc[j][2] = fmaf(iv.w, wv[3].z, acc[j][2]);
+            acc[j][3] = fmaf(iv.w, wv[3].w, acc[j][3]);
+          }
+        }
+      }
+  }
+
+  const float4 bv = *reinterpret_cast<const float4*>(bias + co0 + cq);
+  const int y = y0 + prow;
+  if (y >= H) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int x = x0 + pcol + j;
+    if (x >= W) continue;
+    float4 o = make_float4(acc[j][0] + bv.x, acc[j][1] + bv.y, acc[j][2] + bv.z, acc[j][3] + bv.w);
+    if (relu) {
+      o.x = fmaxf(o.x, 0.f);
+      o.y = fmaxf(o.y, 0.f);
+      o.z = fmaxf(o.z, 0.f);
+      o.w = fmaxf(o.w, 0.f);
+    }
+    const int co = co0 + cq;
+    if (EPI == EPI_ACT) {
+      if (co < Cout)
+        for_each_halo_alias(y, x, H, W, [&](int yy, int xx) {
+          *reinterpret_cast<float4*>(out.px(n, yy, xx) + co) = o;
+        });
+    } else if (EPI == EPI_ACT_UP2) {
+      if (co < Cout)
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb)
+            for_each_halo_alias(2 * y + a, 2 * x + bb, 2 * H, 2 * W, [&](int yy, int xx) {
+              *reinterpret_cast<float4*>(out.px(n, yy, xx) + co) = o;
+            });
+    } else {  // EPI_NCHW_F32
+      const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (co + q < Cout) out_nchw[(((size_t)n * Cout + co + q) * H + y) * W + x] = ov[q];
+    }
+  }
+}
+
+// =====================================================================================
+// 2x2 stride-2 ceil-mode max pool, one thread per (pixel, 16-byte channel vector)
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) pool_kernel(ActView<T> in, ActView<T> out) {
+  constexpr int VEC = VecOf<T>::value;
+  const int cv = in.C / VEC;
+  const size_t total = (size_t)out.N * out.H * out.W * cv;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int c = (int)(i % cv) * VEC;
+    size_t p = i / cv;
+    const int xo = (int)(p % out.W);
+    p /= out.W;
+    const int yo = (int)(p % out.H);
+    const int n = (int)(p / out.H);
+    float m[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int y = 2 * yo + dy, x = 2 * xo + dx;
+        if (y < in.H && x < in.W) {
+          Pack<T, VEC> v;
+          v.v = *reinterpret_cast<const decltype(v.v)*>(in.px(n, y, x) + c);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) m[k] = fmaxf(m[k], v.get(k));
+        }
+      }
+    Pack<T, VEC> o;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) o.set(k, m[k]);
+    for_each_halo_alias(yo, xo, out.H, out.W, [&](int yy, int xx) {
+      *reinterpret_cast<decltype(o.v)*>(out.px(n, yy, xx) + c) = o.v;
+    });
+  }
+}
+
+// =====================================================================================
+// NHWC statistics / AdaIN: CTA = (image n, 64-channel slab).  Thread = VEC channels x a strided
+// subset of the pixels, streaming Welford with a uniform count, merged through shared memory.
+// =====================================================================================
+template <typename T>
+struct NhwcGeom {
+  static constexpr int VEC = VecOf<T>::value;
+  static constexpr int CH_LANES = 64 / VEC;
+  static constexpr int PX_LANES = 256 / CH_LANES;
+};
+
+template <typename T>
+__device__ __forceinline__ void nhwc_plane_stats(const ActView<T>& in, int n, int c0, float* s_mean,
+                                                 float* s_m2, float* s_n) {
+  using G = NhwcGeom<T>;
+  constexpr int VEC = G::VEC;
+  const int cl = threadIdx.x % G::CH_LANES, pl = threadIdx.x / G::CH_LANES;
+  const int HW = in.H * in.W;
+  float mean[VEC], m2[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) mean[k] = 0.f, m2[k] = 0.f;
+  float cnt = 0.f;
+  for (int p = pl; p < HW; p += G::PX_LANES) {
+    const int y = p / in.W, x = p - y * in.W;
+    Pack<T, VEC> v;
+    v.v = *reinterpret_cast<const decltype(v.v)*>(in.px(n, y, x) + c0 + cl * VEC);
+    cnt += 1.f;
+    const float inv = __frcp_rn(cnt);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float xv = v.get(k);
+      const float d = xv - mean[k];
+      mean[k] = fmaf(d, inv, mean[k]);
+      m2[k] = fmaf(d, xv - mean[k], m2[k]);
+    }
+  }
+  // s_*[pl][64]
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    s_mean[pl * 64 + cl * VEC + k] = mean[k];
+    s_m2[pl * 64 + cl * VEC + k] = m2[k];
+  }
+  if (cl == 0) s_n[pl] = cnt;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    Wf acc{s_n[0], s_mean[threadIdx.x], s_m2[threadIdx.x]};
+    for (int l = 1; l < G::PX_LANES; ++l) {
+      Wf o{s_n[l], s_mean[l * 64 + threadIdx.x], s_m2[l * 64 + threadIdx.x]};
+      acc = wf_merge(acc, o);
+    }
+    s_mean[threadIdx.x] = acc.mean;  // row 0 now holds the merged result
+    s_m2[threadIdx.x] = acc.m2;
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) stats_nhwc_kernel(ActView<T> in, float2* __restrict__ raw) {
+  using G = NhwcGeom<T>;
+  __shared__ float s_mean[G::PX_LANES * 64], s_m2[G::PX_LANES * 64], s_n[G::PX_LANES];
+  const int c0 = blockIdx.x * 64, n = blockIdx.y;
+  nhwc_plane_stats(in, n, c0, s_mean, s_m2, s_n);
+  if (threadIdx.x < 64)
+    raw[(size_t)n * in.C + c0 + threadIdx.x] = make_float2(s_mean[threadIdx.x], s_m2[threadIdx.x]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    adain_nhwc_kernel(ActView<T> in, ActView<T> out, const float* __restrict__ mu_s,
+                      const float* __restrict__ sigma_s, int64_t stat_batch_stride, float alpha,
+                      float eps) {
+  using G = NhwcGeom<T>;
+  constexpr int VEC = G::VEC;
+  __shared__ float s_mean[G::PX_LANES * 64], s_m2[G::PX_LANES * 64], s_n[G::PX_LANES];
+  __shared__ float s_A[64], s_B[64], s_mu[64];
+  const int c0 = blockIdx.x * 64, n = blockIdx.y;
+  nhwc_plane_stats(in, n, c0, s_mean, s_m2, s_n);
+  const int HW = in.H * in.W;
+  if (threadIdx.x < 64) {
+    const int c = c0 + threadIdx.x;
+    const float mu_c = s_mean[threadIdx.x];
+    // unbiased like calc_mean_std (function.py:9); HW == 1 -> NaN as the reference
+    const float sg_c = sqrtf(s_m2[threadIdx.x] / ((float)HW - 1.f) + eps);
+    const int64_t si = (int64_t)n * stat_batch_stride + c;
+    const float ms = mu_s[si], ss = sigma_s[si];
+    s_A[threadIdx.x] = alpha * (ss / sg_c) + (1.f - alpha);
+    s_B[threadIdx.x] = alpha * ms + (1.f - alpha) * mu_c;
+    s_mu[threadIdx.x] = mu_c;
+  }
+  __syncthreads();
+  const int cl = threadIdx.x % G::CH_LANES, pl = threadIdx.x / G::CH_LANES;
+  float A[VEC], B[VEC], M[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    A[k] = s_A[cl * VEC + k];
+    B[k] = s_B[cl * VEC + k];
+    M[k] = s_mu[cl * VEC + k];
+  }
+  for (int p = pl; p < HW; p += G::PX_LANES) {
+    const int y = p / in.W, x = p - y * in.W;
+    Pack<T, VEC> v, o;
+    v.v = *reinterpret_cast<const decltype(v.v)*>(in.px(n, y, x) + c0 + cl * VEC);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) o.set(k, fmaf(v.get(k) - M[k], A[k], B[k]));
+    for_each_halo_alias(y, x, in.H, in.W, [&](int yy, int xx) {
+      *reinterpret_cast<decltype(o.v)*>(out.px(n, yy, xx) + c0 + cl * VEC) = o.v;
+    });
+  }
+}
+
+// =====================================================================================
+// layout converters (32 pixels x 32 channels tiles through shared memory)
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) act_to_nchw_kernel(ActView<T> in, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int HW = in.H * in.W;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32, n = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (p < HW && c < in.C) {
+      const int y = p / in.W, x = p - y * in.W;
+      v = to_f32(in.px(n, y, x)[c]);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    if (p < HW && c < in.C) out[((size_t)n * in.C + c) * HW + p] = tile[tx][i];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restrict__ in,
+                                                          ActView<T> out) {
+  __shared__ float tile[32][33];
+  const int HW = out.H * out.W;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32, n = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + tx;
+    tile[i][tx] = (p < HW && c < out.C) ? in[((size_t)n * out.C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + tx;
+    if (p < HW && c < out.C) {
+      const int y = p / out.W, x = p - y * out.W;
+      const T v = from_f32<T>(tile[tx][i]);
+      for_each_halo_alias(y, x, out.H, out.W, [&](int yy, int xx) { out.px(n, yy, xx)[c] = v; });
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_act_kernel(const float* __restrict__ in,
+                                                          ActView<T> out) {
+  const size_t total = (size_t)out.N * out.H * out.W * out.C;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int c = (int)(i % out.C);
+    size_t p = i / out.C;
+    const int x = (int)(p % out.W);
+    p /= out.W;
+    const int y = (int)(p % out.H);
+    const int n = (int)(p / out.H);
+    const T v = from_f32<T>(in[i]);
+    for_each_halo_alias(y, x, out.H, out.W, [&](int yy, int xx) { out.px(n, yy, xx)[c] = v; });
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) act_to_nhwc_kernel(ActView<T> in, float* __restrict__ out) {
+  const size_t total = (size_t)in.N * in.H * in.W * in.C;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int c = (int)(i % in.C);
+    size_t p = i / in.C;
+    const int x = (int)(p % in.W);
+    p /= in.W;
+    const int y = (int)(p % in.H);
+    const int n = (int)(p / in.H);
+    out[i] = to_f32(in.px(n, y, x)[c]);
+  }
+}
+
+int ew_grid(size_t total) {
+  size_t blocks = (total + 255) / 256;
+  size_t cap = (size_t)sm_count() * 16;
+  return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ launch wrappers
+template <typename T>
+int launch_conv_first(const float* img, int N, int H, int W, const float* w27, const float* bias64,
+                      ActView<T> out, cudaStream_t st) {
+  const int tiles_x = (W + kFirstTile - 1) / kFirstTile;
+  const size_t blocks = (size_t)N * H * tiles_x;
+  CCST_CHECK_ARG(blocks < (1ull << 31), "conv_first: grid too large");
+  conv_first_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(img, N, H, W, w27, bias64, out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_conv_first<float>(const float*, int, int, int, const float*, const float*,
+                                      ActView<float>, cudaStream_t);
+template int launch_conv_first<__nv_bfloat16>(const float*, int, int, int, const float*,
+                                              const float*, ActView<__nv_bfloat16>, cudaStream_t);
+
+int launch_conv_ffma(ActView<float> in, const float* w, const float* bias, int Cout, int CoutPad,
+                     int relu, int epi, ActView<float> out, float* out_nchw, cudaStream_t st) {
+  CCST_CHECK_ARG(in.C % kFT_K == 0 && CoutPad % kFT_N == 0, "conv_ffma: channel counts");
+  const int tiles_x = (in.W + kFT_W - 1) / kFT_W, tiles_y = (in.H + kFT_H - 1) / kFT_H;
+  const size_t blocks = (size_t)in.N * tiles_y * tiles_x * (CoutPad / kFT_N);
+  CCST_CHECK_ARG(blocks < (1ull << 31), "conv_ffma: grid too large");
+  const size_t smem =
+      ((size_t)(kFT_H + 2) * (kFT_W + 2) * kFT_K + (size_t)9 * kFT_K * kFT_N) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CCST_CUDA(cudaFuncSetAttribute(conv_ffma_kernel<EPI_ACT>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CCST_CUDA(cudaFuncSetAttribute(conv_ffma_kernel<EPI_ACT_UP2>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CCST_CUDA(cudaFuncSetAttribute(conv_ffma_kernel<EPI_NCHW_F32>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  if (epi == EPI_ACT)
+    conv_ffma_kernel<EPI_ACT><<<(unsigned)blocks, 256, smem, st>>>(in, w, bias, Cout, CoutPad, relu,
+                                                                   out, out_nchw);
+  else if (epi == EPI_ACT_UP2)
+    conv_ffma_kernel<EPI_ACT_UP2><<<(unsigned)blocks, 256, smem, st>>>(in, w, bias, Cout, CoutPad,
+                                                                       relu, out, out_nchw);
+  else if (epi == EPI_NCHW_F32)
+    conv_ffma_kernel<EPI_NCHW_F32><<<(unsigned)blocks, 256, smem, st>>>(in, w, bias, Cout, CoutPad,
+                                                                        relu, out, out_nchw);
+  else
+    CCST_CHECK_ARG(false, "conv_ffma: unsupported epilogue %d", epi);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+template <typename T>
+int launch_pool(ActView<T> in, ActView<T> out, cudaStream_t st) {
+  const size_t total = (size_t)out.N * out.H * out.W * (in.C / VecOf<T>::value);
+  pool_kernel<T><<<ew_grid(total), 256, 0, st>>>(in, out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_pool<float>(ActView<float>, ActView<float>, cudaStream_t);
+template int launch_pool<__nv_bfloat16>(ActView<__nv_bfloat16>, ActView<__nv_bfloat16>,
+                                        cudaStream_t);
+
+template <typename T>
+int launch_adain_nhwc(ActView<T> in, ActView<T> out, const float* mu_s, const float* sigma_s,
+                      int64_t stat_batch_stride, float alpha, float eps, cudaStream_t st) {
+  CCST_CHECK_ARG(in.C % 64 == 0, "adain_nhwc: C must be a multiple of 64");
+  dim3 grid(in.C / 64, in.N);
+  adain_nhwc_kernel<T><<<grid, 256, 0, st>>>(in, out, mu_s, sigma_s, stat_batch_stride, alpha, eps);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_adain_nhwc<float>(ActView<float>, ActView<float>, const float*, const float*,
+                                      int64_t, float, float, cudaStream_t);
+template int launch_adain_nhwc<__nv_bfloat16>(ActView<__nv_bfloat16>, ActView<__nv_bfloat16>,
+                                              const float*, const float*, int64_t, float, float,
+                                              cudaStream_t);
+
+template <typename T>
+int launch_stats_nhwc(ActView<T> in, float2* raw, cudaStream_t st) {
+  CCST_CHECK_ARG(in.C % 64 == 0, "stats_nhwc: C must be a multiple of 64");
+  dim3 grid(in.C / 64, in.N);
+  stats_nhwc_kernel<T><<<grid, 256, 0, st>>>(in, raw);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_stats_nhwc<float>(ActView<float>, float2*, cudaStream_t);
+template int launch_stats_nhwc<__nv_bfloat16>(ActView<__nv_bfloat16>, float2*, cudaStream_t);
+
+template <typename T>
+int launch_act_to_nchw(ActView<T> in, float* out_nchw, cudaStream_t st) {
+  dim3 grid((in.H * in.W + 31) / 32, (in.C + 31) / 32, in.N);
+  act_to_nchw_kernel<T><<<grid, 256, 0, st>>>(in, out_nchw);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_act_to_nchw<float>(ActView<float>, float*, cudaStream_t);
+template int launch_act_to_nchw<__nv_bfloat16>(ActView<__nv_bfloat16>, float*, cudaStream_t);
+
+template <typename T>
+int launch_nchw_to_act(const float* in_nchw, ActView<T> out, cudaStream_t st) {
+  dim3 grid((out.H * out.W + 31) / 32, (out.C + 31) / 32, out.N);
+  nchw_to_act_kernel<T><<<grid, 256, 0, st>>>(in_nchw, out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_nchw_to_act<float>(const float*, ActView<float>, cudaStream_t);
+template int launch_nchw_to_act<__nv_bfloat16>(const float*, ActView<__nv_bfloat16>, cudaStream_t);
+
+template <typename T>
+int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st) {
+  const size_t total = (size_t)out.N * out.H * out.W * out.C;
+  nhwc_to_act_kernel<T><<<ew_grid(total), 256, 0, st>>>(in_nhwc, out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_nhwc_to_act<float>(const float*, ActView<float>, cudaStream_t);
+template int launch_nhwc_to_act<__nv_bfloat16>(const float*, ActView<__nv_bfloat16>, cudaStream_t);
+
+template <typename T>
+int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st) {
+  const size_t total = (size_t)in.N * in.H * in.W * in.C;
+  act_to_nhwc_kernel<T><<<ew_grid(total), 256, 0, st>>>(in, out_nhwc);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_act_to_nhwc<float>(ActView<float>, float*, cudaStream_t);
+template int launch_act_to_nhwc<__nv_bfloat16>(ActView<__nv_bfloat16>, float*, cudaStream_t);
+
+}  // namespace ccst

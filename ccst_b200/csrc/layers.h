@@ -1,0 +1,53 @@
+// Internal (non-ABI) launch wrappers shared by api.cu / layers.cu / conv_umma.cu.
+#pragma once
+#include "common.cuh"
+
+namespace ccst {
+
+enum Epilogue {
+  EPI_ACT = 0,      // bias (+ReLU) -> NHWC activation with reflection halo
+  EPI_ACT_UP2 = 1,  // same, every pixel replicated 2x2 (nearest upsample fused into the store)
+  EPI_NCHW_F32 = 2, // bias (+ReLU) -> caller's NCHW fp32 tensor (last decoder conv)
+  EPI_ACT_POOL = 3, // bias + ReLU + 2x2 ceil-mode max-pool fused into the store (tcgen05 path)
+};
+
+// conv1_1 with the 1x1 colour conv folded in.  img: NCHW fp32 [N,3,H,W]; w27: [27][64] fp32
+// (k = (r*3+s)*3 + ci), bias64.
+template <typename T>
+int launch_conv_first(const float* img, int N, int H, int W, const float* w27, const float* bias64,
+                      ActView<T> out, cudaStream_t st);
+
+// fp32 FFMA implicit GEMM.  w: [9][Cin][CoutPad64] fp32, bias [CoutPad64].
+int launch_conv_ffma(ActView<float> in, const float* w, const float* bias, int Cout, int CoutPad,
+                     int relu, int epi, ActView<float> out, float* out_nchw, cudaStream_t st);
+
+template <typename T>
+int launch_pool(ActView<T> in, ActView<T> out, cudaStream_t st);
+
+template <typename T>
+int launch_adain_nhwc(ActView<T> in, ActView<T> out, const float* mu_s, const float* sigma_s,
+                      int64_t stat_batch_stride, float alpha, float eps, cudaStream_t st);
+
+// per-(n,c) {mean, M2} of an activation -> raw[N*C]
+template <typename T>
+int launch_stats_nhwc(ActView<T> in, float2* raw, cudaStream_t st);
+
+int merge_raw_into_state(const float2* raw, int N, int C, int64_t hw, double* d_state,
+                         cudaStream_t st);
+
+template <typename T>
+int launch_act_to_nchw(ActView<T> in, float* out_nchw, cudaStream_t st);
+template <typename T>
+int launch_nchw_to_act(const float* in_nchw, ActView<T> out, cudaStream_t st);
+template <typename T>
+int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st);
+template <typename T>
+int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st);
+
+// tcgen05 / TMA implicit GEMM (conv_umma.cu).  wk: [CoutPad][9*Cin] bf16 K-major, bias fp32.
+struct UmmaConvPlan;
+int launch_conv_umma(ActView<__nv_bfloat16> in, const __nv_bfloat16* wk, const float* bias,
+                     int Cout, int CoutPad, int relu, int epi, ActView<__nv_bfloat16> out,
+                     float* out_nchw, cudaStream_t st);
+
+}  // namespace ccst

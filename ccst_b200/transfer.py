@@ -1,0 +1,256 @@
+"""`style_transfer(vgg, decoder, content, style, alpha)` on B200.
+
+Drop-in for the driver function of the CCST scripts
+(`CCST_OverallStyleTransfer.py:32-46` == `CCST_SingleStyleTransfer.py:39-53`):
+same positional arguments, same assertion, same result tensor (NCHW fp32 on the
+content's device).  `vgg` / `decoder` are the caller's ``nn.Sequential`` objects
+(the reference's `net.vgg[:31]` / `net.decoder` or `ccst_b200.net`'s); they are
+used as weight containers only -- their conv weights are packed once per
+(model, weight version) into a `ccst_handle` and all arithmetic runs in
+libccst_b200.so.
+
+`style` may be
+  * ``[mean, std]`` (each [1,512,1,1] or [N,512,1,1]) -- the CCST form
+    (`adaIN_StyleStat_ContentFeat`), or
+  * an image batch [N,3,h,w] -- the upstream AdaIN form named in BASELINE.json
+    (`adaptive_instance_normalization` on the encoded style, net.py:138-143).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import function as F_
+
+PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+DEFAULT_PRECISION = "bf16"
+
+
+def _conv_params(seq: nn.Module, count: int, what: str):
+    convs = [m for m in seq.modules() if isinstance(m, nn.Conv2d)]
+    if len(convs) < count:
+        raise RuntimeError(f"{what}: expected at least {count} Conv2d layers, found {len(convs)}")
+    return convs[:count]
+
+
+_ENC_SHAPES = [(3, 3, 1)] + [(o, i, 3) for i, o in
+                             ((3, 64), (64, 64), (64, 128), (128, 128), (128, 256), (256, 256),
+                              (256, 256), (256, 256), (256, 512))]
+_DEC_SHAPES = [(o, i, 3) for i, o in
+               ((512, 256), (256, 256), (256, 256), (256, 256), (256, 128), (128, 128), (128, 64),
+                (64, 64), (64, 3))]
+
+
+def _host_arrays(convs, shapes, what):
+    ws, bs = [], []
+    for k, (conv, (o, i, ks)) in enumerate(zip(convs, shapes)):
+        w = conv.weight.detach()
+        if tuple(w.shape) != (o, i, ks, ks):
+            raise RuntimeError(f"{what}: conv {k} has weight {tuple(w.shape)}, expected {(o, i, ks, ks)}")
+        b = conv.bias.detach() if conv.bias is not None else torch.zeros(o)
+        ws.append(w.to("cpu", torch.float32).contiguous())
+        bs.append(b.to("cpu", torch.float32).contiguous())
+    return ws, bs
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for k, t in enumerate(tensors):
+        arr[k] = t.data_ptr()
+    return arr
+
+
+def _version(seq: nn.Module):
+    return tuple((p.data_ptr(), p._version) for p in seq.parameters())
+
+
+class Engine:
+    """One `ccst_handle` (packed weights + activation arena) on one GPU."""
+
+    def __init__(self, vgg: nn.Module = None, decoder: nn.Module = None, device=None):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ccst_b200.Engine needs a CUDA (B200) device; there is no CPU fallback")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        with torch.cuda.device(self.device):
+            torch.cuda.init()
+            self._h = _lib.lib().ccst_create(idx)
+        if not self._h:
+            raise _lib.CcstError(_lib.ECUDA, _lib.lib().ccst_last_error().decode())
+        self._finalizer = weakref.finalize(self, _lib.lib().ccst_destroy, self._h)
+        self._enc_version = None
+        self._dec_version = None
+        if vgg is not None:
+            self.set_encoder(vgg)
+        if decoder is not None:
+            self.set_decoder(decoder)
+
+    # -- weights -----------------------------------------------------------
+    def set_encoder(self, vgg: nn.Module):
+        ver = _version(vgg)
+        if ver == self._enc_version:
+            return
+        ws, bs = _host_arrays(_conv_params(vgg, 10, "vgg"), _ENC_SHAPES, "vgg")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ccst_set_encoder_weights(self._h, _ptr_array(ws), _ptr_array(bs)))
+        self._enc_version = ver
+
+    def set_decoder(self, decoder: nn.Module):
+        ver = _version(decoder)
+        if ver == self._dec_version:
+            return
+        ws, bs = _host_arrays(_conv_params(decoder, 9, "decoder"), _DEC_SHAPES, "decoder")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ccst_set_decoder_weights(self._h, _ptr_array(ws), _ptr_array(bs)))
+        self._dec_version = ver
+
+    # -- helpers -----------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _img(self, t, name):
+        t = F_._prep(t, name)
+        if t.device != self.device:
+            raise RuntimeError(f"{name} is on {t.device}, engine on {self.device}")
+        if t.dim() != 4 or t.shape[1] != 3:
+            raise RuntimeError(f"{name} must be [N,3,H,W], got {tuple(t.shape)}")
+        return t
+
+    # -- entry points --------------------------------------------------------
+    def encode(self, images, precision=DEFAULT_PRECISION):
+        """vgg(images) -> relu4_1 [N,512,h,w] fp32."""
+        x = self._img(images, "images")
+        n, _, h, w = x.shape
+        fh, fw = _lib.feature_hw(h, w)
+        out = torch.empty((n, 512, fh, fw), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ccst_encoder_fwd(self._h, x.data_ptr(), n, h, w, out.data_ptr(),
+                                                   PRECISIONS[precision], self._stream()))
+        return out
+
+    def decode(self, feat, precision=DEFAULT_PRECISION):
+        """decoder(feat): [N,512,h,w] -> [N,3,8h,8w] fp32."""
+        x = F_._prep(feat, "feat")
+        if x.dim() != 4 or x.shape[1] != 512:
+            raise RuntimeError(f"feat must be [N,512,h,w], got {tuple(x.shape)}")
+        n, _, fh, fw = x.shape
+        out = torch.empty((n, 3, 8 * fh, 8 * fw), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ccst_decoder_fwd(self._h, x.data_ptr(), n, fh, fw, out.data_ptr(),
+                                                   PRECISIONS[precision], self._stream()))
+        return out
+
+    def accumulate(self, images, state: "F_.WelfordState", precision=DEFAULT_PRECISION):
+        """One iteration of the overall-statistics loop
+        (mean_std_computation_effcientMem.py:121-131): encode + fold relu4_1 into `state`."""
+        x = self._img(images, "images")
+        n, _, h, w = x.shape
+        if state.C != 512 or state.device != self.device:
+            raise RuntimeError("state must be a 512-channel WelfordState on the engine's device")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ccst_encoder_accumulate(self._h, x.data_ptr(), n, h, w,
+                                                          state.buf.data_ptr(), PRECISIONS[precision],
+                                                          self._stream()))
+        return state
+
+    def transfer(self, content, style_stat, alpha=1.0, precision=DEFAULT_PRECISION, out=None):
+        """Fused encoder -> AdaIN(+alpha) -> decoder; activations never leave the arena."""
+        assert (0.0 <= alpha <= 1.0)
+        x = self._img(content, "content")
+        n, _, h, w = x.shape
+        mu, sg, stride = F_._style_stat_args(style_stat, n, 512, self.device)
+        fh, fw = _lib.feature_hw(h, w)
+        if out is None:
+            out = torch.empty((n, 3, 8 * fh, 8 * fw), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ccst_style_transfer(
+                self._h, x.data_ptr(), n, h, w, mu.data_ptr(), sg.data_ptr(), stride, float(alpha),
+                out.data_ptr(), PRECISIONS[precision], self._stream()))
+        return out
+
+    # -- profiling -----------------------------------------------------------
+    def profile(self, on: bool):
+        _lib.check(_lib.lib().ccst_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, max_entries=48):
+        ms = (C.c_float * max_entries)()
+        fl = (C.c_double * max_entries)()
+        by = (C.c_double * max_entries)()
+        kd = (C.c_int * max_entries)()
+        n = _lib.check(_lib.lib().ccst_profile_read(self._h, max_entries, ms, fl, by, kd))
+        return [dict(ms=ms[i], flops=fl[i], bytes=by[i], kind=kd[i]) for i in range(n)]
+
+    def debug_conv3x3(self, x_nhwc, weight, bias, relu=True, mode=0, precision=DEFAULT_PRECISION):
+        """Single 3x3 reflect-pad conv through the selected engine (tests only)."""
+        x = F_._prep(x_nhwc, "x_nhwc")
+        n, h, w, cin = x.shape
+        cout = weight.shape[0]
+        wh = weight.detach().to("cpu", torch.float32).contiguous()
+        bh = bias.detach().to("cpu", torch.float32).contiguous()
+        if mode == 0:
+            shape = (n, h, w, cout)
+        elif mode == 1:
+            shape = (n, 2 * h, 2 * w, cout)
+        elif mode == 2:
+            shape = (n, (h + 1) // 2, (w + 1) // 2, cout)
+        else:
+            shape = (n, cout, h, w)
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ccst_debug_conv3x3(
+                self._h, x.data_ptr(), n, h, w, cin, cout, wh.data_ptr(), bh.data_ptr(),
+                1 if relu else 0, mode, out.data_ptr(), PRECISIONS[precision], self._stream()))
+        return out
+
+
+_ENGINES = {}
+
+
+def engine_for(vgg: nn.Module, decoder: nn.Module, device) -> Engine:
+    """Engine cached per (vgg object, decoder object, device); weights are re-packed when the
+    modules' parameters change (load_state_dict, .to(), in-place edits)."""
+    device = torch.device(device)
+    key = (id(vgg), id(decoder), device.index if device.index is not None else torch.cuda.current_device())
+    eng = _ENGINES.get(key)
+    if eng is None or eng._vgg_ref() is not vgg or eng._dec_ref() is not decoder:
+        eng = Engine(device=device)
+        eng._vgg_ref = weakref.ref(vgg)
+        eng._dec_ref = weakref.ref(decoder)
+        _ENGINES[key] = eng
+    eng.set_encoder(vgg)
+    eng.set_decoder(decoder)
+    return eng
+
+
+def style_transfer(vgg, decoder, content, style, alpha=1.0, interpolation_weights=None, *,
+                   precision=None):
+    """Reference signature (CCST_OverallStyleTransfer.py:32).  `precision` is a keyword-only
+    extension: "bf16" (tcgen05 convs, default) or "fp32" (FFMA validation mode)."""
+    assert (0.0 <= alpha <= 1.0)
+    precision = precision or DEFAULT_PRECISION
+    if not isinstance(content, torch.Tensor) or not content.is_cuda:
+        raise RuntimeError("content must be a CUDA tensor: ccst_b200 has no CPU fallback")
+    eng = engine_for(vgg, decoder, content.device)
+    is_image_style = isinstance(style, torch.Tensor) and style.dim() == 4 and style.shape[1] == 3
+    if is_image_style:
+        # upstream AdaIN form: per-sample statistics of the encoded style images
+        assert (content.size()[0] == style.size()[0])
+        style_f = eng.encode(style.to(content.device), precision)
+        style = F_.calc_mean_std(style_f)
+    if interpolation_weights:
+        # CCST_OverallStyleTransfer.py:36-42 (never taken by the CCST drivers; kept for the signature)
+        content_f = eng.encode(content, precision)
+        base = F_.adaIN_StyleStat_ContentFeat(content_f, style)
+        feat = torch.zeros_like(content_f[0:1])
+        for i, w in enumerate(interpolation_weights):
+            feat = feat + w * base[i:i + 1]
+        feat = feat * alpha + content_f[0:1] * (1 - alpha)
+        return eng.decode(feat, precision)
+    return eng.transfer(content, style, alpha, precision)

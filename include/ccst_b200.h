@@ -1,0 +1,177 @@
+/*
+ * ccst_b200.h -- C ABI of libccst_b200.so: the B200 (sm_100a) implementation of
+ * the AdaIN style-transfer hot path of JeremyCJM/CCST.
+ *
+ * The reference has no FFI/plugin interface (it is pure Python calling PyTorch),
+ * so these entry points are what a binding for the reference's hot-path callables
+ * would bind; each one names the reference code it replaces (paths relative to
+ * /root/reference/style_transfer/AdaIN).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a
+ *     host pointer.  Tensors are contiguous NCHW fp32 exactly as the reference
+ *     passes them (function.py:9 requires contiguity for .view()).
+ *   - outputs are caller-allocated; the library never returns memory it owns,
+ *     except through the opaque ccst_handle (packed weights + activation arena).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     All work is enqueued asynchronously; no entry point synchronises unless
+ *     its comment says so.
+ *   - return value: 0 on success, a negative CCST_E* code otherwise;
+ *     ccst_last_error() returns a thread-local message for the last failure.
+ *   - there is no CPU fallback: on a device that is not compute capability 10.x
+ *     every compute entry point returns CCST_EARCH.
+ */
+#ifndef CCST_B200_H_
+#define CCST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCST_ABI_VERSION 1
+
+#define CCST_OK 0
+#define CCST_EINVAL (-1)  /* bad shape / null pointer / bad argument          */
+#define CCST_EARCH (-2)   /* device is not sm_100                             */
+#define CCST_ECUDA (-3)   /* CUDA runtime/driver error (see ccst_last_error)  */
+#define CCST_ESTATE (-4)  /* handle not ready (weights missing ...)           */
+
+/* precision of the encoder/decoder convolutions */
+#define CCST_PREC_FP32 0 /* fp32 activations + fp32 FFMA implicit GEMM (validation mode, 1e-4) */
+#define CCST_PREC_BF16 1 /* bf16 activations + tcgen05/TMEM implicit GEMM fed by TMA (fp32 accum) */
+
+typedef struct ccst_handle ccst_handle;
+
+int ccst_abi_version(void);
+const char* ccst_last_error(void);
+/* 0 if `device` is an sm_100 GPU, CCST_EARCH otherwise. */
+int ccst_check_device(int device);
+
+/* ------------------------------------------------------------------------
+ * Feature statistics
+ * ---------------------------------------------------------------------- */
+
+/* calc_mean_std(feat, eps)  [function.py:4-13]
+ * per (n,c) plane of `hw` contiguous floats: mean and sqrt(var + eps);
+ * unbiased != 0 divides by (hw-1) as torch.var does (hw == 1 -> NaN, as the
+ * reference), unbiased == 0 divides by hw.  d_mean/d_std hold `planes` floats.
+ * Either output may be NULL. */
+int ccst_stats_nchw_f32(const float* d_x, int64_t planes, int64_t hw, float eps, int unbiased,
+                        float* d_mean, float* d_std, void* stream);
+
+/* Running per-channel Welford state of one client
+ * [mean_std_computation_effcientMem.py:117 `all_feat_sum, all_feat_square_sum,
+ * all_count`], kept on the device as 1+2C doubles: {count, mean[C], M2[C]}.
+ * Zero it (cudaMemset) to start a client. */
+
+/* calc_sum(feat) + `all_* += ...`  [mean_std_computation_effcientMem.py:103-115,129-131]
+ * Folds the batch d_x = [N,C,HW] into d_state with one pass over d_x
+ * (per-plane Welford, then a Chan merge over N and into the state, in fp64).
+ * d_scratch must hold 2*N*C floats. */
+int ccst_welford_accumulate_nchw_f32(const float* d_x, int N, int C, int64_t hw, double* d_state,
+                                     float* d_scratch, void* stream);
+
+/* finalise  [mean_std_computation_effcientMem.py:135-137, CCST_SingleStyleTransfer.py:201-203]
+ * mean = state.mean, std = sqrt(M2/count + eps) (biased), as fp32 [C]. */
+int ccst_welford_finalize(const double* d_state, int C, float eps, float* d_mean, float* d_std,
+                          void* stream);
+
+/* calc_sum's return values from a state: sum = n*mean, sqsum = M2 + n*mean^2 (fp32 [C]). */
+int ccst_welford_to_sums(const double* d_state, int C, float* d_sum, float* d_sqsum, void* stream);
+
+/* State <-> exactly-summable moments {n, n*mean[C], M2[C]+n*mean[C]^2} (fp64), the payload of the
+ * single all-reduce(sum) that merges the per-GPU partials of one client. */
+int ccst_welford_to_moments(const double* d_state, int C, double* d_moments, void* stream);
+int ccst_welford_from_moments(const double* d_moments, int C, double* d_state, void* stream);
+
+/* ------------------------------------------------------------------------
+ * AdaIN
+ * ---------------------------------------------------------------------- */
+
+/* adaIN_StyleStat_ContentFeat(content_feat, style_stat) followed by the alpha blend of
+ * style_transfer  [function.py:26-33, CCST_OverallStyleTransfer.py:44-45]:
+ *   out = alpha * ((x - mu_c)/sigma_c * sigma_s + mu_s) + (1 - alpha) * x
+ * with (mu_c, sigma_c) = calc_mean_std(x) computed in the same pass.  d_mu_s/d_sigma_s are
+ * [C] when stat_batch_stride == 0 (the reference's [1,C,1,1] broadcast) or [N,C] with
+ * stat_batch_stride == C.  alpha = 1 gives the bare operator. */
+int ccst_adain_stat_nchw_f32(const float* d_x, int N, int C, int64_t hw, const float* d_mu_s,
+                             const float* d_sigma_s, int64_t stat_batch_stride, float alpha,
+                             float eps, float* d_out, void* stream);
+
+/* adaptive_instance_normalization(content_feat, style_feat)  [function.py:16-24] (+ alpha blend).
+ * style is [N,C,hw_s]; d_scratch must hold 2*N*C floats (style mean/std). */
+int ccst_adain_feat_nchw_f32(const float* d_content, const float* d_style, int N, int C,
+                             int64_t hw_c, int64_t hw_s, float alpha, float eps, float* d_out,
+                             float* d_scratch, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Encoder / decoder / style_transfer
+ * ---------------------------------------------------------------------- */
+
+ccst_handle* ccst_create(int device);
+void ccst_destroy(ccst_handle* h);
+
+/* vgg[:31] weights  [net.py:38-69]: 10 convolutions in order (the 1x1 colour conv first),
+ * HOST pointers, fp32, OIHW contiguous, exactly as in the state_dict.  The library folds
+ * the 1x1 conv into conv1_1, packs K-major bf16 + fp32 copies and uploads them. Synchronous. */
+int ccst_set_encoder_weights(ccst_handle* h, const float* const* h_weights,
+                             const float* const* h_biases);
+/* decoder weights  [net.py:6-36]: 9 convolutions in order. Synchronous. */
+int ccst_set_decoder_weights(ccst_handle* h, const float* const* h_weights,
+                             const float* const* h_biases);
+
+/* vgg(content)  [CCST_OverallStyleTransfer.py:35]: [N,3,H,W] -> relu4_1 [N,512,h,w] with
+ * h = ceil(ceil(ceil(H/2)/2)/2).  H, W >= 8. */
+int ccst_encoder_fwd(ccst_handle* h, const float* d_img, int N, int H, int W, float* d_feat,
+                     int precision, void* stream);
+/* decoder(feat)  [CCST_OverallStyleTransfer.py:46]: [N,512,fh,fw] -> [N,3,8fh,8fw]. */
+int ccst_decoder_fwd(ccst_handle* h, const float* d_feat, int N, int fh, int fw, float* d_img,
+                     int precision, void* stream);
+
+/* style_transfer(vgg, decoder, content, style_stat, alpha)  [CCST_OverallStyleTransfer.py:32-46]
+ * d_out is [N,3,8h,8w] (== [N,3,H,W] when H and W are multiples of 8). Activations stay on the
+ * device in the handle's arena between the layers (NHWC with a reflection halo). */
+int ccst_style_transfer(ccst_handle* h, const float* d_img, int N, int H, int W,
+                        const float* d_mu_s, const float* d_sigma_s, int64_t stat_batch_stride,
+                        float alpha, float* d_out, int precision, void* stream);
+
+/* one iteration of the overall-statistics loop: vgg(data) + calc_sum + accumulate
+ * [mean_std_computation_effcientMem.py:121-131], encoder output never leaves the arena. */
+int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N, int H, int W,
+                            double* d_state, int precision, void* stream);
+
+/* shape helper: relu4_1 spatial size for an input of H x W */
+void ccst_feature_hw(int H, int W, int* fh, int* fw);
+
+/* number of kernels this library has launched in this process (monotonic). */
+int64_t ccst_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Diagnostics (used by tests/ and bench.py only)
+ * ---------------------------------------------------------------------- */
+
+/* One reflect-pad 3x3 convolution through the selected engine on caller data:
+ * d_in  [N,H,W,Cin]  NHWC fp32 (unpadded), h_weight OIHW fp32 [Cout,Cin,3,3], h_bias [Cout].
+ * mode 0: d_out [N,H,W,Cout]; mode 1: nearest x2 fused, d_out [N,2H,2W,Cout]; mode 2: 2x2 ceil-mode
+ * max-pool fused (requires relu), d_out [N,ceil(H/2),ceil(W/2),Cout]; mode 3: Cout <= 16, d_out is
+ * NCHW [N,Cout,H,W] (the last decoder conv's store).  d_out is fp32. Synchronous. */
+int ccst_debug_conv3x3(ccst_handle* h, const float* d_in, int N, int H, int W, int Cin, int Cout,
+                       const float* h_weight, const float* h_bias, int relu, int mode,
+                       float* d_out, int precision, void* stream);
+
+/* Per-launch device timing of the encoder/decoder entry points (CUDA events recorded on the
+ * caller's stream around every kernel the entry point enqueues).  Off by default. */
+int ccst_profile_enable(ccst_handle* h, int on);
+/* Synchronises the recorded events of the LAST encoder/decoder/style_transfer call and returns
+ * the number of launches; for launch i: ms[i] device time, flops[i] algorithmic FLOPs (convs,
+ * else 0), bytes[i] algorithmic HBM bytes, kind[i]: 0 conv_first, 1 tcgen05 conv, 2 ffma conv,
+ * 3 pool, 4 adain/stats, 5 layout convert.  Arrays hold `max` entries. */
+int ccst_profile_read(ccst_handle* h, int max, float* ms, double* flops, double* bytes, int* kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCST_B200_H_ */

@@ -1,0 +1,205 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REAL reference code.
+
+Run in the build container only (needs /root/reference, read-only):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+* `function.py` and `net.py` are imported from
+  /root/reference/style_transfer/AdaIN unchanged.
+* `style_transfer` / `calc_sum` are FunctionDef nodes AST-extracted from
+  CCST_OverallStyleTransfer.py / mean_std_computation_effcientMem.py /
+  CCST_SingleStyleTransfer.py (the scripts cannot be imported: argparse and
+  torch.load run at module level), compiled and exec'd as they are.
+* the accumulate / finalise statements of the scripts
+  (mean_std_computation_effcientMem.py:129-131,135-137 and
+  CCST_SingleStyleTransfer.py:201-203) are exec'd from their source lines.
+
+Inputs and weights come from ccst_b200.synth (seeded, CPU generator).  The
+resulting vectors travel with the repo; the reference does not.
+"""
+from __future__ import annotations
+
+import ast
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("CCST_REF", "/root/reference/style_transfer/AdaIN")
+sys.dont_write_bytecode = True
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+import function as ref_function  # noqa: E402  (reference)
+import net as ref_net  # noqa: E402  (reference)
+
+from ccst_b200 import synth  # noqa: E402
+
+
+def _extract_funcs(path, names, ns):
+    src = open(path).read()
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            mod = ast.Module(body=[node], type_ignores=[])
+            exec(compile(mod, path, "exec"), ns)
+    return ns
+
+
+def _source_lines(path, first, last):
+    import textwrap
+    lines = open(path).read().splitlines()[first - 1:last]
+    return textwrap.dedent("\n".join(lines)) + "\n"
+
+
+def ref_models(seed=0):
+    """Reference nn.Sequential objects carrying the synthetic weights."""
+    vgg_full = ref_net.vgg
+    dec = ref_net.decoder
+    synth.init_vgg_(vgg_full, seed)
+    synth.init_decoder_(dec, seed)
+    vgg = torch.nn.Sequential(*list(vgg_full.children())[:31])
+    return vgg.eval(), dec.eval()
+
+
+def weights_digest(*mods):
+    h = hashlib.sha256()
+    for m in mods:
+        for k, v in m.state_dict().items():
+            h.update(k.encode())
+            h.update(v.detach().cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def main():
+    torch.set_num_threads(1)  # deterministic reduction order
+    out = {}
+    overall_py = os.path.join(REF, "CCST_OverallStyleTransfer.py")
+    single_py = os.path.join(REF, "CCST_SingleStyleTransfer.py")
+    stats_py = os.path.join(REF, "mean_std_computation_effcientMem.py")
+
+    ns_overall = {"torch": torch, "device": torch.device("cpu"),
+                  "adaIN_StyleStat_ContentFeat": ref_function.adaIN_StyleStat_ContentFeat}
+    _extract_funcs(overall_py, {"style_transfer"}, ns_overall)
+    ns_single = dict(ns_overall)
+    _extract_funcs(single_py, {"style_transfer", "calc_sum"}, ns_single)
+    ns_stats = {"torch": torch}
+    _extract_funcs(stats_py, {"calc_sum", "calc_mean_std"}, ns_stats)
+
+    # ---------------- statistics ----------------
+    stats = {}
+    cases = {
+        "s_small": synth.features((3, 16, 9, 7), 11),
+        "s_12x12": synth.features((4, 32, 12, 12), 12),
+        "s_64x64": synth.features((2, 8, 64, 64), 13),
+        "s_odd": synth.features((2, 5, 7, 7), 14),
+        "s_bigmean": synth.features((2, 6, 16, 16), 15, relu=False) + 300.0,
+        "s_hw1": synth.features((2, 4, 1, 1), 16),
+    }
+    const = synth.features((1, 4, 8, 8), 17)
+    const[:, 1] = 0.0
+    const[:, 2] = 2.5
+    cases["s_const"] = const
+    for name, feat in cases.items():
+        m, s = ref_function.calc_mean_std(feat)
+        stats[name + "/x"] = feat.numpy()
+        stats[name + "/mean"] = m.numpy()
+        stats[name + "/std"] = s.numpy()
+        m64, s64 = ref_function.calc_mean_std(feat.double())
+        stats[name + "/mean64"] = m64.numpy()
+        stats[name + "/std64"] = s64.numpy()
+    np.savez_compressed(os.path.join(HERE, "stats.npz"), **stats)
+
+    # ---------------- AdaIN ----------------
+    adain = {}
+    c = synth.features((3, 16, 10, 12), 21)
+    s = synth.features((3, 16, 7, 9), 22)
+    adain["feat/content"] = c.numpy()
+    adain["feat/style"] = s.numpy()
+    adain["feat/out"] = ref_function.adaptive_instance_normalization(c, s).numpy()
+    sm = torch.randn((1, 16, 1, 1), generator=torch.Generator().manual_seed(23))
+    ss = torch.rand((1, 16, 1, 1), generator=torch.Generator().manual_seed(24)) + 0.1
+    adain["stat/content"] = c.numpy()
+    adain["stat/mean"] = sm.numpy()
+    adain["stat/std"] = ss.numpy()
+    adain["stat/out"] = ref_function.adaIN_StyleStat_ContentFeat(c, [sm, ss]).numpy()
+    c2 = synth.features((2, 8, 64, 64), 25)
+    sm2 = torch.randn((1, 8, 1, 1), generator=torch.Generator().manual_seed(26))
+    ss2 = torch.rand((1, 8, 1, 1), generator=torch.Generator().manual_seed(27)) + 0.1
+    adain["stat64/content"] = c2.numpy()
+    adain["stat64/mean"] = sm2.numpy()
+    adain["stat64/std"] = ss2.numpy()
+    adain["stat64/out"] = ref_function.adaIN_StyleStat_ContentFeat(c2, [sm2, ss2]).numpy()
+    np.savez_compressed(os.path.join(HERE, "adain.npz"), **adain)
+
+    # ---------------- calc_sum + accumulation + finalise ----------------
+    acc = {}
+    batches = [synth.features((3, 12, 8, 8), 31), synth.features((3, 12, 8, 8), 32),
+               synth.features((2, 12, 8, 8), 33)]
+    accumulate_src = _source_lines(stats_py, 129, 131)
+    finalize_src = _source_lines(stats_py, 135, 137)
+    assert "all_feat_sum += feat_sum" in accumulate_src, accumulate_src
+    assert "feat_std = torch.sqrt(feat_var + 1e-5)" in finalize_src, finalize_src
+    for tag, cast in (("f32", lambda t: t), ("f64", lambda t: t.double())):
+        env = {"torch": torch, "all_feat_sum": 0, "all_feat_square_sum": 0, "all_count": 0}
+        for i, b in enumerate(batches):
+            fs, fss, cnt = ns_stats["calc_sum"](cast(b))
+            if tag == "f32":
+                acc[f"b{i}/x"] = b.numpy()
+                acc[f"b{i}/sum"] = fs.numpy()
+                acc[f"b{i}/sqsum"] = fss.numpy()
+                acc[f"b{i}/count"] = np.int64(cnt)
+            env.update(feat_sum=fs, feat_square_sum=fss, count=cnt)
+            exec(accumulate_src, env)
+        exec(finalize_src, env)
+        acc[f"final_{tag}/mean"] = env["feat_mean"].numpy()
+        acc[f"final_{tag}/std"] = env["feat_std"].numpy()
+        acc[f"final_{tag}/count"] = np.int64(env["all_count"])
+    # the np.save payload of :146
+    acc["npy_payload"] = np.asarray([acc["final_f32/mean"], acc["final_f32/std"]])
+    np.savez_compressed(os.path.join(HERE, "overall_stats.npz"), **acc)
+
+    # ---------------- encoder / decoder / style_transfer ----------------
+    vgg, dec = ref_models(0)
+    net = {"weights_sha256": np.frombuffer(weights_digest(vgg, dec).encode(), dtype=np.uint8)}
+    single_final_src = _source_lines(single_py, 201, 203)
+    assert "feat_std = torch.sqrt(feat_var + 1e-5)" in single_final_src
+    with torch.no_grad():
+        for tag, (n, h, w) in {"sq40": (2, 40, 40), "odd37x45": (1, 37, 45), "r96": (2, 96, 96)}.items():
+            x = synth.images(n, h, w, 41 + h)
+            f = vgg(x)
+            style_img = synth.images(1, h + 8, w + 3, 77 + h)
+            sf = vgg(style_img)
+            env = {"torch": torch}
+            fs, fss, cnt = ns_single["calc_sum"](sf)
+            env.update(feat_sum=fs, feat_square_sum=fss, count=cnt,
+                       feat_mean=fs / float(cnt))
+            exec(single_final_src, env)
+            style_stat = [env["feat_mean"], env["feat_std"]]
+            net[f"{tag}/x"] = x.numpy()
+            net[f"{tag}/style_img"] = style_img.numpy()
+            net[f"{tag}/feat"] = f.numpy()
+            net[f"{tag}/style_mean"] = style_stat[0].numpy()
+            net[f"{tag}/style_std"] = style_stat[1].numpy()
+            net[f"{tag}/dec_of_feat"] = dec(f).numpy()
+            for alpha in (1.0, 0.6):
+                o = ns_overall["style_transfer"](vgg, dec, x, style_stat, alpha)
+                net[f"{tag}/out_a{alpha}"] = o.numpy()
+                o2 = ns_single["style_transfer"](vgg, dec, x, style_stat, alpha)
+                assert torch.equal(o, o2)
+            if n >= 2:
+                o = ns_overall["style_transfer"](vgg, dec, x, style_stat, 1.0, [0.25, 0.75])
+                net[f"{tag}/out_interp"] = o.numpy()
+    np.savez_compressed(os.path.join(HERE, "net.npz"), **net)
+    for fn in ("stats", "adain", "overall_stats", "net"):
+        p = os.path.join(HERE, fn + ".npz")
+        print(fn, os.path.getsize(p) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,104 @@
+"""CPU: the oracle restatement must reproduce the vectors produced by the REAL reference
+(tests/golden/make_golden.py).  This is what pins the oracle."""
+import hashlib
+
+import numpy as np
+import torch
+
+from oracle import ccst_oracle as O
+
+T = torch.from_numpy
+
+
+def test_calc_mean_std_matches_reference(golden):
+    g = golden["stats"]
+    names = sorted({k.split("/")[0] for k in g.files})
+    assert len(names) >= 7
+    for name in names:
+        x = T(g[name + "/x"])
+        m, s = O.calc_mean_std(x)
+        np.testing.assert_array_equal(m.numpy(), g[name + "/mean"])
+        np.testing.assert_array_equal(s.numpy(), g[name + "/std"])  # NaN == NaN for hw == 1
+        m64, s64 = O.calc_mean_std_f64(x)
+        np.testing.assert_allclose(m64.numpy(), g[name + "/mean64"], rtol=1e-12)
+        np.testing.assert_allclose(s64.numpy(), g[name + "/std64"], rtol=1e-12)
+    assert np.isnan(g["s_hw1/std"]).all()  # the reference's HW == 1 behaviour
+    assert np.allclose(g["s_const/std"][0, 1], np.sqrt(1e-5))  # dead channel -> sqrt(eps)
+
+
+def test_adain_matches_reference(golden):
+    g = golden["adain"]
+    out = O.adaptive_instance_normalization(T(g["feat/content"]), T(g["feat/style"]))
+    np.testing.assert_array_equal(out.numpy(), g["feat/out"])
+    for tag in ("stat", "stat64"):
+        out = O.adaIN_StyleStat_ContentFeat(T(g[tag + "/content"]), [T(g[tag + "/mean"]), T(g[tag + "/std"])])
+        np.testing.assert_array_equal(out.numpy(), g[tag + "/out"])
+
+
+def test_overall_accumulation_matches_reference(golden):
+    g = golden["overall_stats"]
+    batches = [T(g[f"b{i}/x"]) for i in range(3)]
+    for i, b in enumerate(batches):
+        s1, s2, cnt = O.calc_sum(b)
+        np.testing.assert_array_equal(s1.numpy(), g[f"b{i}/sum"])
+        np.testing.assert_array_equal(s2.numpy(), g[f"b{i}/sqsum"])
+        assert cnt == int(g[f"b{i}/count"])
+    mean, std, n, imgs = O.overall_style_stats(batches)
+    np.testing.assert_array_equal(mean.numpy(), g["final_f32/mean"])
+    np.testing.assert_array_equal(std.numpy(), g["final_f32/std"])
+    assert n == int(g["final_f32/count"]) and imgs == 8
+    mean64, std64, _, _ = O.overall_style_stats(batches, dtype=torch.float64)
+    np.testing.assert_allclose(mean64.numpy(), g["final_f64/mean"], rtol=1e-12)
+    np.testing.assert_allclose(std64.numpy(), g["final_f64/std"], rtol=1e-12)
+    payload = O.pack_style_npy(mean, std)
+    assert payload.shape == (2, 1, 12, 1, 1) and payload.dtype == np.float32
+    np.testing.assert_array_equal(payload, g["npy_payload"])
+
+
+def test_synthetic_weights_are_reproducible(golden, models):
+    vgg, dec = models
+    h = hashlib.sha256()
+    for m in (vgg, dec):
+        for k, v in m.state_dict().items():
+            h.update(k.encode())
+            h.update(v.detach().cpu().numpy().tobytes())
+    assert h.hexdigest() == bytes(golden["net"]["weights_sha256"]).decode()
+
+
+def test_network_and_style_transfer_match_reference(golden, models):
+    g = golden["net"]
+    vgg, dec = models
+    torch.set_num_threads(1)
+    with torch.no_grad():
+        for tag in ("sq40", "odd37x45", "r96"):
+            x = T(g[tag + "/x"])
+            f = O.encode_relu4_1(vgg, x)
+            np.testing.assert_allclose(f.numpy(), g[tag + "/feat"], rtol=0, atol=2e-5)
+            ms, ss = O.single_style_stats(O.encode_relu4_1(vgg, T(g[tag + "/style_img"])))
+            np.testing.assert_allclose(ms.numpy(), g[tag + "/style_mean"], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(ss.numpy(), g[tag + "/style_std"], rtol=1e-5, atol=1e-6)
+            stat = [T(g[tag + "/style_mean"]), T(g[tag + "/style_std"])]
+            np.testing.assert_allclose(O.decode(dec, T(g[tag + "/feat"])).numpy(), g[tag + "/dec_of_feat"],
+                                       rtol=0, atol=2e-5)
+            for alpha in (1.0, 0.6):
+                out = O.style_transfer(vgg, dec, x, stat, alpha)
+                np.testing.assert_allclose(out.numpy(), g[f"{tag}/out_a{alpha}"], rtol=0, atol=5e-5)
+            if x.shape[0] >= 2:
+                out = O.style_transfer(vgg, dec, x, stat, 1.0, [0.25, 0.75])
+                assert out.shape[0] == 1
+                np.testing.assert_allclose(out.numpy(), g[tag + "/out_interp"], rtol=0, atol=5e-5)
+    # shapes the survey lists (222 -> 28 -> 224)
+    assert O.encode_relu4_1(vgg, torch.zeros(1, 3, 37, 45)).shape == (1, 512, 5, 6)
+
+
+def test_image_style_form_equals_stat_form(models):
+    """style given as images == per-sample calc_mean_std of the encoded style (function.py:16-24)."""
+    from ccst_b200 import synth
+
+    vgg, dec = models
+    x, s = synth.images(2, 32, 32, 1), synth.images(2, 40, 32, 2)
+    with torch.no_grad():
+        a = O.style_transfer_image_style(vgg, dec, x, s, 0.7)
+        stat = O.calc_mean_std(O.encode_relu4_1(vgg, s))
+        b = O.style_transfer(vgg, dec, x, stat, 0.7)
+    assert torch.allclose(a, b, atol=1e-6)
