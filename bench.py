@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the CCST AdaIN style-transfer hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
+
+Metric (BASELINE.json): stylised images/s @512^2.  One *step* = one batch of the CCST Overall
+transfer (config 3): `style_transfer(vgg, decoder, content[32,3,512,512], overall style stats,
+alpha=1)` -- VGG-19 encoder to relu4_1, AdaIN, decoder.  With N GPUs every rank owns its own
+batches (the path shards by image, no data-path collective) -> weak scaling.
+
+Printed JSON (one line, rank 0):
+  value       images/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e         same metric through the public API `ccst_b200.style_transfer` with pinned HOST
+              buffers: H2D of the batch and D2H of the stylised images inside the timed region
+  roofline    tcgen05 convolution kernels (dominant: ~99 % of the FLOPs) vs the measured bf16
+              peak; extra `roofline_adain` / `roofline_stats` objects for the HBM-bound operators
+  cpu_baseline the oracle port of the reference path (PyTorch CPU, all host cores) on a bounded
+              sample of the same workload
+Weights are random-init (seeded) VGG-19/decoder, images synthetic: no dataset/checkpoint offline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "stylised_images_per_sec_512"
+UNIT = "images/s"
+BATCH = 32
+SIZE = 512
+FLOP_PER_IMG = 253.072e9  # SURVEY.md §8d (enc 126.538 + dec 126.534 GFLOP @512^2)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"],
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_throughput(steps, warmup, sample_imgs, seed=0):
+    """The reference path on the host: oracle port (PyTorch CPU conv/ATen, all cores)."""
+    import torch
+
+    from ccst_b200 import synth
+    from oracle import ccst_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vgg, dec = synth.make_models(seed)
+    g = torch.Generator().manual_seed(7)
+    stat = [torch.randn((1, 512, 1, 1), generator=g).abs(), torch.rand((1, 512, 1, 1), generator=g) + 0.1]
+    x = synth.images(sample_imgs, SIZE, SIZE, 123)
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.style_transfer(vgg, dec, x, stat, 1.0)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.style_transfer(vgg, dec, x, stat, 1.0)
+        dt = time.perf_counter() - t0
+    return sample_imgs * steps / dt, dt / steps, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sample = 2
+    ips, sec_per_step, cores = cpu_reference_throughput(args.steps, args.warmup, sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(ips, 4), "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(sec_per_step * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CCST Overall K=3 transfer step (config 3): style_transfer batch @512x512, "
+                               "random-init VGG-19 relu4_1 encoder + decoder, alpha=1",
+                   "batch_per_step": sample, "image": [3, SIZE, SIZE]},
+        "cpu_baseline": {"value": round(ips, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} images per step (batch {BATCH} of the GPU arm scaled down), "
+                                   "oracle port of the reference path on PyTorch CPU"},
+        "e2e": {"value": round(ips, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def time_op(fn, iters, torch):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters  # ms
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    import ccst_b200
+    from ccst_b200 import _lib, synth
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200 GPU; ccst_b200 has no CPU fallback "
+                           "(use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    precision = args.precision
+    vgg, dec = synth.make_models(0)
+    eng = ccst_b200.engine_for(vgg, dec, dev)
+
+    # every rank owns different images (seed offset by rank); two batches alternate so that a step
+    # never finds its input in L2 (each batch's activations are > 1 GB anyway, L2 is 126 MB)
+    host = [synth.images(args.batch, SIZE, SIZE, 1000 + 10 * rank + i).pin_memory() for i in range(2)]
+    dev_in = [h.to(dev) for h in host]
+    g = torch.Generator().manual_seed(7)
+    stat = [torch.randn((1, 512, 1, 1), generator=g).abs().to(dev),
+            (torch.rand((1, 512, 1, 1), generator=g) + 0.1).to(dev)]
+    out = torch.empty((args.batch, 3, SIZE, SIZE), dtype=torch.float32, device=dev)
+    host_out = torch.empty((args.batch, 3, SIZE, SIZE), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, prec=None):
+        eng.transfer(dev_in[i & 1], stat, 1.0, prec or precision, out=out)
+
+    def timed_steps(prec):
+        for i in range(3):
+            step(i, prec)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            step(i, prec)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / args.steps
+
+    # ---------------- device-resident throughput ----------------
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.lib().ccst_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    launches = _lib.lib().ccst_launch_count() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    value = world * args.batch * args.steps / (ms_total / 1e3)
+
+    # ---------------- end to end through the public API (host buffers) ----------------
+    def e2e_step(i):
+        x = host[i & 1].to(dev, non_blocking=True)                       # H2D of this step's batch
+        y = ccst_b200.style_transfer(vgg, dec, x, stat, 1.0, precision=precision)  # the user's call
+        host_out.copy_(y, non_blocking=True)                             # D2H of the result
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.batch * args.steps / t.item()
+    img_bytes = args.batch * 3 * SIZE * SIZE * 4
+
+    line = None
+    if rank == 0:
+        # ---------------- per-kernel roofline (separate profiled pass, events per launch) ----------
+        eng.profile(True)
+        agg = {}
+        psteps = min(args.steps, 5)
+        for i in range(psteps):
+            step(i)
+            for rec in eng.profile_read():
+                a = agg.setdefault(rec["kind"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+                a["ms"] += rec["ms"]
+                a["flops"] += rec["flops"]
+                a["bytes"] += rec["bytes"]
+                a["n"] += 1
+        eng.profile(False)
+        conv_kind = 2 if precision == "fp32" else 1
+        conv = agg.get(conv_kind, dict(ms=1e-9, flops=0, n=1))
+        step_ms_prof = sum(a["ms"] for a in agg.values()) / psteps
+        conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+        peak_tf = peaks["tf_sust"]
+        roofline = {
+            "kernel": "conv_umma_kernel (tcgen05.mma + TMA implicit-GEMM 3x3 conv, 17 launches/step)"
+            if precision != "fp32" else "conv_ffma_kernel (fp32 validation mode)",
+            "bound": "tensor", "achieved": round(conv_tflops, 2), "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": round(conv_tflops / peak_tf, 4),
+            "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
+            "frac_of_burst_peak": round(conv_tflops / peaks["tf_burst"], 4),
+            "flops_per_launch_avg": conv["flops"] / max(conv["n"], 1),
+            "ms_per_launch_avg": round(conv["ms"] / max(conv["n"], 1), 4),
+            "share_of_step": round(conv["ms"] / psteps / step_ms_prof, 4), "traffic": None,
+            "timing": f"cudaEvent pair around every launch on the launch stream, {psteps}-step pass after the timed region",
+            "per_kind_ms_per_step": {str(k): round(a["ms"] / psteps, 4) for k, a in sorted(agg.items())},
+        }
+
+        # ---------------- HBM-bound operators on [32,512,64,64] fp32 ----------------
+        feat = torch.randn((BATCH, 512, 64, 64), device=dev).relu_()
+        feat2 = torch.randn((BATCH, 512, 64, 64), device=dev).relu_()  # alternate: 268 MB each > L2
+        mu, sg = stat
+        cnt = [0]
+
+        def f_stats():
+            cnt[0] += 1
+            ccst_b200.calc_mean_std(feat if cnt[0] & 1 else feat2)
+
+        def f_adain():
+            cnt[0] += 1
+            ccst_b200.adaIN_StyleStat_ContentFeat(feat if cnt[0] & 1 else feat2, [mu, sg])
+
+        ms_stats = time_op(f_stats, 20, torch)
+        ms_adain = time_op(f_adain, 20, torch)
+        nbytes = feat.numel() * 4
+        b_stats = nbytes + 8 * BATCH * 512
+        b_adain = 2 * nbytes + 8 * 512
+        roofline_stats = {"kernel": "stats_regs_kernel<256,4> (calc_mean_std [32,512,64,64] fp32)", "bound": "hbm",
+                          "achieved": round(b_stats / ms_stats / 1e6, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                          "frac": round(b_stats / ms_stats / 1e6 / peaks["hbm"], 4), "traffic": None,
+                          "ms": round(ms_stats, 5), "peak_source": peaks["src"] + " copy bandwidth",
+                          "note": "includes torch.empty of the outputs and the ctypes call per launch"}
+        roofline_adain = {"kernel": "adain_regs_kernel<256,4> (adaIN_StyleStat_ContentFeat [32,512,64,64] fp32)",
+                          "bound": "hbm", "achieved": round(b_adain / ms_adain / 1e6, 1), "peak": peaks["hbm"],
+                          "unit": "GB/s", "frac": round(b_adain / ms_adain / 1e6 / peaks["hbm"], 4), "traffic": None,
+                          "ms": round(ms_adain, 5), "peak_source": peaks["src"] + " copy bandwidth"}
+        del feat, feat2
+
+        # ---------------- same step with the other operand type (single GPU, informative) ----------
+        other = {}
+        for alt in ("bf16", "fp16"):
+            if alt != precision and precision != "fp32":
+                ms_alt = timed_steps(alt)
+                other[alt] = {"ms_per_step": round(ms_alt, 4), "images_per_s_per_gpu": round(args.batch / ms_alt * 1e3, 2)}
+
+        # ---------------- CPU baseline beside it (bounded sample) ----------------
+        cpu = None
+        if not args.no_cpu_baseline:
+            ips, sec, cores = cpu_reference_throughput(steps=2, warmup=1, sample_imgs=2)
+            cpu = {"value": round(ips, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "2 steps x 2 images @512x512 (batch 32 scaled down), oracle port of the "
+                             "reference style_transfer on PyTorch CPU, 1 warm-up"}
+
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[precision], "data": "synthetic",
+            "dtype_note": "tcgen05 kind::f16 MMA, f16 operands, fp32 accumulation in TMEM (same tensor peak as "
+                          "bf16; meets the 1e-2 image tolerance, bf16 operands do not -- see DESIGN.md Numerics)",
+            "other_precisions": other,
+            "config": {"workload": "CCST Overall K=3 transfer step (config 3): style_transfer batch 32 @512x512, "
+                                   "random-init VGG-19 relu4_1 encoder + decoder, overall style stats, alpha=1",
+                       "batch_per_gpu": args.batch, "image": [3, SIZE, SIZE], "parallelism": f"image-sharded x{world}",
+                       "l2": "two input batches alternate; per-step activations (>1 GB) exceed the 126 MB L2"},
+            "tflops_per_gpu": round(value / world * FLOP_PER_IMG / 1e12, 2),
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": img_bytes,
+                    "d2h_bytes_per_step": img_bytes,
+                    "api": "ccst_b200.style_transfer(vgg, decoder, content, style_stat, alpha) with pinned host in/out"},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "roofline_stats": roofline_stats, "roofline_adain": roofline_adain,
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+    barrier()
+    if dist is not None:
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), __file__] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "libccst_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "ccst_b200.h")
 
 OK, EINVAL, EARCH, ECUDA, ESTATE = 0, -1, -2, -3, -4
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pp = C.POINTER(C.c_void_p)
@@ -25,6 +25,7 @@ PROTOTYPES = {
     "ccst_abi_version": (_i, []),
     "ccst_last_error": (C.c_char_p, []),
     "ccst_check_device": (_i, [_i]),
+    "ccst_set_device": (_i, [_i]),
     "ccst_stats_nchw_f32": (_i, [_vp, _i64, _i64, _f, _i, _vp, _vp, _vp]),
     "ccst_welford_accumulate_nchw_f32": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp]),
     "ccst_welford_finalize": (_i, [_vp, _i, _f, _vp, _vp, _vp]),
@@ -88,6 +89,29 @@ def check(code: int) -> int:
     if code < 0:
         raise CcstError(code, lib().ccst_last_error().decode(errors="replace"))
     return code
+
+
+class on_device:
+    """Context manager: make `device` current for torch AND for the library's own runtime."""
+
+    def __init__(self, device):
+        import torch
+
+        self.device = device
+        self._ctx = torch.cuda.device(device)
+
+    def __enter__(self):
+        self._ctx.__enter__()
+        idx = self.device.index
+        if idx is None:
+            import torch
+
+            idx = torch.cuda.current_device()
+        check(lib().ccst_set_device(idx))
+        return self
+
+    def __exit__(self, *exc):
+        return self._ctx.__exit__(*exc)
 
 
 def feature_hw(h: int, w: int):

@@ -78,7 +78,8 @@ struct ConvLayer {
   int pad64 = 0;     // Cout rounded up to 64 (ffma weights / bias)
   int pad_umma = 0;  // Cout, or 16 for the 3-channel last conv
   float* w_ffma = nullptr;  // [9][cin][pad64]
-  bf16* w_umma = nullptr;   // [pad_umma][9*cin]
+  bf16* w_umma = nullptr;   // [pad_umma][9*cin] bf16
+  __half* w_umma_h = nullptr;  // same, fp16
   float* bias = nullptr;    // [pad64]
 };
 
@@ -97,8 +98,10 @@ struct ProfSlot {
 struct ccst_handle {
   int device = 0;
   bool enc_ready = false, dec_ready = false;
-  float* first_w27 = nullptr;
+  float* first_w27 = nullptr;   // folded conv1_1 weights [27][64] fp32 (FFMA path)
   float* first_b64 = nullptr;
+  bf16* first_wk_b = nullptr;   // same, [64][32] K-major bf16 / f16 (tcgen05 path)
+  __half* first_wk_h = nullptr;
   ConvLayer enc[kEncLayers];
   ConvLayer dec[kDecLayers];
   void* arena[2] = {nullptr, nullptr};
@@ -133,6 +136,7 @@ struct ProfScope {
 void free_layer(ConvLayer& L) {
   cudaFree(L.w_ffma);
   cudaFree(L.w_umma);
+  cudaFree(L.w_umma_h);
   cudaFree(L.bias);
   L = ConvLayer();
 }
@@ -147,8 +151,9 @@ int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b) 
   const int K = 9 * cin;
   std::vector<float> wf((size_t)K * L.pad64, 0.f);
   std::vector<bf16> wu((size_t)L.pad_umma * K);
+  std::vector<__half> wh((size_t)L.pad_umma * K);
   std::vector<float> bp(L.pad64, 0.f);
-  for (size_t i = 0; i < wu.size(); ++i) wu[i] = __float2bfloat16(0.f);
+  for (size_t i = 0; i < wu.size(); ++i) wu[i] = __float2bfloat16(0.f), wh[i] = __float2half(0.f);
   for (int o = 0; o < cout; ++o) {
     bp[o] = b[o];
     for (int c = 0; c < cin; ++c)
@@ -156,11 +161,14 @@ int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b) 
         const float v = w[((size_t)o * cin + c) * 9 + t];
         wf[((size_t)t * cin + c) * L.pad64 + o] = v;
         wu[(size_t)o * K + (size_t)t * cin + c] = __float2bfloat16(v);
+        wh[(size_t)o * K + (size_t)t * cin + c] = __float2half(v);
       }
   }
   CCST_CUDA(cudaMalloc(&L.w_ffma, wf.size() * sizeof(float)));
   CCST_CUDA(cudaMalloc(&L.w_umma, wu.size() * sizeof(bf16)));
+  CCST_CUDA(cudaMalloc(&L.w_umma_h, wh.size() * sizeof(__half)));
   CCST_CUDA(cudaMalloc(&L.bias, bp.size() * sizeof(float)));
+  CCST_CUDA(cudaMemcpy(L.w_umma_h, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(L.w_ffma, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(L.w_umma, wu.data(), wu.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -243,12 +251,13 @@ struct Pipe {
 
   int conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* out_nchw);
 
+  int first_launch(const float* img, int N, int H, int W);
   int first(const float* img, int N, int H, int W) {
     cur_slot = 0;
     cur = view(0, N, H, W, 64);
     ProfScope ps(h, st, 0, 2.0 * 27 * 64 * (double)N * H * W,
                  (double)N * H * W * (12.0 + 64.0 * sizeof(T)));
-    return launch_conv_first<T>(img, N, H, W, h->first_w27, h->first_b64, cur, st);
+    return first_launch(img, N, H, W);
   }
 
   // conv (+ fused or separate pool / fused upsample); result becomes `cur`
@@ -303,23 +312,40 @@ struct Pipe {
 };
 
 template <>
+int Pipe<float>::first_launch(const float* img, int N, int H, int W) {
+  return launch_conv_first<float>(img, N, H, W, h->first_w27, h->first_b64, cur, st);
+}
+template <>
+int Pipe<bf16>::first_launch(const float* img, int N, int H, int W) {
+  return launch_conv_first_umma<bf16>(img, N, H, W, h->first_wk_b, h->first_b64, cur, st);
+}
+template <>
+int Pipe<__half>::first_launch(const float* img, int N, int H, int W) {
+  return launch_conv_first_umma<__half>(img, N, H, W, h->first_wk_h, h->first_b64, cur, st);
+}
+template <>
 int Pipe<float>::conv(const ConvLayer& L, int relu, int epi, ActView<float> out, float* out_nchw) {
   return launch_conv_ffma(cur, L.w_ffma, L.bias, L.cout, L.pad64, relu, epi, out, out_nchw, st);
 }
 template <>
 int Pipe<bf16>::conv(const ConvLayer& L, int relu, int epi, ActView<bf16> out, float* out_nchw) {
-  return launch_conv_umma(cur, L.w_umma, L.bias, L.cout, L.pad_umma, relu, epi, out, out_nchw, st);
+  return launch_conv_umma<bf16>(cur, L.w_umma, L.bias, L.cout, L.pad_umma, relu, epi, out, out_nchw,
+                                st);
+}
+template <>
+int Pipe<__half>::conv(const ConvLayer& L, int relu, int epi, ActView<__half> out,
+                       float* out_nchw) {
+  return launch_conv_umma<__half>(cur, L.w_umma_h, L.bias, L.cout, L.pad_umma, relu, epi, out,
+                                  out_nchw, st);
 }
 
 int check_common(ccst_handle* h, int precision) {
   CCST_CHECK_ARG(h != nullptr, "null handle");
-  CCST_CHECK_ARG(precision == CCST_PREC_FP32 || precision == CCST_PREC_BF16, "bad precision %d",
-                 precision);
+  CCST_CHECK_ARG(precision == CCST_PREC_FP32 || precision == CCST_PREC_BF16 ||
+                     precision == CCST_PREC_FP16,
+                 "bad precision %d", precision);
+  CCST_CUDA(cudaSetDevice(h->device));
   if (int e = require_sm100()) return e;
-  int dev = -1;
-  cudaGetDevice(&dev);
-  CCST_CHECK_ARG(dev == h->device, "handle belongs to device %d but current device is %d",
-                 h->device, dev);
   h->prof_n = 0;
   return CCST_OK;
 }
@@ -388,6 +414,12 @@ extern "C" int ccst_check_device(int device) {
   return CCST_OK;
 }
 
+extern "C" int ccst_set_device(int device) {
+  if (int e = ccst_check_device(device)) return e;
+  CCST_CUDA(cudaSetDevice(device));
+  return CCST_OK;
+}
+
 extern "C" void ccst_feature_hw(int H, int W, int* fh, int* fw) {
   int hh = H, ww = W;
   for (int i = 0; i < 3; ++i) hh = (hh + 1) / 2, ww = (ww + 1) / 2;
@@ -413,6 +445,8 @@ extern "C" void ccst_destroy(ccst_handle* h) {
   cudaSetDevice(h->device);
   cudaFree(h->first_w27);
   cudaFree(h->first_b64);
+  cudaFree(h->first_wk_b);
+  cudaFree(h->first_wk_h);
   for (auto& L : h->enc) free_layer(L);
   for (auto& L : h->dec) free_layer(L);
   cudaFree(h->arena[0]);
@@ -452,6 +486,18 @@ extern "C" int ccst_set_encoder_weights(ccst_handle* h, const float* const* w,
   if (!h->first_b64) CCST_CUDA(cudaMalloc(&h->first_b64, b64.size() * sizeof(float)));
   CCST_CUDA(cudaMemcpy(h->first_w27, w27.data(), w27.size() * 4, cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(h->first_b64, b64.data(), b64.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<bf16> wkb(64 * 32);
+  std::vector<__half> wkh(64 * 32);
+  for (int o = 0; o < 64; ++o)
+    for (int k = 0; k < 32; ++k) {
+      const float v = k < 27 ? w27[(size_t)k * 64 + o] : 0.f;
+      wkb[o * 32 + k] = __float2bfloat16(v);
+      wkh[o * 32 + k] = __float2half(v);
+    }
+  if (!h->first_wk_b) CCST_CUDA(cudaMalloc(&h->first_wk_b, wkb.size() * sizeof(bf16)));
+  if (!h->first_wk_h) CCST_CUDA(cudaMalloc(&h->first_wk_h, wkh.size() * sizeof(__half)));
+  CCST_CUDA(cudaMemcpy(h->first_wk_b, wkb.data(), wkb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  CCST_CUDA(cudaMemcpy(h->first_wk_h, wkh.data(), wkh.size() * sizeof(__half), cudaMemcpyHostToDevice));
   for (int i = 0; i < kEncLayers; ++i)
     if (int e = pack_layer(h->enc[i], kEncCh[i][0], kEncCh[i][1], w[2 + i], b[2 + i])) return e;
   h->enc_ready = true;
@@ -470,6 +516,21 @@ extern "C" int ccst_set_decoder_weights(ccst_handle* h, const float* const* w,
   return CCST_OK;
 }
 
+// expands `call` for the activation type selected by `precision`
+#define CCST_DISPATCH(precision, call_T)                       \
+  do {                                                         \
+    if ((precision) == CCST_PREC_BF16) {                       \
+      typedef bf16 T;                                          \
+      return call_T;                                           \
+    } else if ((precision) == CCST_PREC_FP16) {                \
+      typedef __half T;                                        \
+      return call_T;                                           \
+    } else {                                                   \
+      typedef float T;                                         \
+      return call_T;                                           \
+    }                                                          \
+  } while (0)
+
 #define CCST_REQUIRE_STATE(cond, msg) \
   do {                                \
     if (!(cond)) {                    \
@@ -483,9 +544,7 @@ extern "C" int ccst_encoder_fwd(ccst_handle* h, const float* d_img, int N, int H
   if (int e = check_common(h, precision)) return e;
   CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_fwd: encoder weights not set");
   CCST_CHECK_ARG(d_img && d_feat && N >= 1 && H >= 8 && W >= 8, "ccst_encoder_fwd: bad argument");
-  return precision == CCST_PREC_BF16
-             ? run_encoder<bf16>(h, d_img, N, H, W, d_feat, nullptr, (cudaStream_t)stream)
-             : run_encoder<float>(h, d_img, N, H, W, d_feat, nullptr, (cudaStream_t)stream);
+  CCST_DISPATCH(precision, run_encoder<T>(h, d_img, N, H, W, d_feat, nullptr, (cudaStream_t)stream));
 }
 
 extern "C" int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N, int H, int W,
@@ -494,9 +553,7 @@ extern "C" int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N
   CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_accumulate: encoder weights not set");
   CCST_CHECK_ARG(d_img && d_state && N >= 1 && H >= 8 && W >= 8,
                  "ccst_encoder_accumulate: bad argument");
-  return precision == CCST_PREC_BF16
-             ? run_encoder<bf16>(h, d_img, N, H, W, nullptr, d_state, (cudaStream_t)stream)
-             : run_encoder<float>(h, d_img, N, H, W, nullptr, d_state, (cudaStream_t)stream);
+  CCST_DISPATCH(precision, run_encoder<T>(h, d_img, N, H, W, nullptr, d_state, (cudaStream_t)stream));
 }
 
 extern "C" int ccst_decoder_fwd(ccst_handle* h, const float* d_feat, int N, int fh, int fw,
@@ -504,9 +561,7 @@ extern "C" int ccst_decoder_fwd(ccst_handle* h, const float* d_feat, int N, int 
   if (int e = check_common(h, precision)) return e;
   CCST_REQUIRE_STATE(h->dec_ready, "ccst_decoder_fwd: decoder weights not set");
   CCST_CHECK_ARG(d_feat && d_img && N >= 1 && fh >= 2 && fw >= 2, "ccst_decoder_fwd: bad argument");
-  return precision == CCST_PREC_BF16
-             ? run_decoder<bf16>(h, d_feat, N, fh, fw, d_img, (cudaStream_t)stream)
-             : run_decoder<float>(h, d_feat, N, fh, fw, d_img, (cudaStream_t)stream);
+  CCST_DISPATCH(precision, run_decoder<T>(h, d_feat, N, fh, fw, d_img, (cudaStream_t)stream));
 }
 
 extern "C" int ccst_style_transfer(ccst_handle* h, const float* d_img, int N, int H, int W,
@@ -520,11 +575,9 @@ extern "C" int ccst_style_transfer(ccst_handle* h, const float* d_img, int N, in
   CCST_CHECK_ARG(stat_batch_stride == 0 || stat_batch_stride == 512,
                  "ccst_style_transfer: stat_batch_stride must be 0 or 512");
   CCST_CHECK_ARG(alpha >= 0.f && alpha <= 1.f, "ccst_style_transfer: alpha outside [0,1]");
-  return precision == CCST_PREC_BF16
-             ? run_style_transfer<bf16>(h, d_img, N, H, W, d_mu_s, d_sigma_s, stat_batch_stride,
-                                        alpha, d_out, (cudaStream_t)stream)
-             : run_style_transfer<float>(h, d_img, N, H, W, d_mu_s, d_sigma_s, stat_batch_stride,
-                                         alpha, d_out, (cudaStream_t)stream);
+  CCST_DISPATCH(precision, run_style_transfer<T>(h, d_img, N, H, W, d_mu_s, d_sigma_s,
+                                                 stat_batch_stride, alpha, d_out,
+                                                 (cudaStream_t)stream));
 }
 
 extern "C" int ccst_profile_enable(ccst_handle* h, int on) {
@@ -609,12 +662,16 @@ extern "C" int ccst_debug_conv3x3(ccst_handle* h, const float* d_in, int N, int 
   CCST_CHECK_ARG(mode != 2 || relu, "ccst_debug_conv3x3: pool mode requires relu");
   ConvLayer L;
   int rc = pack_layer(L, Cin, Cout, h_weight, h_bias);
-  if (rc == CCST_OK)
-    rc = precision == CCST_PREC_BF16
-             ? debug_conv<bf16>(h, d_in, N, H, W, Cin, Cout, L, relu, mode, d_out,
-                                (cudaStream_t)stream)
-             : debug_conv<float>(h, d_in, N, H, W, Cin, Cout, L, relu, mode, d_out,
-                                 (cudaStream_t)stream);
+  if (rc == CCST_OK) {
+    if (precision == CCST_PREC_BF16)
+      rc = debug_conv<bf16>(h, d_in, N, H, W, Cin, Cout, L, relu, mode, d_out, (cudaStream_t)stream);
+    else if (precision == CCST_PREC_FP16)
+      rc = debug_conv<__half>(h, d_in, N, H, W, Cin, Cout, L, relu, mode, d_out,
+                              (cudaStream_t)stream);
+    else
+      rc = debug_conv<float>(h, d_in, N, H, W, Cin, Cout, L, relu, mode, d_out,
+                             (cudaStream_t)stream);
+  }
   free_layer(L);
   return rc;
 }

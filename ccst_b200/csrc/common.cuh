@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -117,6 +118,7 @@ __device__ __forceinline__ void for_each_halo_alias(int y, int x, int H, int W, 
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 template <typename T>
 __device__ __forceinline__ T from_f32(float v);
 template <>
@@ -128,8 +130,22 @@ __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
   return __float2bfloat16_rn(v);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// fp16 activations saturate instead of overflowing to inf (fp32 accumulators can exceed 65504)
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) {
+  return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t pack16x2<__nv_bfloat16>(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <>
+__device__ __forceinline__ uint32_t pack16x2<__half>(float lo, float hi) {
+  __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
   return *reinterpret_cast<uint32_t*>(&v);
 }
 

@@ -25,7 +25,18 @@ namespace ccst {
 
 namespace {
 
-typedef __nv_bfloat16 bf16;
+template <typename T16>
+struct Fmt16;  // operand format code of the kind::f16 instruction descriptor + TMA data type
+template <>
+struct Fmt16<__nv_bfloat16> {
+  static constexpr uint32_t kIdescFmt = 1;  // BF16
+  static constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+};
+template <>
+struct Fmt16<__half> {
+  static constexpr uint32_t kIdescFmt = 0;  // F16
+  static constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+};
 
 constexpr int kTileH = 8, kTileW = 16, kBlockM = kTileH * kTileW, kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
@@ -43,13 +54,14 @@ struct UmmaCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+template <typename T16>
 struct ConvParams {
   int N, H, W, Cin;
   int Cout, CoutPad;
   int tiles_x, tiles_y, n_tiles, total_tiles;
   int relu;
   const float* bias;
-  ActView<bf16> out;
+  ActView<T16> out;
   float* out_nchw;
 };
 
@@ -179,17 +191,18 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
-// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128, N = BN
-template <int BN>
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16 or f16, both K-major, M = 128, N = BN
+template <typename T16, int BN>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
-  return (1u << 4) /*D fp32*/ | (1u << 7) /*A bf16*/ | (1u << 10) /*B bf16*/ |
+  return (1u << 4) /*D fp32*/ | (Fmt16<T16>::kIdescFmt << 7) /*A*/ | (Fmt16<T16>::kIdescFmt << 10) /*B*/ |
          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 }
 
 struct TileCoord {
   int n, y0, x0, nt;
 };
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+template <typename P>
+__device__ __forceinline__ TileCoord decode_tile(const P& p, int tile) {
   TileCoord t;
   t.nt = tile % p.n_tiles;
   int m = tile / p.n_tiles;
@@ -201,7 +214,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
 }
 
 // ------------------------------------------------------------------ epilogue stores
-__device__ __forceinline__ void store_act_chunk(const ConvParams& p, int n, int y, int x, int co,
+template <typename P>
+__device__ __forceinline__ void store_act_chunk(const P& p, int n, int y, int x, int co,
                                                 const uint32_t (&pk)[16]) {
   for_each_halo_alias(y, x, p.out.H, p.out.W, [&](int yy, int xx) {
     uint4* dst = reinterpret_cast<uint4*>(p.out.px(n, yy, xx) + co);
@@ -210,10 +224,10 @@ __device__ __forceinline__ void store_act_chunk(const ConvParams& p, int n, int 
   });
 }
 
-template <int BN, int EPI>
+template <typename T16, int BN, int EPI>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                     const __grid_constant__ CUtensorMap tmap_b, ConvParams p) {
+                     const __grid_constant__ CUtensorMap tmap_b, ConvParams<T16> p) {
   using Cfg = UmmaCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte aligned stage bases
@@ -279,7 +293,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc<BN>();
+    constexpr uint32_t idesc = make_idesc<T16, BN>();
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -370,7 +384,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           }
           uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          for (int j = 0; j < 16; ++j) pk[j] = pack16x2<T16>(v[2 * j], v[2 * j + 1]);
           if (EPI == EPI_ACT) {
             if (valid) store_act_chunk(p, t.n, y, x, co, pk);
           } else if (EPI == EPI_ACT_UP2) {
@@ -398,6 +412,151 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
+// =====================================================================================
+// conv1_1 (+ folded 1x1 colour conv, net.py:39-42) on the tensor cores.
+// K = 27 is too thin for TMA-fed tiles, so the 128 threads of a CTA build the im2col rows
+// themselves: CTA tile = 128 consecutive pixels of one image row; thread p gathers the 27 taps of
+// pixel p from a staged fp32 window of the NCHW image (reflection applied while staging), converts
+// to T16 and writes one 64-byte K-major row (K padded to 32) into shared memory with the 128-byte
+// swizzle applied by hand (16-byte chunk j of row r lives at chunk j ^ (r & 7)).  One thread then
+// issues two tcgen05.mma (M=128, N=64, K=16), the accumulator comes back through tcgen05.ld and is
+// stored as NHWC (the tile is one contiguous 16 KiB span of the activation).
+// =====================================================================================
+constexpr int kFirstPx = 128;
+
+template <typename T16>
+struct FirstParams {
+  const float* img;  // [N,3,H,W]
+  int N, H, W;
+  const T16* wk;     // [64][32] K-major (k = (r*3+s)*3 + ci, 27..31 zero)
+  const float* bias; // [64]
+  ActView<T16> out;
+  int total_tiles, tiles_x;
+};
+
+template <typename T16>
+__global__ void __launch_bounds__(kFirstPx) conv_first_umma_kernel(FirstParams<T16> p) {
+  __shared__ __align__(1024) uint8_t sA[kFirstPx * 128];
+  __shared__ __align__(1024) uint8_t sB[64 * 128];
+  __shared__ float sin[3][3][kFirstPx + 2];
+  __shared__ float sbias[64];
+  __shared__ __align__(8) uint64_t bar_store;
+  __shared__ uint32_t tmem_slot_store;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar = smem_u32(&bar_store);
+
+  // one-time: weights -> swizzled K-major B tile, barrier, TMEM
+  for (int i = tid; i < 64 * 4; i += kFirstPx) {
+    const int o = i >> 2, j = i & 3;
+    const uint4 v = reinterpret_cast<const uint4*>(p.wk)[o * 4 + j];
+    *reinterpret_cast<uint4*>(sB + o * 128 + ((j ^ (o & 7)) << 4)) = v;
+  }
+  if (tid < 64) sbias[tid] = p.bias[tid];
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<64>(smem_u32(&tmem_slot_store));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_store);
+  const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA));
+  const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB));
+  constexpr uint32_t idesc = make_idesc<T16, 64>();
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int b = tile;
+    const int x0 = (b % p.tiles_x) * kFirstPx;
+    b /= p.tiles_x;
+    const int y = b % p.H;
+    const int n = b / p.H;
+    // (1) stage the 3 x 3 x 130 input window, reflection resolved here
+    for (int i = tid; i < 9 * (kFirstPx + 2); i += kFirstPx) {
+      const int col = i % (kFirstPx + 2);
+      const int rc = i / (kFirstPx + 2);  // ci*3 + row
+      const int row = rc % 3, ci = rc / 3;
+      int yy = y + row - 1;
+      yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
+      int xx = x0 + col - 1;
+      float v = 0.f;
+      if (xx <= p.W) {
+        xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
+        v = __ldg(p.img + (((size_t)n * 3 + ci) * p.H + yy) * p.W + xx);
+      }
+      sin[ci][row][col] = v;
+    }
+    __syncthreads();
+    // (2) im2col row of pixel tid -> swizzled K-major A tile
+    {
+      uint32_t pk[16];
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = 2 * k2 + e;
+          if (k < 27) {
+            const int tap = k / 3, ci = k - 3 * tap;
+            const int r = tap / 3, s = tap - 3 * r;
+            v[e] = sin[ci][r][tid + s];
+          } else {
+            v[e] = 0.f;
+          }
+        }
+        pk[k2] = pack16x2<T16>(v[0], v[1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) << 4)) =
+            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy
+    tc_fence_before();
+    __syncthreads();
+    // (3) two K=16 steps
+    if (tid == 0) {
+      tc_fence_after();
+      umma_bf16(tmem_base, adesc, bdesc, idesc, 0u);
+      umma_bf16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
+      umma_commit(bar);
+    }
+    // (4) accumulator ready
+    mbar_wait(bar, phase, 900);
+    phase ^= 1;
+    tc_fence_after();
+    // (5) epilogue: row tid of the accumulator = pixel x0 + tid
+    const int x = x0 + tid;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(taddr + ch * 32, r);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        pk[j] = pack16x2<T16>(fmaxf(__uint_as_float(r[2 * j]) + sbias[ch * 32 + 2 * j], 0.f),
+                              fmaxf(__uint_as_float(r[2 * j + 1]) + sbias[ch * 32 + 2 * j + 1], 0.f));
+      if (x < p.W) {
+        for_each_halo_alias(y, x, p.H, p.W, [&](int yy, int xx) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out.px(n, yy, xx) + ch * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        });
+      }
+    }
+    // TMEM reads are complete (wait::ld) before any thread passes the barrier in (1)/(2) of the
+    // next tile, after which thread 0 may overwrite the accumulator
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem_base);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -417,7 +576,8 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-int make_act_map(CUtensorMap* m, const ActView<bf16>& v) {
+template <typename T16>
+int make_act_map(CUtensorMap* m, const ActView<T16>& v) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -429,7 +589,7 @@ int make_act_map(CUtensorMap* m, const ActView<bf16>& v) {
                                  (cuuint64_t)(v.H + 2) * (v.W + 2) * v.C * 2};
   const cuuint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)v.p, dims, strides, box, estr,
+  CUresult r = enc(m, Fmt16<T16>::kTmaType, 4, (void*)v.p, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -440,7 +600,8 @@ int make_act_map(CUtensorMap* m, const ActView<bf16>& v) {
   return CCST_OK;
 }
 
-int make_weight_map(CUtensorMap* m, const bf16* wk, int K, int CoutPad, int BN) {
+template <typename T16>
+int make_weight_map(CUtensorMap* m, const T16* wk, int K, int CoutPad, int BN) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -450,7 +611,7 @@ int make_weight_map(CUtensorMap* m, const bf16* wk, int K, int CoutPad, int BN) 
   const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
   const cuuint32_t box[2] = {kBlockK, (cuuint32_t)BN};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wk, dims, strides, box, estr,
+  CUresult r = enc(m, Fmt16<T16>::kTmaType, 2, (void*)wk, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -461,31 +622,32 @@ int make_weight_map(CUtensorMap* m, const bf16* wk, int K, int CoutPad, int BN) 
   return CCST_OK;
 }
 
-template <int BN, int EPI>
-int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, cudaStream_t st) {
+template <typename T16, int BN, int EPI>
+int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams<T16>& p,
+               cudaStream_t st) {
   using Cfg = UmmaCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    CCST_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, EPI>,
+    CCST_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T16, BN, EPI>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  conv_umma_kernel<BN, EPI><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  conv_umma_kernel<T16, BN, EPI><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, p);
   CCST_LAUNCHED();
   return CCST_OK;
 }
 
-template <int BN>
-int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, int epi,
+template <typename T16, int BN>
+int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams<T16>& p, int epi,
               cudaStream_t st) {
   switch (epi) {
     case EPI_ACT:
-      return launch_cfg<BN, EPI_ACT>(ma, mb, p, st);
+      return launch_cfg<T16, BN, EPI_ACT>(ma, mb, p, st);
     case EPI_ACT_UP2:
-      return launch_cfg<BN, EPI_ACT_UP2>(ma, mb, p, st);
+      return launch_cfg<T16, BN, EPI_ACT_UP2>(ma, mb, p, st);
     case EPI_ACT_POOL:
-      return launch_cfg<BN, EPI_ACT_POOL>(ma, mb, p, st);
+      return launch_cfg<T16, BN, EPI_ACT_POOL>(ma, mb, p, st);
     default:
       set_error("conv_umma: epilogue %d not available for BN=%d", epi, BN);
       return CCST_EINVAL;
@@ -494,8 +656,9 @@ int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p,
 
 }  // namespace
 
-int launch_conv_umma(ActView<bf16> in, const bf16* wk, const float* bias, int Cout, int CoutPad,
-                     int relu, int epi, ActView<bf16> out, float* out_nchw, cudaStream_t st) {
+template <typename T16>
+int launch_conv_umma(ActView<T16> in, const T16* wk, const float* bias, int Cout, int CoutPad,
+                     int relu, int epi, ActView<T16> out, float* out_nchw, cudaStream_t st) {
   CCST_CHECK_ARG(in.C % kBlockK == 0, "conv_umma: Cin=%d must be a multiple of 64", in.C);
   int BN;
   if (epi == EPI_NCHW_F32) {
@@ -507,7 +670,7 @@ int launch_conv_umma(ActView<bf16> in, const bf16* wk, const float* bias, int Co
     BN = Cout >= 256 ? 256 : Cout;  // 64, 128, 256
     CCST_CHECK_ARG(BN == 64 || BN == 128 || BN == 256, "conv_umma: unsupported Cout=%d", Cout);
   }
-  ConvParams p;
+  ConvParams<T16> p;
   p.N = in.N, p.H = in.H, p.W = in.W, p.Cin = in.C;
   p.Cout = Cout, p.CoutPad = CoutPad;
   p.tiles_x = (in.W + kTileW - 1) / kTileW;
@@ -525,14 +688,40 @@ int launch_conv_umma(ActView<bf16> in, const bf16* wk, const float* bias, int Co
   if (int e = make_weight_map(&mb, wk, 9 * in.C, CoutPad, BN)) return e;
   switch (BN) {
     case 16:
-      return launch_cfg<16, EPI_NCHW_F32>(ma, mb, p, st);
+      return launch_cfg<T16, 16, EPI_NCHW_F32>(ma, mb, p, st);
     case 64:
-      return launch_bn<64>(ma, mb, p, epi, st);
+      return launch_bn<T16, 64>(ma, mb, p, epi, st);
     case 128:
-      return launch_bn<128>(ma, mb, p, epi, st);
+      return launch_bn<T16, 128>(ma, mb, p, epi, st);
     default:
-      return launch_bn<256>(ma, mb, p, epi, st);
+      return launch_bn<T16, 256>(ma, mb, p, epi, st);
   }
 }
+template int launch_conv_umma<__nv_bfloat16>(ActView<__nv_bfloat16>, const __nv_bfloat16*,
+                                             const float*, int, int, int, int,
+                                             ActView<__nv_bfloat16>, float*, cudaStream_t);
+template int launch_conv_umma<__half>(ActView<__half>, const __half*, const float*, int, int, int,
+                                      int, ActView<__half>, float*, cudaStream_t);
+
+template <typename T16>
+int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk, const float* bias,
+                           ActView<T16> out, cudaStream_t st) {
+  FirstParams<T16> p;
+  p.img = img, p.N = N, p.H = H, p.W = W, p.wk = wk, p.bias = bias, p.out = out;
+  p.tiles_x = (W + kFirstPx - 1) / kFirstPx;
+  const int64_t total = (int64_t)N * H * p.tiles_x;
+  CCST_CHECK_ARG(total < (1ll << 31), "conv_first_umma: too many tiles");
+  p.total_tiles = (int)total;
+  const int64_t cap = (int64_t)sm_count() * 6;
+  const int grid = (int)(total < cap ? total : cap);
+  conv_first_umma_kernel<T16><<<grid, kFirstPx, 0, st>>>(p);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_conv_first_umma<__nv_bfloat16>(const float*, int, int, int,
+                                                   const __nv_bfloat16*, const float*,
+                                                   ActView<__nv_bfloat16>, cudaStream_t);
+template int launch_conv_first_umma<__half>(const float*, int, int, int, const __half*,
+                                            const float*, ActView<__half>, cudaStream_t);
 
 }  // namespace ccst

@@ -40,6 +40,16 @@ struct Pack<__nv_bfloat16, 8> {
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(&v)[i]);
   }
 };
+template <>
+struct Pack<__half, 8> {
+  uint4 v;
+  __device__ __forceinline__ void set(int i, float f) {
+    reinterpret_cast<__half*>(&v)[i] = from_f32<__half>(f);
+  }
+  __device__ __forceinline__ float get(int i) const {
+    return __half2float(reinterpret_cast<const __half*>(&v)[i]);
+  }
+};
 template <typename T>
 struct VecOf {
   static constexpr int value = 16 / sizeof(T);
@@ -500,6 +510,8 @@ template int launch_conv_first<float>(const float*, int, int, int, const float*,
                                       ActView<float>, cudaStream_t);
 template int launch_conv_first<__nv_bfloat16>(const float*, int, int, int, const float*,
                                               const float*, ActView<__nv_bfloat16>, cudaStream_t);
+template int launch_conv_first<__half>(const float*, int, int, int, const float*,
+                                              const float*, ActView<__half>, cudaStream_t);
 
 int launch_conv_ffma(ActView<float> in, const float* w, const float* bias, int Cout, int CoutPad,
                      int relu, int epi, ActView<float> out, float* out_nchw, cudaStream_t st) {
@@ -544,6 +556,8 @@ int launch_pool(ActView<T> in, ActView<T> out, cudaStream_t st) {
 template int launch_pool<float>(ActView<float>, ActView<float>, cudaStream_t);
 template int launch_pool<__nv_bfloat16>(ActView<__nv_bfloat16>, ActView<__nv_bfloat16>,
                                         cudaStream_t);
+template int launch_pool<__half>(ActView<__half>, ActView<__half>,
+                                        cudaStream_t);
 
 template <typename T>
 int launch_adain_nhwc(ActView<T> in, ActView<T> out, const float* mu_s, const float* sigma_s,
@@ -559,6 +573,9 @@ template int launch_adain_nhwc<float>(ActView<float>, ActView<float>, const floa
 template int launch_adain_nhwc<__nv_bfloat16>(ActView<__nv_bfloat16>, ActView<__nv_bfloat16>,
                                               const float*, const float*, int64_t, float, float,
                                               cudaStream_t);
+template int launch_adain_nhwc<__half>(ActView<__half>, ActView<__half>,
+                                              const float*, const float*, int64_t, float, float,
+                                              cudaStream_t);
 
 template <typename T>
 int launch_stats_nhwc(ActView<T> in, float2* raw, cudaStream_t st) {
@@ -570,6 +587,7 @@ int launch_stats_nhwc(ActView<T> in, float2* raw, cudaStream_t st) {
 }
 template int launch_stats_nhwc<float>(ActView<float>, float2*, cudaStream_t);
 template int launch_stats_nhwc<__nv_bfloat16>(ActView<__nv_bfloat16>, float2*, cudaStream_t);
+template int launch_stats_nhwc<__half>(ActView<__half>, float2*, cudaStream_t);
 
 template <typename T>
 int launch_act_to_nchw(ActView<T> in, float* out_nchw, cudaStream_t st) {
@@ -580,6 +598,7 @@ int launch_act_to_nchw(ActView<T> in, float* out_nchw, cudaStream_t st) {
 }
 template int launch_act_to_nchw<float>(ActView<float>, float*, cudaStream_t);
 template int launch_act_to_nchw<__nv_bfloat16>(ActView<__nv_bfloat16>, float*, cudaStream_t);
+template int launch_act_to_nchw<__half>(ActView<__half>, float*, cudaStream_t);
 
 template <typename T>
 int launch_nchw_to_act(const float* in_nchw, ActView<T> out, cudaStream_t st) {
@@ -590,6 +609,7 @@ int launch_nchw_to_act(const float* in_nchw, ActView<T> out, cudaStream_t st) {
 }
 template int launch_nchw_to_act<float>(const float*, ActView<float>, cudaStream_t);
 template int launch_nchw_to_act<__nv_bfloat16>(const float*, ActView<__nv_bfloat16>, cudaStream_t);
+template int launch_nchw_to_act<__half>(const float*, ActView<__half>, cudaStream_t);
 
 template <typename T>
 int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st) {
@@ -600,6 +620,7 @@ int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st) {
 }
 template int launch_nhwc_to_act<float>(const float*, ActView<float>, cudaStream_t);
 template int launch_nhwc_to_act<__nv_bfloat16>(const float*, ActView<__nv_bfloat16>, cudaStream_t);
+template int launch_nhwc_to_act<__half>(const float*, ActView<__half>, cudaStream_t);
 
 template <typename T>
 int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st) {
@@ -610,5 +631,6 @@ int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st) {
 }
 template int launch_act_to_nhwc<float>(ActView<float>, float*, cudaStream_t);
 template int launch_act_to_nhwc<__nv_bfloat16>(ActView<__nv_bfloat16>, float*, cudaStream_t);
+template int launch_act_to_nhwc<__half>(ActView<__half>, float*, cudaStream_t);
 
 }  // namespace ccst

@@ -44,10 +44,16 @@ int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st);
 template <typename T>
 int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st);
 
-// tcgen05 / TMA implicit GEMM (conv_umma.cu).  wk: [CoutPad][9*Cin] bf16 K-major, bias fp32.
-struct UmmaConvPlan;
-int launch_conv_umma(ActView<__nv_bfloat16> in, const __nv_bfloat16* wk, const float* bias,
-                     int Cout, int CoutPad, int relu, int epi, ActView<__nv_bfloat16> out,
-                     float* out_nchw, cudaStream_t st);
+// tcgen05 / TMA implicit GEMM (conv_umma.cu), T16 = __nv_bfloat16 or __half operands, fp32
+// accumulation in TMEM.  wk: [CoutPad][9*Cin] T16 K-major, bias fp32.
+template <typename T16>
+int launch_conv_umma(ActView<T16> in, const T16* wk, const float* bias, int Cout, int CoutPad,
+                     int relu, int epi, ActView<T16> out, float* out_nchw, cudaStream_t st);
+
+// conv1_1 (+ folded 1x1) on tcgen05: thread-built im2col rows (K = 27 padded to 32).
+// wk: [64][32] T16 K-major, bias fp32 [64].
+template <typename T16>
+int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk, const float* bias,
+                           ActView<T16> out, cudaStream_t st);
 
 }  // namespace ccst

@@ -45,7 +45,7 @@ def calc_mean_std(feat, eps=EPS):
     hw = size[2] * size[3]
     mean = torch.empty((n, c, 1, 1), dtype=torch.float32, device=feat.device)
     std = torch.empty_like(mean)
-    with torch.cuda.device(feat.device):
+    with _lib.on_device(feat.device):
         _lib.check(_lib.lib().ccst_stats_nchw_f32(
             feat.data_ptr(), n * c, hw, float(eps), 1, mean.data_ptr(), std.data_ptr(), _stream(feat)))
     return mean, std
@@ -91,7 +91,7 @@ def adain_blend(content_feat, style_stat, alpha=1.0, eps=EPS):
     hw = size[2] * size[3]
     mu, sg, stride = _style_stat_args(style_stat, n, c, x.device)
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         _lib.check(_lib.lib().ccst_adain_stat_nchw_f32(
             x.data_ptr(), n, c, hw, mu.data_ptr(), sg.data_ptr(), stride, float(alpha), float(eps),
             out.data_ptr(), _stream(x)))
@@ -116,7 +116,7 @@ def adaptive_instance_normalization(content_feat, style_feat, alpha=1.0):
     n, c = x.shape[:2]
     out = torch.empty_like(x)
     scratch = torch.empty((2 * n * c,), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _lib.on_device(x.device):
         _lib.check(_lib.lib().ccst_adain_feat_nchw_f32(
             x.data_ptr(), s.data_ptr(), n, c, x.shape[2] * x.shape[3], s.shape[2] * s.shape[3],
             float(alpha), EPS, out.data_ptr(), scratch.data_ptr(), _stream(x)))
@@ -145,7 +145,7 @@ class WelfordState:
         if c != self.C:
             raise RuntimeError(f"feature has {c} channels, state has {self.C}")
         scratch = torch.empty((2 * n * c,), dtype=torch.float32, device=feat.device)
-        with torch.cuda.device(feat.device):
+        with _lib.on_device(feat.device):
             _lib.check(_lib.lib().ccst_welford_accumulate_nchw_f32(
                 feat.data_ptr(), n, c, h * w, self.buf.data_ptr(), scratch.data_ptr(), _stream(feat)))
         return self
@@ -158,7 +158,7 @@ class WelfordState:
         """(mean, std) [1,C,1,1] fp32 with the biased variance of :135-137."""
         mean = torch.empty((1, self.C, 1, 1), dtype=torch.float32, device=self.device)
         std = torch.empty_like(mean)
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             _lib.check(_lib.lib().ccst_welford_finalize(
                 self.buf.data_ptr(), self.C, float(eps), mean.data_ptr(), std.data_ptr(),
                 torch.cuda.current_stream(self.device).cuda_stream))
@@ -168,7 +168,7 @@ class WelfordState:
         """(sum, square_sum) [1,C,1,1] fp32 -- what calc_sum would have accumulated."""
         s1 = torch.empty((1, self.C, 1, 1), dtype=torch.float32, device=self.device)
         s2 = torch.empty_like(s1)
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             _lib.check(_lib.lib().ccst_welford_to_sums(
                 self.buf.data_ptr(), self.C, s1.data_ptr(), s2.data_ptr(),
                 torch.cuda.current_stream(self.device).cuda_stream))
@@ -177,7 +177,7 @@ class WelfordState:
     def moments(self):
         """Exactly-summable fp64 vector {n, n*mean, M2 + n*mean^2} (the all-reduce payload)."""
         m = torch.empty_like(self.buf)
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             _lib.check(_lib.lib().ccst_welford_to_moments(
                 self.buf.data_ptr(), self.C, m.data_ptr(),
                 torch.cuda.current_stream(self.device).cuda_stream))
@@ -185,7 +185,7 @@ class WelfordState:
 
     def load_moments(self, moments):
         moments = moments.to(device=self.device, dtype=torch.float64).contiguous()
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             _lib.check(_lib.lib().ccst_welford_from_moments(
                 moments.data_ptr(), self.C, self.buf.data_ptr(),
                 torch.cuda.current_stream(self.device).cuda_stream))

@@ -42,6 +42,7 @@ extern "C" {
 /* precision of the encoder/decoder convolutions */
 #define CCST_PREC_FP32 0 /* fp32 activations + fp32 FFMA implicit GEMM (validation mode, 1e-4) */
 #define CCST_PREC_BF16 1 /* bf16 activations + tcgen05/TMEM implicit GEMM fed by TMA (fp32 accum) */
+#define CCST_PREC_FP16 2 /* same kernels with f16 operands (11-bit significand, saturating stores) */
 
 typedef struct ccst_handle ccst_handle;
 
@@ -49,6 +50,9 @@ int ccst_abi_version(void);
 const char* ccst_last_error(void);
 /* 0 if `device` is an sm_100 GPU, CCST_EARCH otherwise. */
 int ccst_check_device(int device);
+/* Make `device` current for the calling thread inside the library (the library links its own
+ * CUDA runtime; hosts that switch devices call this before enqueueing work). */
+int ccst_set_device(int device);
 
 /* ------------------------------------------------------------------------
  * Feature statistics
