@@ -19,6 +19,8 @@
 //   warp 2        : TMEM alloc / dealloc  warps 4..7    : epilogue (TMEM -> regs -> bias/ReLU -> HBM)
 #include <cuda.h>
 
+#include <cstring>
+
 #include "layers.h"
 
 namespace ccst {
@@ -49,9 +51,13 @@ struct UmmaCfg {
   // B stage must keep every stage base 1024-byte aligned (SWIZZLE_128B atoms)
   static constexpr int kBStride = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kABytes + kBStride;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 5 : 7);
+  static constexpr int kStoreBufs = (BN >= 256) ? 1 : 2;  // BN = 256 has epilogue slack to spare
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStoreStageBytes = (BN >= 64) ? kStoreBufs * kBlockM * 128 : 0;  // 16 KiB TMA-store staging buffers
+  static constexpr int kBiasBytes = 2048;  // up to 512 fp32 biases
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kStoreStageBytes + kBiasBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <typename T16>
@@ -213,26 +219,75 @@ __device__ __forceinline__ TileCoord decode_tile(const P& p, int tile) {
   return t;
 }
 
-// ------------------------------------------------------------------ epilogue stores
-template <typename P>
-__device__ __forceinline__ void store_act_chunk(const P& p, int n, int y, int x, int co,
-                                                const uint32_t (&pk)[16]) {
-  for_each_halo_alias(y, x, p.out.H, p.out.W, [&](int yy, int xx) {
-    uint4* dst = reinterpret_cast<uint4*>(p.out.px(n, yy, xx) + co);
+// ------------------------------------------------------------------ main kernel
+// One elected lane of a converged warp (the compiler keeps descriptors / barrier addresses in
+// uniform registers; a `lane == 0` branch instead makes it wrap every tcgen05/TMA instruction in a
+// per-lane waterfall loop that costs ~600 issue cycles per K block).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// barrier among the 128 epilogue threads only (id 1; id 0 is __syncthreads)
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+constexpr int kStoreBytes = kBlockM * 128;  // one 64-channel chunk of a 128-pixel tile, 16 KiB
+
+// Output tensor maps: [0] main store; [1..3] the other three 2x2 replicas of the fused upsample.
+struct OutMaps {
+  CUtensorMap m[4];
+};
+
+// direct (register) stores of the reflection-halo aliases of pixel (y, x); the pixel itself goes
+// out through the TMA store of the staged tile
+template <typename T16>
+__device__ __forceinline__ void store_aliases(const ActView<T16>& out, int n, int y, int x, int co,
+                                              const uint32_t (&pk)[32]) {
+  const bool ya = (y == 1) || (y == out.H - 2), xa = (x == 1) || (x == out.W - 2);
+  if (!(ya || xa)) return;
+  for_each_halo_alias(y, x, out.H, out.W, [&](int yy, int xx) {
+    if (yy == y && xx == x) return;
+    uint4* dst = reinterpret_cast<uint4*>(out.px(n, yy, xx) + co);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    for (int q = 0; q < 8; ++q)
+      dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
   });
 }
 
 template <typename T16, int BN, int EPI>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                     const __grid_constant__ CUtensorMap tmap_b, ConvParams<T16> p) {
+                     const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ OutMaps tmap_out, ConvParams<T16> p) {
   using Cfg = UmmaCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte aligned stage bases
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic alias of smem_base
+  const uint32_t store_base = smem_base + Cfg::kStages * Cfg::kStageBytes;  // 2 x 16 KiB staging
+  const uint32_t bias_off = Cfg::kStages * Cfg::kStageBytes + Cfg::kStoreStageBytes;
+  const uint32_t bar_base = smem_base + bias_off + Cfg::kBiasBytes;
+  float* s_bias = reinterpret_cast<float*>(smem_gen + bias_off);
   auto a_smem = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
   auto b_smem = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -240,7 +295,6 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
   auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic alias of smem_base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = p.Cin / kBlockK;
@@ -249,6 +303,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (EPI != EPI_NCHW_F32) prefetch_tmap(&tmap_out.m[0]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -262,15 +317,15 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  for (int i = threadIdx.x; i < p.CoutPad; i += kThreadsUmma) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base =
-      *reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kStages * Cfg::kStageBytes +
-                                            8 * (2 * Cfg::kStages + 4));
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(
+      smem_gen + bias_off + Cfg::kBiasBytes + 8 * (2 * Cfg::kStages + 4));
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp converged, one lane issues) ==============
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -279,11 +334,15 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         for (int tap = 0; tap < 9; ++tap) {
           const int r = tap / 3, s = tap - 3 * r;
           mbar_wait(empty_bar(stage), phase ^ 1, 100 + stage);
-          mbar_expect_tx(full_bar(stage), kABytes + Cfg::kBBytes);
-          // padded coords: interior pixel (y, x) is stored at (y+1, x+1); tap (r,s) reads (y+r-1, x+s-1)
-          tma_load_4d(a_smem(stage), &tmap_a, full_bar(stage), kc * kBlockK, t.x0 + s, t.y0 + r, t.n);
-          tma_load_2d(b_smem(stage), &tmap_b, full_bar(stage), tap * p.Cin + kc * kBlockK,
-                      t.nt * BN);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(stage), kABytes + Cfg::kBBytes);
+            // interior pixel (y, x) is stored at (y+1, x+1); tap (r,s) reads (y+r-1, x+s-1)
+            tma_load_4d(a_smem(stage), &tmap_a, full_bar(stage), kc * kBlockK, t.x0 + s, t.y0 + r,
+                        t.n);
+            tma_load_2d(b_smem(stage), &tmap_b, full_bar(stage), tap * p.Cin + kc * kBlockK,
+                        t.nt * BN);
+          }
+          __syncwarp();
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -291,8 +350,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp converged, one lane issues) ================
     constexpr uint32_t idesc = make_idesc<T16, BN>();
     int stage = 0;
     uint32_t phase = 0;
@@ -306,16 +365,18 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase, 300 + stage);
         tc_fence_after();
-        const uint64_t adesc = make_kmajor_sw128_desc(a_smem(stage));
-        const uint64_t bdesc = make_kmajor_sw128_desc(b_smem(stage));
+        if (elect_one()) {
+          const uint64_t adesc = make_kmajor_sw128_desc(a_smem(stage));
+          const uint64_t bdesc = make_kmajor_sw128_desc(b_smem(stage));
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          // advancing 16 bf16 (32 bytes) along K inside the 128-byte swizzle atom = +2 in the
-          // 16-byte-granular start-address field
-          umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +16 bf16 (32 bytes) along K inside the 128-byte swizzle atom = +2 in the start field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tmem_full_bar(as));
         }
-        umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
-        if (kb == num_kb - 1) umma_commit(tmem_full_bar(as));
+        __syncwarp();
         if (++stage == Cfg::kStages) {
           stage = 0;
           phase ^= 1;
@@ -327,7 +388,11 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     const int quad = warp & 3;           // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;    // accumulator row = pixel inside the tile
     const int py = row / kTileW, px = row % kTileW;
+    // warp 4 owns the bulk-store async groups: all its lanes execute the waits (a no-op for lanes
+    // without groups), one elected lane -- always the same one -- issues and commits the stores
+    const bool issuer_warp = (warp == kEpiWarp0);
     int it = 0;
+    uint32_t nstore = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(p, tile);
       const int as = it & 1;
@@ -345,7 +410,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             if (c < p.Cout) {
-              float v = __uint_as_float(r[c]) + __ldg(p.bias + c);
+              float v = __uint_as_float(r[c]) + s_bias[c];
               if (p.relu) v = fmaxf(v, 0.f);
               p.out_nchw[(((size_t)t.n * p.Cout + c) * p.H + y) * p.W + x] = v;
             }
@@ -353,49 +418,81 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         }
       } else {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld32(taddr + ch * 32, r);
+        for (int ch = 0; ch < BN / 64; ++ch, ++nstore) {
+          const uint32_t sbuf = store_base + (nstore % Cfg::kStoreBufs) * kStoreBytes;
+          uint32_t r[64];
+          {
+            uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+            uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+            tmem_ld32(taddr + ch * 64, r0);
+            tmem_ld32(taddr + ch * 64 + 32, r1);
+          }
+          // the staging buffer about to be rewritten must have been read out by its TMA store
+          if (issuer_warp) bulk_wait_read<Cfg::kStoreBufs - 1>();
           tmem_ld_wait();
-          const int co = t.nt * BN + ch * 32;
-          float v[32];
+          epi_barrier();
+          const int co = t.nt * BN + ch * 64;
+          uint32_t pk[32];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co) + q);
-            v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
-            v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
-            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
-            v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+          for (int j = 0; j < 32; ++j) {
+            float v0 = __uint_as_float(r[2 * j]) + s_bias[co + 2 * j];
+            float v1 = __uint_as_float(r[2 * j + 1]) + s_bias[co + 2 * j + 1];
+            if (p.relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+            if (EPI == EPI_ACT_POOL) {
+              // 2x2 window = lanes {l, l^1, l^16, l^17}; out-of-image pixels contribute 0, the
+              // identity for post-ReLU values
+              v0 = valid ? v0 : 0.f;
+              v1 = valid ? v1 : 0.f;
+              v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
+              v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
+              v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 16));
+              v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 16));
+            }
+            pk[j] = pack16x2<T16>(v0, v1);
           }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
+          // stage the row (128 bytes = 8 chunks) with the 128-byte swizzle the TMA store expects
+          int srow = row;
+          bool writer = true;
           if (EPI == EPI_ACT_POOL) {
-            // 2x2 window = lanes {l, l^1, l^16, l^17} (tile rows are 16 lanes apart, 2 rows per
-            // warp); out-of-image pixels contribute 0, the identity for post-ReLU values.
+            writer = !(lane & 1) && lane < 16;  // anchor of a 2x2 window
+            srow = (py >> 1) * (kTileW / 2) + (px >> 1);
+          }
+          if (writer) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float m = valid ? v[j] : 0.f;
-              m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-              m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-              v[j] = m;
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t dst = sbuf + srow * 128 + ((j ^ (srow & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                           "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                           : "memory");
             }
           }
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack16x2<T16>(v[2 * j], v[2 * j + 1]);
-          if (EPI == EPI_ACT) {
-            if (valid) store_act_chunk(p, t.n, y, x, co, pk);
-          } else if (EPI == EPI_ACT_UP2) {
-            if (valid) {
+          if (valid) {
+            if (EPI == EPI_ACT) {
+              store_aliases(p.out, t.n, y, x, co, pk);
+            } else if (EPI == EPI_ACT_UP2) {
 #pragma unroll
               for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int b = 0; b < 2; ++b) store_act_chunk(p, t.n, 2 * y + a, 2 * x + b, co, pk);
+                for (int b = 0; b < 2; ++b) store_aliases(p.out, t.n, 2 * y + a, 2 * x + b, co, pk);
+            } else if (EPI == EPI_ACT_POOL) {
+              if (writer) store_aliases(p.out, t.n, y >> 1, x >> 1, co, pk);
             }
-          } else if (EPI == EPI_ACT_POOL) {
-            if (valid && !(lane & 1) && lane < 16) store_act_chunk(p, t.n, y >> 1, x >> 1, co, pk);
+          }
+          fence_async_smem();
+          epi_barrier();
+          if (issuer_warp && elect_one()) {
+            // coordinates are interior pixels; TMA clips the box at the image border
+            if (EPI == EPI_ACT_POOL) {
+              tma_store_4d(&tmap_out.m[0], sbuf, co, t.x0 >> 1, t.y0 >> 1, t.n);
+            } else {
+              tma_store_4d(&tmap_out.m[0], sbuf, co, t.x0, t.y0, t.n);
+              if (EPI == EPI_ACT_UP2) {
+                tma_store_4d(&tmap_out.m[1], sbuf, co, t.x0, t.y0, t.n);
+                tma_store_4d(&tmap_out.m[2], sbuf, co, t.x0, t.y0, t.n);
+                tma_store_4d(&tmap_out.m[3], sbuf, co, t.x0, t.y0, t.n);
+              }
+            }
+            bulk_commit();
           }
         }
       }
@@ -404,6 +501,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar(as));
     }
+    if (issuer_warp) bulk_wait_all();
   }
 
   __syncwarp();
@@ -600,6 +698,35 @@ int make_act_map(CUtensorMap* m, const ActView<T16>& v) {
   return CCST_OK;
 }
 
+// 4-D map over the INTERIOR of an activation (halo excluded, so TMA clips ragged tiles at the
+// image border): dims (C, W/sx, H/sy, N) starting at interior pixel (oy, ox), pixel step (sy, sx).
+template <typename T16>
+int make_out_map(CUtensorMap* m, const ActView<T16>& v, int oy, int ox, int sy, int sx, int box_w,
+                 int box_h) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return CCST_ECUDA;
+  }
+  const size_t pitch_y = (size_t)(v.W + 2) * v.C, pitch_n = (size_t)(v.H + 2) * (v.W + 2) * v.C;
+  T16* base = v.p + (size_t)(1 + oy) * pitch_y + (size_t)(1 + ox) * v.C;
+  const cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)((v.W - ox + sx - 1) / sx),
+                              (cuuint64_t)((v.H - oy + sy - 1) / sy), (cuuint64_t)v.N};
+  const cuuint64_t strides[3] = {(cuuint64_t)sx * v.C * 2, (cuuint64_t)sy * pitch_y * 2,
+                                 (cuuint64_t)pitch_n * 2};
+  const cuuint32_t box[4] = {kBlockK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, Fmt16<T16>::kTmaType, 4, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(output %dx%dx%dx%d) failed: CUresult %d", v.N, v.H, v.W, v.C,
+              (int)r);
+    return CCST_ECUDA;
+  }
+  return CCST_OK;
+}
+
 template <typename T16>
 int make_weight_map(CUtensorMap* m, const T16* wk, int K, int CoutPad, int BN) {
   PFN_encodeTiled enc = get_encode_fn();
@@ -625,6 +752,17 @@ int make_weight_map(CUtensorMap* m, const T16* wk, int K, int CoutPad, int BN) {
 template <typename T16, int BN, int EPI>
 int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams<T16>& p,
                cudaStream_t st) {
+  OutMaps mo;
+  memset(&mo, 0, sizeof(mo));
+  if (EPI == EPI_ACT) {
+    if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kTileW, kTileH)) return e;
+  } else if (EPI == EPI_ACT_POOL) {
+    if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kTileW / 2, kTileH / 2)) return e;
+  } else if (EPI == EPI_ACT_UP2) {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, kTileW, kTileH)) return e;
+  }
   using Cfg = UmmaCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -633,7 +771,7 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams<T1
     attr_done = true;
   }
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  conv_umma_kernel<T16, BN, EPI><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  conv_umma_kernel<T16, BN, EPI><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, mo, p);
   CCST_LAUNCHED();
   return CCST_OK;
 }
