@@ -41,23 +41,38 @@ struct Fmt16<__half> {
 };
 
 constexpr int kTileH = 8, kTileW = 16, kBlockM = kTileH * kTileW, kBlockK = 64;
-constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kThreadsUmma = 256;
 constexpr int kEpiWarp0 = 4;
 
-template <int BN>
+// Shared-memory plan of the main kernel.
+//   A ring : kAStages slabs of {64 ch, 16 px, 10 rows} = 20 KiB.  One slab serves the three filter
+//            rows r = 0,1,2 of one (channel chunk, filter column s): the operand of tap (r,s) is the
+//            slab shifted by r tile rows = r * 2048 bytes, which keeps the 1024-byte swizzle phase.
+//            (A bytes per tile: 3 slabs instead of 9 tiles per channel chunk -> 2.4x less L2->SM traffic.)
+//   B      : BRES = false: ring of kBStages weight tiles {64 k, BN}, one per tap and channel chunk;
+//            BRES = true (9*Cin*BN*2 bytes fit): all weights loaded once per CTA and kept resident.
+//   store  : kStoreBufs x 16 KiB staging tiles for the TMA store of the epilogue.
+template <int BN, bool BRES>
 struct UmmaCfg {
+  static constexpr int kSlabRows = kTileH + 2;
+  static constexpr int kASlabBytes = kSlabRows * kTileW * 128;  // 20480
   static constexpr int kBBytes = BN * kBlockK * 2;
-  // B stage must keep every stage base 1024-byte aligned (SWIZZLE_128B atoms)
   static constexpr int kBStride = (kBBytes + 1023) / 1024 * 1024;
-  static constexpr int kStageBytes = kABytes + kBStride;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 5 : 7);
-  static constexpr int kStoreBufs = (BN >= 256) ? 1 : 2;  // BN = 256 has epilogue slack to spare
-  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int kStoreStageBytes = (BN >= 64) ? kStoreBufs * kBlockM * 128 : 0;  // 16 KiB TMA-store staging buffers
+  static constexpr int kAStages = BRES ? (BN >= 64 ? 5 : 6) : (BN >= 256 ? 3 : 4);
+  static constexpr int kBStages = BRES ? 9 /* resident: 9 taps x (Cin == 64) */
+                                       : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 9));
+  static constexpr int kStoreBufs = (BN >= 256) ? 1 : 2;
+  static constexpr int kStoreStageBytes = (BN >= 64) ? kStoreBufs * kBlockM * 128 : 0;
   static constexpr int kBiasBytes = 2048;  // up to 512 fp32 biases
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + kStoreStageBytes + kBiasBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kAOff = 0;
+  static constexpr int kBOff = kAStages * kASlabBytes;
+  static constexpr int kStoreOff = kBOff + kBStages * kBStride;
+  static constexpr int kBiasOff = kStoreOff + kStoreStageBytes;
+  static constexpr int kBarOff = kBiasOff + kBiasBytes;
+  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4 + 1;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024 /*align slack*/;
+  static_assert(kSmemBytes <= 232448, "shared memory plan exceeds 227 KiB");
 };
 
 template <typename T16>
@@ -274,31 +289,33 @@ __device__ __forceinline__ void store_aliases(const ActView<T16>& out, int n, in
   });
 }
 
-template <typename T16, int BN, int EPI>
+template <typename T16, int BN, int EPI, bool BRES>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ OutMaps tmap_out, ConvParams<T16> p) {
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, BRES>;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B atoms need 1024-byte aligned stage bases
+  // SWIZZLE_128B atoms need 1024-byte aligned bases
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic alias of smem_base
-  const uint32_t store_base = smem_base + Cfg::kStages * Cfg::kStageBytes;  // 2 x 16 KiB staging
-  const uint32_t bias_off = Cfg::kStages * Cfg::kStageBytes + Cfg::kStoreStageBytes;
-  const uint32_t bar_base = smem_base + bias_off + Cfg::kBiasBytes;
-  float* s_bias = reinterpret_cast<float*>(smem_gen + bias_off);
-  auto a_smem = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
-  auto b_smem = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
-  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  const uint32_t store_base = smem_base + Cfg::kStoreOff;
+  const uint32_t bar_base = smem_base + Cfg::kBarOff;
+  float* s_bias = reinterpret_cast<float*>(smem_gen + Cfg::kBiasOff);
+  auto a_smem = [&](int s) { return smem_base + Cfg::kAOff + s * Cfg::kASlabBytes; };
+  auto b_smem = [&](int s) { return smem_base + Cfg::kBOff + s * Cfg::kBStride; };
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::kAStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + Cfg::kBStages + s); };
+  constexpr int kBar2 = 2 * Cfg::kAStages + 2 * Cfg::kBStages;
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (kBar2 + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (kBar2 + 2 + s); };
+  const uint32_t bres_bar = bar_base + 8u * (kBar2 + 4);  // resident weights landed
+  const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = p.Cin / kBlockK;
-  const int num_kb = 9 * kchunks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -306,14 +323,19 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     if (EPI != EPI_NCHW_F32) prefetch_tmap(&tmap_out.m[0]);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < Cfg::kAStages; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < Cfg::kBStages; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full_bar(s), 1);
       mbar_init(tmem_empty_bar(s), 4);  // one arrive per epilogue warp
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -321,31 +343,46 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(
-      smem_gen + bias_off + Cfg::kBiasBytes + 8 * (2 * Cfg::kStages + 4));
+  const uint32_t tmem_base =
+      *reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOff + 8 * Cfg::kNumBars);
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one lane issues) ==============
-    int stage = 0;
-    uint32_t phase = 0;
+    if (BRES) {
+      // all 9 weight tiles of this (Cin == 64) layer, once
+      if (elect_one()) {
+        mbar_expect_tx(bres_bar, 9 * Cfg::kBBytes);
+        for (int tap = 0; tap < 9; ++tap)
+          tma_load_2d(b_smem(tap), &tmap_b, bres_bar, tap * p.Cin, 0);
+      }
+      __syncwarp();
+    }
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       for (int kc = 0; kc < kchunks; ++kc) {
-        for (int tap = 0; tap < 9; ++tap) {
-          const int r = tap / 3, s = tap - 3 * r;
-          mbar_wait(empty_bar(stage), phase ^ 1, 100 + stage);
+        for (int s = 0; s < 3; ++s) {
+          mbar_wait(a_empty(as), aph ^ 1, 100 + as);
           if (elect_one()) {
-            mbar_expect_tx(full_bar(stage), kABytes + Cfg::kBBytes);
-            // interior pixel (y, x) is stored at (y+1, x+1); tap (r,s) reads (y+r-1, x+s-1)
-            tma_load_4d(a_smem(stage), &tmap_a, full_bar(stage), kc * kBlockK, t.x0 + s, t.y0 + r,
-                        t.n);
-            tma_load_2d(b_smem(stage), &tmap_b, full_bar(stage), tap * p.Cin + kc * kBlockK,
-                        t.nt * BN);
+            mbar_expect_tx(a_full(as), Cfg::kASlabBytes);
+            // interior pixel (y, x) is stored at (y+1, x+1): the slab for filter column s starts at
+            // padded (y0, x0 + s) and spans the 10 rows needed by r = 0..2
+            tma_load_4d(a_smem(as), &tmap_a, a_full(as), kc * kBlockK, t.x0 + s, t.y0, t.n);
           }
           __syncwarp();
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
+          if (++as == Cfg::kAStages) as = 0, aph ^= 1;
+          if (!BRES) {
+            for (int r = 0; r < 3; ++r) {
+              mbar_wait(b_empty(bs), bph ^ 1, 150 + bs);
+              if (elect_one()) {
+                mbar_expect_tx(b_full(bs), Cfg::kBBytes);
+                tma_load_2d(b_smem(bs), &tmap_b, b_full(bs), (r * 3 + s) * p.Cin + kc * kBlockK,
+                            t.nt * BN);
+              }
+              __syncwarp();
+              if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
+            }
           }
         }
       }
@@ -353,33 +390,53 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one lane issues) ================
     constexpr uint32_t idesc = make_idesc<T16, BN>();
-    int stage = 0;
-    uint32_t phase = 0;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(tmem_empty_bar(as), aphase ^ 1, 200 + as);
+    if (BRES) {
+      mbar_wait(bres_bar, 0, 250);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase, 300 + stage);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t adesc = make_kmajor_sw128_desc(a_smem(stage));
-          const uint64_t bdesc = make_kmajor_sw128_desc(b_smem(stage));
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acs = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tmem_empty_bar(acs), aphase ^ 1, 200 + acs);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acs * BN);
+      for (int kc = 0; kc < kchunks; ++kc) {
+        for (int s = 0; s < 3; ++s) {
+          mbar_wait(a_full(as), aph, 300 + as);
+          tc_fence_after();
+          for (int r = 0; r < 3; ++r) {
+            uint32_t bsm;
+            if (BRES) {
+              bsm = b_smem(r * 3 + s);
+            } else {
+              mbar_wait(b_full(bs), bph, 350 + bs);
+              tc_fence_after();
+              bsm = b_smem(bs);
+            }
+            if (elect_one()) {
+              // tap (r,s): slab shifted by r tile rows (16 px * 128 B = 2048 B, swizzle-phase neutral)
+              const uint64_t adesc = make_kmajor_sw128_desc(a_smem(as) + r * (kTileW * 128));
+              const uint64_t bdesc = make_kmajor_sw128_desc(bsm);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +16 bf16 (32 bytes) along K inside the 128-byte swizzle atom = +2 in the start field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // +16 elements (32 bytes) along K inside the swizzle atom = +2 in the start field
+                umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | s | r | k) ? 1u : 0u);
+              }
+              if (!BRES) umma_commit(b_empty(bs));  // frees the weight tile when these MMAs retire
+              if (r == 2) {
+                umma_commit(a_empty(as));  // ... and the slab after its third tap
+                if (kc == kchunks - 1 && s == 2) umma_commit(tmem_full_bar(acs));
+              }
+            }
+            __syncwarp();
+            if (!BRES) {
+              if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
+            }
           }
-          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
-          if (kb == num_kb - 1) umma_commit(tmem_full_bar(as));
-        }
-        __syncwarp();
-        if (++stage == Cfg::kStages) {
-          stage = 0;
-          phase ^= 1;
+          if (++as == Cfg::kAStages) as = 0, aph ^= 1;
         }
       }
     }
@@ -685,7 +742,8 @@ int make_act_map(CUtensorMap* m, const ActView<T16>& v) {
                               (cuuint64_t)v.N};
   const cuuint64_t strides[3] = {(cuuint64_t)v.C * 2, (cuuint64_t)(v.W + 2) * v.C * 2,
                                  (cuuint64_t)(v.H + 2) * (v.W + 2) * v.C * 2};
-  const cuuint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
+  // slab = the tile plus the two extra rows the filter rows r = 1, 2 reach into
+  const cuuint32_t box[4] = {kBlockK, kTileW, kTileH + 2, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, Fmt16<T16>::kTmaType, 4, (void*)v.p, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -749,7 +807,7 @@ int make_weight_map(CUtensorMap* m, const T16* wk, int K, int CoutPad, int BN) {
   return CCST_OK;
 }
 
-template <typename T16, int BN, int EPI>
+template <typename T16, int BN, int EPI, bool BRES>
 int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams<T16>& p,
                cudaStream_t st) {
   OutMaps mo;
@@ -763,29 +821,29 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams<T1
       for (int b = 0; b < 2; ++b)
         if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, kTileW, kTileH)) return e;
   }
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, BRES>;
   static bool attr_done = false;
   if (!attr_done) {
-    CCST_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T16, BN, EPI>,
+    CCST_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T16, BN, EPI, BRES>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  conv_umma_kernel<T16, BN, EPI><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, mo, p);
+  conv_umma_kernel<T16, BN, EPI, BRES><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, mo, p);
   CCST_LAUNCHED();
   return CCST_OK;
 }
 
-template <typename T16, int BN>
+template <typename T16, int BN, bool BRES>
 int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams<T16>& p, int epi,
               cudaStream_t st) {
   switch (epi) {
     case EPI_ACT:
-      return launch_cfg<T16, BN, EPI_ACT>(ma, mb, p, st);
+      return launch_cfg<T16, BN, EPI_ACT, BRES>(ma, mb, p, st);
     case EPI_ACT_UP2:
-      return launch_cfg<T16, BN, EPI_ACT_UP2>(ma, mb, p, st);
+      return launch_cfg<T16, BN, EPI_ACT_UP2, BRES>(ma, mb, p, st);
     case EPI_ACT_POOL:
-      return launch_cfg<T16, BN, EPI_ACT_POOL>(ma, mb, p, st);
+      return launch_cfg<T16, BN, EPI_ACT_POOL, BRES>(ma, mb, p, st);
     default:
       set_error("conv_umma: epilogue %d not available for BN=%d", epi, BN);
       return CCST_EINVAL;
@@ -826,13 +884,17 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const float* bias, int Cout
   if (int e = make_weight_map(&mb, wk, 9 * in.C, CoutPad, BN)) return e;
   switch (BN) {
     case 16:
-      return launch_cfg<T16, 16, EPI_NCHW_F32>(ma, mb, p, st);
+      // the last decoder conv (64 -> 3): weights always resident
+      CCST_CHECK_ARG(in.C == kBlockK, "conv_umma: the NCHW epilogue expects Cin == 64");
+      return launch_cfg<T16, 16, EPI_NCHW_F32, true>(ma, mb, p, st);
     case 64:
-      return launch_bn<T16, 64>(ma, mb, p, epi, st);
+      // 64 -> 64 layers keep all 9 weight tiles (72 KiB) resident in shared memory
+      return in.C == kBlockK ? launch_bn<T16, 64, true>(ma, mb, p, epi, st)
+                             : launch_bn<T16, 64, false>(ma, mb, p, epi, st);
     case 128:
-      return launch_bn<T16, 128>(ma, mb, p, epi, st);
+      return launch_bn<T16, 128, false>(ma, mb, p, epi, st);
     default:
-      return launch_bn<T16, 256>(ma, mb, p, epi, st);
+      return launch_bn<T16, 256, false>(ma, mb, p, epi, st);
   }
 }
 template int launch_conv_umma<__nv_bfloat16>(ActView<__nv_bfloat16>, const __nv_bfloat16*,
