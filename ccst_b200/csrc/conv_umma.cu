@@ -41,7 +41,7 @@ struct Fmt16<__half> {
 };
 
 constexpr int kTileH = 8, kTileW = 16, kBlockM = kTileH * kTileW, kBlockK = 64;
-constexpr int kThreadsUmma = 256;
+constexpr int kThreadsUmma = 384;  // 4 control warps + 2 epilogue groups of 4 warps
 constexpr int kEpiWarp0 = 4;
 
 // Shared-memory plan of the main kernel.
@@ -61,7 +61,7 @@ struct UmmaCfg {
   static constexpr int kAStages = BRES ? (BN >= 64 ? 5 : 6) : (BN >= 256 ? 3 : 4);
   static constexpr int kBStages = BRES ? 9 /* resident: 9 taps x (Cin == 64) */
                                        : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 9));
-  static constexpr int kStoreBufs = (BN >= 256) ? 1 : 2;
+  static constexpr int kStoreBufs = 2;  // one staging tile per epilogue group
   static constexpr int kStoreStageBytes = (BN >= 64) ? kStoreBufs * kBlockM * 128 : 0;
   static constexpr int kBiasBytes = 2048;  // up to 512 fp32 biases
   static constexpr int kAOff = 0;
@@ -263,8 +263,10 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// barrier among the 128 epilogue threads only (id 1; id 0 is __syncthreads)
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// barrier among the 128 threads of one epilogue group (ids 1, 2; id 0 is __syncthreads)
+__device__ __forceinline__ void epi_barrier(int group) {
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
 
 constexpr int kStoreBytes = kBlockM * 128;  // one 64-channel chunk of a 128-pixel tile, 16 KiB
 
@@ -441,16 +443,20 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue =====================
+    // ===================== epilogue: two groups of 4 warps, group g drains accumulator stage g
+    // (tiles it = g, g+2, ...), so each group has two tile-times to finish one tile ==========
+    const int grp = (warp - kEpiWarp0) >> 2;
     const int quad = warp & 3;           // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;    // accumulator row = pixel inside the tile
     const int py = row / kTileW, px = row % kTileW;
     // warp 4 owns the bulk-store async groups: all its lanes execute the waits (a no-op for lanes
     // without groups), one elected lane -- always the same one -- issues and commits the stores
-    const bool issuer_warp = (warp == kEpiWarp0);
-    int it = 0;
-    uint32_t nstore = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    const bool issuer_warp = (quad == 0);
+    const uint32_t sbuf = store_base + grp * kStoreBytes;
+    for (int it = grp;; it += 2) {
+      const long long tile_ll = (long long)blockIdx.x + (long long)it * gridDim.x;
+      if (tile_ll >= p.total_tiles) break;
+      const int tile = (int)tile_ll;
       const TileCoord t = decode_tile(p, tile);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -475,8 +481,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         }
       } else {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 64; ++ch, ++nstore) {
-          const uint32_t sbuf = store_base + (nstore % Cfg::kStoreBufs) * kStoreBytes;
+        for (int ch = 0; ch < BN / 64; ++ch) {
           uint32_t r[64];
           {
             uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
@@ -485,9 +490,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
             tmem_ld32(taddr + ch * 64 + 32, r1);
           }
           // the staging buffer about to be rewritten must have been read out by its TMA store
-          if (issuer_warp) bulk_wait_read<Cfg::kStoreBufs - 1>();
+          if (issuer_warp) bulk_wait_read<0>();
           tmem_ld_wait();
-          epi_barrier();
+          epi_barrier(grp);
           const int co = t.nt * BN + ch * 64;
           uint32_t pk[32];
 #pragma unroll
@@ -536,7 +541,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
             }
           }
           fence_async_smem();
-          epi_barrier();
+          epi_barrier(grp);
           if (issuer_warp && elect_one()) {
             // coordinates are interior pixels; TMA clips the box at the image border
             if (EPI == EPI_ACT_POOL) {
@@ -590,9 +595,11 @@ struct FirstParams {
 };
 
 template <typename T16>
-__global__ void __launch_bounds__(kFirstPx) conv_first_umma_kernel(FirstParams<T16> p) {
+__global__ void __launch_bounds__(kFirstPx)
+    conv_first_umma_kernel(const __grid_constant__ CUtensorMap tmap_out, FirstParams<T16> p) {
   __shared__ __align__(1024) uint8_t sA[kFirstPx * 128];
   __shared__ __align__(1024) uint8_t sB[64 * 128];
+  __shared__ __align__(1024) uint8_t sOut[kFirstPx * 128];  // staged output tile (swizzled) for the TMA store
   __shared__ float sin[3][3][kFirstPx + 2];
   __shared__ float sbias[64];
   __shared__ __align__(8) uint64_t bar_store;
@@ -610,9 +617,10 @@ __global__ void __launch_bounds__(kFirstPx) conv_first_umma_kernel(FirstParams<T
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
+    prefetch_tmap(&tmap_out);
   }
   if (warp == 0) tmem_alloc<64>(smem_u32(&tmem_slot_store));
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -620,6 +628,7 @@ __global__ void __launch_bounds__(kFirstPx) conv_first_umma_kernel(FirstParams<T
   const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA));
   const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB));
   constexpr uint32_t idesc = make_idesc<T16, 64>();
+  const uint32_t sout = smem_u32(sOut);
   uint32_t phase = 0;
 
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -643,6 +652,8 @@ __global__ void __launch_bounds__(kFirstPx) conv_first_umma_kernel(FirstParams<T
       }
       sin[ci][row][col] = v;
     }
+    // the previous tile's TMA store must have read sOut before the epilogue below rewrites it
+    if (warp == 0) bulk_wait_read<0>();
     __syncthreads();
     // (2) im2col row of pixel tid -> swizzled K-major A tile
     {
@@ -668,15 +679,18 @@ __global__ void __launch_bounds__(kFirstPx) conv_first_umma_kernel(FirstParams<T
         *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) << 4)) =
             make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy
+    fence_async_smem();  // generic smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
-    // (3) two K=16 steps
-    if (tid == 0) {
+    // (3) two K=16 steps, issued by one elected lane of the converged warp 0
+    if (warp == 0) {
       tc_fence_after();
-      umma_bf16(tmem_base, adesc, bdesc, idesc, 0u);
-      umma_bf16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
-      umma_commit(bar);
+      if (elect_one()) {
+        umma_bf16(tmem_base, adesc, bdesc, idesc, 0u);
+        umma_bf16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
+        umma_commit(bar);
+      }
+      __syncwarp();
     }
     // (4) accumulator ready
     mbar_wait(bar, phase, 900);
@@ -685,29 +699,37 @@ __global__ void __launch_bounds__(kFirstPx) conv_first_umma_kernel(FirstParams<T
     // (5) epilogue: row tid of the accumulator = pixel x0 + tid
     const int x = x0 + tid;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t r0[32], r1[32];
+    tmem_ld32(taddr, r0);
+    tmem_ld32(taddr + 32, r1);
+    tmem_ld_wait();
+    uint32_t pk[32];
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(taddr + ch * 32, r);
-      tmem_ld_wait();
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        pk[j] = pack16x2<T16>(fmaxf(__uint_as_float(r[2 * j]) + sbias[ch * 32 + 2 * j], 0.f),
-                              fmaxf(__uint_as_float(r[2 * j + 1]) + sbias[ch * 32 + 2 * j + 1], 0.f));
-      if (x < p.W) {
-        for_each_halo_alias(y, x, p.H, p.W, [&](int yy, int xx) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out.px(n, yy, xx) + ch * 32);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        });
-      }
+    for (int j = 0; j < 16; ++j) {
+      pk[j] = pack16x2<T16>(fmaxf(__uint_as_float(r0[2 * j]) + sbias[2 * j], 0.f),
+                            fmaxf(__uint_as_float(r0[2 * j + 1]) + sbias[2 * j + 1], 0.f));
+      pk[16 + j] = pack16x2<T16>(fmaxf(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j], 0.f),
+                                 fmaxf(__uint_as_float(r1[2 * j + 1]) + sbias[33 + 2 * j], 0.f));
     }
-    // TMEM reads are complete (wait::ld) before any thread passes the barrier in (1)/(2) of the
-    // next tile, after which thread 0 may overwrite the accumulator
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t dst = sout + tid * 128 + ((j ^ (tid & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                   "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                   : "memory");
+    }
+    if (x < p.W) store_aliases(p.out, n, y, x, 0, pk);
+    fence_async_smem();
+    // TMEM reads are complete (wait::ld) before any thread passes this barrier, after which warp 0
+    // may overwrite the accumulator with the next tile
     tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) {
+      tma_store_4d(&tmap_out, sout, 0, x0, y, n);  // one contiguous row segment, clipped at W
+      bulk_commit();
+    }
   }
+  if (warp == 0) bulk_wait_all();
   __syncthreads();
   if (warp == 0) tmem_dealloc<64>(tmem_base);
 }
@@ -912,9 +934,11 @@ int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk,
   const int64_t total = (int64_t)N * H * p.tiles_x;
   CCST_CHECK_ARG(total < (1ll << 31), "conv_first_umma: too many tiles");
   p.total_tiles = (int)total;
-  const int64_t cap = (int64_t)sm_count() * 6;
+  CUtensorMap mo;
+  if (int e = make_out_map(&mo, out, 0, 0, 1, 1, kFirstPx, 1)) return e;
+  const int64_t cap = (int64_t)sm_count() * 4;
   const int grid = (int)(total < cap ? total : cap);
-  conv_first_umma_kernel<T16><<<grid, kFirstPx, 0, st>>>(p);
+  conv_first_umma_kernel<T16><<<grid, kFirstPx, 0, st>>>(mo, p);
   CCST_LAUNCHED();
   return CCST_OK;
 }
