@@ -594,24 +594,32 @@ struct FirstParams {
   int total_tiles, tiles_x;
 };
 
+constexpr int kFirstWin = 9 * (kFirstPx + 2);         // 3 channels x 3 rows x 130 columns
+constexpr int kFirstWinBytes = (kFirstWin * 4 + 127) / 128 * 128;
+constexpr int kFirstSmem = 1024 /*align*/ + kFirstPx * 128 * 2 + 64 * 128 + 2 * kFirstWinBytes + 256 + 64;
+
 template <typename T16>
 __global__ void __launch_bounds__(kFirstPx)
     conv_first_umma_kernel(const __grid_constant__ CUtensorMap tmap_out, FirstParams<T16> p) {
-  __shared__ __align__(1024) uint8_t sA[kFirstPx * 128];
-  __shared__ __align__(1024) uint8_t sB[64 * 128];
-  __shared__ __align__(1024) uint8_t sOut[kFirstPx * 128];  // staged output tile (swizzled) for the TMA store
-  __shared__ float sin[3][3][kFirstPx + 2];
-  __shared__ float sbias[64];
-  __shared__ __align__(8) uint64_t bar_store;
-  __shared__ uint32_t tmem_slot_store;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base;                              // im2col rows, 128 x 128 B (swizzled)
+  const uint32_t sOut = base + kFirstPx * 128;           // staged output tile for the TMA store
+  uint8_t* sB_gen = gen + 2 * kFirstPx * 128;            // weights, 64 x 128 B (swizzled)
+  const uint32_t sB = base + 2 * kFirstPx * 128;
+  const uint32_t win_off = 2 * kFirstPx * 128 + 64 * 128;
+  float* sbias = reinterpret_cast<float*>(gen + win_off + 2 * kFirstWinBytes);
+  const uint32_t bar = base + win_off + 2 * kFirstWinBytes + 256;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(gen + win_off + 2 * kFirstWinBytes + 256 + 16);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const uint32_t bar = smem_u32(&bar_store);
 
   // one-time: weights -> swizzled K-major B tile, barrier, TMEM
   for (int i = tid; i < 64 * 4; i += kFirstPx) {
     const int o = i >> 2, j = i & 3;
     const uint4 v = reinterpret_cast<const uint4*>(p.wk)[o * 4 + j];
-    *reinterpret_cast<uint4*>(sB + o * 128 + ((j ^ (o & 7)) << 4)) = v;
+    *reinterpret_cast<uint4*>(sB_gen + o * 128 + ((j ^ (o & 7)) << 4)) = v;
   }
   if (tid < 64) sbias[tid] = p.bias[tid];
   if (tid == 0) {
@@ -619,42 +627,67 @@ __global__ void __launch_bounds__(kFirstPx)
     fence_barrier_init();
     prefetch_tmap(&tmap_out);
   }
-  if (warp == 0) tmem_alloc<64>(smem_u32(&tmem_slot_store));
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_store);
-  const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA));
-  const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB));
-  constexpr uint32_t idesc = make_idesc<T16, 64>();
-  const uint32_t sout = smem_u32(sOut);
-  uint32_t phase = 0;
+  if (warp == 0) tmem_alloc<64>(base + win_off + 2 * kFirstWinBytes + 256 + 16);
 
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+  // Input window of one tile: 3 ch x 3 rows x 130 cols of the NCHW fp32 image, reflection resolved
+  // per element, fetched with 4-byte cp.async one tile AHEAD of its use (the loads are the only
+  // DRAM-latency-bound part of this kernel).
+  auto stage_window = [&](int tile, int buf) {
     int b = tile;
     const int x0 = (b % p.tiles_x) * kFirstPx;
     b /= p.tiles_x;
     const int y = b % p.H;
     const int n = b / p.H;
-    // (1) stage the 3 x 3 x 130 input window, reflection resolved here
-    for (int i = tid; i < 9 * (kFirstPx + 2); i += kFirstPx) {
+    const uint32_t dst0 = base + win_off + buf * kFirstWinBytes;
+    for (int i = tid; i < kFirstWin; i += kFirstPx) {
       const int col = i % (kFirstPx + 2);
       const int rc = i / (kFirstPx + 2);  // ci*3 + row
       const int row = rc % 3, ci = rc / 3;
       int yy = y + row - 1;
       yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
       int xx = x0 + col - 1;
-      float v = 0.f;
       if (xx <= p.W) {
         xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
-        v = __ldg(p.img + (((size_t)n * 3 + ci) * p.H + yy) * p.W + xx);
+        const float* src = p.img + (((size_t)n * 3 + ci) * p.H + yy) * p.W + xx;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + 4 * i), "l"(src)
+                     : "memory");
+      } else {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst0 + 4 * i), "r"(0u) : "memory");
       }
-      sin[ci][row][col] = v;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if ((int)blockIdx.x < p.total_tiles) stage_window(blockIdx.x, 0);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  const uint64_t adesc = make_kmajor_sw128_desc(sA);
+  const uint64_t bdesc = make_kmajor_sw128_desc(sB);
+  constexpr uint32_t idesc = make_idesc<T16, 64>();
+  uint32_t phase = 0;
+  int buf = 0;
+
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, buf ^= 1) {
+    int b = tile;
+    const int x0 = (b % p.tiles_x) * kFirstPx;
+    b /= p.tiles_x;
+    const int y = b % p.H;
+    const int n = b / p.H;
+    // (1) prefetch the next tile's window, then wait for this tile's
+    const int next = tile + gridDim.x;
+    if (next < p.total_tiles) {
+      stage_window(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     // the previous tile's TMA store must have read sOut before the epilogue below rewrites it
     if (warp == 0) bulk_wait_read<0>();
     __syncthreads();
+    const float* win = reinterpret_cast<const float*>(gen + win_off + buf * kFirstWinBytes);
     // (2) im2col row of pixel tid -> swizzled K-major A tile
     {
       uint32_t pk[16];
@@ -667,7 +700,7 @@ __global__ void __launch_bounds__(kFirstPx)
           if (k < 27) {
             const int tap = k / 3, ci = k - 3 * tap;
             const int r = tap / 3, s = tap - 3 * r;
-            v[e] = sin[ci][r][tid + s];
+            v[e] = win[(ci * 3 + r) * (kFirstPx + 2) + tid + s];
           } else {
             v[e] = 0.f;
           }
@@ -675,9 +708,12 @@ __global__ void __launch_bounds__(kFirstPx)
         pk[k2] = pack16x2<T16>(v[0], v[1]);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<uint4*>(sA + tid * 128 + ((j ^ (tid & 7)) << 4)) =
-            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t dst = sA + tid * 128 + ((j ^ (tid & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                     "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                     : "memory");
+      }
     }
     fence_async_smem();  // generic smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
@@ -713,7 +749,7 @@ __global__ void __launch_bounds__(kFirstPx)
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint32_t dst = sout + tid * 128 + ((j ^ (tid & 7)) << 4);
+      const uint32_t dst = sOut + tid * 128 + ((j ^ (tid & 7)) << 4);
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
                    "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                    : "memory");
@@ -725,7 +761,7 @@ __global__ void __launch_bounds__(kFirstPx)
     tc_fence_before();
     __syncthreads();
     if (warp == 0 && elect_one()) {
-      tma_store_4d(&tmap_out, sout, 0, x0, y, n);  // one contiguous row segment, clipped at W
+      tma_store_4d(&tmap_out, sOut, 0, x0, y, n);  // one contiguous row segment, clipped at W
       bulk_commit();
     }
   }
@@ -936,9 +972,15 @@ int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk,
   p.total_tiles = (int)total;
   CUtensorMap mo;
   if (int e = make_out_map(&mo, out, 0, 0, 1, 1, kFirstPx, 1)) return e;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CCST_CUDA(cudaFuncSetAttribute(conv_first_umma_kernel<T16>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kFirstSmem));
+    attr_done = true;
+  }
   const int64_t cap = (int64_t)sm_count() * 4;
   const int grid = (int)(total < cap ? total : cap);
-  conv_first_umma_kernel<T16><<<grid, kFirstPx, 0, st>>>(mo, p);
+  conv_first_umma_kernel<T16><<<grid, kFirstPx, kFirstSmem, st>>>(mo, p);
   CCST_LAUNCHED();
   return CCST_OK;
 }
