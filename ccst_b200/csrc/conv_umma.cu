@@ -684,8 +684,6 @@ __global__ void __launch_bounds__(kFirstPx)
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    // the previous tile's TMA store must have read sOut before the epilogue below rewrites it
-    if (warp == 0) bulk_wait_read<0>();
     __syncthreads();
     const float* win = reinterpret_cast<const float*>(gen + win_off + buf * kFirstWinBytes);
     // (2) im2col row of pixel tid -> swizzled K-major A tile
@@ -747,6 +745,13 @@ __global__ void __launch_bounds__(kFirstPx)
       pk[16 + j] = pack16x2<T16>(fmaxf(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j], 0.f),
                                  fmaxf(__uint_as_float(r1[2 * j + 1]) + sbias[33 + 2 * j], 0.f));
     }
+    // TMEM reads are complete (wait::ld); every thread passes two more block barriers before warp 0
+    // overwrites the accumulator with the next tile
+    tc_fence_before();
+    // each warp stages and stores its own 32-pixel quarter of the row segment, so only its own
+    // previous TMA store has to have drained (no block-wide barrier on the store path)
+    bulk_wait_read<0>();
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t dst = sOut + tid * 128 + ((j ^ (tid & 7)) << 4);
@@ -756,16 +761,14 @@ __global__ void __launch_bounds__(kFirstPx)
     }
     if (x < p.W) store_aliases(p.out, n, y, x, 0, pk);
     fence_async_smem();
-    // TMEM reads are complete (wait::ld) before any thread passes this barrier, after which warp 0
-    // may overwrite the accumulator with the next tile
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0 && elect_one()) {
-      tma_store_4d(&tmap_out, sOut, 0, x0, y, n);  // one contiguous row segment, clipped at W
+    __syncwarp();
+    if (elect_one()) {
+      tma_store_4d(&tmap_out, sOut + warp * (32 * 128), 0, x0 + warp * 32, y, n);  // clipped at W
       bulk_commit();
     }
+    __syncwarp();
   }
-  if (warp == 0) bulk_wait_all();
+  bulk_wait_all();
   __syncthreads();
   if (warp == 0) tmem_dealloc<64>(tmem_base);
 }
@@ -971,7 +974,7 @@ int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk,
   CCST_CHECK_ARG(total < (1ll << 31), "conv_first_umma: too many tiles");
   p.total_tiles = (int)total;
   CUtensorMap mo;
-  if (int e = make_out_map(&mo, out, 0, 0, 1, 1, kFirstPx, 1)) return e;
+  if (int e = make_out_map(&mo, out, 0, 0, 1, 1, 32, 1)) return e;  // one warp's quarter
   static bool attr_done = false;
   if (!attr_done) {
     CCST_CUDA(cudaFuncSetAttribute(conv_first_umma_kernel<T16>,
