@@ -311,6 +311,207 @@ __global__ void from_moments_kernel(const double* __restrict__ mom, int C,
   state[1 + C + c] = m2 > 0 ? m2 : 0.0;
 }
 
+// =====================================================================================
+// Bulk-staged variant (the fast path): planes are contiguous in memory, so a CTA streams 16 KiB
+// chunks of consecutive planes into a shared-memory ring with 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx), 8 chunks = 128 KiB in flight per SM, issued by one
+// producer lane far ahead of the consumers.  Each of the 8 consumer warps owns one ring slot and
+// reduces its chunk from shared memory with an exact two-pass (sum, then sum of squared deviations;
+// warp shuffles combine the lanes of a plane), then -- for AdaIN -- makes a third pass that applies
+// the affine and writes 128-bit coalesced stores.  HBM sees exactly one read (+ one write).
+// =====================================================================================
+constexpr int kSlotBytes = 16384;
+constexpr int kSlots = 8;
+constexpr int kBulkThreads = 32 * (1 + kSlots);
+
+struct BulkArgs {
+  const float* x;
+  float* out;      // AdaIN only
+  int64_t planes;
+  int hw;          // elements per plane, hw % 4 == 0, hw * 4 <= kSlotBytes
+  int ppc;         // planes per chunk
+  int64_t chunks;
+  float eps;
+  int unbiased;
+  float* mean;     // MODE 0
+  float* stdv;
+  float2* raw;     // MODE 1
+  int C;           // MODE 2 (AdaIN)
+  const float* mu_s;
+  const float* sigma_s;
+  int64_t stat_batch_stride;
+  float alpha;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ bool bar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+  if (bar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!bar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // never hang the GPU on a pipeline bug
+      printf("ccst stats: mbarrier timeout block=%d thread=%d\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// G lanes cooperate on one plane (G = 8 for planes <= 1 KiB, else 32)
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// MODE 0: mean/std, 1: raw {mean, M2}, 2: AdaIN
+template <int MODE, int G>
+__global__ void __launch_bounds__(kBulkThreads, 1) plane_bulk_kernel(BulkArgs a) {
+  extern __shared__ __align__(128) uint8_t ring[];  // kSlots * kSlotBytes, then the barriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kSlots * kSlotBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSlots; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[s])));           // full
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[kSlots + s])));  // empty
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t plane_bytes = (int64_t)a.hw * 4;
+  // this CTA's chunks: blockIdx.x, blockIdx.x + gridDim.x, ...; its i-th chunk uses slot i % kSlots
+  if (warp == 0) {
+    if (lane == 0) {
+      int64_t i = 0;
+      for (int64_t c = blockIdx.x; c < a.chunks; c += gridDim.x, ++i) {
+        const int slot = (int)(i % kSlots);
+        const uint32_t use = (uint32_t)(i / kSlots);
+        bar_wait(smem_addr(&bars[kSlots + slot]), (use & 1) ^ 1);
+        const int64_t p0 = c * a.ppc;
+        const int64_t np = (a.planes - p0) < a.ppc ? (a.planes - p0) : a.ppc;
+        const uint32_t bytes = (uint32_t)(np * plane_bytes);
+        const uint32_t full = smem_addr(&bars[slot]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_addr(ring + slot * kSlotBytes)),
+            "l"(a.x + p0 * a.hw), "r"(bytes), "r"(full)
+            : "memory");
+      }
+    }
+    return;
+  }
+  // ---- consumer warp w owns slot w: the CTA's chunks i = w, w + 8, ...
+  const int slot = warp - 1;
+  const float4* buf = reinterpret_cast<const float4*>(ring + slot * kSlotBytes);
+  const int n4 = a.hw >> 2;              // float4 per plane
+  constexpr int kGroups = 32 / G;        // planes processed concurrently by the warp
+  const int grp = lane / G, sub = lane % G;
+  int64_t i = slot;
+  for (int64_t c = (int64_t)blockIdx.x + (int64_t)slot * gridDim.x; c < a.chunks;
+       c += (int64_t)kSlots * gridDim.x, i += kSlots) {
+    const uint32_t use = (uint32_t)(i / kSlots);
+    bar_wait(smem_addr(&bars[slot]), use & 1);
+    const int64_t p0 = c * a.ppc;
+    const int np = (int)((a.planes - p0) < a.ppc ? (a.planes - p0) : a.ppc);
+    for (int pb = 0; pb < np; pb += kGroups) {
+      const int pl = pb + grp;  // plane inside the chunk handled by this lane group
+      const bool active = pl < np;
+      const float4* src = buf + (size_t)(active ? pl : 0) * n4;
+      // pass 1: mean
+      float s = 0.f;
+      if (active)
+        for (int k = sub; k < n4; k += G) {
+          const float4 v = src[k];
+          s += (v.x + v.y) + (v.z + v.w);
+        }
+      s = group_sum<G>(s);
+      const float mean = s / (float)a.hw;
+      // pass 2: sum of squared deviations (exact two-pass, no cancellation)
+      float q = 0.f;
+      if (active)
+        for (int k = sub; k < n4; k += G) {
+          const float4 v = src[k];
+          const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+          q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+      q = group_sum<G>(q);
+      const int64_t plane = p0 + pl;
+      if (MODE == 0) {
+        if (active && sub == 0) {
+          const float denom = a.unbiased ? (float)(a.hw - 1) : (float)a.hw;
+          if (a.mean) a.mean[plane] = mean;
+          if (a.stdv) a.stdv[plane] = sqrtf(q / denom + a.eps);  // hw == 1, unbiased: 0/0 = NaN (function.py:9)
+        }
+      } else if (MODE == 1) {
+        if (active && sub == 0) a.raw[plane] = make_float2(mean, q);
+      } else {
+        if (active) {
+          const int64_t n = plane / a.C;
+          const int ch = (int)(plane - n * a.C);
+          const int64_t si = n * a.stat_batch_stride + ch;
+          const float sg_c = sqrtf(q / (float)(a.hw - 1) + a.eps);
+          const float A = a.alpha * (__ldg(a.sigma_s + si) / sg_c) + (1.f - a.alpha);
+          const float B = a.alpha * __ldg(a.mu_s + si) + (1.f - a.alpha) * mean;
+          float4* dst = reinterpret_cast<float4*>(a.out + plane * a.hw);
+          for (int k = sub; k < n4; k += G) {
+            float4 v = src[k];
+            v.x = fmaf(v.x - mean, A, B);
+            v.y = fmaf(v.y - mean, A, B);
+            v.z = fmaf(v.z - mean, A, B);
+            v.w = fmaf(v.w - mean, A, B);
+            st_stream(dst + k, v);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bars[kSlots + slot]))
+                   : "memory");
+  }
+}
+
+constexpr int kBulkSmem = kSlots * kSlotBytes + 2 * kSlots * 8;
+
+bool bulk_ok(const void* p, int64_t hw) {
+  return hw % 4 == 0 && hw * 4 <= kSlotBytes && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+
+template <int MODE>
+int launch_bulk(BulkArgs a, cudaStream_t st) {
+  a.ppc = (int)(kSlotBytes / ((int64_t)a.hw * 4));
+  a.chunks = ceil_div64(a.planes, a.ppc);
+  const int grid = (int)(a.chunks < sm_count() ? a.chunks : sm_count());
+  static bool attr_done = false;
+  if (!attr_done) {
+    CCST_CUDA(cudaFuncSetAttribute(plane_bulk_kernel<MODE, 8>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSmem));
+    CCST_CUDA(cudaFuncSetAttribute(plane_bulk_kernel<MODE, 32>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSmem));
+    attr_done = true;
+  }
+  if (a.hw <= 256)
+    plane_bulk_kernel<MODE, 8><<<grid, kBulkThreads, kBulkSmem, st>>>(a);
+  else
+    plane_bulk_kernel<MODE, 32><<<grid, kBulkThreads, kBulkSmem, st>>>(a);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
 int grid_for(int64_t groups) {
   int64_t cap = (int64_t)sm_count() * 8;  // 8 resident 256-thread CTAs per SM
   return (int)(groups < cap ? (groups > 0 ? groups : 1) : cap);
@@ -323,6 +524,12 @@ bool vec_ok(const void* p, int64_t hw) {
 template <int OUT>
 int launch_stats(const StatsArgs& a, cudaStream_t st) {
   const int64_t P = a.planes, hw = a.hw;
+  if (bulk_ok(a.x, hw)) {
+    BulkArgs b{};
+    b.x = a.x, b.planes = P, b.hw = (int)hw, b.eps = a.eps, b.unbiased = a.unbiased;
+    b.mean = a.mean, b.stdv = a.stdv, b.raw = a.raw;
+    return launch_bulk<OUT == OUT_MEAN_STD ? 0 : 1>(b, st);
+  }
   if (vec_ok(a.x, hw) && hw <= 256) {
     stats_regs_kernel<32, 2, OUT><<<grid_for(ceil_div64(P, 8)), kThreads, 0, st>>>(a);
   } else if (vec_ok(a.x, hw) && hw <= 1024) {
@@ -340,6 +547,13 @@ int launch_stats(const StatsArgs& a, cudaStream_t st) {
 
 int launch_adain(const AdainArgs& a, cudaStream_t st) {
   const int64_t P = a.planes, hw = a.hw;
+  if (bulk_ok(a.x, hw) && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) {
+    BulkArgs b{};
+    b.x = a.x, b.out = a.out, b.planes = P, b.hw = (int)hw, b.eps = a.eps, b.unbiased = 1;
+    b.C = a.C, b.mu_s = a.mu_s, b.sigma_s = a.sigma_s, b.stat_batch_stride = a.stat_batch_stride;
+    b.alpha = a.alpha;
+    return launch_bulk<2>(b, st);
+  }
   const bool v = vec_ok(a.x, hw) && vec_ok(a.out, hw);
   if (v && hw <= 256) {
     adain_regs_kernel<32, 2><<<grid_for(ceil_div64(P, 8)), kThreads, 0, st>>>(a);
