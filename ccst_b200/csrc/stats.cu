@@ -247,18 +247,34 @@ __global__ void __launch_bounds__(kThreads) adain_stream_kernel(AdainArgs a) {
 }
 
 // ---- per-channel merge over the batch and into the running state (fp64) ----
-// state = {count, mean[C], M2[C]}
-__global__ void merge_planes_kernel(const float2* __restrict__ raw, int N, int C, double hw,
-                                    double* __restrict__ state) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// state = {count, mean[C], M2[C]}.  Block = 32 channels x 8 batch lanes; each thread Chan-merges its
+// strided share of the N per-plane results, the 8 partials are combined through shared memory.
+__global__ void __launch_bounds__(256) merge_planes_kernel(const float2* __restrict__ raw, int N,
+                                                            int C, double hw,
+                                                            double* __restrict__ state) {
+  __shared__ double s_n[8][32], s_mean[8][32], s_m2[8][32];
+  const int cl = threadIdx.x & 31, nl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   const double n0 = state[0];
-  if (c < C) {
-    double n = n0, mean = state[1 + c], m2 = state[1 + C + c];
-    for (int i = 0; i < N; ++i) {
-      float2 r = raw[(size_t)i * C + c];
-      double nb = hw, d = (double)r.x - mean, nn = n + nb;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  if (c < C)
+    for (int i = nl; i < N; i += 8) {
+      const float2 r = raw[(size_t)i * C + c];
+      const double nn = n + hw, d = (double)r.x - mean;
+      mean += d * (hw / nn);
+      m2 += (double)r.y + d * d * (n * hw / nn);
+      n = nn;
+    }
+  s_n[nl][cl] = n, s_mean[nl][cl] = mean, s_m2[nl][cl] = m2;
+  __syncthreads();
+  if (nl == 0 && c < C) {
+    n = n0, mean = state[1 + c], m2 = state[1 + C + c];
+    for (int l = 0; l < 8; ++l) {
+      const double nb = s_n[l][cl];
+      if (nb == 0.0) continue;
+      const double nn = n + nb, d = s_mean[l][cl] - mean;
       mean += d * (nb / nn);
-      m2 += (double)r.y + d * d * (n * nb / nn);
+      m2 += s_m2[l][cl] + d * d * (n * nb / nn);
       n = nn;
     }
     state[1 + c] = mean;
@@ -368,7 +384,7 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// G lanes cooperate on one plane (G = 8 for planes <= 1 KiB, else 32)
+// G lanes cooperate on one plane (G = 8 for planes <= 4 KiB, else 32)
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
@@ -431,24 +447,41 @@ __global__ void __launch_bounds__(kBulkThreads, 1) plane_bulk_kernel(BulkArgs a)
       const int pl = pb + grp;  // plane inside the chunk handled by this lane group
       const bool active = pl < np;
       const float4* src = buf + (size_t)(active ? pl : 0) * n4;
-      // pass 1: mean
-      float s = 0.f;
-      if (active)
-        for (int k = sub; k < n4; k += G) {
-          const float4 v = src[k];
-          s += (v.x + v.y) + (v.z + v.w);
+      // pass 1: mean (4 independent accumulators hide the shared-memory latency)
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      if (active) {
+        int k = sub;
+        for (; k + 3 * G < n4; k += 4 * G) {
+          const float4 v0 = src[k], v1 = src[k + G], v2 = src[k + 2 * G], v3 = src[k + 3 * G];
+          s0 += (v0.x + v0.y) + (v0.z + v0.w);
+          s1 += (v1.x + v1.y) + (v1.z + v1.w);
+          s2 += (v2.x + v2.y) + (v2.z + v2.w);
+          s3 += (v3.x + v3.y) + (v3.z + v3.w);
         }
-      s = group_sum<G>(s);
-      const float mean = s / (float)a.hw;
+        for (; k < n4; k += G) {
+          const float4 v = src[k];
+          s0 += (v.x + v.y) + (v.z + v.w);
+        }
+      }
+      const float mean = group_sum<G>((s0 + s1) + (s2 + s3)) / (float)a.hw;
       // pass 2: sum of squared deviations (exact two-pass, no cancellation)
-      float q = 0.f;
-      if (active)
-        for (int k = sub; k < n4; k += G) {
-          const float4 v = src[k];
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+      if (active) {
+        auto sq = [mean](const float4 v) {
           const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-          q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+          return (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        };
+        int k = sub;
+        for (; k + 3 * G < n4; k += 4 * G) {
+          const float4 v0 = src[k], v1 = src[k + G], v2 = src[k + 2 * G], v3 = src[k + 3 * G];
+          q0 += sq(v0);
+          q1 += sq(v1);
+          q2 += sq(v2);
+          q3 += sq(v3);
         }
-      q = group_sum<G>(q);
+        for (; k < n4; k += G) q0 += sq(src[k]);
+      }
+      const float q = group_sum<G>((q0 + q1) + (q2 + q3));
       const int64_t plane = p0 + pl;
       if (MODE == 0) {
         if (active && sub == 0) {
@@ -467,14 +500,22 @@ __global__ void __launch_bounds__(kBulkThreads, 1) plane_bulk_kernel(BulkArgs a)
           const float A = a.alpha * (__ldg(a.sigma_s + si) / sg_c) + (1.f - a.alpha);
           const float B = a.alpha * __ldg(a.mu_s + si) + (1.f - a.alpha) * mean;
           float4* dst = reinterpret_cast<float4*>(a.out + plane * a.hw);
-          for (int k = sub; k < n4; k += G) {
-            float4 v = src[k];
+          auto tf = [mean, A, B](float4 v) {
             v.x = fmaf(v.x - mean, A, B);
             v.y = fmaf(v.y - mean, A, B);
             v.z = fmaf(v.z - mean, A, B);
             v.w = fmaf(v.w - mean, A, B);
-            st_stream(dst + k, v);
+            return v;
+          };
+          int k = sub;
+          for (; k + 3 * G < n4; k += 4 * G) {
+            const float4 v0 = src[k], v1 = src[k + G], v2 = src[k + 2 * G], v3 = src[k + 3 * G];
+            st_stream(dst + k, tf(v0));
+            st_stream(dst + k + G, tf(v1));
+            st_stream(dst + k + 2 * G, tf(v2));
+            st_stream(dst + k + 3 * G, tf(v3));
           }
+          for (; k < n4; k += G) st_stream(dst + k, tf(src[k]));
         }
       }
     }
@@ -504,7 +545,7 @@ int launch_bulk(BulkArgs a, cudaStream_t st) {
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSmem));
     attr_done = true;
   }
-  if (a.hw <= 256)
+  if (a.hw <= 1024)  // up to 4 KiB planes: 8 lanes per plane, 4 planes in flight per warp
     plane_bulk_kernel<MODE, 8><<<grid, kBulkThreads, kBulkSmem, st>>>(a);
   else
     plane_bulk_kernel<MODE, 32><<<grid, kBulkThreads, kBulkSmem, st>>>(a);
@@ -574,9 +615,8 @@ int launch_adain(const AdainArgs& a, cudaStream_t st) {
 
 int merge_raw_into_state(const float2* raw, int N, int C, int64_t hw, double* d_state,
                          cudaStream_t st) {
-  const int threads = 128;
-  const int blocks = (C + threads - 1) / threads;
-  merge_planes_kernel<<<blocks, threads, 0, st>>>(raw, N, C, (double)hw, d_state);
+  const int blocks = (C + 31) / 32;
+  merge_planes_kernel<<<blocks, 256, 0, st>>>(raw, N, C, (double)hw, d_state);
   CCST_LAUNCHED();
   if (blocks > 1) {
     bump_count_kernel<<<1, 1, 0, st>>>(d_state, (double)hw * N);

@@ -1,0 +1,162 @@
+"""Batch loops of the three CCST scripts, restructured for a GPU that is faster than its PCIe link.
+
+Reference loops (all in `style_transfer/AdaIN/`):
+
+* `CCST_OverallStyleTransfer.py:138-167` -- for each style domain, for each content batch:
+  `data.to(device)` -> `style_transfer` -> `output.cpu()` -> save.
+* `CCST_SingleStyleTransfer.py:176-223`  -- same, but one random style image per *batch* whose
+  relu4_1 statistics are computed on the fly (`:195-205`).
+* `mean_std_computation_effcientMem.py:117-137` -- for each batch: `vgg(data)`, `calc_sum`, accumulate.
+
+The reference does H2D, compute and D2H strictly one after the other on the default stream.  On a
+B200 the encoder/decoder take ~8 ms per 32-image batch while moving 100 MB in and 100 MB out over
+PCIe takes ~4 ms, so `TransferPipeline` double-buffers: the upload of batch i+1 and the download of
+batch i-1 run on their own streams underneath the compute of batch i.  Results are identical to
+calling `style_transfer` per batch.
+
+Image decoding / resizing / `save_image` are out of scope; batches are tensors.
+"""
+from __future__ import annotations
+
+import random
+from typing import Callable, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import function as F_
+from .overall import OverallStyleAccumulator
+from .transfer import DEFAULT_PRECISION, Engine
+
+
+class TransferPipeline:
+    """Pinned-host batches in, pinned-host stylised batches out, three streams, two slots."""
+
+    def __init__(self, engine: Engine, precision: str = DEFAULT_PRECISION, slots: int = 2):
+        self.engine = engine
+        self.precision = precision
+        self.slots = slots
+        dev = engine.device
+        self.s_in = torch.cuda.Stream(dev)
+        self.s_cmp = torch.cuda.Stream(dev)
+        self.s_out = torch.cuda.Stream(dev)
+        self._in: List[Optional[torch.Tensor]] = [None] * slots
+        self._out: List[Optional[torch.Tensor]] = [None] * slots
+        self._host: List[Optional[torch.Tensor]] = [None] * slots
+        self._ev_in = [torch.cuda.Event() for _ in range(slots)]
+        self._ev_cmp = [torch.cuda.Event() for _ in range(slots)]
+        self._ev_out = [torch.cuda.Event() for _ in range(slots)]
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _buffers(self, slot: int, shape, out_shape):
+        dev = self.engine.device
+        if self._in[slot] is None or tuple(self._in[slot].shape) != tuple(shape):
+            self._in[slot] = torch.empty(shape, dtype=torch.float32, device=dev)
+        if self._out[slot] is None or tuple(self._out[slot].shape) != tuple(out_shape):
+            self._out[slot] = torch.empty(out_shape, dtype=torch.float32, device=dev)
+            self._host[slot] = torch.empty(out_shape, dtype=torch.float32).pin_memory()
+        return self._in[slot], self._out[slot], self._host[slot]
+
+    def run(self, host_batches: Iterable[torch.Tensor],
+            style_for_batch: Callable[[int, torch.Tensor], Sequence[torch.Tensor]],
+            alpha: float = 1.0) -> Iterator[Tuple[int, torch.Tensor]]:
+        """Yields (batch index, stylised batch as a pinned host tensor).  The yielded tensor is a
+        pipeline buffer: consume (save/copy) it before requesting the batch after the next one.
+
+        `style_for_batch(i, device_batch)` returns the `[mean, std]` to use for batch i (called on
+        the compute stream, so it may itself run GPU work, e.g. encode a style image)."""
+        from . import _lib
+
+        pending: List[Tuple[int, int]] = []  # (batch index, slot) whose D2H has been issued
+        cur = torch.cuda.current_stream(self.engine.device)
+        for st in (self.s_in, self.s_cmp, self.s_out):
+            st.wait_stream(cur)  # whatever prepared the inputs / statistics on the caller's stream
+        for i, hb in enumerate(host_batches):
+            slot = i % self.slots
+            n, _, h, w = hb.shape
+            fh, fw = _lib.feature_hw(h, w)
+            d_in, d_out, h_out = self._buffers(slot, hb.shape, (n, 3, 8 * fh, 8 * fw))
+            if len(pending) >= self.slots:  # the slot's previous result must have been handed out
+                j, s = pending.pop(0)
+                self._ev_out[s].synchronize()
+                yield j, self._host[s]
+            with torch.cuda.stream(self.s_in):
+                self.s_in.wait_event(self._ev_cmp[slot])  # compute of batch i-slots has read d_in
+                d_in.copy_(hb, non_blocking=True)
+                self._ev_in[slot].record(self.s_in)
+            self.h2d_bytes += hb.numel() * 4
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(self._ev_in[slot])
+                self.s_cmp.wait_event(self._ev_out[slot])  # download of batch i-slots has read d_out
+                stat = style_for_batch(i, d_in)
+                self.engine.transfer(d_in, stat, alpha, self.precision, out=d_out)
+                self._ev_cmp[slot].record(self.s_cmp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self._ev_cmp[slot])
+                h_out.copy_(d_out, non_blocking=True)
+                self._ev_out[slot].record(self.s_out)
+            self.d2h_bytes += d_out.numel() * 4
+            pending.append((i, slot))
+        for j, s in pending:
+            self._ev_out[s].synchronize()
+            yield j, self._host[s]
+
+
+def overall_transfer(engine: Engine, host_batches: Iterable[torch.Tensor], style_stat, alpha: float = 1.0,
+                     precision: str = DEFAULT_PRECISION):
+    """Inner loop of CCST_OverallStyleTransfer.py:149-167 for one (content domain, style) pair."""
+    pipe = TransferPipeline(engine, precision)
+    stat = [t.to(engine.device) for t in style_stat]
+    return pipe.run(host_batches, lambda i, x: stat, alpha)
+
+
+def single_style_stat(engine: Engine, style_image: torch.Tensor, precision: str = DEFAULT_PRECISION):
+    """CCST_SingleStyleTransfer.py:196-205: relu4_1 statistics (biased variance) of ONE style image
+    [1,3,h,w] -> [mean, std] each [1,512,1,1]."""
+    acc = OverallStyleAccumulator(engine, precision)
+    acc.add_images(style_image)
+    return list(acc.state.finalize())
+
+
+def single_transfer(engine: Engine, host_batches: Iterable[torch.Tensor], style_images: Sequence[torch.Tensor],
+                    alpha: float = 1.0, precision: str = DEFAULT_PRECISION, seed: int = 1):
+    """Inner loop of CCST_SingleStyleTransfer.py:176-223: per BATCH one style image drawn with
+    python's `random.choice` (seeded like the reference, `:22-26`), its statistics computed on the
+    GPU, then the transfer."""
+    rng = random.Random(seed)
+    pipe = TransferPipeline(engine, precision)
+
+    def stat_for(i, x):
+        img = rng.choice(style_images)
+        return single_style_stat(engine, img.to(engine.device, non_blocking=True), precision)
+
+    return pipe.run(host_batches, stat_for, alpha)
+
+
+def overall_statistics(engine: Engine, host_batches: Iterable[torch.Tensor], precision: str = DEFAULT_PRECISION,
+                       group=None):
+    """Loop of mean_std_computation_effcientMem.py:117-137 over this rank's share of one client;
+    uploads are double-buffered under the encoder.  Returns (mean, std, images seen by all ranks)."""
+    dev = engine.device
+    acc = OverallStyleAccumulator(engine, precision)
+    s_in, s_cmp = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    bufs: List[Optional[torch.Tensor]] = [None, None]
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_cmp = [torch.cuda.Event(), torch.cuda.Event()]
+    s_cmp.wait_stream(torch.cuda.current_stream(dev))  # the zeroed Welford state
+    for i, hb in enumerate(host_batches):
+        s = i & 1
+        if bufs[s] is None or bufs[s].shape != hb.shape:
+            bufs[s] = torch.empty(hb.shape, dtype=torch.float32, device=dev)
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_cmp[s])
+            bufs[s].copy_(hb, non_blocking=True)
+            ev_in[s].record(s_in)
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(ev_in[s])
+            acc.add_images(bufs[s])
+            ev_cmp[s].record(s_cmp)
+    torch.cuda.current_stream(dev).wait_stream(s_cmp)
+    s_cmp.synchronize()
+    mean, std = acc.finalize(group)
+    return mean, std, acc.img_count

@@ -19,6 +19,7 @@ for s in $STAGES; do
     conv32) run conv32 600 python -m pytest tests/test_gpu_net.py -q -m gpu --timeout 120 -k "single_conv and fp32" ;;
     conv16) run conv16 600 python -m pytest tests/test_gpu_net.py -q -m gpu --timeout 120 -k "single_conv and (bf16 or fp16)" ;;
     net)    run net 900 python -m pytest tests/test_gpu_net.py -q -m gpu --timeout 300 -k "not single_conv" ;;
+    drivers) run drivers 600 python -m pytest tests/test_gpu_drivers.py -q -m gpu --timeout 300 ;;
     smoke)  run smoke 300 python __graft_entry__.py smoke ;;
     bench)  run bench 900 python bench.py --steps 5 --warmup 3 ;;
     bench32) run bench32 900 python bench.py --steps 2 --warmup 1 --precision fp32 --batch 4 --no-cpu-baseline ;;
