@@ -75,11 +75,11 @@ class TransferPipeline:
             slot = i % self.slots
             n, _, h, w = hb.shape
             fh, fw = _lib.feature_hw(h, w)
-            d_in, d_out, h_out = self._buffers(slot, hb.shape, (n, 3, 8 * fh, 8 * fw))
             if len(pending) >= self.slots:  # the slot's previous result must have been handed out
-                j, s = pending.pop(0)
+                j, s = pending.pop(0)       # (before _buffers may re-shape the slot for a ragged batch)
                 self._ev_out[s].synchronize()
                 yield j, self._host[s]
+            d_in, d_out, h_out = self._buffers(slot, hb.shape, (n, 3, 8 * fh, 8 * fw))
             with torch.cuda.stream(self.s_in):
                 self.s_in.wait_event(self._ev_cmp[slot])  # compute of batch i-slots has read d_in
                 d_in.copy_(hb, non_blocking=True)
