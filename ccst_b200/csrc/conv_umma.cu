@@ -19,6 +19,7 @@
 //   warp 2        : TMEM alloc / dealloc  warps 4..7    : epilogue (TMEM -> regs -> bias/ReLU -> HBM)
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "layers.h"
@@ -52,15 +53,21 @@ constexpr int kEpiWarp0 = 4;
 //   B      : BRES = false: ring of kBStages weight tiles {64 k, BN}, one per tap and channel chunk;
 //            BRES = true (9*Cin*BN*2 bytes fit): all weights loaded once per CTA and kept resident.
 //   store  : kStoreBufs x 16 KiB staging tiles for the TMA store of the epilogue.
-template <int BN, bool BRES>
+template <int BN, bool BRES, int CG>
 struct UmmaCfg {
   static constexpr int kSlabRows = kTileH + 2;
   static constexpr int kASlabBytes = kSlabRows * kTileW * 128;  // 20480
-  static constexpr int kBBytes = BN * kBlockK * 2;
+  // CG = 2 (CTA pair, tcgen05 cta_group::2): the pair computes M = 256 pixels x BN channels per MMA;
+  // each CTA stages the A slab of its own 128-pixel tile and HALF of the weight tile (BN/2 rows),
+  // so the per-SM shared-memory traffic of the B operand (TMA writes and tensor-core reads) halves.
+  static constexpr int kBRows = BN / CG;
+  static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kBStride = (kBBytes + 1023) / 1024 * 1024;
-  static constexpr int kAStages = BRES ? (BN >= 64 ? 5 : 6) : (BN >= 256 ? 3 : 4);
+  static constexpr int kAStages =
+      CG == 2 ? (BRES ? 6 : (BN >= 256 ? 4 : 5)) : (BRES ? (BN >= 64 ? 5 : 6) : (BN >= 256 ? 3 : 4));
   static constexpr int kBStages = BRES ? 9 /* resident: 9 taps x (Cin == 64) */
-                                       : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 9));
+                                  : CG == 2 ? (BN >= 256 ? 6 : 9)
+                                            : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 9));
   static constexpr int kStoreBufs = 2;  // one staging tile per epilogue group
   static constexpr int kStoreStageBytes = (BN >= 64) ? kStoreBufs * kBlockM * 128 : 0;
   static constexpr int kBiasBytes = 2048;  // up to 512 fp32 biases
@@ -73,13 +80,15 @@ struct UmmaCfg {
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024 /*align slack*/;
   static_assert(kSmemBytes <= 232448, "shared memory plan exceeds 227 KiB");
+  static_assert(CG == 1 || (BN >= 32 && BN % 32 == 0), "cta_group::2 needs N % 32 == 0");
 };
 
 template <typename T16>
 struct ConvParams {
   int N, H, W, Cin;
   int Cout, CoutPad;
-  int tiles_x, tiles_y, n_tiles, total_tiles;
+  int tiles_x, tiles_y, n_tiles, m_tiles;  // m_tiles = pixel tiles (N * tiles_y * tiles_x)
+  int total_tiles;                        // work units: (pixel tile | pair of pixel tiles) x n_tiles
   int relu;
   const float* bias;
   ActView<T16> out;
@@ -205,6 +214,135 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants.  CG = 1 forwards to the single-CTA forms above.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t ncluster_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// wait on a barrier that CTAs of the whole cluster arrive on
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("ccst conv_umma: cluster mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag,
+             (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+// TMA loads whose completion bytes are credited to `bar`, a shared::cluster address that may belong
+// to the peer CTA of the pair (the leader's "full" barrier counts the bytes of both CTAs)
+template <int CG>
+__device__ __forceinline__ void tma_load_4d_cg(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                               int c0, int c1, int c2, int c3) {
+  if (CG == 1) {
+    tma_load_4d(dst, map, bar, c0, c1, c2, c3);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_cg(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                               int c0, int c1) {
+  if (CG == 1) {
+    tma_load_2d(dst, map, bar, c0, c1);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+template <int CG, int COLS>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t smem_dst) {
+  if (CG == 1) {
+    tmem_alloc<COLS>(smem_dst);
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+                 "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG, int COLS>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr) {
+  if (CG == 1) {
+    tmem_dealloc<COLS>(taddr);
+  } else {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS)
+                 : "memory");
+  }
+}
+// CG = 2: ONE thread of the leader CTA issues the MMA for the pair: D[256 x N] lives in the TMEM of
+// both CTAs (128 lanes each), A = each CTA's own slab, B = the two N-halves held by the two CTAs.
+template <int CG>
+__device__ __forceinline__ void umma_f16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  if (CG == 1) {
+    umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// CG = 2: the arrive is multicast to the barrier at the same offset in both CTAs of the pair
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
+  if (CG == 1) {
+    umma_commit(bar);
+  } else {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+            "r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+  }
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) |
 //   [32,46) SBO >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2
@@ -213,20 +351,27 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
          (2ull << 61);
 }
 // kind::f16 instruction descriptor: D = fp32, A = B = bf16 or f16, both K-major, M = 128, N = BN
-template <typename T16, int BN>
+template <typename T16, int BN, int CG = 1>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4) /*D fp32*/ | (Fmt16<T16>::kIdescFmt << 7) /*A*/ | (Fmt16<T16>::kIdescFmt << 10) /*B*/ |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((CG * kBlockM) >> 4) << 24);
 }
 
 struct TileCoord {
   int n, y0, x0, nt;
 };
-template <typename P>
-__device__ __forceinline__ TileCoord decode_tile(const P& p, int tile) {
+// work unit -> (N tile, pixel tile of CTA `rank` of the pair).  A pair takes two consecutive pixel
+// tiles; when the number of pixel tiles is odd the last pair's second tile is a dummy at image
+// index n = N: its TMA loads are out of bounds (zero fill) and its stores are clipped away.
+template <int CG, typename P>
+__device__ __forceinline__ TileCoord decode_tile(const P& p, int unit, int rank) {
   TileCoord t;
-  t.nt = tile % p.n_tiles;
-  int m = tile / p.n_tiles;
+  t.nt = unit % p.n_tiles;
+  int m = (unit / p.n_tiles) * CG + rank;
+  if (CG == 2 && m >= p.m_tiles) {
+    t.x0 = 0, t.y0 = 0, t.n = p.N;
+    return t;
+  }
   t.x0 = (m % p.tiles_x) * kTileW;
   m /= p.tiles_x;
   t.y0 = (m % p.tiles_y) * kTileH;
@@ -291,14 +436,15 @@ __device__ __forceinline__ void store_aliases(const ActView<T16>& out, int n, in
   });
 }
 
-template <typename T16, int BN, int EPI, bool BRES>
+template <typename T16, int BN, int EPI, bool BRES, int CG>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ OutMaps tmap_out, ConvParams<T16> p) {
-  using Cfg = UmmaCfg<BN, BRES>;
+  using Cfg = UmmaCfg<BN, BRES, CG>;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B atoms need 1024-byte aligned bases
+  // SWIZZLE_128B atoms need 1024-byte aligned bases (the dynamic shared window starts at the same
+  // offset in both CTAs of a pair, so the carve-up below is identical in both)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic alias of smem_base
   const uint32_t store_base = smem_base + Cfg::kStoreOff;
@@ -318,6 +464,14 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = p.Cin / kBlockK;
+  // CTA pair: "full" and "accumulator drained" barriers are the LEADER's (rank 0); the peer's TMA
+  // bytes and epilogue arrivals are credited to them through their shared::cluster address.  The
+  // "empty" / "accumulator ready" barriers exist in both CTAs and are signalled by multicast commits.
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  auto lead = [&](uint32_t bar) { return CG == 2 ? mapa_rank(bar, 0) : bar; };
+  const int unit0 = CG == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_step = CG == 2 ? (int)ncluster_x() : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -335,42 +489,45 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full_bar(s), 1);
-      mbar_init(tmem_empty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tmem_empty_bar(s), 4 * CG);  // one arrive per epilogue warp (of both CTAs)
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) tmem_alloc_cg<CG, Cfg::kTmemCols>(tmem_slot);
   for (int i = threadIdx.x; i < p.CoutPad; i += kThreadsUmma) s_bias[i] = p.bias[i];
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base =
       *reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOff + 8 * Cfg::kNumBars);
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one lane issues) ==============
+    const int b_row0 = (int)cta_rank * Cfg::kBRows;  // this CTA's half of the N tile
     if (BRES) {
       // all 9 weight tiles of this (Cin == 64) layer, once
       if (elect_one()) {
-        mbar_expect_tx(bres_bar, 9 * Cfg::kBBytes);
+        if (leader) mbar_expect_tx(bres_bar, CG * 9 * Cfg::kBBytes);
+        const uint32_t bar = lead(bres_bar);
         for (int tap = 0; tap < 9; ++tap)
-          tma_load_2d(b_smem(tap), &tmap_b, bres_bar, tap * p.Cin, 0);
+          tma_load_2d_cg<CG>(b_smem(tap), &tmap_b, bar, tap * p.Cin, b_row0);
       }
       __syncwarp();
     }
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int unit = unit0; unit < p.total_tiles; unit += unit_step) {
+      const TileCoord t = decode_tile<CG>(p, unit, (int)cta_rank);
       for (int kc = 0; kc < kchunks; ++kc) {
         for (int s = 0; s < 3; ++s) {
           mbar_wait(a_empty(as), aph ^ 1, 100 + as);
           if (elect_one()) {
-            mbar_expect_tx(a_full(as), Cfg::kASlabBytes);
+            if (leader) mbar_expect_tx(a_full(as), CG * Cfg::kASlabBytes);
             // interior pixel (y, x) is stored at (y+1, x+1): the slab for filter column s starts at
             // padded (y0, x0 + s) and spans the 10 rows needed by r = 0..2
-            tma_load_4d(a_smem(as), &tmap_a, a_full(as), kc * kBlockK, t.x0 + s, t.y0, t.n);
+            tma_load_4d_cg<CG>(a_smem(as), &tmap_a, lead(a_full(as)), kc * kBlockK, t.x0 + s, t.y0,
+                               t.n);
           }
           __syncwarp();
           if (++as == Cfg::kAStages) as = 0, aph ^= 1;
@@ -378,9 +535,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
             for (int r = 0; r < 3; ++r) {
               mbar_wait(b_empty(bs), bph ^ 1, 150 + bs);
               if (elect_one()) {
-                mbar_expect_tx(b_full(bs), Cfg::kBBytes);
-                tma_load_2d(b_smem(bs), &tmap_b, b_full(bs), (r * 3 + s) * p.Cin + kc * kBlockK,
-                            t.nt * BN);
+                if (leader) mbar_expect_tx(b_full(bs), CG * Cfg::kBBytes);
+                tma_load_2d_cg<CG>(b_smem(bs), &tmap_b, lead(b_full(bs)),
+                                   (r * 3 + s) * p.Cin + kc * kBlockK, t.nt * BN + b_row0);
               }
               __syncwarp();
               if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
@@ -390,55 +547,59 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp converged, one lane issues) ================
-    constexpr uint32_t idesc = make_idesc<T16, BN>();
-    int as = 0, bs = 0;
-    uint32_t aph = 0, bph = 0;
-    int it = 0;
-    if (BRES) {
-      mbar_wait(bres_bar, 0, 250);
-      tc_fence_after();
-    }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int acs = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(tmem_empty_bar(acs), aphase ^ 1, 200 + acs);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acs * BN);
-      for (int kc = 0; kc < kchunks; ++kc) {
-        for (int s = 0; s < 3; ++s) {
-          mbar_wait(a_full(as), aph, 300 + as);
-          tc_fence_after();
-          for (int r = 0; r < 3; ++r) {
-            uint32_t bsm;
-            if (BRES) {
-              bsm = b_smem(r * 3 + s);
-            } else {
-              mbar_wait(b_full(bs), bph, 350 + bs);
-              tc_fence_after();
-              bsm = b_smem(bs);
-            }
-            if (elect_one()) {
-              // tap (r,s): slab shifted by r tile rows (16 px * 128 B = 2048 B, swizzle-phase neutral)
-              const uint64_t adesc = make_kmajor_sw128_desc(a_smem(as) + r * (kTileW * 128));
-              const uint64_t bdesc = make_kmajor_sw128_desc(bsm);
+    // ===================== MMA issuer (leader CTA; whole warp converged, one lane issues) =====
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc<T16, BN, CG>();
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      if (BRES) {
+        mbar_wait(bres_bar, 0, 250);
+        tc_fence_after();
+      }
+      for (int unit = unit0; unit < p.total_tiles; unit += unit_step, ++it) {
+        const int acs = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        if (CG == 2) mbar_wait_cluster(tmem_empty_bar(acs), aphase ^ 1, 200 + acs);
+        else mbar_wait(tmem_empty_bar(acs), aphase ^ 1, 200 + acs);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acs * BN);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          for (int s = 0; s < 3; ++s) {
+            mbar_wait(a_full(as), aph, 300 + as);
+            tc_fence_after();
+            for (int r = 0; r < 3; ++r) {
+              uint32_t bsm;
+              if (BRES) {
+                bsm = b_smem(r * 3 + s);
+              } else {
+                mbar_wait(b_full(bs), bph, 350 + bs);
+                tc_fence_after();
+                bsm = b_smem(bs);
+              }
+              if (elect_one()) {
+                // tap (r,s): slab shifted by r tile rows (16 px * 128 B = 2048 B, swizzle-phase neutral)
+                const uint64_t adesc = make_kmajor_sw128_desc(a_smem(as) + r * (kTileW * 128));
+                const uint64_t bdesc = make_kmajor_sw128_desc(bsm);
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                // +16 elements (32 bytes) along K inside the swizzle atom = +2 in the start field
-                umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | s | r | k) ? 1u : 0u);
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  // +16 elements (32 bytes) along K inside the swizzle atom = +2 in the start field
+                  umma_f16_cg<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                  (kc | s | r | k) ? 1u : 0u);
+                }
+                if (!BRES) umma_commit_cg<CG>(b_empty(bs));  // frees the weight tile when these MMAs retire
+                if (r == 2) {
+                  umma_commit_cg<CG>(a_empty(as));  // ... and the slab after its third tap
+                  if (kc == kchunks - 1 && s == 2) umma_commit_cg<CG>(tmem_full_bar(acs));
+                }
               }
-              if (!BRES) umma_commit(b_empty(bs));  // frees the weight tile when these MMAs retire
-              if (r == 2) {
-                umma_commit(a_empty(as));  // ... and the slab after its third tap
-                if (kc == kchunks - 1 && s == 2) umma_commit(tmem_full_bar(acs));
+              __syncwarp();
+              if (!BRES) {
+                if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
               }
             }
-            __syncwarp();
-            if (!BRES) {
-              if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
-            }
+            if (++as == Cfg::kAStages) as = 0, aph ^= 1;
           }
-          if (++as == Cfg::kAStages) as = 0, aph ^= 1;
         }
       }
     }
@@ -454,14 +615,13 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     const bool issuer_warp = (quad == 0);
     const uint32_t sbuf = store_base + grp * kStoreBytes;
     for (int it = grp;; it += 2) {
-      const long long tile_ll = (long long)blockIdx.x + (long long)it * gridDim.x;
-      if (tile_ll >= p.total_tiles) break;
-      const int tile = (int)tile_ll;
-      const TileCoord t = decode_tile(p, tile);
+      const long long unit_ll = (long long)unit0 + (long long)it * unit_step;
+      if (unit_ll >= p.total_tiles) break;
+      const TileCoord t = decode_tile<CG>(p, (int)unit_ll, (int)cta_rank);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int y = t.y0 + py, x = t.x0 + px;
-      const bool valid = (y < p.H) && (x < p.W);
+      const bool valid = (y < p.H) && (x < p.W) && (CG == 1 || t.n < p.N);
       mbar_wait(tmem_full_bar(as), aphase, 400 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
@@ -543,7 +703,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           fence_async_smem();
           epi_barrier(grp);
           if (issuer_warp && elect_one()) {
-            // coordinates are interior pixels; TMA clips the box at the image border
+            // coordinates are interior pixels; TMA clips the box at the image border (and drops the
+            // dummy tile of an odd pair entirely: n = N is out of bounds)
             if (EPI == EPI_ACT_POOL) {
               tma_store_4d(&tmap_out.m[0], sbuf, co, t.x0 >> 1, t.y0 >> 1, t.n);
             } else {
@@ -561,15 +722,19 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       // all TMEM reads of this accumulator stage are complete (wait::ld above)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(lead(tmem_empty_bar(as)));
+        else mbar_arrive(tmem_empty_bar(as));
+      }
     }
     if (issuer_warp) bulk_wait_all();
   }
 
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  // pair: the peer's shared memory / TMEM are operands of the leader's MMAs until the very end
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc_cg<CG, Cfg::kTmemCols>(tmem_base);
 }
 
 // =====================================================================================
@@ -868,9 +1033,11 @@ int make_weight_map(CUtensorMap* m, const T16* wk, int K, int CoutPad, int BN) {
   return CCST_OK;
 }
 
-template <typename T16, int BN, int EPI, bool BRES>
-int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams<T16>& p,
-               cudaStream_t st) {
+template <typename T16, int BN, int EPI, bool BRES, int CG>
+int launch_cfg(const CUtensorMap& ma, const T16* wk, ConvParams<T16> p, cudaStream_t st) {
+  using Cfg = UmmaCfg<BN, BRES, CG>;
+  CUtensorMap mb;
+  if (int e = make_weight_map(&mb, wk, 9 * p.Cin, p.CoutPad, Cfg::kBRows)) return e;
   OutMaps mo;
   memset(&mo, 0, sizeof(mo));
   if (EPI == EPI_ACT) {
@@ -882,33 +1049,68 @@ int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams<T1
       for (int b = 0; b < 2; ++b)
         if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, kTileW, kTileH)) return e;
   }
-  using Cfg = UmmaCfg<BN, BRES>;
   static bool attr_done = false;
   if (!attr_done) {
-    CCST_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T16, BN, EPI, BRES>,
+    CCST_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T16, BN, EPI, BRES, CG>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  conv_umma_kernel<T16, BN, EPI, BRES><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, mo, p);
+  const int64_t units = ((int64_t)p.m_tiles + CG - 1) / CG * p.n_tiles;
+  p.total_tiles = (int)units;
+  const int slots = sm_count() / CG;  // persistent: one CTA (or CTA pair) per SM (pair)
+  const int grid = (int)(units < slots ? units : slots) * CG;
+  if (CG == 1) {
+    conv_umma_kernel<T16, BN, EPI, BRES, CG><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, mo, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreadsUmma);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    CCST_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T16, BN, EPI, BRES, CG>, ma, mb, mo, p));
+  }
   CCST_LAUNCHED();
   return CCST_OK;
 }
 
-template <typename T16, int BN, bool BRES>
-int launch_bn(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams<T16>& p, int epi,
+template <typename T16, int BN, bool BRES, int CG>
+int launch_bn(const CUtensorMap& ma, const T16* wk, const ConvParams<T16>& p, int epi,
               cudaStream_t st) {
   switch (epi) {
     case EPI_ACT:
-      return launch_cfg<T16, BN, EPI_ACT, BRES>(ma, mb, p, st);
+      return launch_cfg<T16, BN, EPI_ACT, BRES, CG>(ma, wk, p, st);
     case EPI_ACT_UP2:
-      return launch_cfg<T16, BN, EPI_ACT_UP2, BRES>(ma, mb, p, st);
+      return launch_cfg<T16, BN, EPI_ACT_UP2, BRES, CG>(ma, wk, p, st);
     case EPI_ACT_POOL:
-      return launch_cfg<T16, BN, EPI_ACT_POOL, BRES>(ma, mb, p, st);
+      return launch_cfg<T16, BN, EPI_ACT_POOL, BRES, CG>(ma, wk, p, st);
     default:
       set_error("conv_umma: epilogue %d not available for BN=%d", epi, BN);
       return CCST_EINVAL;
   }
+}
+
+// CTA pairs (cta_group::2) are the default for the N >= 128 layers (measured on B200, batch 32
+// @512^2: N=256 layers 1.50 -> 1.67 PFLOP/s, N=128 layers 1.15 -> 1.27); the N=64 layers are
+// slower paired (0.96 -> 0.82) and stay single-CTA.  CCST_CTA_PAIR=0 forces single-CTA kernels
+// everywhere, CCST_CTA_PAIR=2 pairs everywhere (A/B measurements).
+int cta_pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CCST_CTA_PAIR");
+    v = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1);
+  }
+  return v;
+}
+
+template <typename T16, int BN, bool BRES>
+int launch_cg(const CUtensorMap& ma, const T16* wk, const ConvParams<T16>& p, int epi,
+              cudaStream_t st) {
+  const int mode = cta_pair_mode();
+  const bool pair = mode == 2 || (mode == 1 && BN >= 128);
+  return pair ? launch_bn<T16, BN, BRES, 2>(ma, wk, p, epi, st)
+              : launch_bn<T16, BN, BRES, 1>(ma, wk, p, epi, st);
 }
 
 }  // namespace
@@ -933,29 +1135,29 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const float* bias, int Cout
   p.tiles_x = (in.W + kTileW - 1) / kTileW;
   p.tiles_y = (in.H + kTileH - 1) / kTileH;
   p.n_tiles = CoutPad / BN;
-  const int64_t total = (int64_t)in.N * p.tiles_x * p.tiles_y * p.n_tiles;
-  CCST_CHECK_ARG(total < (1ll << 31), "conv_umma: too many tiles");
-  p.total_tiles = (int)total;
+  const int64_t m_tiles = (int64_t)in.N * p.tiles_x * p.tiles_y;
+  CCST_CHECK_ARG(m_tiles * p.n_tiles < (1ll << 31), "conv_umma: too many tiles");
+  p.m_tiles = (int)m_tiles;
+  p.total_tiles = 0;  // set per kernel variant (tiles or tile pairs)
   p.relu = relu;
   p.bias = bias;
   p.out = out;
   p.out_nchw = out_nchw;
-  CUtensorMap ma, mb;
+  CUtensorMap ma;
   if (int e = make_act_map(&ma, in)) return e;
-  if (int e = make_weight_map(&mb, wk, 9 * in.C, CoutPad, BN)) return e;
   switch (BN) {
     case 16:
       // the last decoder conv (64 -> 3): weights always resident
       CCST_CHECK_ARG(in.C == kBlockK, "conv_umma: the NCHW epilogue expects Cin == 64");
-      return launch_cfg<T16, 16, EPI_NCHW_F32, true>(ma, mb, p, st);
+      return launch_cfg<T16, 16, EPI_NCHW_F32, true, 1>(ma, wk, p, st);
     case 64:
-      // 64 -> 64 layers keep all 9 weight tiles (72 KiB) resident in shared memory
-      return in.C == kBlockK ? launch_bn<T16, 64, true>(ma, mb, p, epi, st)
-                             : launch_bn<T16, 64, false>(ma, mb, p, epi, st);
+      // 64 -> 64 layers keep all 9 weight tiles resident in shared memory
+      return in.C == kBlockK ? launch_cg<T16, 64, true>(ma, wk, p, epi, st)
+                             : launch_cg<T16, 64, false>(ma, wk, p, epi, st);
     case 128:
-      return launch_bn<T16, 128, false>(ma, mb, p, epi, st);
+      return launch_cg<T16, 128, false>(ma, wk, p, epi, st);
     default:
-      return launch_bn<T16, 256, false>(ma, mb, p, epi, st);
+      return launch_cg<T16, 256, false>(ma, wk, p, epi, st);
   }
 }
 template int launch_conv_umma<__nv_bfloat16>(ActView<__nv_bfloat16>, const __nv_bfloat16*,
