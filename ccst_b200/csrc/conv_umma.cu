@@ -938,6 +938,231 @@ __global__ void __launch_bounds__(kFirstPx)
   if (warp == 0) tmem_dealloc<64>(tmem_base);
 }
 
+// =====================================================================================
+// conv1_1, warp-specialised persistent variant (used when W % 4 == 0, i.e. the image rows are
+// 16-byte aligned and TMA can fetch the input window).  Same math as conv_first_umma_kernel; the
+// per-tile chain  window -> im2col rows -> MMA -> epilogue -> store  is cut into four roles that
+// run on different tiles at the same time, so the kernel is bound by its HBM writes (128 B per
+// pixel) instead of by the latency of the chain:
+//   warp 0      TMA producer: {136 col, 3 row, 3 ch} fp32 window of the NCHW image per tile, ring
+//               of kF2WinStages (out-of-image rows / columns arrive as zeros and are never read:
+//               reflection is an index remap in the builders)
+//   warps 1-4   builders: thread p gathers the 27 taps of pixel p, converts to T16 and writes the
+//               swizzled K-major row p of the A tile (ring of 2)
+//   warp 5      MMA issuer: 2 x tcgen05.mma (M=128, N=64, K=16) per tile into one of 2 TMEM stages
+//   warps 6-9   epilogue: tcgen05.ld -> bias + ReLU -> T16 -> per-warp staging -> TMA store
+// =====================================================================================
+constexpr int kF2Threads = 320;
+constexpr int kF2WinCols = 136;  // columns x0-4 .. x0+131: a non-swizzled TMA box must start 16-byte aligned
+constexpr int kF2WinX0 = 4;     // window column of pixel x0
+constexpr int kF2WinElems = 9 * kF2WinCols;
+constexpr int kF2WinTx = kF2WinElems * 4;                      // 4896 bytes per TMA box
+constexpr int kF2WinBytes = (kF2WinTx + 127) / 128 * 128;      // 4992
+constexpr int kF2WinStages = 4;
+constexpr int kF2ABytes = kFirstPx * 128;                      // 16 KiB
+constexpr int kF2OffA = 0;                                     // 2 A tiles
+constexpr int kF2OffOut = 2 * kF2ABytes;                       // 2 staging tiles
+constexpr int kF2OffB = 4 * kF2ABytes;                         // weights 64 x 128 B
+constexpr int kF2OffWin = kF2OffB + 64 * 128;
+constexpr int kF2OffBias = kF2OffWin + kF2WinStages * kF2WinBytes;
+constexpr int kF2OffBar = kF2OffBias + 256;
+constexpr int kF2NumBars = 2 * kF2WinStages + 8;
+constexpr int kF2Smem = 1024 + kF2OffBar + 8 * kF2NumBars + 16;
+
+template <typename T16>
+__global__ void __launch_bounds__(kF2Threads, 2)
+    conv_first_umma_ws_kernel(const __grid_constant__ CUtensorMap tmap_img,
+                              const __grid_constant__ CUtensorMap tmap_out, FirstParams<T16> p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + kF2OffBar;
+  auto win_full = [&](int s) { return bar0 + 8u * s; };
+  auto win_empty = [&](int s) { return bar0 + 8u * (kF2WinStages + s); };
+  auto a_full = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + s); };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + 2 + s); };
+  auto t_full = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + 4 + s); };
+  auto t_empty = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + 6 + s); };
+  const uint32_t tmem_slot = bar0 + 8u * kF2NumBars;
+  float* sbias = reinterpret_cast<float*>(gen + kF2OffBias);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // one-time: weights -> swizzled K-major B tile, bias, barriers, TMEM (2 stages x 64 columns)
+  for (int i = tid; i < 64 * 4; i += kF2Threads) {
+    const int o = i >> 2, j = i & 3;
+    const uint4 v = reinterpret_cast<const uint4*>(p.wk)[o * 4 + j];
+    *reinterpret_cast<uint4*>(gen + kF2OffB + o * 128 + ((j ^ (o & 7)) << 4)) = v;
+  }
+  if (tid < 64) sbias[tid] = p.bias[tid];
+  if (tid == 0) {
+    for (int s = 0; s < kF2WinStages; ++s) {
+      mbar_init(win_full(s), 1);
+      mbar_init(win_empty(s), 4);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_full(s), 4);
+      mbar_init(a_empty(s), 1);
+      mbar_init(t_full(s), 1);
+      mbar_init(t_empty(s), 4);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmap_img);
+    prefetch_tmap(&tmap_out);
+  }
+  if (warp == 5) tmem_alloc<128>(tmem_slot);
+  fence_async_smem();  // the weight tile is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + kF2OffBar + 8 * kF2NumBars);
+
+  auto tile_coord = [&](int tile, int& n, int& y, int& x0) {
+    x0 = (tile % p.tiles_x) * kFirstPx;
+    const int b = tile / p.tiles_x;
+    y = b % p.H;
+    n = b / p.H;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int ws = it % kF2WinStages;
+      const uint32_t ph = (it / kF2WinStages) & 1;
+      int n, y, x0;
+      tile_coord(tile, n, y, x0);
+      mbar_wait(win_empty(ws), ph ^ 1, 910);
+      if (elect_one()) {
+        mbar_expect_tx(win_full(ws), kF2WinTx);
+        tma_load_4d(base + kF2OffWin + ws * kF2WinBytes, &tmap_img, win_full(ws), x0 - kF2WinX0, y - 1, 0, n);
+      }
+      __syncwarp();
+    }
+  } else if (warp <= 4) {
+    // ===================== builders: im2col row of pixel px of the tile
+    const int px = tid - 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int ws = it % kF2WinStages, as = it & 1;
+      int n, y, x0;
+      tile_coord(tile, n, y, x0);
+      // reflection = index remap inside the window (rows y-1..y+1 at 0..2, columns from x0-4)
+      int ridx[3] = {0, 1, 2};
+      if (y == 0) ridx[0] = 2;
+      if (y == p.H - 1) ridx[2] = 0;
+      int cidx[3];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int xx = x0 + px + s - 1;
+        xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
+        int c = xx - (x0 - kF2WinX0);
+        cidx[s] = c < 0 ? 0 : (c > kF2WinCols - 1 ? kF2WinCols - 1 : c);  // only for pixels past W
+      }
+      mbar_wait(win_full(ws), (it / kF2WinStages) & 1, 920);
+      const float* win = reinterpret_cast<const float*>(gen + kF2OffWin + ws * kF2WinBytes);
+      float v[28];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        const int tap = k / 3, ci = k - 3 * tap;
+        const int r = tap / 3, s = tap - 3 * r;
+        v[k] = win[(ci * 3 + ridx[r]) * kF2WinCols + cidx[s]];
+      }
+      v[27] = 0.f;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(win_empty(ws));  // values are in registers
+      uint32_t pk[16];
+#pragma unroll
+      for (int k2 = 0; k2 < 14; ++k2) pk[k2] = pack16x2<T16>(v[2 * k2], v[2 * k2 + 1]);
+      pk[14] = 0u, pk[15] = 0u;
+      mbar_wait(a_empty(as), ((it >> 1) & 1) ^ 1, 930);
+      const uint32_t sA = base + kF2OffA + as * kF2ABytes;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t dst = sA + px * 128 + ((j ^ (px & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                     "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                     : "memory");
+      }
+      fence_async_smem();  // generic writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(as));
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer
+    constexpr uint32_t idesc = make_idesc<T16, 64>();
+    const uint64_t bdesc = make_kmajor_sw128_desc(base + kF2OffB);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(t_empty(as), ph ^ 1, 940);
+      mbar_wait(a_full(as), ph, 941);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = make_kmajor_sw128_desc(base + kF2OffA + as * kF2ABytes);
+        const uint32_t d = tmem_base + (uint32_t)(as * 64);
+        umma_bf16(d, adesc, bdesc, idesc, 0u);
+        umma_bf16(d, adesc + 2, bdesc + 2, idesc, 1u);
+        umma_commit(a_empty(as));
+        umma_commit(t_full(as));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: warp q owns TMEM lanes 32q..32q+31 = pixels 32q.. of the tile
+    const int q = warp & 3;  // warps 6,7,8,9 -> lane quadrants 2,3,0,1
+    const int px = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      int n, y, x0;
+      tile_coord(tile, n, y, x0);
+      mbar_wait(t_full(as), (it >> 1) & 1, 950);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 64);
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr, r0);
+      tmem_ld32(taddr + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty(as));
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        pk[j] = pack16x2<T16>(fmaxf(__uint_as_float(r0[2 * j]) + sbias[2 * j], 0.f),
+                              fmaxf(__uint_as_float(r0[2 * j + 1]) + sbias[2 * j + 1], 0.f));
+        pk[16 + j] = pack16x2<T16>(fmaxf(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j], 0.f),
+                                   fmaxf(__uint_as_float(r1[2 * j + 1]) + sbias[33 + 2 * j], 0.f));
+      }
+      // per-warp staging (two buffers): the store issued two tiles ago must have read its buffer
+      bulk_wait_read<1>();
+      __syncwarp();
+      const uint32_t sOut = base + kF2OffOut + as * kF2ABytes;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t dst = sOut + px * 128 + ((j ^ (px & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                     "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                     : "memory");
+      }
+      const int x = x0 + px;
+      if (x < p.W) store_aliases(p.out, n, y, x, 0, pk);
+      fence_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        tma_store_4d(&tmap_out, sOut + q * (32 * 128), 0, x0 + q * 32, y, n);  // clipped at W
+        bulk_commit();
+      }
+      __syncwarp();
+    }
+    bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<128>(tmem_base);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -1177,6 +1402,38 @@ int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk,
   p.total_tiles = (int)total;
   CUtensorMap mo;
   if (int e = make_out_map(&mo, out, 0, 0, 1, 1, 32, 1)) return e;  // one warp's quarter
+  static const bool ws_off = [] { const char* e = getenv("CCST_FIRST_WS"); return e && e[0] == '0'; }();
+  if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 && !ws_off) {
+    // rows are 16-byte aligned: TMA-fed warp-specialised kernel
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+      set_error("cuTensorMapEncodeTiled entry point not available");
+      return CCST_ECUDA;
+    }
+    CUtensorMap mi;
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+    const cuuint32_t box[4] = {kF2WinCols, 3, 3, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&mi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)img, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(image %dx3x%dx%d) failed: CUresult %d", N, H, W, (int)r);
+      return CCST_ECUDA;
+    }
+    static bool attr2_done = false;
+    if (!attr2_done) {
+      CCST_CUDA(cudaFuncSetAttribute(conv_first_umma_ws_kernel<T16>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kF2Smem));
+      attr2_done = true;
+    }
+    const int64_t cap2 = (int64_t)sm_count() * 2;
+    const int grid2 = (int)(total < cap2 ? total : cap2);
+    conv_first_umma_ws_kernel<T16><<<grid2, kF2Threads, kF2Smem, st>>>(mi, mo, p);
+    CCST_LAUNCHED();
+    return CCST_OK;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     CCST_CUDA(cudaFuncSetAttribute(conv_first_umma_kernel<T16>,
