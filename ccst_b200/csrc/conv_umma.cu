@@ -1163,6 +1163,172 @@ __global__ void __launch_bounds__(kF2Threads, 2)
   if (warp == 5) tmem_dealloc<128>(tmem_base);
 }
 
+// =====================================================================================
+// Last decoder conv (net.py:34-35, 64 -> 3 channels, no ReLU, fp32 NCHW result).
+// With only 3 output channels the tap-by-tap implicit GEMM reads its A operand nine times from
+// shared memory for N = 16 columns each and is bound by shared-memory bandwidth (measured 0.56 ms
+// for batch 32 @512^2, HBM floor 0.17 ms).  Here the taps move into the N dimension instead:
+//   P[j, (tap, co)] = sum_c X[j, c] * W[tap][c][co]        one 1x1 GEMM, N = 27 (padded to 32), K = 64
+//   out[y, x, co]   = bias[co] + sum_tap P[(y + r, x + s), (tap, co)]     9-point gather
+// X is the {64 ch, 18 px, 10 rows} halo slab of an 8x16 output tile (180 pixels, ONE TMA load,
+// every input pixel read from shared memory once per K step instead of nine times); two M = 128
+// MMA chains cover slab pixels 0..127 and 128..255 (pixels >= 180 are whatever follows in shared
+// memory; their accumulator rows are never read).  The epilogue moves P through shared memory
+// (fp32, pitch 29 words: conflict-free both ways) and every thread gathers one output pixel.
+// =====================================================================================
+constexpr int kLSlabW = kTileW + 2, kLSlabH = kTileH + 2;
+constexpr int kLSlabPx = kLSlabW * kLSlabH;            // 180
+constexpr int kLSlabBytes = kLSlabPx * 128;            // 23040
+constexpr int kLStageStride = (kLSlabBytes + 1023) / 1024 * 1024;  // 23552
+constexpr int kLStages = 4;
+constexpr int kLPitch = 29;                            // words per P row
+constexpr int kLPBytes = (kLSlabPx * kLPitch * 4 + 127) / 128 * 128;
+constexpr int kLOffB = kLStages * kLStageStride;       // B' 32 x 128 B (the second MMA chain of the
+                                                       // last stage reads past its slab into here)
+constexpr int kLOffP = kLOffB + 32 * 128 + 8192;       // + slack so slab + 32 KiB stays in bounds
+constexpr int kLOffBar = kLOffP + 2 * kLPBytes;
+constexpr int kLNumBars = 2 * kLStages + 4;
+constexpr int kLSmem = 1024 + kLOffBar + 8 * kLNumBars + 16;
+static_assert((kLStages - 1) * kLStageStride + 256 * 128 <= kLOffP, "second MMA chain must stay inside the buffer");
+
+template <typename T16>
+__global__ void __launch_bounds__(kThreadsUmma, 1)
+    conv_last_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const T16* __restrict__ wk,
+                          ConvParams<T16> p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + kLOffBar;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (kLStages + s); };
+  auto t_full = [&](int s) { return bar0 + 8u * (2 * kLStages + s); };
+  auto t_empty = [&](int s) { return bar0 + 8u * (2 * kLStages + 2 + s); };
+  const uint32_t tmem_slot = bar0 + 8u * kLNumBars;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // B'[n = tap*3 + co][k = c] from the packed weights wk[co][tap*64 + c]; rows 27..31 are zero
+  for (int i = threadIdx.x; i < 32 * 8; i += kThreadsUmma) {
+    const int n = i >> 3, j = i & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    const int tap = n / 3, co = n - 3 * tap;
+    if (n < 27 && co < p.Cout) v = *reinterpret_cast<const uint4*>(wk + (size_t)co * (9 * kBlockK) + tap * kBlockK + j * 8);
+    *reinterpret_cast<uint4*>(gen + kLOffB + n * 128 + ((j ^ (n & 7)) << 4)) = v;
+  }
+  if (warp == 0 && lane == 0) prefetch_tmap(&tmap_a);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kLStages; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(t_full(s), 1);
+      mbar_init(t_empty(s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<128>(tmem_slot);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + kLOffBar + 8 * kLNumBars);
+
+  if (warp == 0) {
+    // ===================== TMA producer: one halo slab per tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile<1>(p, tile, 0);
+      const int s = it % kLStages;
+      mbar_wait(a_empty(s), ((it / kLStages) & 1) ^ 1, 700 + s);
+      if (elect_one()) {
+        mbar_expect_tx(a_full(s), kLSlabBytes);
+        tma_load_4d(base + s * kLStageStride, &tmap_a, a_full(s), 0, t.x0, t.y0, t.n);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: 2 chains (slab pixels 0..127, 128..255) x 4 K steps, N = 32
+    constexpr uint32_t idesc = make_idesc<T16, 32>();
+    const uint64_t bdesc = make_kmajor_sw128_desc(base + kLOffB);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int s = it % kLStages, acs = it & 1;
+      mbar_wait(t_empty(acs), ((it >> 1) & 1) ^ 1, 710 + acs);
+      mbar_wait(a_full(s), (it / kLStages) & 1, 720 + s);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t adesc = make_kmajor_sw128_desc(base + s * kLStageStride + h * (kBlockM * 128));
+          const uint32_t d = tmem_base + (uint32_t)(acs * 64 + h * 32);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
+        }
+        umma_commit(a_empty(s));
+        umma_commit(t_full(acs));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue: group g takes tiles g, g+2, ...
+    const int grp = (warp - kEpiWarp0) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;  // slab pixel (first chain) / output pixel of the tile
+    const int py = row / kTileW, px = row % kTileW;
+    float* P = reinterpret_cast<float*>(gen + kLOffP + grp * kLPBytes);
+    float bias[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) bias[c] = c < p.Cout ? p.bias[c] : 0.f;
+    for (int it = grp;; it += 2) {
+      const long long tile_ll = (long long)blockIdx.x + (long long)it * gridDim.x;
+      if (tile_ll >= p.total_tiles) break;
+      const TileCoord t = decode_tile<1>(p, (int)tile_ll, 0);
+      const int acs = it & 1;
+      mbar_wait(t_full(acs), (it >> 1) & 1, 730 + acs);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acs * 64);
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr, r0);
+      tmem_ld32(taddr + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty(acs));
+#pragma unroll
+      for (int c = 0; c < 27; ++c) P[row * kLPitch + c] = __uint_as_float(r0[c]);
+      if (row + kBlockM < kLSlabPx) {
+#pragma unroll
+        for (int c = 0; c < 27; ++c) P[(row + kBlockM) * kLPitch + c] = __uint_as_float(r1[c]);
+      }
+      epi_barrier(grp);
+      float acc[3] = {bias[0], bias[1], bias[2]};
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int r = tap / 3, s = tap - 3 * r;
+        const float* src = P + ((py + r) * kLSlabW + px + s) * kLPitch + tap * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += src[c];
+      }
+      const int y = t.y0 + py, x = t.x0 + px;
+      if (y < p.H && x < p.W) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (c < p.Cout) {
+            float v = acc[c];
+            if (p.relu) v = fmaxf(v, 0.f);
+            p.out_nchw[(((size_t)t.n * p.Cout + c) * p.H + y) * p.W + x] = v;
+          }
+        }
+      }
+      epi_barrier(grp);  // P is rewritten by this group's next tile
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<128>(tmem_base);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -1183,7 +1349,7 @@ PFN_encodeTiled get_encode_fn() {
 }
 
 template <typename T16>
-int make_act_map(CUtensorMap* m, const ActView<T16>& v) {
+int make_act_map(CUtensorMap* m, const ActView<T16>& v, int box_w = kTileW, int box_h = kTileH + 2) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -1194,7 +1360,7 @@ int make_act_map(CUtensorMap* m, const ActView<T16>& v) {
   const cuuint64_t strides[3] = {(cuuint64_t)v.C * 2, (cuuint64_t)(v.W + 2) * v.C * 2,
                                  (cuuint64_t)(v.H + 2) * (v.W + 2) * v.C * 2};
   // slab = the tile plus the two extra rows the filter rows r = 1, 2 reach into
-  const cuuint32_t box[4] = {kBlockK, kTileW, kTileH + 2, 1};
+  const cuuint32_t box[4] = {kBlockK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, Fmt16<T16>::kTmaType, 4, (void*)v.p, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1371,10 +1537,26 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const float* bias, int Cout
   CUtensorMap ma;
   if (int e = make_act_map(&ma, in)) return e;
   switch (BN) {
-    case 16:
-      // the last decoder conv (64 -> 3): weights always resident
+    case 16: {
+      // the last decoder conv (64 -> 3)
       CCST_CHECK_ARG(in.C == kBlockK, "conv_umma: the NCHW epilogue expects Cin == 64");
-      return launch_cfg<T16, 16, EPI_NCHW_F32, true, 1>(ma, wk, p, st);
+      static const bool gather_off = [] { const char* e = getenv("CCST_LAST_GATHER"); return e && e[0] == '0'; }();
+      if (Cout > 3 || gather_off) return launch_cfg<T16, 16, EPI_NCHW_F32, true, 1>(ma, wk, p, st);
+      // taps in the N dimension + 9-point gather (see conv_last_umma_kernel)
+      CUtensorMap ml;
+      if (int e = make_act_map(&ml, in, kLSlabW, kLSlabH)) return e;
+      static bool attr_done = false;
+      if (!attr_done) {
+        CCST_CUDA(cudaFuncSetAttribute(conv_last_umma_kernel<T16>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kLSmem));
+        attr_done = true;
+      }
+      p.total_tiles = p.m_tiles;
+      const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+      conv_last_umma_kernel<T16><<<grid, kThreadsUmma, kLSmem, st>>>(ml, wk, p);
+      CCST_LAUNCHED();
+      return CCST_OK;
+    }
     case 64:
       // 64 -> 64 layers keep all 9 weight tiles resident in shared memory
       return in.C == kBlockK ? launch_cg<T16, 64, true>(ma, wk, p, epi, st)
