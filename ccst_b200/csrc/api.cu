@@ -293,8 +293,9 @@ struct Pipe {
 
   int adain(const float* mu_s, const float* sigma_s, int64_t stride, float alpha) {
     ActView<T> out = view(cur_slot ^ 1, cur.N, cur.H, cur.W, cur.C);
+    if (int e = ensure_raw(h, nhwc_scratch_elems(cur.N, cur.C, cur.H * cur.W))) return e;
     ProfScope ps(h, st, 4, 0, 2.0 * (double)cur.N * cur.H * cur.W * cur.C * sizeof(T));
-    if (int e = launch_adain_nhwc<T>(cur, out, mu_s, sigma_s, stride, alpha, 1e-5f, st)) return e;
+    if (int e = launch_adain_nhwc<T>(cur, out, mu_s, sigma_s, stride, alpha, 1e-5f, h->raw, st)) return e;
     cur = out, cur_slot ^= 1;
     return CCST_OK;
   }
@@ -375,7 +376,7 @@ int run_encoder(ccst_handle* h, const float* d_img, int N, int H, int W, float* 
     if (int e = launch_act_to_nchw<T>(p.cur, d_feat, st)) return e;
   }
   if (d_state) {
-    if (int e = ensure_raw(h, (size_t)N * 512)) return e;
+    if (int e = ensure_raw(h, nhwc_scratch_elems(N, 512, fh * fw))) return e;
     ProfScope ps(h, st, 4, 0, (double)N * fh * fw * 512 * sizeof(T));
     if (int e = launch_stats_nhwc<T>(p.cur, h->raw, st)) return e;
     if (int e = merge_raw_into_state(h->raw, N, 512, (int64_t)fh * fw, d_state, st)) return e;

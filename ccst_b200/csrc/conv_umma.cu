@@ -997,10 +997,10 @@ __global__ void __launch_bounds__(kF2Threads, 2)
   if (tid == 0) {
     for (int s = 0; s < kF2WinStages; ++s) {
       mbar_init(win_full(s), 1);
-      mbar_init(win_empty(s), 4);
+      mbar_init(win_empty(s), 128);  // every builder thread arrives for itself
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(a_full(s), 4);
+      mbar_init(a_full(s), 128);
       mbar_init(a_empty(s), 1);
       mbar_init(t_full(s), 1);
       mbar_init(t_empty(s), 4);
@@ -1068,8 +1068,11 @@ __global__ void __launch_bounds__(kF2Threads, 2)
         v[k] = win[(ci * 3 + ridx[r]) * kF2WinCols + cidx[s]];
       }
       v[27] = 0.f;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(win_empty(ws));  // values are in registers
+      // The window is rewritten by TMA (async proxy): this thread's generic-proxy reads must be
+      // ordered before that write, which takes a proxy fence before the release (without it a
+      // 32-pixel quarter of a tile came out wrong about once per 10^5 tiles).
+      fence_async_smem();
+      mbar_arrive(win_empty(ws));
       uint32_t pk[16];
 #pragma unroll
       for (int k2 = 0; k2 < 14; ++k2) pk[k2] = pack16x2<T16>(v[2 * k2], v[2 * k2 + 1]);
@@ -1083,9 +1086,8 @@ __global__ void __launch_bounds__(kF2Threads, 2)
                      "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                      : "memory");
       }
-      fence_async_smem();  // generic writes -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full(as));
+      fence_async_smem();  // this thread's generic writes -> visible to the tensor core
+      mbar_arrive(a_full(as));
     }
   } else if (warp == 5) {
     // ===================== MMA issuer

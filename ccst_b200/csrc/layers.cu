@@ -55,6 +55,40 @@ struct VecOf {
   static constexpr int value = 16 / sizeof(T);
 };
 
+// whole-vector conversions (two elements per instruction for the 16-bit types)
+__device__ __forceinline__ void unpack_vec(const Pack<float, 4>& p, float (&f)[4]) {
+  f[0] = p.v.x, f[1] = p.v.y, f[2] = p.v.z, f[3] = p.v.w;
+}
+__device__ __forceinline__ void unpack_vec(const Pack<__half, 8>& p, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&p.v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x, f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void unpack_vec(const Pack<__nv_bfloat16, 8>& p, float (&f)[8]) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&p.v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void pack_vec(Pack<float, 4>& p, const float (&f)[4]) {
+  p.v = make_float4(f[0], f[1], f[2], f[3]);
+}
+__device__ __forceinline__ void pack_vec(Pack<__half, 8>& p, const float (&f)[8]) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&p.v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = pack16x2<__half>(f[2 * i], f[2 * i + 1]);
+}
+__device__ __forceinline__ void pack_vec(Pack<__nv_bfloat16, 8>& p, const float (&f)[8]) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&p.v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = pack16x2<__nv_bfloat16>(f[2 * i], f[2 * i + 1]);
+}
+
 // =====================================================================================
 // conv1_1 (+ folded 1x1): one CTA = 64 consecutive pixels of one image row, 4 threads per pixel
 // (16 output channels each).
@@ -311,102 +345,174 @@ struct NhwcGeom {
   static constexpr int PX_LANES = 256 / CH_LANES;
 };
 
+// Statistics / AdaIN on the arena layout.  CTA = (image n, chunk of kNhwcChunk pixels) x ALL channels:
+// a warp reads 512 contiguous bytes of one pixel (the earlier one-CTA-per-64-channel-slab mapping
+// read 128-byte pieces at a 1 KiB stride from eight different SMs and reached 2.3 TB/s).  Every
+// chunk CTA writes its {mean, M2} partials (the count follows from the geometry); consumers merge
+// the partials of a plane with Chan's formula in fixed chunk order (deterministic).
+constexpr int kNhwcChunk = 256;
+constexpr int kNhwcBatch = 8;  // 16-byte loads in flight per thread
+
+__host__ __device__ inline int nhwc_chunks(int HW) { return (HW + kNhwcChunk - 1) / kNhwcChunk; }
+
+// grid (chunks, N): part[(n * chunks + chunk) * C + c] = {mean, M2} of the chunk.
+// Thread = VEC channels x every PX_LANES-th pixel, as pivoted sums (d = x - x_first: the
+// cancellation in  M2 = sum d^2 - (sum d)^2 / n  scales with the spread of the values, not with
+// their mean; 3 instructions per element instead of a Welford update); pixel lanes are merged
+// through shared memory (Chan).
 template <typename T>
-__device__ __forceinline__ void nhwc_plane_stats(const ActView<T>& in, int n, int c0, float* s_mean,
-                                                 float* s_m2, float* s_n) {
-  using G = NhwcGeom<T>;
-  constexpr int VEC = G::VEC;
-  const int cl = threadIdx.x % G::CH_LANES, pl = threadIdx.x / G::CH_LANES;
+__global__ void __launch_bounds__(256)
+    nhwc_stats_partial_kernel(ActView<T> in, float2* __restrict__ part) {
+  constexpr int VEC = VecOf<T>::value;
+  extern __shared__ float s_part[];  // [PX_LANES][C] mean, [PX_LANES][C] M2, [PX_LANES] count
+  const int C = in.C, ch_lanes = C / VEC, px_lanes = 256 / ch_lanes;
+  float* s_mean = s_part;
+  float* s_m2 = s_part + px_lanes * C;
+  float* s_n = s_part + 2 * px_lanes * C;
+  const int chunk = blockIdx.x, n = blockIdx.y;
   const int HW = in.H * in.W;
-  float mean[VEC], m2[VEC];
-#pragma unroll
-  for (int k = 0; k < VEC; ++k) mean[k] = 0.f, m2[k] = 0.f;
+  const int p0 = chunk * kNhwcChunk, p1 = min(HW, p0 + kNhwcChunk);
+  const int cl = threadIdx.x % ch_lanes, pl = threadIdx.x / ch_lanes;
+  const T* src0 = in.px(n, 0, 0) + cl * VEC;
+  float piv[VEC], s1[VEC], s2[VEC];
   float cnt = 0.f;
-  for (int p = pl; p < HW; p += G::PX_LANES) {
-    const int y = p / in.W, x = p - y * in.W;
-    Pack<T, VEC> v;
-    v.v = *reinterpret_cast<const decltype(v.v)*>(in.px(n, y, x) + c0 + cl * VEC);
-    cnt += 1.f;
-    const float inv = __frcp_rn(cnt);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      const float xv = v.get(k);
-      const float d = xv - mean[k];
-      mean[k] = fmaf(d, inv, mean[k]);
-      m2[k] = fmaf(d, xv - mean[k], m2[k]);
+  for (int k = 0; k < VEC; ++k) piv[k] = 0.f, s1[k] = 0.f, s2[k] = 0.f;
+  for (int pb = p0 + pl; pb < p1; pb += kNhwcBatch * px_lanes) {
+    Pack<T, VEC> v[kNhwcBatch];
+#pragma unroll
+    for (int i = 0; i < kNhwcBatch; ++i) {  // all loads of the batch first
+      const int p = pb + i * px_lanes;
+      if (p < p1) {
+        const int y = p / in.W, x = p - y * in.W;
+        v[i].v = *reinterpret_cast<const decltype(v[i].v)*>(src0 + (size_t)y * in.pitch_y() + (size_t)x * C);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kNhwcBatch; ++i) {
+      const int p = pb + i * px_lanes;
+      if (p < p1) {
+        float f[VEC];
+        unpack_vec(v[i], f);
+        if (cnt == 0.f) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) piv[k] = f[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float d = f[k] - piv[k];
+            s1[k] += d;
+            s2[k] = fmaf(d, d, s2[k]);
+          }
+        }
+        cnt += 1.f;
+      }
     }
   }
-  // s_*[pl][64]
+  const float inv = cnt > 0.f ? __frcp_rn(cnt) : 0.f;
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
-    s_mean[pl * 64 + cl * VEC + k] = mean[k];
-    s_m2[pl * 64 + cl * VEC + k] = m2[k];
+    s_mean[pl * C + cl * VEC + k] = fmaf(s1[k], inv, piv[k]);
+    s_m2[pl * C + cl * VEC + k] = fmaxf(s2[k] - s1[k] * s1[k] * inv, 0.f);
   }
   if (cl == 0) s_n[pl] = cnt;
   __syncthreads();
-  if (threadIdx.x < 64) {
-    Wf acc{s_n[0], s_mean[threadIdx.x], s_m2[threadIdx.x]};
-    for (int l = 1; l < G::PX_LANES; ++l) {
-      Wf o{s_n[l], s_mean[l * 64 + threadIdx.x], s_m2[l * 64 + threadIdx.x]};
-      acc = wf_merge(acc, o);
-    }
-    s_mean[threadIdx.x] = acc.mean;  // row 0 now holds the merged result
-    s_m2[threadIdx.x] = acc.m2;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    Wf acc{s_n[0], s_mean[c], s_m2[c]};
+    for (int l = 1; l < px_lanes; ++l) acc = wf_merge(acc, Wf{s_n[l], s_mean[l * C + c], s_m2[l * C + c]});
+    part[((size_t)n * gridDim.x + chunk) * C + c] = make_float2(acc.mean, acc.m2);
   }
-  __syncthreads();
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) stats_nhwc_kernel(ActView<T> in, float2* __restrict__ raw) {
-  using G = NhwcGeom<T>;
-  __shared__ float s_mean[G::PX_LANES * 64], s_m2[G::PX_LANES * 64], s_n[G::PX_LANES];
-  const int c0 = blockIdx.x * 64, n = blockIdx.y;
-  nhwc_plane_stats(in, n, c0, s_mean, s_m2, s_n);
-  if (threadIdx.x < 64)
-    raw[(size_t)n * in.C + c0 + threadIdx.x] = make_float2(s_mean[threadIdx.x], s_m2[threadIdx.x]);
+// Chan merge of the chunk partials of plane (n, c), fixed order
+__device__ __forceinline__ Wf nhwc_merge_partials(const float2* __restrict__ part, int n, int c, int C,
+                                                  int HW) {
+  const int chunks = nhwc_chunks(HW);
+  Wf acc{0.f, 0.f, 0.f};
+  for (int ch = 0; ch < chunks; ++ch) {
+    const float2 o = part[((size_t)n * chunks + ch) * C + c];
+    const int cnt = min(kNhwcChunk, HW - ch * kNhwcChunk);
+    acc = wf_merge(acc, Wf{(float)cnt, o.x, o.y});
+  }
+  return acc;
 }
 
+// raw[n * C + c] = {mean, M2} of the whole plane (input of merge_raw_into_state)
+__global__ void __launch_bounds__(256)
+    nhwc_stats_merge_kernel(const float2* __restrict__ part, float2* __restrict__ raw, int NC, int C,
+                            int HW) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= NC) return;
+  const Wf acc = nhwc_merge_partials(part, i / C, i % C, C, HW);
+  raw[i] = make_float2(acc.mean, acc.m2);
+}
+
+// coef[n * C + c] = {mu_c, A, B}:  out = (x - mu_c) * A + B,
+//   A = alpha * sigma_s / sigma_c + (1 - alpha),  B = alpha * mu_s + (1 - alpha) * mu_c
+__global__ void __launch_bounds__(256)
+    adain_nhwc_coef_kernel(const float2* __restrict__ part, float4* __restrict__ coef, int NC, int C,
+                           int HW, const float* __restrict__ mu_s, const float* __restrict__ sigma_s,
+                           int64_t stat_batch_stride, float alpha, float eps) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= NC) return;
+  const int n = i / C, c = i % C;
+  const Wf st = nhwc_merge_partials(part, n, c, C, HW);
+  // unbiased like calc_mean_std (function.py:9); HW == 1 -> NaN as the reference
+  const float sg_c = sqrtf(st.m2 / ((float)HW - 1.f) + eps);
+  const int64_t si = (int64_t)n * stat_batch_stride + c;
+  const float ms = mu_s[si], ss = sigma_s[si];
+  coef[i] = make_float4(st.mean, alpha * (ss / sg_c) + (1.f - alpha), alpha * ms + (1.f - alpha) * st.mean,
+                        0.f);
+}
+
+// grid (chunks, N): the affine on the chunk's pixels, out = x * A + (B - mu_c * A); same thread
+// mapping as the statistics kernel (VEC channels x every PX_LANES-th pixel)
 template <typename T>
 __global__ void __launch_bounds__(256)
-    adain_nhwc_kernel(ActView<T> in, ActView<T> out, const float* __restrict__ mu_s,
-                      const float* __restrict__ sigma_s, int64_t stat_batch_stride, float alpha,
-                      float eps) {
-  using G = NhwcGeom<T>;
-  constexpr int VEC = G::VEC;
-  __shared__ float s_mean[G::PX_LANES * 64], s_m2[G::PX_LANES * 64], s_n[G::PX_LANES];
-  __shared__ float s_A[64], s_B[64], s_mu[64];
-  const int c0 = blockIdx.x * 64, n = blockIdx.y;
-  nhwc_plane_stats(in, n, c0, s_mean, s_m2, s_n);
+    adain_nhwc_apply_kernel(ActView<T> in, ActView<T> out, const float4* __restrict__ coef) {
+  constexpr int VEC = VecOf<T>::value;
+  const int C = in.C, ch_lanes = C / VEC, px_lanes = 256 / ch_lanes;
+  const int chunk = blockIdx.x, n = blockIdx.y;
   const int HW = in.H * in.W;
-  if (threadIdx.x < 64) {
-    const int c = c0 + threadIdx.x;
-    const float mu_c = s_mean[threadIdx.x];
-    // unbiased like calc_mean_std (function.py:9); HW == 1 -> NaN as the reference
-    const float sg_c = sqrtf(s_m2[threadIdx.x] / ((float)HW - 1.f) + eps);
-    const int64_t si = (int64_t)n * stat_batch_stride + c;
-    const float ms = mu_s[si], ss = sigma_s[si];
-    s_A[threadIdx.x] = alpha * (ss / sg_c) + (1.f - alpha);
-    s_B[threadIdx.x] = alpha * ms + (1.f - alpha) * mu_c;
-    s_mu[threadIdx.x] = mu_c;
-  }
-  __syncthreads();
-  const int cl = threadIdx.x % G::CH_LANES, pl = threadIdx.x / G::CH_LANES;
-  float A[VEC], B[VEC], M[VEC];
+  const int p0 = chunk * kNhwcChunk, p1 = min(HW, p0 + kNhwcChunk);
+  const int cl = threadIdx.x % ch_lanes, pl = threadIdx.x / ch_lanes;
+  const size_t coff = (size_t)cl * VEC;
+  const T* src0 = in.px(n, 0, 0) + coff;
+  float A[VEC], B[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
-    A[k] = s_A[cl * VEC + k];
-    B[k] = s_B[cl * VEC + k];
-    M[k] = s_mu[cl * VEC + k];
+    const float4 q = coef[(size_t)n * C + coff + k];
+    A[k] = q.y, B[k] = fmaf(-q.x, q.y, q.z);
   }
-  for (int p = pl; p < HW; p += G::PX_LANES) {
-    const int y = p / in.W, x = p - y * in.W;
-    Pack<T, VEC> v, o;
-    v.v = *reinterpret_cast<const decltype(v.v)*>(in.px(n, y, x) + c0 + cl * VEC);
+  for (int pb = p0 + pl; pb < p1; pb += kNhwcBatch * px_lanes) {
+    Pack<T, VEC> v[kNhwcBatch];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) o.set(k, fmaf(v.get(k) - M[k], A[k], B[k]));
-    for_each_halo_alias(y, x, in.H, in.W, [&](int yy, int xx) {
-      *reinterpret_cast<decltype(o.v)*>(out.px(n, yy, xx) + c0 + cl * VEC) = o.v;
-    });
+    for (int i = 0; i < kNhwcBatch; ++i) {
+      const int p = pb + i * px_lanes;
+      if (p < p1) {
+        const int y = p / in.W, x = p - y * in.W;
+        v[i].v = *reinterpret_cast<const decltype(v[i].v)*>(src0 + (size_t)y * in.pitch_y() + (size_t)x * C);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kNhwcBatch; ++i) {
+      const int p = pb + i * px_lanes;
+      if (p < p1) {
+        const int y = p / in.W, x = p - y * in.W;
+        float f[VEC];
+        unpack_vec(v[i], f);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) f[k] = fmaf(f[k], A[k], B[k]);
+        Pack<T, VEC> o;
+        pack_vec(o, f);
+        *reinterpret_cast<decltype(o.v)*>(out.px(n, y, x) + coff) = o.v;
+        if (y == 1 || y == in.H - 2 || x == 1 || x == in.W - 2) {  // reflection-halo aliases
+          for_each_halo_alias(y, x, in.H, in.W, [&](int yy, int xx) {
+            if (yy != y || xx != x) *reinterpret_cast<decltype(o.v)*>(out.px(n, yy, xx) + coff) = o.v;
+          });
+        }
+      }
+    }
   }
 }
 
@@ -559,29 +665,59 @@ template int launch_pool<__nv_bfloat16>(ActView<__nv_bfloat16>, ActView<__nv_bfl
 template int launch_pool<__half>(ActView<__half>, ActView<__half>,
                                         cudaStream_t);
 
+size_t nhwc_scratch_elems(int N, int C, int HW) { return (size_t)N * C * (nhwc_chunks(HW) + 2); }
+
+template <typename T>
+int nhwc_geometry_ok(const ActView<T>& in, const char* who) {
+  constexpr int VEC = VecOf<T>::value;
+  CCST_CHECK_ARG(in.C % VEC == 0 && in.C / VEC <= 256 && 256 % (in.C / VEC) == 0,
+                 "%s: C=%d must be %d x a power of two <= 256", who, in.C, VEC);
+  CCST_CHECK_ARG(in.N <= 65535, "%s: batch too large", who);
+  return CCST_OK;
+}
+template <typename T>
+size_t nhwc_stats_smem(const ActView<T>& in) {
+  const int px_lanes = 256 / (in.C / VecOf<T>::value);
+  return (size_t)(2 * px_lanes * in.C + px_lanes) * sizeof(float);
+}
+
 template <typename T>
 int launch_adain_nhwc(ActView<T> in, ActView<T> out, const float* mu_s, const float* sigma_s,
-                      int64_t stat_batch_stride, float alpha, float eps, cudaStream_t st) {
-  CCST_CHECK_ARG(in.C % 64 == 0, "adain_nhwc: C must be a multiple of 64");
-  dim3 grid(in.C / 64, in.N);
-  adain_nhwc_kernel<T><<<grid, 256, 0, st>>>(in, out, mu_s, sigma_s, stat_batch_stride, alpha, eps);
+                      int64_t stat_batch_stride, float alpha, float eps, float2* scratch,
+                      cudaStream_t st) {
+  if (int e = nhwc_geometry_ok(in, "adain_nhwc")) return e;
+  const int chunks = nhwc_chunks(in.H * in.W);
+  dim3 grid(chunks, in.N);
+  const int NC = in.N * in.C;
+  float4* coef = reinterpret_cast<float4*>(scratch);          // NC float4 = 2 NC float2
+  float2* part = scratch + 2 * (size_t)NC;                    // NC * chunks float2
+  nhwc_stats_partial_kernel<T><<<grid, 256, nhwc_stats_smem(in), st>>>(in, part);
+  CCST_LAUNCHED();
+  adain_nhwc_coef_kernel<<<(NC + 255) / 256, 256, 0, st>>>(part, coef, NC, in.C, in.H * in.W, mu_s,
+                                                           sigma_s, stat_batch_stride, alpha, eps);
+  CCST_LAUNCHED();
+  adain_nhwc_apply_kernel<T><<<grid, 256, 0, st>>>(in, out, coef);
   CCST_LAUNCHED();
   return CCST_OK;
 }
 template int launch_adain_nhwc<float>(ActView<float>, ActView<float>, const float*, const float*,
-                                      int64_t, float, float, cudaStream_t);
+                                      int64_t, float, float, float2*, cudaStream_t);
 template int launch_adain_nhwc<__nv_bfloat16>(ActView<__nv_bfloat16>, ActView<__nv_bfloat16>,
                                               const float*, const float*, int64_t, float, float,
-                                              cudaStream_t);
-template int launch_adain_nhwc<__half>(ActView<__half>, ActView<__half>,
-                                              const float*, const float*, int64_t, float, float,
-                                              cudaStream_t);
+                                              float2*, cudaStream_t);
+template int launch_adain_nhwc<__half>(ActView<__half>, ActView<__half>, const float*, const float*,
+                                       int64_t, float, float, float2*, cudaStream_t);
 
+// scratch: nhwc_scratch_elems() float2; the merged per-plane {mean, M2} land in its first N*C entries
 template <typename T>
-int launch_stats_nhwc(ActView<T> in, float2* raw, cudaStream_t st) {
-  CCST_CHECK_ARG(in.C % 64 == 0, "stats_nhwc: C must be a multiple of 64");
-  dim3 grid(in.C / 64, in.N);
-  stats_nhwc_kernel<T><<<grid, 256, 0, st>>>(in, raw);
+int launch_stats_nhwc(ActView<T> in, float2* scratch, cudaStream_t st) {
+  if (int e = nhwc_geometry_ok(in, "stats_nhwc")) return e;
+  const int HW = in.H * in.W, chunks = nhwc_chunks(HW);
+  const int NC = in.N * in.C;
+  dim3 grid(chunks, in.N);
+  nhwc_stats_partial_kernel<T><<<grid, 256, nhwc_stats_smem(in), st>>>(in, scratch + NC);
+  CCST_LAUNCHED();
+  nhwc_stats_merge_kernel<<<(NC + 255) / 256, 256, 0, st>>>(scratch + NC, scratch, NC, in.C, HW);
   CCST_LAUNCHED();
   return CCST_OK;
 }

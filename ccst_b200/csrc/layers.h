@@ -24,13 +24,17 @@ int launch_conv_ffma(ActView<float> in, const float* w, const float* bias, int C
 template <typename T>
 int launch_pool(ActView<T> in, ActView<T> out, cudaStream_t st);
 
+// float2 elements of the scratch buffer the two launchers below need (chunk partials + merged planes)
+size_t nhwc_scratch_elems(int N, int C, int HW);
+
 template <typename T>
 int launch_adain_nhwc(ActView<T> in, ActView<T> out, const float* mu_s, const float* sigma_s,
-                      int64_t stat_batch_stride, float alpha, float eps, cudaStream_t st);
+                      int64_t stat_batch_stride, float alpha, float eps, float2* scratch,
+                      cudaStream_t st);
 
-// per-(n,c) {mean, M2} of an activation -> raw[N*C]
+// per-(n,c) {mean, M2} of an activation -> scratch[0 .. N*C)
 template <typename T>
-int launch_stats_nhwc(ActView<T> in, float2* raw, cudaStream_t st);
+int launch_stats_nhwc(ActView<T> in, float2* scratch, cudaStream_t st);
 
 int merge_raw_into_state(const float2* raw, int N, int C, int64_t hw, double* d_state,
                          cudaStream_t st);

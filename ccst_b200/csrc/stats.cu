@@ -519,6 +519,8 @@ __global__ void __launch_bounds__(kBulkThreads, 1) plane_bulk_kernel(BulkArgs a)
         }
       }
     }
+    // generic-proxy reads of the slot -> ordered before the producer's next bulk copy (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0)
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bars[kSlots + slot]))
