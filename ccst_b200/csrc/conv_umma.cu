@@ -659,18 +659,17 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           for (int j = 0; j < 32; ++j) {
             float v0 = __uint_as_float(r[2 * j]) + s_bias[co + 2 * j];
             float v1 = __uint_as_float(r[2 * j + 1]) + s_bias[co + 2 * j + 1];
-            if (p.relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
             if (EPI == EPI_ACT_POOL) {
-              // 2x2 window = lanes {l, l^1, l^16, l^17}; out-of-image pixels contribute 0, the
-              // identity for post-ReLU values
-              v0 = valid ? v0 : 0.f;
-              v1 = valid ? v1 : 0.f;
+              // 2x2 window = lanes {l, l^1, l^16, l^17}; out-of-image pixels never win the max
+              // (ReLU commutes with max and is applied by the conversion below)
+              v0 = valid ? v0 : -INFINITY;
+              v1 = valid ? v1 : -INFINITY;
               v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
               v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
               v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 16));
               v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 16));
             }
-            pk[j] = pack16x2<T16>(v0, v1);
+            pk[j] = p.relu ? pack16x2_relu<T16>(v0, v1) : pack16x2<T16>(v0, v1);
           }
           // stage the row (128 bytes = 8 chunks) with the 128-byte swizzle the TMA store expects
           int srow = row;
@@ -733,6 +732,339 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   __syncwarp();
   tc_fence_before();
   // pair: the peer's shared memory / TMEM are operands of the leader's MMAs until the very end
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc_cg<CG, Cfg::kTmemCols>(tmem_base);
+}
+
+// =====================================================================================
+// 64-output-channel layers (conv1_2, dec7, dec8), "s-merged" variant.
+// With N = 64 every tcgen05.mma reads 4 KiB of A and 2 KiB of B from shared memory for 32 cycles of
+// math: the tap-by-tap kernel above is bound by shared-memory bandwidth at ~45 % tensor-pipe use.
+// Here the three filter COLUMNS move into the N dimension:
+//   P[(jy, jx), (s, co)] = sum_{r, c} X[(jy + r, jx), c] * W[co][c][r][s]        N = 192, K = 3 * Cin
+//   out[(jy, ox), co]    = P[(jy, ox), (0, co)] + P[(jy, ox + 1), (1, co)] + P[(jy, ox + 2), (2, co)]
+// so one slab {64 ch, 16 px, 10 rows} per channel chunk feeds three MMAs of N = 192 (A is read 3x per
+// chunk instead of 9x) and the shifted sum over s is two warp shuffles per value in the epilogue
+// (TMEM lane = slab pixel; jx neighbours are adjacent lanes).  A 16-pixel-wide slab yields 14 output
+// columns, so tiles step by 14 pixels in x (12.5 % of the MMA rows are halo).
+// =====================================================================================
+constexpr int kSmOutW = kTileW - 2;                 // 14 output columns per tile
+constexpr int kSmN = 192;
+constexpr int kSmStoreBytes = kTileH * kSmOutW * 128;  // 14336 = 14 x 1024
+
+template <bool BRES, int CG>
+struct SmergeCfg {
+  static constexpr int kASlabBytes = (kTileH + 2) * kTileW * 128;  // 20480
+  static constexpr int kBRows = kSmN / CG;
+  static constexpr int kBBytes = kBRows * kBlockK * 2;             // 24576 / CG
+  static constexpr int kAStages = BRES ? 5 : 4;
+  static constexpr int kBStages = BRES ? 3 : (CG == 2 ? 6 : 4);    // resident: 3 filter rows x (Cin == 64)
+  static constexpr int kAOff = 0;
+  static constexpr int kBOff = kAStages * kASlabBytes;
+  static constexpr int kStoreOff = kBOff + kBStages * kBBytes;
+  static constexpr int kBiasOff = kStoreOff + 2 * kSmStoreBytes;
+  static constexpr int kBarOff = kBiasOff + 256;
+  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4 + 1;
+  static constexpr int kTmemCols = 512;                            // 2 stages x 192 columns
+  static constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024;
+  static_assert(kSmemBytes <= 232448, "shared memory plan exceeds 227 KiB");
+  static_assert(kBBytes % 1024 == 0, "B tiles must keep the swizzle phase");
+};
+
+template <int CG, typename P>
+__device__ __forceinline__ TileCoord decode_tile_sm(const P& p, int unit, int rank) {
+  TileCoord t;
+  t.nt = 0;
+  int m = unit * CG + rank;
+  if (CG == 2 && m >= p.m_tiles) {
+    t.x0 = 0, t.y0 = 0, t.n = p.N;
+    return t;
+  }
+  t.x0 = (m % p.tiles_x) * kSmOutW;
+  m /= p.tiles_x;
+  t.y0 = (m % p.tiles_y) * kTileH;
+  t.n = m / p.tiles_y;
+  return t;
+}
+
+template <typename T16, int EPI, bool BRES, int CG>
+__global__ void __launch_bounds__(kThreadsUmma, 1)
+    conv_smerge_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                       const __grid_constant__ CUtensorMap tmap_b,
+                       const __grid_constant__ OutMaps tmap_out, ConvParams<T16> p) {
+  using Cfg = SmergeCfg<BRES, CG>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t store_base = smem_base + Cfg::kStoreOff;
+  const uint32_t bar_base = smem_base + Cfg::kBarOff;
+  float* s_bias = reinterpret_cast<float*>(smem_gen + Cfg::kBiasOff);
+  auto a_smem = [&](int s) { return smem_base + Cfg::kAOff + s * Cfg::kASlabBytes; };
+  auto b_smem = [&](int s) { return smem_base + Cfg::kBOff + s * Cfg::kBBytes; };
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::kAStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + Cfg::kBStages + s); };
+  constexpr int kBar2 = 2 * Cfg::kAStages + 2 * Cfg::kBStages;
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (kBar2 + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (kBar2 + 2 + s); };
+  const uint32_t bres_bar = bar_base + 8u * (kBar2 + 4);
+  const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = p.Cin / kBlockK;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  auto lead = [&](uint32_t bar) { return CG == 2 ? mapa_rank(bar, 0) : bar; };
+  const int unit0 = CG == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_step = CG == 2 ? (int)ncluster_x() : (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_out.m[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kAStages; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < Cfg::kBStages; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full_bar(s), 1);
+      mbar_init(tmem_empty_bar(s), 8 * CG);  // every epilogue warp of both CTAs
+    }
+    mbar_init(bres_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_cg<CG, Cfg::kTmemCols>(tmem_slot);
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base =
+      *reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOff + 8 * Cfg::kNumBars);
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    const int b_row0 = (int)cta_rank * Cfg::kBRows;
+    if (BRES) {
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(bres_bar, CG * 3 * Cfg::kBBytes);
+        const uint32_t bar = lead(bres_bar);
+        for (int r = 0; r < 3; ++r) tma_load_2d_cg<CG>(b_smem(r), &tmap_b, bar, r * p.Cin, b_row0);
+      }
+      __syncwarp();
+    }
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int unit = unit0; unit < p.total_tiles; unit += unit_step) {
+      const TileCoord t = decode_tile_sm<CG>(p, unit, (int)cta_rank);
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(a_empty(as), aph ^ 1, 500 + as);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(a_full(as), CG * Cfg::kASlabBytes);
+          // slab column jx <-> interior x0 - 1 + jx <-> padded x0 + jx; rows y0 - 1 .. y0 + 8
+          tma_load_4d_cg<CG>(a_smem(as), &tmap_a, lead(a_full(as)), kc * kBlockK, t.x0, t.y0, t.n);
+        }
+        __syncwarp();
+        if (++as == Cfg::kAStages) as = 0, aph ^= 1;
+        if (!BRES) {
+          for (int r = 0; r < 3; ++r) {
+            mbar_wait(b_empty(bs), bph ^ 1, 550 + bs);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(b_full(bs), CG * Cfg::kBBytes);
+              tma_load_2d_cg<CG>(b_smem(bs), &tmap_b, lead(b_full(bs)), r * p.Cin + kc * kBlockK, b_row0);
+            }
+            __syncwarp();
+            if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: per channel chunk 3 filter rows x 4 K steps, N = 192
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc<T16, kSmN, CG>();
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      if (BRES) {
+        mbar_wait(bres_bar, 0, 560);
+        tc_fence_after();
+      }
+      for (int unit = unit0; unit < p.total_tiles; unit += unit_step, ++it) {
+        const int acs = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        if (CG == 2) mbar_wait_cluster(tmem_empty_bar(acs), aphase ^ 1, 570 + acs);
+        else mbar_wait(tmem_empty_bar(acs), aphase ^ 1, 570 + acs);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acs * kSmN);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(a_full(as), aph, 580 + as);
+          tc_fence_after();
+          for (int r = 0; r < 3; ++r) {
+            uint32_t bsm;
+            if (BRES) {
+              bsm = b_smem(r);
+            } else {
+              mbar_wait(b_full(bs), bph, 590 + bs);
+              tc_fence_after();
+              bsm = b_smem(bs);
+            }
+            if (elect_one()) {
+              const uint64_t adesc = make_kmajor_sw128_desc(a_smem(as) + r * (kTileW * 128));
+              const uint64_t bdesc = make_kmajor_sw128_desc(bsm);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16_cg<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | r | k) ? 1u : 0u);
+              if (!BRES) umma_commit_cg<CG>(b_empty(bs));
+              if (r == 2) {
+                umma_commit_cg<CG>(a_empty(as));
+                if (kc == kchunks - 1) umma_commit_cg<CG>(tmem_full_bar(acs));
+              }
+            }
+            __syncwarp();
+            if (!BRES) {
+              if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
+            }
+          }
+          if (++as == Cfg::kAStages) as = 0, aph ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue: all 8 warps work on EVERY tile -- warp (quad, half) drains TMEM
+    // lanes 32*quad.. for output channels 32*half..32*half+31 -- so an accumulator stage (192
+    // columns, only two fit in TMEM) is held for half as long as with one 4-warp group per tile
+    // (measured: the stage hold time, not the MMAs, paced the kernel).
+    const int half = (warp - kEpiWarp0) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;   // TMEM lane = slab pixel (jy, jx)
+    const int jy = row / kTileW, jx = row % kTileW;
+    const int ox = jx - 1;              // output column inside the tile
+    const bool col_ok = jx >= 1 && jx <= kSmOutW;
+    const bool issuer_warp = (warp == kEpiWarp0);
+    auto epi_barrier_all = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    // reflection-halo aliases of pixel (yy, xx), this warp's 32 channels
+    auto store_aliases_half = [&](int n, int yy0, int xx0, const uint32_t (&pk)[16]) {
+      const bool ya = (yy0 == 1) || (yy0 == p.out.H - 2), xa = (xx0 == 1) || (xx0 == p.out.W - 2);
+      if (!(ya || xa)) return;
+      for_each_halo_alias(yy0, xx0, p.out.H, p.out.W, [&](int yy, int xx) {
+        if (yy == yy0 && xx == xx0) return;
+        uint4* dst = reinterpret_cast<uint4*>(p.out.px(n, yy, xx) + 32 * half);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      });
+    };
+    for (int it = 0;; ++it) {
+      const long long unit_ll = (long long)unit0 + (long long)it * unit_step;
+      if (unit_ll >= p.total_tiles) break;
+      const TileCoord t = decode_tile_sm<CG>(p, (int)unit_ll, (int)cta_rank);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int y = t.y0 + jy, x = t.x0 + ox;
+      const bool valid = col_ok && (y < p.H) && (x < p.W) && (CG == 1 || t.n < p.N);
+      mbar_wait(tmem_full_bar(as), aphase, 600 + as);
+      tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kSmN + half * 32);
+      uint32_t pk[16];
+#pragma unroll
+      for (int cq = 0; cq < 2; ++cq) {
+        uint32_t a[16], b[16], c[16];
+        tmem_ld16(taddr + 0 * 64 + cq * 16, a);
+        tmem_ld16(taddr + 1 * 64 + cq * 16, b);
+        tmem_ld16(taddr + 2 * 64 + cq * 16, c);
+        tmem_ld_wait();
+        if (cq == 1) {
+          // all TMEM reads of this warp are complete: hand the accumulator stage back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(lead(tmem_empty_bar(as)));
+            else mbar_arrive(tmem_empty_bar(as));
+          }
+        }
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float lft = __shfl_up_sync(0xffffffffu, __uint_as_float(a[j]), 1);    // P[jx-1][s=0]
+          const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(c[j]), 1);  // P[jx+1][s=2]
+          float f = (lft + (__uint_as_float(b[j]) + s_bias[half * 32 + cq * 16 + j])) + rgt;
+          if (EPI == EPI_ACT_POOL) {
+            // 2x2 window: columns (jx odd, jx + 1), rows (jy even, jy + 1) = lanes l, l+1, l^16, ...;
+            // ReLU commutes with max and is applied by the conversion below
+            f = valid ? f : -INFINITY;
+            f = fmaxf(f, __shfl_down_sync(0xffffffffu, f, 1));
+            f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, 16));
+          }
+          v[j] = f;
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[cq * 8 + j] = pack16x2_relu<T16>(v[2 * j], v[2 * j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[cq * 8 + j] = pack16x2<T16>(v[2 * j], v[2 * j + 1]);
+        }
+      }
+      // staging buffer it & 1 was last read by the TMA store of tile it - 2
+      const uint32_t sbuf = store_base + (it & 1) * kSmStoreBytes;
+      if (issuer_warp) bulk_wait_read<1>();
+      epi_barrier_all();
+      int srow = jy * kSmOutW + ox;
+      bool writer = col_ok;
+      if (EPI == EPI_ACT_POOL) {
+        writer = col_ok && (jx & 1) && lane < 16;  // anchor of a 2x2 window
+        srow = (jy >> 1) * (kSmOutW / 2) + (ox >> 1);
+      }
+      if (writer) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t dst = sbuf + srow * 128 + (((4 * half + j) ^ (srow & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                       "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                       : "memory");
+        }
+      }
+      if (valid) {
+        if (EPI == EPI_ACT) {
+          store_aliases_half(t.n, y, x, pk);
+        } else if (EPI == EPI_ACT_UP2) {
+#pragma unroll
+          for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) store_aliases_half(t.n, 2 * y + aa, 2 * x + bb, pk);
+        } else if (EPI == EPI_ACT_POOL) {
+          if (writer) store_aliases_half(t.n, y >> 1, x >> 1, pk);
+        }
+      }
+      fence_async_smem();
+      epi_barrier_all();
+      if (issuer_warp && elect_one()) {
+        if (EPI == EPI_ACT_POOL) {
+          tma_store_4d(&tmap_out.m[0], sbuf, 0, t.x0 >> 1, t.y0 >> 1, t.n);
+        } else {
+          tma_store_4d(&tmap_out.m[0], sbuf, 0, t.x0, t.y0, t.n);
+          if (EPI == EPI_ACT_UP2) {
+            tma_store_4d(&tmap_out.m[1], sbuf, 0, t.x0, t.y0, t.n);
+            tma_store_4d(&tmap_out.m[2], sbuf, 0, t.x0, t.y0, t.n);
+            tma_store_4d(&tmap_out.m[3], sbuf, 0, t.x0, t.y0, t.n);
+          }
+        }
+        bulk_commit();
+      }
+    }
+    if (issuer_warp) bulk_wait_all();
+  }
+
+  __syncwarp();
+  tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) tmem_dealloc_cg<CG, Cfg::kTmemCols>(tmem_base);
 }
@@ -905,10 +1237,10 @@ __global__ void __launch_bounds__(kFirstPx)
     uint32_t pk[32];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      pk[j] = pack16x2<T16>(fmaxf(__uint_as_float(r0[2 * j]) + sbias[2 * j], 0.f),
-                            fmaxf(__uint_as_float(r0[2 * j + 1]) + sbias[2 * j + 1], 0.f));
-      pk[16 + j] = pack16x2<T16>(fmaxf(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j], 0.f),
-                                 fmaxf(__uint_as_float(r1[2 * j + 1]) + sbias[33 + 2 * j], 0.f));
+      pk[j] = pack16x2_relu<T16>(__uint_as_float(r0[2 * j]) + sbias[2 * j],
+                                 __uint_as_float(r0[2 * j + 1]) + sbias[2 * j + 1]);
+      pk[16 + j] = pack16x2_relu<T16>(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j],
+                                      __uint_as_float(r1[2 * j + 1]) + sbias[33 + 2 * j]);
     }
     // TMEM reads are complete (wait::ld); every thread passes two more block barriers before warp 0
     // overwrites the accumulator with the next tile
@@ -1132,10 +1464,10 @@ __global__ void __launch_bounds__(kF2Threads, 2)
       uint32_t pk[32];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        pk[j] = pack16x2<T16>(fmaxf(__uint_as_float(r0[2 * j]) + sbias[2 * j], 0.f),
-                              fmaxf(__uint_as_float(r0[2 * j + 1]) + sbias[2 * j + 1], 0.f));
-        pk[16 + j] = pack16x2<T16>(fmaxf(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j], 0.f),
-                                   fmaxf(__uint_as_float(r1[2 * j + 1]) + sbias[33 + 2 * j], 0.f));
+        pk[j] = pack16x2_relu<T16>(__uint_as_float(r0[2 * j]) + sbias[2 * j],
+                                   __uint_as_float(r0[2 * j + 1]) + sbias[2 * j + 1]);
+        pk[16 + j] = pack16x2_relu<T16>(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j],
+                                        __uint_as_float(r1[2 * j + 1]) + sbias[33 + 2 * j]);
       }
       // per-warp staging (two buffers): the store issued two tiles ago must have read its buffer
       bulk_wait_read<1>();
@@ -1506,11 +1838,96 @@ int launch_cg(const CUtensorMap& ma, const T16* wk, const ConvParams<T16>& p, in
               : launch_bn<T16, BN, BRES, 1>(ma, wk, p, epi, st);
 }
 
+// CCST_SMERGE=0 falls back to the tap-by-tap kernel for the 64-channel layers; =2 uses CTA pairs
+int smerge_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CCST_SMERGE");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+template <typename T16, int EPI, bool BRES, int CG>
+int launch_smerge_cfg(const CUtensorMap& ma, const T16* wk_sm, ConvParams<T16> p, cudaStream_t st) {
+  using Cfg = SmergeCfg<BRES, CG>;
+  CUtensorMap mb;
+  if (int e = make_weight_map(&mb, wk_sm, 3 * p.Cin, kSmN, Cfg::kBRows)) return e;
+  OutMaps mo;
+  memset(&mo, 0, sizeof(mo));
+  if (EPI == EPI_ACT) {
+    if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kSmOutW, kTileH)) return e;
+  } else if (EPI == EPI_ACT_POOL) {
+    if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kSmOutW / 2, kTileH / 2)) return e;
+  } else {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, kSmOutW, kTileH)) return e;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    CCST_CUDA(cudaFuncSetAttribute(conv_smerge_kernel<T16, EPI, BRES, CG>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  p.tiles_x = (p.W + kSmOutW - 1) / kSmOutW;
+  p.n_tiles = 1;
+  const int64_t m_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
+  CCST_CHECK_ARG(m_tiles < (1ll << 31), "conv_smerge: too many tiles");
+  p.m_tiles = (int)m_tiles;
+  const int64_t units = (m_tiles + CG - 1) / CG;
+  p.total_tiles = (int)units;
+  const int slots = sm_count() / CG;
+  const int grid = (int)(units < slots ? units : slots) * CG;
+  if (CG == 1) {
+    conv_smerge_kernel<T16, EPI, BRES, CG><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, mo, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreadsUmma);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    CCST_CUDA(cudaLaunchKernelEx(&cfg, conv_smerge_kernel<T16, EPI, BRES, CG>, ma, mb, mo, p));
+  }
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+template <typename T16, bool BRES, int CG>
+int launch_smerge_epi(const CUtensorMap& ma, const T16* wk_sm, const ConvParams<T16>& p, int epi,
+                      cudaStream_t st) {
+  switch (epi) {
+    case EPI_ACT:
+      return launch_smerge_cfg<T16, EPI_ACT, BRES, CG>(ma, wk_sm, p, st);
+    case EPI_ACT_UP2:
+      return launch_smerge_cfg<T16, EPI_ACT_UP2, BRES, CG>(ma, wk_sm, p, st);
+    case EPI_ACT_POOL:
+      return launch_smerge_cfg<T16, EPI_ACT_POOL, BRES, CG>(ma, wk_sm, p, st);
+    default:
+      set_error("conv_smerge: epilogue %d not available", epi);
+      return CCST_EINVAL;
+  }
+}
+
+template <typename T16>
+int launch_smerge(const CUtensorMap& ma, const T16* wk_sm, const ConvParams<T16>& p, int epi,
+                  cudaStream_t st) {
+  const bool pair = smerge_mode() == 2;
+  if (p.Cin == kBlockK)
+    return pair ? launch_smerge_epi<T16, true, 2>(ma, wk_sm, p, epi, st)
+                : launch_smerge_epi<T16, true, 1>(ma, wk_sm, p, epi, st);
+  return pair ? launch_smerge_epi<T16, false, 2>(ma, wk_sm, p, epi, st)
+              : launch_smerge_epi<T16, false, 1>(ma, wk_sm, p, epi, st);
+}
+
 }  // namespace
 
 template <typename T16>
-int launch_conv_umma(ActView<T16> in, const T16* wk, const float* bias, int Cout, int CoutPad,
-                     int relu, int epi, ActView<T16> out, float* out_nchw, cudaStream_t st) {
+int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const float* bias, int Cout,
+                     int CoutPad, int relu, int epi, ActView<T16> out, float* out_nchw,
+                     cudaStream_t st) {
   CCST_CHECK_ARG(in.C % kBlockK == 0, "conv_umma: Cin=%d must be a multiple of 64", in.C);
   int BN;
   if (epi == EPI_NCHW_F32) {
@@ -1560,6 +1977,7 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const float* bias, int Cout
       return CCST_OK;
     }
     case 64:
+      if (wk_sm && smerge_mode() != 0 && epi != EPI_NCHW_F32) return launch_smerge<T16>(ma, wk_sm, p, epi, st);
       // 64 -> 64 layers keep all 9 weight tiles resident in shared memory
       return in.C == kBlockK ? launch_cg<T16, 64, true>(ma, wk, p, epi, st)
                              : launch_cg<T16, 64, false>(ma, wk, p, epi, st);
@@ -1570,10 +1988,10 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const float* bias, int Cout
   }
 }
 template int launch_conv_umma<__nv_bfloat16>(ActView<__nv_bfloat16>, const __nv_bfloat16*,
-                                             const float*, int, int, int, int,
+                                             const __nv_bfloat16*, const float*, int, int, int, int,
                                              ActView<__nv_bfloat16>, float*, cudaStream_t);
-template int launch_conv_umma<__half>(ActView<__half>, const __half*, const float*, int, int, int,
-                                      int, ActView<__half>, float*, cudaStream_t);
+template int launch_conv_umma<__half>(ActView<__half>, const __half*, const __half*, const float*,
+                                      int, int, int, int, ActView<__half>, float*, cudaStream_t);
 
 template <typename T16>
 int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk, const float* bias,
