@@ -80,6 +80,8 @@ struct ConvLayer {
   float* w_ffma = nullptr;  // [9][cin][pad64]
   bf16* w_umma = nullptr;   // [pad_umma][9*cin] bf16
   __half* w_umma_h = nullptr;  // same, fp16
+  bf16* w_sm = nullptr;     // cout == 64: [192 = s*64 + co][3*cin = r*cin + c] (s-merged kernel)
+  __half* w_sm_h = nullptr;
   float* bias = nullptr;    // [pad64]
 };
 
@@ -137,6 +139,8 @@ void free_layer(ConvLayer& L) {
   cudaFree(L.w_ffma);
   cudaFree(L.w_umma);
   cudaFree(L.w_umma_h);
+  cudaFree(L.w_sm);
+  cudaFree(L.w_sm_h);
   cudaFree(L.bias);
   L = ConvLayer();
 }
@@ -172,6 +176,24 @@ int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b) 
   CCST_CUDA(cudaMemcpy(L.w_ffma, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(L.w_umma, wu.data(), wu.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (cout == 64) {
+    const int K3 = 3 * cin;
+    std::vector<bf16> sb((size_t)192 * K3);
+    std::vector<__half> sh((size_t)192 * K3);
+    for (int sc = 0; sc < 3; ++sc)
+      for (int o = 0; o < 64; ++o)
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < cin; ++c) {
+            const float v = w[((size_t)o * cin + c) * 9 + r * 3 + sc];
+            const size_t idx = (size_t)(sc * 64 + o) * K3 + (size_t)r * cin + c;
+            sb[idx] = __float2bfloat16(v);
+            sh[idx] = __float2half(v);
+          }
+    CCST_CUDA(cudaMalloc(&L.w_sm, sb.size() * sizeof(bf16)));
+    CCST_CUDA(cudaMalloc(&L.w_sm_h, sh.size() * sizeof(__half)));
+    CCST_CUDA(cudaMemcpy(L.w_sm, sb.data(), sb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    CCST_CUDA(cudaMemcpy(L.w_sm_h, sh.data(), sh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
   return CCST_OK;
 }
 
@@ -249,7 +271,9 @@ struct Pipe {
     return v;
   }
 
-  int conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* out_nchw);
+  // smerge_ok = false keeps a 64-channel layer on the tap-by-tap kernel (the un-fused pool path must
+  // produce the same bits as the fused one, which always uses that kernel)
+  int conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* out_nchw, bool smerge_ok = true);
 
   int first_launch(const float* img, int N, int H, int W);
   int first(const float* img, int N, int H, int W) {
@@ -272,7 +296,7 @@ struct Pipe {
       const double flops = 2.0 * 9 * L.cin * L.cout * (double)N * H * W;
       const double bytes = (double)cur.elems() * sizeof(T) + (double)out.elems() * sizeof(T);
       ProfScope ps(h, st, sizeof(T) == 2 ? 1 : 2, flops, bytes);
-      if (int e = conv(L, 1, epi, out, nullptr)) return e;
+      if (int e = conv(L, 1, epi, out, nullptr, !(pool_after && !fused_pool))) return e;
     }
     cur = out, cur_slot ^= 1;
     if (pool_after && !fused_pool) {
@@ -325,19 +349,21 @@ int Pipe<__half>::first_launch(const float* img, int N, int H, int W) {
   return launch_conv_first_umma<__half>(img, N, H, W, h->first_wk_h, h->first_b64, cur, st);
 }
 template <>
-int Pipe<float>::conv(const ConvLayer& L, int relu, int epi, ActView<float> out, float* out_nchw) {
+int Pipe<float>::conv(const ConvLayer& L, int relu, int epi, ActView<float> out, float* out_nchw,
+                      bool) {
   return launch_conv_ffma(cur, L.w_ffma, L.bias, L.cout, L.pad64, relu, epi, out, out_nchw, st);
 }
 template <>
-int Pipe<bf16>::conv(const ConvLayer& L, int relu, int epi, ActView<bf16> out, float* out_nchw) {
-  return launch_conv_umma<bf16>(cur, L.w_umma, L.bias, L.cout, L.pad_umma, relu, epi, out, out_nchw,
-                                st);
+int Pipe<bf16>::conv(const ConvLayer& L, int relu, int epi, ActView<bf16> out, float* out_nchw,
+                     bool smerge_ok) {
+  return launch_conv_umma<bf16>(cur, L.w_umma, smerge_ok ? L.w_sm : nullptr, L.bias, L.cout, L.pad_umma, relu, epi, out,
+                                out_nchw, st);
 }
 template <>
 int Pipe<__half>::conv(const ConvLayer& L, int relu, int epi, ActView<__half> out,
-                       float* out_nchw) {
-  return launch_conv_umma<__half>(cur, L.w_umma_h, L.bias, L.cout, L.pad_umma, relu, epi, out,
-                                  out_nchw, st);
+                       float* out_nchw, bool smerge_ok) {
+  return launch_conv_umma<__half>(cur, L.w_umma_h, smerge_ok ? L.w_sm_h : nullptr, L.bias, L.cout, L.pad_umma, relu, epi,
+                                  out, out_nchw, st);
 }
 
 int check_common(ccst_handle* h, int precision) {

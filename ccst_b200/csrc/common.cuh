@@ -136,17 +136,36 @@ __device__ __forceinline__ __half from_f32<__half>(float v) {
   return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
 }
 
+// Two fp32 -> one packed pair in ONE instruction (F2FP): round-to-nearest; fp16 saturates to
+// +-65504 instead of overflowing to inf (fp32 accumulators can exceed the fp16 range); the `_relu`
+// forms clamp negatives to zero in the same instruction (ReLU fused into the store conversion).
 template <typename T>
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi);
 template <>
 __device__ __forceinline__ uint32_t pack16x2<__nv_bfloat16>(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 template <>
 __device__ __forceinline__ uint32_t pack16x2<__half>(float lo, float hi) {
-  __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ uint32_t pack16x2_relu(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t pack16x2_relu<__nv_bfloat16>(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <>
+__device__ __forceinline__ uint32_t pack16x2_relu<__half>(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 }  // namespace ccst

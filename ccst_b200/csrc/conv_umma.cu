@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full_bar(s), 1);
-      mbar_init(tmem_empty_bar(s), 8 * CG);  // every epilogue warp of both CTAs
+      mbar_init(tmem_empty_bar(s), 4 * CG);
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
@@ -937,31 +937,19 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue: all 8 warps work on EVERY tile -- warp (quad, half) drains TMEM
-    // lanes 32*quad.. for output channels 32*half..32*half+31 -- so an accumulator stage (192
-    // columns, only two fit in TMEM) is held for half as long as with one 4-warp group per tile
-    // (measured: the stage hold time, not the MMAs, paced the kernel).
-    const int half = (warp - kEpiWarp0) >> 2;
+    // ===================== epilogue: two groups of 4 warps, group g drains accumulator stage g.
+    // (Letting all 8 warps share every tile -- half the channels each, to halve the time an
+    // accumulator stage is held -- was measured SLOWER: 0.59 -> 0.73 ms on dec8, the two 256-thread
+    // barriers per tile serialise the warps.)
+    const int grp = (warp - kEpiWarp0) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;   // TMEM lane = slab pixel (jy, jx)
     const int jy = row / kTileW, jx = row % kTileW;
     const int ox = jx - 1;              // output column inside the tile
     const bool col_ok = jx >= 1 && jx <= kSmOutW;
-    const bool issuer_warp = (warp == kEpiWarp0);
-    auto epi_barrier_all = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-    // reflection-halo aliases of pixel (yy, xx), this warp's 32 channels
-    auto store_aliases_half = [&](int n, int yy0, int xx0, const uint32_t (&pk)[16]) {
-      const bool ya = (yy0 == 1) || (yy0 == p.out.H - 2), xa = (xx0 == 1) || (xx0 == p.out.W - 2);
-      if (!(ya || xa)) return;
-      for_each_halo_alias(yy0, xx0, p.out.H, p.out.W, [&](int yy, int xx) {
-        if (yy == yy0 && xx == xx0) return;
-        uint4* dst = reinterpret_cast<uint4*>(p.out.px(n, yy, xx) + 32 * half);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-      });
-    };
-    for (int it = 0;; ++it) {
+    const bool issuer_warp = (quad == 0);
+    const uint32_t sbuf = store_base + grp * kSmStoreBytes;
+    for (int it = grp;; it += 2) {
       const long long unit_ll = (long long)unit0 + (long long)it * unit_step;
       if (unit_ll >= p.total_tiles) break;
       const TileCoord t = decode_tile_sm<CG>(p, (int)unit_ll, (int)cta_rank);
@@ -971,18 +959,17 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       const bool valid = col_ok && (y < p.H) && (x < p.W) && (CG == 1 || t.n < p.N);
       mbar_wait(tmem_full_bar(as), aphase, 600 + as);
       tc_fence_after();
-      const uint32_t taddr =
-          tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kSmN + half * 32);
-      uint32_t pk[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kSmN);
+      uint32_t pk[32];
 #pragma unroll
-      for (int cq = 0; cq < 2; ++cq) {
+      for (int cq = 0; cq < 4; ++cq) {
         uint32_t a[16], b[16], c[16];
         tmem_ld16(taddr + 0 * 64 + cq * 16, a);
         tmem_ld16(taddr + 1 * 64 + cq * 16, b);
         tmem_ld16(taddr + 2 * 64 + cq * 16, c);
         tmem_ld_wait();
-        if (cq == 1) {
-          // all TMEM reads of this warp are complete: hand the accumulator stage back
+        if (cq == 3) {
+          // all TMEM reads of this accumulator stage are complete: hand it back before the math
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -995,7 +982,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         for (int j = 0; j < 16; ++j) {
           const float lft = __shfl_up_sync(0xffffffffu, __uint_as_float(a[j]), 1);    // P[jx-1][s=0]
           const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(c[j]), 1);  // P[jx+1][s=2]
-          float f = (lft + (__uint_as_float(b[j]) + s_bias[half * 32 + cq * 16 + j])) + rgt;
+          float f = (lft + (__uint_as_float(b[j]) + s_bias[cq * 16 + j])) + rgt;
           if (EPI == EPI_ACT_POOL) {
             // 2x2 window: columns (jx odd, jx + 1), rows (jy even, jy + 1) = lanes l, l+1, l^16, ...;
             // ReLU commutes with max and is applied by the conversion below
@@ -1013,10 +1000,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           for (int j = 0; j < 8; ++j) pk[cq * 8 + j] = pack16x2<T16>(v[2 * j], v[2 * j + 1]);
         }
       }
-      // staging buffer it & 1 was last read by the TMA store of tile it - 2
-      const uint32_t sbuf = store_base + (it & 1) * kSmStoreBytes;
-      if (issuer_warp) bulk_wait_read<1>();
-      epi_barrier_all();
+      // the staging buffer about to be rewritten must have been read out by its TMA store
+      if (issuer_warp) bulk_wait_read<0>();
+      epi_barrier(grp);
       int srow = jy * kSmOutW + ox;
       bool writer = col_ok;
       if (EPI == EPI_ACT_POOL) {
@@ -1025,8 +1011,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       }
       if (writer) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t dst = sbuf + srow * 128 + (((4 * half + j) ^ (srow & 7)) << 4);
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = sbuf + srow * 128 + ((j ^ (srow & 7)) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
                        "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                        : "memory");
@@ -1034,18 +1020,18 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       }
       if (valid) {
         if (EPI == EPI_ACT) {
-          store_aliases_half(t.n, y, x, pk);
+          store_aliases(p.out, t.n, y, x, 0, pk);
         } else if (EPI == EPI_ACT_UP2) {
 #pragma unroll
           for (int aa = 0; aa < 2; ++aa)
 #pragma unroll
-            for (int bb = 0; bb < 2; ++bb) store_aliases_half(t.n, 2 * y + aa, 2 * x + bb, pk);
+            for (int bb = 0; bb < 2; ++bb) store_aliases(p.out, t.n, 2 * y + aa, 2 * x + bb, 0, pk);
         } else if (EPI == EPI_ACT_POOL) {
-          if (writer) store_aliases_half(t.n, y >> 1, x >> 1, pk);
+          if (writer) store_aliases(p.out, t.n, y >> 1, x >> 1, 0, pk);
         }
       }
       fence_async_smem();
-      epi_barrier_all();
+      epi_barrier(grp);
       if (issuer_warp && elect_one()) {
         if (EPI == EPI_ACT_POOL) {
           tma_store_4d(&tmap_out.m[0], sbuf, 0, t.x0 >> 1, t.y0 >> 1, t.n);
@@ -1977,7 +1963,12 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const flo
       return CCST_OK;
     }
     case 64:
-      if (wk_sm && smerge_mode() != 0 && epi != EPI_NCHW_F32) return launch_smerge<T16>(ma, wk_sm, p, epi, st);
+      // s-merged kernel for the plain / upsampling 64-channel layers (dec8 0.606 -> 0.591 ms, dec7
+      // 0.446 -> 0.422); with the fused max-pool its epilogue needs 4 shuffles per value and is
+      // slower than the tap-by-tap kernel (conv1_2 0.613 vs 0.672 ms), so that layer stays there
+      // unless CCST_SMERGE=3
+      if (wk_sm && smerge_mode() != 0 && (epi != EPI_ACT_POOL || smerge_mode() == 3))
+        return launch_smerge<T16>(ma, wk_sm, p, epi, st);
       // 64 -> 64 layers keep all 9 weight tiles resident in shared memory
       return in.C == kBlockK ? launch_cg<T16, 64, true>(ma, wk, p, epi, st)
                              : launch_cg<T16, 64, false>(ma, wk, p, epi, st);

@@ -50,9 +50,12 @@ int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st);
 
 // tcgen05 / TMA implicit GEMM (conv_umma.cu), T16 = __nv_bfloat16 or __half operands, fp32
 // accumulation in TMEM.  wk: [CoutPad][9*Cin] T16 K-major, bias fp32.
+// wk_sm (optional, Cout == 64 only): the same weights packed [192 = (s, co)][3*Cin = (r, c)] for the
+// s-merged kernel.
 template <typename T16>
-int launch_conv_umma(ActView<T16> in, const T16* wk, const float* bias, int Cout, int CoutPad,
-                     int relu, int epi, ActView<T16> out, float* out_nchw, cudaStream_t st);
+int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const float* bias, int Cout,
+                     int CoutPad, int relu, int epi, ActView<T16> out, float* out_nchw,
+                     cudaStream_t st);
 
 // conv1_1 (+ folded 1x1) on tcgen05: thread-built im2col rows (K = 27 padded to 32).
 // wk: [64][32] T16 K-major, bias fp32 [64].
