@@ -153,6 +153,21 @@ __device__ __forceinline__ uint32_t pack16x2<__half>(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// elementwise max of two packed pairs (exact: rounding is monotonic, so pooling may run on the
+// already-converted values and needs half as many shuffles as pooling in fp32)
+template <typename T>
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b);
+template <>
+__device__ __forceinline__ uint32_t max16x2<__half>(uint32_t a, uint32_t b) {
+  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <>
+__device__ __forceinline__ uint32_t max16x2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r =
+      __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 template <typename T>
 __device__ __forceinline__ uint32_t pack16x2_relu(float lo, float hi);
 template <>

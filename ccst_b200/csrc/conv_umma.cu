@@ -657,19 +657,18 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           uint32_t pk[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float v0 = __uint_as_float(r[2 * j]) + s_bias[co + 2 * j];
-            float v1 = __uint_as_float(r[2 * j + 1]) + s_bias[co + 2 * j + 1];
-            if (EPI == EPI_ACT_POOL) {
-              // 2x2 window = lanes {l, l^1, l^16, l^17}; out-of-image pixels never win the max
-              // (ReLU commutes with max and is applied by the conversion below)
-              v0 = valid ? v0 : -INFINITY;
-              v1 = valid ? v1 : -INFINITY;
-              v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 1));
-              v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
-              v0 = fmaxf(v0, __shfl_xor_sync(0xffffffffu, v0, 16));
-              v1 = fmaxf(v1, __shfl_xor_sync(0xffffffffu, v1, 16));
-            }
+            const float v0 = __uint_as_float(r[2 * j]) + s_bias[co + 2 * j];
+            const float v1 = __uint_as_float(r[2 * j + 1]) + s_bias[co + 2 * j + 1];
             pk[j] = p.relu ? pack16x2_relu<T16>(v0, v1) : pack16x2<T16>(v0, v1);
+            if (EPI == EPI_ACT_POOL) {
+              // 2x2 window = lanes {l, l^1, l^16, l^17}, pooled on the packed pairs (rounding and
+              // ReLU are monotonic, so max commutes with them: half the shuffles of fp32 pooling);
+              // out-of-image pixels contribute 0, the identity for post-ReLU values
+              uint32_t w = valid ? pk[j] : 0u;
+              w = max16x2<T16>(w, __shfl_xor_sync(0xffffffffu, w, 1));
+              w = max16x2<T16>(w, __shfl_xor_sync(0xffffffffu, w, 16));
+              pk[j] = w;
+            }
           }
           // stage the row (128 bytes = 8 chunks) with the 128-byte swizzle the TMA store expects
           int srow = row;
@@ -939,8 +938,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue: two groups of 4 warps, group g drains accumulator stage g.
     // (Letting all 8 warps share every tile -- half the channels each, to halve the time an
-    // accumulator stage is held -- was measured SLOWER: 0.59 -> 0.73 ms on dec8, the two 256-thread
-    // barriers per tile serialise the warps.)
+    // accumulator stage is held -- was measured SLOWER, 0.59 -> 0.73 ms on dec8, both with a joint
+    // 256-thread barrier per tile and with two fully independent half-channel groups.)
     const int grp = (warp - kEpiWarp0) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;   // TMEM lane = slab pixel (jy, jx)
@@ -982,22 +981,20 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         for (int j = 0; j < 16; ++j) {
           const float lft = __shfl_up_sync(0xffffffffu, __uint_as_float(a[j]), 1);    // P[jx-1][s=0]
           const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(c[j]), 1);  // P[jx+1][s=2]
-          float f = (lft + (__uint_as_float(b[j]) + s_bias[cq * 16 + j])) + rgt;
-          if (EPI == EPI_ACT_POOL) {
-            // 2x2 window: columns (jx odd, jx + 1), rows (jy even, jy + 1) = lanes l, l+1, l^16, ...;
-            // ReLU commutes with max and is applied by the conversion below
-            f = valid ? f : -INFINITY;
-            f = fmaxf(f, __shfl_down_sync(0xffffffffu, f, 1));
-            f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, 16));
-          }
-          v[j] = f;
+          v[j] = (lft + (__uint_as_float(b[j]) + s_bias[cq * 16 + j])) + rgt;
         }
-        if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) pk[cq * 8 + j] = pack16x2_relu<T16>(v[2 * j], v[2 * j + 1]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) pk[cq * 8 + j] = pack16x2<T16>(v[2 * j], v[2 * j + 1]);
+        for (int j = 0; j < 8; ++j) {
+          uint32_t w = p.relu ? pack16x2_relu<T16>(v[2 * j], v[2 * j + 1])
+                              : pack16x2<T16>(v[2 * j], v[2 * j + 1]);
+          if (EPI == EPI_ACT_POOL) {
+            // 2x2 window: columns (jx odd, jx + 1), rows (jy even, jy + 1) = lanes l, l+1, l^16, ...,
+            // pooled on the packed pairs (exact, see max16x2); invalid pixels contribute 0
+            w = valid ? w : 0u;
+            w = max16x2<T16>(w, __shfl_down_sync(0xffffffffu, w, 1));
+            w = max16x2<T16>(w, __shfl_xor_sync(0xffffffffu, w, 16));
+          }
+          pk[cq * 8 + j] = w;
         }
       }
       // the staging buffer about to be rewritten must have been read out by its TMA store
