@@ -82,6 +82,8 @@ struct ConvLayer {
   __half* w_umma_h = nullptr;  // same, fp16
   bf16* w_sm = nullptr;     // cout == 64: [192 = s*64 + co][3*cin = r*cin + c] (s-merged kernel)
   __half* w_sm_h = nullptr;
+  bf16* w_up = nullptr;     // layer after a nearest-x2 upsample: phase weights [4][cout][4*cin] (EPI_UPS)
+  __half* w_up_h = nullptr;
   float* bias = nullptr;    // [pad64]
 };
 
@@ -111,6 +113,7 @@ struct ccst_handle {
   float2* raw = nullptr;
   size_t raw_elems = 0;
   bool fuse_pool = true;
+  bool fuse_up = true;  // nearest-x2 upsample folded into the NEXT conv (EPI_UPS) instead of the store
   bool profiling = false;
   int prof_n = 0;
   ProfSlot prof[kMaxProf];
@@ -141,12 +144,14 @@ void free_layer(ConvLayer& L) {
   cudaFree(L.w_umma_h);
   cudaFree(L.w_sm);
   cudaFree(L.w_sm_h);
+  cudaFree(L.w_up);
+  cudaFree(L.w_up_h);
   cudaFree(L.bias);
   L = ConvLayer();
 }
 
 // OIHW fp32 host weights -> device packs
-int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b) {
+int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b, bool up_before = false) {
   free_layer(L);
   L.cin = cin, L.cout = cout;
   L.pad64 = (cout + 63) / 64 * 64;
@@ -193,6 +198,35 @@ int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b) 
     CCST_CUDA(cudaMalloc(&L.w_sm_h, sh.size() * sizeof(__half)));
     CCST_CUDA(cudaMemcpy(L.w_sm, sb.data(), sb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
     CCST_CUDA(cudaMemcpy(L.w_sm_h, sh.data(), sh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
+  if (up_before && cout % 64 == 0) {
+    // conv3x3(reflect_pad(nearest_up2(S))) as four 2x2 phase convolutions over S (net.py:10-11,
+    // 23-24, 30-31).  Output pixel (2y + a, 2x + b) reads U[2y + a + r - 1] = S[(2y + a + r - 1) >> 1]:
+    //   a = 0: r = 0 -> S[y - 1], r = 1, 2 -> S[y];   a = 1: r = 0, 1 -> S[y], r = 2 -> S[y + 1]
+    // (same in x), so the taps that land on the same source pixel are summed once here, in double,
+    // and rounded once to the operand type.  Reflection of U at the border = clamping S.
+    const int K4 = 4 * cin;
+    std::vector<bf16> ub((size_t)4 * cout * K4);
+    std::vector<__half> uh((size_t)4 * cout * K4);
+    static const int lo[2][2] = {{0, 1}, {0, 2}}, hi[2][2] = {{0, 2}, {1, 2}};  // [phase][d] -> taps lo..hi
+    for (int a = 0; a < 2; ++a)
+      for (int bb = 0; bb < 2; ++bb)
+        for (int o = 0; o < cout; ++o)
+          for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx)
+              for (int c = 0; c < cin; ++c) {
+                double acc = 0;
+                for (int r = lo[a][dy]; r <= hi[a][dy]; ++r)
+                  for (int sc = lo[bb][dx]; sc <= hi[bb][dx]; ++sc)
+                    acc += (double)w[((size_t)o * cin + c) * 9 + r * 3 + sc];
+                const size_t idx = ((size_t)(a * 2 + bb) * cout + o) * K4 + (size_t)(dy * 2 + dx) * cin + c;
+                ub[idx] = __float2bfloat16((float)acc);
+                uh[idx] = __float2half((float)acc);
+              }
+    CCST_CUDA(cudaMalloc(&L.w_up, ub.size() * sizeof(bf16)));
+    CCST_CUDA(cudaMalloc(&L.w_up_h, uh.size() * sizeof(__half)));
+    CCST_CUDA(cudaMemcpy(L.w_up, ub.data(), ub.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    CCST_CUDA(cudaMemcpy(L.w_up_h, uh.data(), uh.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
   return CCST_OK;
 }
@@ -263,6 +297,7 @@ struct Pipe {
   cudaStream_t st;
   int cur_slot = 0;
   ActView<T> cur;
+  bool up_pending = false;  // `cur` is a low-resolution map (replicate halo) awaiting its x2 upsample
 
   ActView<T> view(int slot, int N, int H, int W, int C) {
     ActView<T> v;
@@ -273,7 +308,8 @@ struct Pipe {
 
   // smerge_ok = false keeps a 64-channel layer on the tap-by-tap kernel (the un-fused pool path must
   // produce the same bits as the fused one, which always uses that kernel)
-  int conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* out_nchw, bool smerge_ok = true);
+  int conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* out_nchw, bool smerge_ok = true,
+           int halo_edge = 1);
 
   int first_launch(const float* img, int N, int H, int W);
   int first(const float* img, int N, int H, int W) {
@@ -288,17 +324,30 @@ struct Pipe {
   int step(const ConvLayer& L, bool pool_after, bool up_after) {
     const int N = cur.N, H = cur.H, W = cur.W;
     const bool fused_pool = pool_after && h->fuse_pool && sizeof(T) == 2;
-    int oh = H, ow = W, epi = EPI_ACT;
-    if (up_after) oh = 2 * H, ow = 2 * W, epi = EPI_ACT_UP2;
+    // tcgen05 path: a layer followed by `Upsample` stores its low-resolution output with a replicate
+    // halo and the NEXT conv consumes it through the phase-decomposed kernel (EPI_UPS): 16 instead of
+    // 36 tap-GEMMs per source pixel and no 4x-replicated activation in HBM.
+    const bool defer_up = up_after && h->fuse_up && sizeof(T) == 2 && !pool_after;
+    const bool ups = up_pending;
+    CCST_CHECK_ARG(!ups || (!pool_after && !up_after && L.w_up != nullptr),
+                   "upsample-fused conv cannot pool/upsample itself and needs phase weights");
+    int oh = H, ow = W, epi = EPI_ACT, halo_edge = 1;
+    if (ups) oh = 2 * H, ow = 2 * W, epi = EPI_UPS;
+    else if (defer_up) halo_edge = 0;
+    else if (up_after) oh = 2 * H, ow = 2 * W, epi = EPI_ACT_UP2;
     if (fused_pool) oh = (H + 1) / 2, ow = (W + 1) / 2, epi = EPI_ACT_POOL;
     ActView<T> out = view(cur_slot ^ 1, N, oh, ow, L.cout);
     {
-      const double flops = 2.0 * 9 * L.cin * L.cout * (double)N * H * W;
+      // executed FLOPs: the phase form runs 4 phases x 4 taps per SOURCE pixel (= 4 taps per output
+      // pixel) where the plain form runs 9 taps per output pixel
+      const double flops = ups ? 2.0 * 16 * L.cin * L.cout * (double)N * H * W
+                               : 2.0 * 9 * L.cin * L.cout * (double)N * H * W;
       const double bytes = (double)cur.elems() * sizeof(T) + (double)out.elems() * sizeof(T);
       ProfScope ps(h, st, sizeof(T) == 2 ? 1 : 2, flops, bytes);
-      if (int e = conv(L, 1, epi, out, nullptr, !(pool_after && !fused_pool))) return e;
+      if (int e = conv(L, 1, epi, out, nullptr, !(pool_after && !fused_pool), halo_edge)) return e;
     }
     cur = out, cur_slot ^= 1;
+    up_pending = defer_up;
     if (pool_after && !fused_pool) {
       ActView<T> po = view(cur_slot ^ 1, N, (H + 1) / 2, (W + 1) / 2, L.cout);
       ProfScope ps(h, st, 3, 0, (double)(cur.elems() + po.elems()) * sizeof(T));
@@ -350,20 +399,20 @@ int Pipe<__half>::first_launch(const float* img, int N, int H, int W) {
 }
 template <>
 int Pipe<float>::conv(const ConvLayer& L, int relu, int epi, ActView<float> out, float* out_nchw,
-                      bool) {
+                      bool, int) {
   return launch_conv_ffma(cur, L.w_ffma, L.bias, L.cout, L.pad64, relu, epi, out, out_nchw, st);
 }
 template <>
 int Pipe<bf16>::conv(const ConvLayer& L, int relu, int epi, ActView<bf16> out, float* out_nchw,
-                     bool smerge_ok) {
-  return launch_conv_umma<bf16>(cur, L.w_umma, smerge_ok ? L.w_sm : nullptr, L.bias, L.cout, L.pad_umma, relu, epi, out,
-                                out_nchw, st);
+                     bool smerge_ok, int halo_edge) {
+  return launch_conv_umma<bf16>(cur, L.w_umma, smerge_ok ? L.w_sm : nullptr, L.w_up, L.bias, L.cout,
+                                L.pad_umma, relu, epi, out, out_nchw, halo_edge, st);
 }
 template <>
 int Pipe<__half>::conv(const ConvLayer& L, int relu, int epi, ActView<__half> out,
-                       float* out_nchw, bool smerge_ok) {
-  return launch_conv_umma<__half>(cur, L.w_umma_h, smerge_ok ? L.w_sm_h : nullptr, L.bias, L.cout, L.pad_umma, relu, epi,
-                                  out, out_nchw, st);
+                       float* out_nchw, bool smerge_ok, int halo_edge) {
+  return launch_conv_umma<__half>(cur, L.w_umma_h, smerge_ok ? L.w_sm_h : nullptr, L.w_up_h, L.bias,
+                                  L.cout, L.pad_umma, relu, epi, out, out_nchw, halo_edge, st);
 }
 
 int check_common(ccst_handle* h, int precision) {
@@ -464,6 +513,8 @@ extern "C" ccst_handle* ccst_create(int device) {
   h->device = device;
   const char* fp = getenv("CCST_FUSE_POOL");
   if (fp && fp[0] == '0') h->fuse_pool = false;
+  const char* fu = getenv("CCST_FUSE_UP");
+  if (fu && fu[0] == '0') h->fuse_up = false;
   return h;
 }
 
@@ -537,7 +588,8 @@ extern "C" int ccst_set_decoder_weights(ccst_handle* h, const float* const* w,
   CCST_CUDA(cudaSetDevice(h->device));
   for (int i = 0; i < kDecLayers; ++i) {
     CCST_CHECK_ARG(w[i] && b[i], "ccst_set_decoder_weights: null tensor %d", i);
-    if (int e = pack_layer(h->dec[i], kDecCh[i][0], kDecCh[i][1], w[i], b[i])) return e;
+    if (int e = pack_layer(h->dec[i], kDecCh[i][0], kDecCh[i][1], w[i], b[i], i > 0 && kDecUpAfter[i - 1]))
+      return e;
   }
   h->dec_ready = true;
   return CCST_OK;
@@ -642,10 +694,12 @@ int debug_conv(ccst_handle* h, const float* d_in, int N, int H, int W, int Cin, 
   if (mode == 1) oh = 2 * H, ow = 2 * W, epi = EPI_ACT_UP2;
   if (mode == 2) oh = (H + 1) / 2, ow = (W + 1) / 2, epi = EPI_ACT_POOL;
   if (mode == 3) epi = EPI_NCHW_F32;
+  if (mode == 4) oh = 2 * H, ow = 2 * W, epi = EPI_UPS;  // upsample BEFORE the conv, fused
+  const int in_edge = mode == 4 ? 0 : 1;
   T *bin = nullptr, *bout = nullptr, *btmp = nullptr;
   CCST_CUDA(cudaMalloc(&bin, act_bytes(N, H, W, Cin, sizeof(T))));
   ActView<T> vin{bin, N, H, W, Cin};
-  int rc = launch_nhwc_to_act<T>(d_in, vin, st);
+  int rc = launch_nhwc_to_act<T>(d_in, vin, st, in_edge);
   ActView<T> vout{nullptr, N, oh, ow, L.cout};
   if (rc == CCST_OK && mode != 3) {
     if (cudaMalloc(&bout, act_bytes(N, oh, ow, L.cout, sizeof(T))) != cudaSuccess) rc = CCST_ECUDA;
@@ -683,12 +737,14 @@ extern "C" int ccst_debug_conv3x3(ccst_handle* h, const float* d_in, int N, int 
                                   int mode, float* d_out, int precision, void* stream) {
   if (int e = check_common(h, precision)) return e;
   CCST_CHECK_ARG(d_in && d_out && h_weight && h_bias, "ccst_debug_conv3x3: null pointer");
-  CCST_CHECK_ARG(N >= 1 && H >= 2 && W >= 2 && Cin % 64 == 0 && mode >= 0 && mode <= 3,
+  CCST_CHECK_ARG(N >= 1 && H >= 2 && W >= 2 && Cin % 64 == 0 && mode >= 0 && mode <= 4,
                  "ccst_debug_conv3x3: bad shape/mode");
+  CCST_CHECK_ARG(mode != 4 || precision != CCST_PREC_FP32,
+                 "ccst_debug_conv3x3: the upsample-fused conv exists on the tcgen05 path only");
   CCST_CHECK_ARG(mode == 3 ? Cout <= 16 : Cout % 64 == 0, "ccst_debug_conv3x3: bad Cout");
   CCST_CHECK_ARG(mode != 2 || relu, "ccst_debug_conv3x3: pool mode requires relu");
   ConvLayer L;
-  int rc = pack_layer(L, Cin, Cout, h_weight, h_bias);
+  int rc = pack_layer(L, Cin, Cout, h_weight, h_bias, mode == 4);
   if (rc == CCST_OK) {
     if (precision == CCST_PREC_BF16)
       rc = debug_conv<bf16>(h, d_in, N, H, W, Cin, Cout, L, relu, mode, d_out, (cudaStream_t)stream);

@@ -102,16 +102,19 @@ struct ActView {
 };
 
 // Calls f(yy, xx) for (y, x) itself and for every halo position that mirrors it.
+// edge = 1: reflection halo (halo(-1) = interior(1), the layout every 3x3 reflect-pad conv reads);
+// edge = 0: replicate halo (halo(-1) = interior(0)), written by the layers whose consumer is the
+// fused nearest-x2-upsample conv: reflect(upsample(S))[-1] = upsample(S)[1] = S[0].
 template <typename F>
-__device__ __forceinline__ void for_each_halo_alias(int y, int x, int H, int W, F&& f) {
+__device__ __forceinline__ void for_each_halo_alias(int y, int x, int H, int W, F&& f, int edge = 1) {
   int ys[3], xs[3];
   int ny = 0, nx = 0;
   ys[ny++] = y;
-  if (y == 1) ys[ny++] = -1;
-  if (y == H - 2) ys[ny++] = H;
+  if (y == edge) ys[ny++] = -1;
+  if (y == H - 1 - edge) ys[ny++] = H;
   xs[nx++] = x;
-  if (x == 1) xs[nx++] = -1;
-  if (x == W - 2) xs[nx++] = W;
+  if (x == edge) xs[nx++] = -1;
+  if (x == W - 1 - edge) xs[nx++] = W;
   for (int i = 0; i < ny; ++i)
     for (int j = 0; j < nx; ++j) f(ys[i], xs[j]);
 }

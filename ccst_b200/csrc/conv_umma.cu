@@ -53,7 +53,7 @@ constexpr int kEpiWarp0 = 4;
 //   B      : BRES = false: ring of kBStages weight tiles {64 k, BN}, one per tap and channel chunk;
 //            BRES = true (9*Cin*BN*2 bytes fit): all weights loaded once per CTA and kept resident.
 //   store  : kStoreBufs x 16 KiB staging tiles for the TMA store of the epilogue.
-template <int BN, bool BRES, int CG>
+template <int BN, bool BRES, int CG, bool UPS = false>
 struct UmmaCfg {
   static constexpr int kSlabRows = kTileH + 2;
   static constexpr int kASlabBytes = kSlabRows * kTileW * 128;  // 20480
@@ -63,9 +63,10 @@ struct UmmaCfg {
   static constexpr int kBRows = BN / CG;
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kBStride = (kBBytes + 1023) / 1024 * 1024;
+  static constexpr int kTaps = UPS ? 4 : 9;  // UPS: 2x2 phase convolution (see EPI_UPS)
   static constexpr int kAStages =
-      CG == 2 ? (BRES ? 6 : (BN >= 256 ? 4 : 5)) : (BRES ? (BN >= 64 ? 5 : 6) : (BN >= 256 ? 3 : 4));
-  static constexpr int kBStages = BRES ? 9 /* resident: 9 taps x (Cin == 64) */
+      CG == 2 ? (BRES ? 6 : (BN >= 256 ? 4 : 5)) : (BRES ? (BN >= 64 ? (UPS ? 6 : 5) : 6) : (BN >= 256 ? 3 : 4));
+  static constexpr int kBStages = BRES ? kTaps /* resident: all taps x (Cin == 64) */
                                   : CG == 2 ? (BN >= 256 ? 6 : 9)
                                             : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 9));
   static constexpr int kStoreBufs = 2;  // one staging tile per epilogue group
@@ -90,6 +91,7 @@ struct ConvParams {
   int tiles_x, tiles_y, n_tiles, m_tiles;  // m_tiles = pixel tiles (N * tiles_y * tiles_x)
   int total_tiles;                        // work units: (pixel tile | pair of pixel tiles) x n_tiles
   int relu;
+  int halo_edge;  // halo written around `out`: 1 reflection, 0 replicate (for_each_halo_alias)
   const float* bias;
   ActView<T16> out;
   float* out_nchw;
@@ -358,16 +360,21 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 }
 
 struct TileCoord {
-  int n, y0, x0, nt;
+  int n, y0, x0, nt, ph;
 };
 // work unit -> (N tile, pixel tile of CTA `rank` of the pair).  A pair takes two consecutive pixel
 // tiles; when the number of pixel tiles is odd the last pair's second tile is a dummy at image
 // index n = N: its TMA loads are out of bounds (zero fill) and its stores are clipped away.
-template <int CG, typename P>
+// UPS: the four output phases (a, b) of one pixel tile are consecutive units, so the CTAs that run
+// them concurrently share the tile's input slabs in L2.
+template <int CG, bool UPS = false, typename P>
 __device__ __forceinline__ TileCoord decode_tile(const P& p, int unit, int rank) {
   TileCoord t;
   t.nt = unit % p.n_tiles;
-  int m = (unit / p.n_tiles) * CG + rank;
+  int u = unit / p.n_tiles;
+  t.ph = 0;
+  if (UPS) t.ph = u & 3, u >>= 2;
+  int m = u * CG + rank;
   if (CG == 2 && m >= p.m_tiles) {
     t.x0 = 0, t.y0 = 0, t.n = p.N;
     return t;
@@ -424,8 +431,8 @@ struct OutMaps {
 // out through the TMA store of the staged tile
 template <typename T16>
 __device__ __forceinline__ void store_aliases(const ActView<T16>& out, int n, int y, int x, int co,
-                                              const uint32_t (&pk)[32]) {
-  const bool ya = (y == 1) || (y == out.H - 2), xa = (x == 1) || (x == out.W - 2);
+                                              const uint32_t (&pk)[32], int edge = 1) {
+  const bool ya = (y == edge) || (y == out.H - 1 - edge), xa = (x == edge) || (x == out.W - 1 - edge);
   if (!(ya || xa)) return;
   for_each_halo_alias(y, x, out.H, out.W, [&](int yy, int xx) {
     if (yy == y && xx == x) return;
@@ -433,7 +440,7 @@ __device__ __forceinline__ void store_aliases(const ActView<T16>& out, int n, in
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-  });
+  }, edge);
 }
 
 template <typename T16, int BN, int EPI, bool BRES, int CG>
@@ -441,7 +448,12 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ OutMaps tmap_out, ConvParams<T16> p) {
-  using Cfg = UmmaCfg<BN, BRES, CG>;
+  // UPS (EPI_UPS): `p.H x p.W` is the low-resolution input S (replicate halo); output phase (a, b)
+  // holds pixels (2y + a, 2x + b) = sum over the 2x2 source window S[y + a - 1 + dy][x + b - 1 + dx]
+  // with the 3x3 taps that fall on the same source pixel pre-summed (api.cu pack_layer).
+  constexpr bool UPS = (EPI == EPI_UPS);
+  constexpr int kTR = UPS ? 2 : 3, kTS = UPS ? 2 : 3;
+  using Cfg = UmmaCfg<BN, BRES, CG, UPS>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte aligned bases (the dynamic shared window starts at the same
   // offset in both CTAs of a pair, so the carve-up below is identical in both)
@@ -506,38 +518,43 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     // ===================== TMA producer (whole warp converged, one lane issues) ==============
     const int b_row0 = (int)cta_rank * Cfg::kBRows;  // this CTA's half of the N tile
     if (BRES) {
-      // all 9 weight tiles of this (Cin == 64) layer, once
+      // all weight tiles of this (Cin == 64) layer, once.  UPS: the grid is a multiple of 4 (or has
+      // one unit per CTA), so every unit of this CTA has the same phase and only its taps are kept.
       if (elect_one()) {
-        if (leader) mbar_expect_tx(bres_bar, CG * 9 * Cfg::kBBytes);
+        if (leader) mbar_expect_tx(bres_bar, CG * Cfg::kTaps * Cfg::kBBytes);
         const uint32_t bar = lead(bres_bar);
-        for (int tap = 0; tap < 9; ++tap)
-          tma_load_2d_cg<CG>(b_smem(tap), &tmap_b, bar, tap * p.Cin, b_row0);
+        const int row_ph = UPS ? (unit0 & 3) * p.CoutPad : 0;
+        for (int tap = 0; tap < Cfg::kTaps; ++tap)
+          tma_load_2d_cg<CG>(b_smem(tap), &tmap_b, bar, tap * p.Cin, row_ph + b_row0);
       }
       __syncwarp();
     }
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     for (int unit = unit0; unit < p.total_tiles; unit += unit_step) {
-      const TileCoord t = decode_tile<CG>(p, unit, (int)cta_rank);
+      const TileCoord t = decode_tile<CG, UPS>(p, unit, (int)cta_rank);
+      const int xs0 = t.x0 + (UPS ? (t.ph & 1) : 0);
+      const int b_row = (UPS ? t.ph * p.CoutPad : 0) + t.nt * BN + b_row0;
       for (int kc = 0; kc < kchunks; ++kc) {
-        for (int s = 0; s < 3; ++s) {
+        for (int s = 0; s < kTS; ++s) {
           mbar_wait(a_empty(as), aph ^ 1, 100 + as);
           if (elect_one()) {
             if (leader) mbar_expect_tx(a_full(as), CG * Cfg::kASlabBytes);
             // interior pixel (y, x) is stored at (y+1, x+1): the slab for filter column s starts at
-            // padded (y0, x0 + s) and spans the 10 rows needed by r = 0..2
-            tma_load_4d_cg<CG>(a_smem(as), &tmap_a, lead(a_full(as)), kc * kBlockK, t.x0 + s, t.y0,
+            // padded (y0, x0 + s) and spans the 10 rows needed by r = 0..2 (UPS: source column
+            // x + b - 1 + s, rows a + r of the slab)
+            tma_load_4d_cg<CG>(a_smem(as), &tmap_a, lead(a_full(as)), kc * kBlockK, xs0 + s, t.y0,
                                t.n);
           }
           __syncwarp();
           if (++as == Cfg::kAStages) as = 0, aph ^= 1;
           if (!BRES) {
-            for (int r = 0; r < 3; ++r) {
+            for (int r = 0; r < kTR; ++r) {
               mbar_wait(b_empty(bs), bph ^ 1, 150 + bs);
               if (elect_one()) {
                 if (leader) mbar_expect_tx(b_full(bs), CG * Cfg::kBBytes);
                 tma_load_2d_cg<CG>(b_smem(bs), &tmap_b, lead(b_full(bs)),
-                                   (r * 3 + s) * p.Cin + kc * kBlockK, t.nt * BN + b_row0);
+                                   (r * kTS + s) * p.Cin + kc * kBlockK, b_row);
               }
               __syncwarp();
               if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
@@ -564,14 +581,16 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         else mbar_wait(tmem_empty_bar(acs), aphase ^ 1, 200 + acs);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acs * BN);
+        // UPS: row phase a of this unit shifts the slab rows of the two taps to a + r
+        const int row_shift = UPS ? (((unit / p.n_tiles) & 3) >> 1) : 0;
         for (int kc = 0; kc < kchunks; ++kc) {
-          for (int s = 0; s < 3; ++s) {
+          for (int s = 0; s < kTS; ++s) {
             mbar_wait(a_full(as), aph, 300 + as);
             tc_fence_after();
-            for (int r = 0; r < 3; ++r) {
+            for (int r = 0; r < kTR; ++r) {
               uint32_t bsm;
               if (BRES) {
-                bsm = b_smem(r * 3 + s);
+                bsm = b_smem(r * kTS + s);
               } else {
                 mbar_wait(b_full(bs), bph, 350 + bs);
                 tc_fence_after();
@@ -579,7 +598,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
               }
               if (elect_one()) {
                 // tap (r,s): slab shifted by r tile rows (16 px * 128 B = 2048 B, swizzle-phase neutral)
-                const uint64_t adesc = make_kmajor_sw128_desc(a_smem(as) + r * (kTileW * 128));
+                const uint64_t adesc =
+                    make_kmajor_sw128_desc(a_smem(as) + (r + row_shift) * (kTileW * 128));
                 const uint64_t bdesc = make_kmajor_sw128_desc(bsm);
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
@@ -588,9 +608,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
                                   (kc | s | r | k) ? 1u : 0u);
                 }
                 if (!BRES) umma_commit_cg<CG>(b_empty(bs));  // frees the weight tile when these MMAs retire
-                if (r == 2) {
-                  umma_commit_cg<CG>(a_empty(as));  // ... and the slab after its third tap
-                  if (kc == kchunks - 1 && s == 2) umma_commit_cg<CG>(tmem_full_bar(acs));
+                if (r == kTR - 1) {
+                  umma_commit_cg<CG>(a_empty(as));  // ... and the slab after its last tap
+                  if (kc == kchunks - 1 && s == kTS - 1) umma_commit_cg<CG>(tmem_full_bar(acs));
                 }
               }
               __syncwarp();
@@ -617,7 +637,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     for (int it = grp;; it += 2) {
       const long long unit_ll = (long long)unit0 + (long long)it * unit_step;
       if (unit_ll >= p.total_tiles) break;
-      const TileCoord t = decode_tile<CG>(p, (int)unit_ll, (int)cta_rank);
+      const TileCoord t = decode_tile<CG, UPS>(p, (int)unit_ll, (int)cta_rank);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int y = t.y0 + py, x = t.x0 + px;
@@ -688,7 +708,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           }
           if (valid) {
             if (EPI == EPI_ACT) {
-              store_aliases(p.out, t.n, y, x, co, pk);
+              store_aliases(p.out, t.n, y, x, co, pk, p.halo_edge);
+            } else if (EPI == EPI_UPS) {
+              store_aliases(p.out, t.n, 2 * y + (t.ph >> 1), 2 * x + (t.ph & 1), co, pk);
             } else if (EPI == EPI_ACT_UP2) {
 #pragma unroll
               for (int a = 0; a < 2; ++a)
@@ -705,6 +727,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
             // dummy tile of an odd pair entirely: n = N is out of bounds)
             if (EPI == EPI_ACT_POOL) {
               tma_store_4d(&tmap_out.m[0], sbuf, co, t.x0 >> 1, t.y0 >> 1, t.n);
+            } else if (EPI == EPI_UPS) {
+              tma_store_4d(&tmap_out.m[t.ph], sbuf, co, t.x0, t.y0, t.n);
             } else {
               tma_store_4d(&tmap_out.m[0], sbuf, co, t.x0, t.y0, t.n);
               if (EPI == EPI_ACT_UP2) {
@@ -1017,7 +1041,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       }
       if (valid) {
         if (EPI == EPI_ACT) {
-          store_aliases(p.out, t.n, y, x, 0, pk);
+          store_aliases(p.out, t.n, y, x, 0, pk, p.halo_edge);
         } else if (EPI == EPI_ACT_UP2) {
 #pragma unroll
           for (int aa = 0; aa < 2; ++aa)
@@ -1743,16 +1767,17 @@ int make_weight_map(CUtensorMap* m, const T16* wk, int K, int CoutPad, int BN) {
 
 template <typename T16, int BN, int EPI, bool BRES, int CG>
 int launch_cfg(const CUtensorMap& ma, const T16* wk, ConvParams<T16> p, cudaStream_t st) {
-  using Cfg = UmmaCfg<BN, BRES, CG>;
+  constexpr bool UPS = (EPI == EPI_UPS);
+  using Cfg = UmmaCfg<BN, BRES, CG, UPS>;
   CUtensorMap mb;
-  if (int e = make_weight_map(&mb, wk, 9 * p.Cin, p.CoutPad, Cfg::kBRows)) return e;
+  if (int e = make_weight_map(&mb, wk, Cfg::kTaps * p.Cin, (UPS ? 4 : 1) * p.CoutPad, Cfg::kBRows)) return e;
   OutMaps mo;
   memset(&mo, 0, sizeof(mo));
   if (EPI == EPI_ACT) {
     if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kTileW, kTileH)) return e;
   } else if (EPI == EPI_ACT_POOL) {
     if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kTileW / 2, kTileH / 2)) return e;
-  } else if (EPI == EPI_ACT_UP2) {
+  } else if (EPI == EPI_ACT_UP2 || EPI == EPI_UPS) {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
         if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, kTileW, kTileH)) return e;
@@ -1763,9 +1788,11 @@ int launch_cfg(const CUtensorMap& ma, const T16* wk, ConvParams<T16> p, cudaStre
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  const int64_t units = ((int64_t)p.m_tiles + CG - 1) / CG * p.n_tiles;
+  const int64_t units = ((int64_t)p.m_tiles + CG - 1) / CG * p.n_tiles * (UPS ? 4 : 1);
+  CCST_CHECK_ARG(units < (1ll << 31), "conv_umma: too many tiles");
   p.total_tiles = (int)units;
-  const int slots = sm_count() / CG;  // persistent: one CTA (or CTA pair) per SM (pair)
+  int slots = sm_count() / CG;  // persistent: one CTA (or CTA pair) per SM (pair)
+  if (UPS && BRES) slots &= ~3;  // resident weights of ONE phase per CTA: unit stride % 4 == 0
   const int grid = (int)(units < slots ? units : slots) * CG;
   if (CG == 1) {
     conv_umma_kernel<T16, BN, EPI, BRES, CG><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, mo, p);
@@ -1793,6 +1820,8 @@ int launch_bn(const CUtensorMap& ma, const T16* wk, const ConvParams<T16>& p, in
       return launch_cfg<T16, BN, EPI_ACT_UP2, BRES, CG>(ma, wk, p, st);
     case EPI_ACT_POOL:
       return launch_cfg<T16, BN, EPI_ACT_POOL, BRES, CG>(ma, wk, p, st);
+    case EPI_UPS:
+      return launch_cfg<T16, BN, EPI_UPS, BRES, CG>(ma, wk, p, st);
     default:
       set_error("conv_umma: epilogue %d not available for BN=%d", epi, BN);
       return CCST_EINVAL;
@@ -1908,9 +1937,9 @@ int launch_smerge(const CUtensorMap& ma, const T16* wk_sm, const ConvParams<T16>
 }  // namespace
 
 template <typename T16>
-int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const float* bias, int Cout,
-                     int CoutPad, int relu, int epi, ActView<T16> out, float* out_nchw,
-                     cudaStream_t st) {
+int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16* wk_up,
+                     const float* bias, int Cout, int CoutPad, int relu, int epi, ActView<T16> out,
+                     float* out_nchw, int halo_edge, cudaStream_t st) {
   CCST_CHECK_ARG(in.C % kBlockK == 0, "conv_umma: Cin=%d must be a multiple of 64", in.C);
   int BN;
   if (epi == EPI_NCHW_F32) {
@@ -1933,11 +1962,29 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const flo
   p.m_tiles = (int)m_tiles;
   p.total_tiles = 0;  // set per kernel variant (tiles or tile pairs)
   p.relu = relu;
+  p.halo_edge = halo_edge;
   p.bias = bias;
   p.out = out;
   p.out_nchw = out_nchw;
+  CCST_CHECK_ARG(halo_edge == 1 || (halo_edge == 0 && epi == EPI_ACT),
+                 "conv_umma: a replicate halo is only written by the plain epilogue");
   CUtensorMap ma;
   if (int e = make_act_map(&ma, in)) return e;
+  if (epi == EPI_UPS) {
+    // fused nearest-x2 upsample: `in` is the low-resolution map, `out` twice its size
+    CCST_CHECK_ARG(wk_up != nullptr, "conv_umma: EPI_UPS needs the phase-packed weights");
+    CCST_CHECK_ARG(out.H == 2 * in.H && out.W == 2 * in.W, "conv_umma: EPI_UPS output must be 2x the input");
+    CCST_CHECK_ARG(m_tiles * p.n_tiles * 4 < (1ll << 31), "conv_umma: too many tiles");
+    switch (BN) {
+      case 64:
+        return in.C == kBlockK ? launch_cg<T16, 64, true>(ma, wk_up, p, epi, st)
+                               : launch_cg<T16, 64, false>(ma, wk_up, p, epi, st);
+      case 128:
+        return launch_cg<T16, 128, false>(ma, wk_up, p, epi, st);
+      default:
+        return launch_cg<T16, 256, false>(ma, wk_up, p, epi, st);
+    }
+  }
   switch (BN) {
     case 16: {
       // the last decoder conv (64 -> 3)
@@ -1976,10 +2023,12 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const flo
   }
 }
 template int launch_conv_umma<__nv_bfloat16>(ActView<__nv_bfloat16>, const __nv_bfloat16*,
-                                             const __nv_bfloat16*, const float*, int, int, int, int,
-                                             ActView<__nv_bfloat16>, float*, cudaStream_t);
-template int launch_conv_umma<__half>(ActView<__half>, const __half*, const __half*, const float*,
-                                      int, int, int, int, ActView<__half>, float*, cudaStream_t);
+                                             const __nv_bfloat16*, const __nv_bfloat16*, const float*,
+                                             int, int, int, int, ActView<__nv_bfloat16>, float*, int,
+                                             cudaStream_t);
+template int launch_conv_umma<__half>(ActView<__half>, const __half*, const __half*, const __half*,
+                                      const float*, int, int, int, int, ActView<__half>, float*, int,
+                                      cudaStream_t);
 
 template <typename T16>
 int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk, const float* bias,

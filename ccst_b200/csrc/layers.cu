@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restric
 
 template <typename T>
 __global__ void __launch_bounds__(256) nhwc_to_act_kernel(const float* __restrict__ in,
-                                                          ActView<T> out) {
+                                                          ActView<T> out, int edge) {
   const size_t total = (size_t)out.N * out.H * out.W * out.C;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
     const int c = (int)(i % out.C);
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(256) nhwc_to_act_kernel(const float* __restric
     const int y = (int)(p % out.H);
     const int n = (int)(p / out.H);
     const T v = from_f32<T>(in[i]);
-    for_each_halo_alias(y, x, out.H, out.W, [&](int yy, int xx) { out.px(n, yy, xx)[c] = v; });
+    for_each_halo_alias(y, x, out.H, out.W, [&](int yy, int xx) { out.px(n, yy, xx)[c] = v; }, edge);
   }
 }
 
@@ -748,15 +748,15 @@ template int launch_nchw_to_act<__nv_bfloat16>(const float*, ActView<__nv_bfloat
 template int launch_nchw_to_act<__half>(const float*, ActView<__half>, cudaStream_t);
 
 template <typename T>
-int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st) {
+int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st, int halo_edge) {
   const size_t total = (size_t)out.N * out.H * out.W * out.C;
-  nhwc_to_act_kernel<T><<<ew_grid(total), 256, 0, st>>>(in_nhwc, out);
+  nhwc_to_act_kernel<T><<<ew_grid(total), 256, 0, st>>>(in_nhwc, out, halo_edge);
   CCST_LAUNCHED();
   return CCST_OK;
 }
-template int launch_nhwc_to_act<float>(const float*, ActView<float>, cudaStream_t);
-template int launch_nhwc_to_act<__nv_bfloat16>(const float*, ActView<__nv_bfloat16>, cudaStream_t);
-template int launch_nhwc_to_act<__half>(const float*, ActView<__half>, cudaStream_t);
+template int launch_nhwc_to_act<float>(const float*, ActView<float>, cudaStream_t, int);
+template int launch_nhwc_to_act<__nv_bfloat16>(const float*, ActView<__nv_bfloat16>, cudaStream_t, int);
+template int launch_nhwc_to_act<__half>(const float*, ActView<__half>, cudaStream_t, int);
 
 template <typename T>
 int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st) {

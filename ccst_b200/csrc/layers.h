@@ -9,6 +9,10 @@ enum Epilogue {
   EPI_ACT_UP2 = 1,  // same, every pixel replicated 2x2 (nearest upsample fused into the store)
   EPI_NCHW_F32 = 2, // bias (+ReLU) -> caller's NCHW fp32 tensor (last decoder conv)
   EPI_ACT_POOL = 3, // bias + ReLU + 2x2 ceil-mode max-pool fused into the store (tcgen05 path)
+  EPI_UPS = 4,      // tcgen05 path: the INPUT is the low-resolution activation (replicate halo) of a
+                    // nearest-x2 upsample; conv(reflect_pad(upsample(S))) is computed as four 2x2
+                    // phase convolutions with pre-summed weights (16 instead of 36 tap-GEMMs per source
+                    // pixel) and stored like EPI_ACT at twice the input resolution
 };
 
 // conv1_1 with the 1x1 colour conv folded in.  img: NCHW fp32 [N,3,H,W]; w27: [27][64] fp32
@@ -43,8 +47,9 @@ template <typename T>
 int launch_act_to_nchw(ActView<T> in, float* out_nchw, cudaStream_t st);
 template <typename T>
 int launch_nchw_to_act(const float* in_nchw, ActView<T> out, cudaStream_t st);
+// halo_edge: 1 = reflection halo, 0 = replicate halo (see for_each_halo_alias)
 template <typename T>
-int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st);
+int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st, int halo_edge = 1);
 template <typename T>
 int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st);
 
@@ -52,10 +57,12 @@ int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st);
 // accumulation in TMEM.  wk: [CoutPad][9*Cin] T16 K-major, bias fp32.
 // wk_sm (optional, Cout == 64 only): the same weights packed [192 = (s, co)][3*Cin = (r, c)] for the
 // s-merged kernel.
+// wk_up (EPI_UPS only): phase weights [4 = (a, b)][Cout][4*Cin], k = (dy*2 + dx)*Cin + c.
+// halo_edge: halo the epilogue writes around `out` (1 reflection, 0 replicate; EPI_ACT only).
 template <typename T16>
-int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const float* bias, int Cout,
-                     int CoutPad, int relu, int epi, ActView<T16> out, float* out_nchw,
-                     cudaStream_t st);
+int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16* wk_up,
+                     const float* bias, int Cout, int CoutPad, int relu, int epi, ActView<T16> out,
+                     float* out_nchw, int halo_edge, cudaStream_t st);
 
 // conv1_1 (+ folded 1x1) on tcgen05: thread-built im2col rows (K = 27 padded to 32).
 // wk: [64][32] T16 K-major, bias fp32 [64].

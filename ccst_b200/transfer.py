@@ -199,7 +199,7 @@ class Engine:
         bh = bias.detach().to("cpu", torch.float32).contiguous()
         if mode == 0:
             shape = (n, h, w, cout)
-        elif mode == 1:
+        elif mode in (1, 4):  # 1: upsample after the conv; 4: upsample before it (fused, tcgen05 only)
             shape = (n, 2 * h, 2 * w, cout)
         elif mode == 2:
             shape = (n, (h + 1) // 2, (w + 1) // 2, cout)

@@ -161,7 +161,9 @@ int64_t ccst_launch_count(void);
  * d_in  [N,H,W,Cin]  NHWC fp32 (unpadded), h_weight OIHW fp32 [Cout,Cin,3,3], h_bias [Cout].
  * mode 0: d_out [N,H,W,Cout]; mode 1: nearest x2 fused, d_out [N,2H,2W,Cout]; mode 2: 2x2 ceil-mode
  * max-pool fused (requires relu), d_out [N,ceil(H/2),ceil(W/2),Cout]; mode 3: Cout <= 16, d_out is
- * NCHW [N,Cout,H,W] (the last decoder conv's store).  d_out is fp32. Synchronous. */
+ * NCHW [N,Cout,H,W] (the last decoder conv's store); mode 4 (16-bit precisions only): the input is
+ * nearest-x2 upsampled BEFORE the reflect-pad conv (net.py:10-11), computed by the phase-decomposed
+ * kernel straight from the low-resolution map, d_out [N,2H,2W,Cout].  d_out is fp32. Synchronous. */
 int ccst_debug_conv3x3(ccst_handle* h, const float* d_in, int N, int H, int W, int Cin, int Cout,
                        const float* h_weight, const float* h_bias, int relu, int mode,
                        float* d_out, int precision, void* stream);

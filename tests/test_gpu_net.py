@@ -35,6 +35,8 @@ def engine(models):
 
 def ref_conv(x_nhwc, w, b, relu, mode):
     x = x_nhwc.permute(0, 3, 1, 2).double()
+    if mode == 4:  # Upsample -> ReflectionPad2d -> Conv2d (net.py:10-11)
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
     y = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w.double(), b.double())
     if relu:
         y = F.relu(y)
@@ -60,6 +62,13 @@ CONV_CASES = [
     (1, 9, 11, 256, 256, True, 2),
     (2, 16, 24, 64, 3, False, 3),     # last decoder conv: 3 channels, NCHW fp32 store
     (1, 5, 7, 64, 3, False, 3),
+    # mode 4: nearest x2 BEFORE the conv, fused as four 2x2 phase convolutions (tcgen05 path only)
+    (1, 8, 16, 64, 64, True, 4),      # dec8 shape class: resident phase weights, one tile
+    (2, 13, 19, 64, 64, True, 4),     # ragged, several tiles per phase
+    (1, 2, 2, 64, 64, False, 4),      # smallest map: every pixel is a corner
+    (2, 10, 14, 128, 128, True, 4),   # dec6 class (CTA pairs, odd tile count)
+    (1, 12, 12, 256, 256, True, 4),   # dec2 class @96^2
+    (1, 9, 20, 128, 64, True, 4),
 ]
 
 
@@ -67,6 +76,8 @@ CONV_CASES = [
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 def test_single_conv_engines(engine, case, precision):
     n, h, w, cin, cout, relu, mode = case
+    if mode == 4 and precision == "fp32":
+        pytest.skip("the upsample-fused conv exists on the tcgen05 path only")
     g = torch.Generator().manual_seed(h * 131 + w)
     x = torch.randn((n, h, w, cin), generator=g)
     wt = torch.randn((cout, cin, 3, 3), generator=g) * (2.0 / (9 * cin)) ** 0.5
@@ -84,6 +95,8 @@ def test_single_conv_engines(engine, case, precision):
     scale = ref.abs().max().item()
     if precision == "fp32" or mode == 3:
         assert err < 2e-5 * max(1.0, scale), (err, scale)
+    elif mode == 4:  # + one more rounding of the pre-summed phase weights
+        assert err < (2 ** -6 if precision == "bf16" else 2 ** -9) * max(1.0, scale), (err, scale)
     else:  # one rounding of the stored output
         assert err < (2 ** -8 if precision == "bf16" else 2 ** -11) * max(1.0, scale), (err, scale)
 
@@ -172,6 +185,20 @@ def test_fused_pool_equals_separate_pool(models, monkeypatch):
         monkeypatch.setenv("CCST_FUSE_POOL", "0")
         b = ccst_b200.Engine(vgg, dec, DEV).encode(x, prec)
         assert torch.equal(a, b)
+
+
+def test_fused_upsample_matches_unfused_decoder(models, monkeypatch):
+    """Upsample folded into the next conv (phase-decomposed 2x2 kernels) vs the 4x-replicating store:
+    same function, weights pre-summed and rounded once more, so equal within the 16-bit rounding."""
+    vgg, dec = models
+    feat = synth.features((2, 512, 9, 13), 11).to(DEV)
+    for prec, tol in (("fp16", 2e-3), ("bf16", 1.6e-2)):
+        monkeypatch.setenv("CCST_FUSE_UP", "1")
+        a = ccst_b200.Engine(vgg, dec, DEV).decode(feat, prec)
+        monkeypatch.setenv("CCST_FUSE_UP", "0")
+        b = ccst_b200.Engine(vgg, dec, DEV).decode(feat, prec)
+        assert a.shape == b.shape == (2, 3, 72, 104)
+        assert (a - b).abs().max().item() < tol
 
 
 def test_overall_statistics_loop(models):
