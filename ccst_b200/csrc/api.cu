@@ -112,6 +112,8 @@ struct ccst_handle {
   size_t arena_bytes[2] = {0, 0};
   float2* raw = nullptr;
   size_t raw_elems = 0;
+  float* io_f32 = nullptr;  // uint8 I/O: ToTensor'd input batch / fp32-engine output before quantisation
+  size_t io_elems = 0;
   bool fuse_pool = true;
   bool fuse_up = true;  // nearest-x2 upsample folded into the NEXT conv (EPI_UPS) instead of the store
   bool profiling = false;
@@ -298,6 +300,7 @@ struct Pipe {
   int cur_slot = 0;
   ActView<T> cur;
   bool up_pending = false;  // `cur` is a low-resolution map (replicate halo) awaiting its x2 upsample
+  uint8_t* out_u8 = nullptr;  // decoder(): store NHWC uint8 (save_image quantisation) instead of NCHW fp32
 
   ActView<T> view(int slot, int N, int H, int W, int C) {
     ActView<T> v;
@@ -406,13 +409,15 @@ template <>
 int Pipe<bf16>::conv(const ConvLayer& L, int relu, int epi, ActView<bf16> out, float* out_nchw,
                      bool smerge_ok, int halo_edge) {
   return launch_conv_umma<bf16>(cur, L.w_umma, smerge_ok ? L.w_sm : nullptr, L.w_up, L.bias, L.cout,
-                                L.pad_umma, relu, epi, out, out_nchw, halo_edge, st);
+                                L.pad_umma, relu, epi, out, out_nchw,
+                                epi == EPI_NCHW_F32 ? out_u8 : nullptr, halo_edge, st);
 }
 template <>
 int Pipe<__half>::conv(const ConvLayer& L, int relu, int epi, ActView<__half> out,
                        float* out_nchw, bool smerge_ok, int halo_edge) {
   return launch_conv_umma<__half>(cur, L.w_umma_h, smerge_ok ? L.w_sm_h : nullptr, L.w_up_h, L.bias,
-                                  L.cout, L.pad_umma, relu, epi, out, out_nchw, halo_edge, st);
+                                  L.cout, L.pad_umma, relu, epi, out, out_nchw,
+                                  epi == EPI_NCHW_F32 ? out_u8 : nullptr, halo_edge, st);
 }
 
 int check_common(ccst_handle* h, int precision) {
@@ -426,6 +431,15 @@ int check_common(ccst_handle* h, int precision) {
   return CCST_OK;
 }
 
+int ensure_io(ccst_handle* h, size_t elems) {
+  if (h->io_elems >= elems) return CCST_OK;
+  if (h->io_f32) CCST_CUDA(cudaFree(h->io_f32));
+  h->io_f32 = nullptr, h->io_elems = 0;
+  CCST_CUDA(cudaMalloc(&h->io_f32, elems * sizeof(float)));
+  h->io_elems = elems;
+  return CCST_OK;
+}
+
 template <typename T>
 int run_style_transfer(ccst_handle* h, const float* d_img, int N, int H, int W, const float* mu,
                        const float* sg, int64_t stride, float alpha, float* d_out, cudaStream_t st) {
@@ -436,6 +450,34 @@ int run_style_transfer(ccst_handle* h, const float* d_img, int N, int H, int W, 
   if (int e = p.encoder(d_img, N, H, W)) return e;
   if (int e = p.adain(mu, sg, stride, alpha)) return e;
   return p.decoder(d_out);
+}
+
+// uint8 HWC in (the loader's PIL image before ToTensor) -> uint8 HWC out (what save_image encodes)
+template <typename T>
+int run_style_transfer_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W, const float* mu,
+                          const float* sg, int64_t stride, float alpha, uint8_t* d_out,
+                          cudaStream_t st) {
+  int fh, fw;
+  ccst_feature_hw(H, W, &fh, &fw);
+  const size_t in_elems = (size_t)N * 3 * H * W, out_elems = (size_t)N * 3 * (8 * fh) * (8 * fw);
+  const bool fused_store = sizeof(T) == 2;  // tcgen05 path: quantisation fused into the last conv
+  if (int e = ensure_io(h, in_elems + (fused_store ? 0 : out_elems))) return e;
+  if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T), true, true))) return e;
+  {
+    ProfScope ps(h, st, 5, 0, (double)in_elems * 5.0);
+    if (int e = launch_u8_nhwc_to_f32_nchw(d_img, N, 3, H, W, h->io_f32, st)) return e;
+  }
+  Pipe<T> p{h, st};
+  if (int e = p.encoder(h->io_f32, N, H, W)) return e;
+  if (int e = p.adain(mu, sg, stride, alpha)) return e;
+  if (fused_store) {
+    p.out_u8 = d_out;
+    return p.decoder(nullptr);
+  }
+  float* tmp = h->io_f32 + in_elems;
+  if (int e = p.decoder(tmp)) return e;
+  ProfScope ps(h, st, 5, 0, (double)out_elems * 5.0);
+  return launch_quantize_nchw_to_u8_nhwc(tmp, N, 3, 8 * fh, 8 * fw, d_out, st);
 }
 
 template <typename T>
@@ -530,6 +572,7 @@ extern "C" void ccst_destroy(ccst_handle* h) {
   cudaFree(h->arena[0]);
   cudaFree(h->arena[1]);
   cudaFree(h->raw);
+  cudaFree(h->io_f32);
   for (auto& s : h->prof) {
     if (s.a) cudaEventDestroy(s.a);
     if (s.b) cudaEventDestroy(s.b);
@@ -657,6 +700,38 @@ extern "C" int ccst_style_transfer(ccst_handle* h, const float* d_img, int N, in
   CCST_DISPATCH(precision, run_style_transfer<T>(h, d_img, N, H, W, d_mu_s, d_sigma_s,
                                                  stat_batch_stride, alpha, d_out,
                                                  (cudaStream_t)stream));
+}
+
+extern "C" int ccst_style_transfer_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W,
+                                      const float* d_mu_s, const float* d_sigma_s,
+                                      int64_t stat_batch_stride, float alpha, uint8_t* d_out,
+                                      int precision, void* stream) {
+  if (int e = check_common(h, precision)) return e;
+  CCST_REQUIRE_STATE(h->enc_ready && h->dec_ready, "ccst_style_transfer_u8: weights not set");
+  CCST_CHECK_ARG(d_img && d_out && d_mu_s && d_sigma_s && N >= 1 && H >= 16 && W >= 16,
+                 "ccst_style_transfer_u8: bad argument");
+  CCST_CHECK_ARG(stat_batch_stride == 0 || stat_batch_stride == 512,
+                 "ccst_style_transfer_u8: stat_batch_stride must be 0 or 512");
+  CCST_CHECK_ARG(alpha >= 0.f && alpha <= 1.f, "ccst_style_transfer_u8: alpha outside [0,1]");
+  CCST_DISPATCH(precision, run_style_transfer_u8<T>(h, d_img, N, H, W, d_mu_s, d_sigma_s,
+                                                    stat_batch_stride, alpha, d_out,
+                                                    (cudaStream_t)stream));
+}
+
+extern "C" int ccst_u8_to_tensor(const uint8_t* d_img_nhwc, int N, int C, int H, int W,
+                                 float* d_out_nchw, void* stream) {
+  if (int e = require_sm100()) return e;
+  CCST_CHECK_ARG(d_img_nhwc && d_out_nchw && N >= 1 && C >= 1 && H >= 1 && W >= 1,
+                 "ccst_u8_to_tensor: bad argument");
+  return launch_u8_nhwc_to_f32_nchw(d_img_nhwc, N, C, H, W, d_out_nchw, (cudaStream_t)stream);
+}
+
+extern "C" int ccst_quantize_u8(const float* d_img_nchw, int N, int C, int H, int W,
+                                uint8_t* d_out_nhwc, void* stream) {
+  if (int e = require_sm100()) return e;
+  CCST_CHECK_ARG(d_img_nchw && d_out_nhwc && N >= 1 && C >= 1 && H >= 1 && W >= 1,
+                 "ccst_quantize_u8: bad argument");
+  return launch_quantize_nchw_to_u8_nhwc(d_img_nchw, N, C, H, W, d_out_nhwc, (cudaStream_t)stream);
 }
 
 extern "C" int ccst_profile_enable(ccst_handle* h, int on) {

@@ -119,6 +119,13 @@ __device__ __forceinline__ void for_each_halo_alias(int y, int x, int H, int W, 
     for (int j = 0; j < nx; ++j) f(ys[i], xs[j]);
 }
 
+// torchvision.utils.save_image: grid.mul(255).add_(0.5).clamp_(0, 255).to(uint8) -- two separately
+// rounded fp32 operations (no FMA contraction), then truncation.
+__device__ __forceinline__ uint8_t quantize_u8(float v) {
+  const float t = __fadd_rn(__fmul_rn(v, 255.f), 0.5f);
+  return (uint8_t)fminf(fmaxf(t, 0.f), 255.f);
+}
+
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }

@@ -95,6 +95,7 @@ struct ConvParams {
   const float* bias;
   ActView<T16> out;
   float* out_nchw;
+  uint8_t* out_u8;  // last conv only: NHWC uint8 store quantised like torchvision's save_image
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -655,7 +656,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
             if (c < p.Cout) {
               float v = __uint_as_float(r[c]) + s_bias[c];
               if (p.relu) v = fmaxf(v, 0.f);
-              p.out_nchw[(((size_t)t.n * p.Cout + c) * p.H + y) * p.W + x] = v;
+              if (p.out_u8) p.out_u8[(((size_t)t.n * p.H + y) * p.W + x) * p.Cout + c] = quantize_u8(v);
+              else p.out_nchw[(((size_t)t.n * p.Cout + c) * p.H + y) * p.W + x] = v;
             }
           }
         }
@@ -1657,7 +1659,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           if (c < p.Cout) {
             float v = acc[c];
             if (p.relu) v = fmaxf(v, 0.f);
-            p.out_nchw[(((size_t)t.n * p.Cout + c) * p.H + y) * p.W + x] = v;
+            if (p.out_u8) p.out_u8[(((size_t)t.n * p.H + y) * p.W + x) * p.Cout + c] = quantize_u8(v);
+            else p.out_nchw[(((size_t)t.n * p.Cout + c) * p.H + y) * p.W + x] = v;
           }
         }
       }
@@ -1939,7 +1942,7 @@ int launch_smerge(const CUtensorMap& ma, const T16* wk_sm, const ConvParams<T16>
 template <typename T16>
 int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16* wk_up,
                      const float* bias, int Cout, int CoutPad, int relu, int epi, ActView<T16> out,
-                     float* out_nchw, int halo_edge, cudaStream_t st) {
+                     float* out_nchw, uint8_t* out_u8, int halo_edge, cudaStream_t st) {
   CCST_CHECK_ARG(in.C % kBlockK == 0, "conv_umma: Cin=%d must be a multiple of 64", in.C);
   int BN;
   if (epi == EPI_NCHW_F32) {
@@ -1966,6 +1969,8 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
   p.bias = bias;
   p.out = out;
   p.out_nchw = out_nchw;
+  p.out_u8 = out_u8;
+  CCST_CHECK_ARG(out_u8 == nullptr || epi == EPI_NCHW_F32, "conv_umma: uint8 store is the last conv's");
   CCST_CHECK_ARG(halo_edge == 1 || (halo_edge == 0 && epi == EPI_ACT),
                  "conv_umma: a replicate halo is only written by the plain epilogue");
   CUtensorMap ma;
@@ -2024,11 +2029,11 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
 }
 template int launch_conv_umma<__nv_bfloat16>(ActView<__nv_bfloat16>, const __nv_bfloat16*,
                                              const __nv_bfloat16*, const __nv_bfloat16*, const float*,
-                                             int, int, int, int, ActView<__nv_bfloat16>, float*, int,
-                                             cudaStream_t);
+                                             int, int, int, int, ActView<__nv_bfloat16>, float*,
+                                             uint8_t*, int, cudaStream_t);
 template int launch_conv_umma<__half>(ActView<__half>, const __half*, const __half*, const __half*,
-                                      const float*, int, int, int, int, ActView<__half>, float*, int,
-                                      cudaStream_t);
+                                      const float*, int, int, int, int, ActView<__half>, float*,
+                                      uint8_t*, int, cudaStream_t);
 
 template <typename T16>
 int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk, const float* bias,

@@ -593,6 +593,27 @@ __global__ void __launch_bounds__(256) act_to_nhwc_kernel(ActView<T> in, float* 
   }
 }
 
+// ToTensor of a uint8 HWC batch: out[n][c][y][x] = float(in[n][y][x][c]) / 255 (IEEE division, as
+// torch's div).  One thread per pixel.
+__global__ void __launch_bounds__(256) u8_nhwc_to_f32_nchw_kernel(const uint8_t* __restrict__ in,
+                                                                  int C, size_t HW, size_t total_px,
+                                                                  float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total_px; i += (size_t)gridDim.x * 256) {
+    const size_t n = i / HW, p = i - n * HW;
+    for (int c = 0; c < C; ++c)
+      out[(n * C + c) * HW + p] = __fdiv_rn((float)in[i * C + c], 255.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) quantize_nchw_to_u8_nhwc_kernel(const float* __restrict__ in,
+                                                                       int C, size_t HW, size_t total_px,
+                                                                       uint8_t* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total_px; i += (size_t)gridDim.x * 256) {
+    const size_t n = i / HW, p = i - n * HW;
+    for (int c = 0; c < C; ++c) out[i * C + c] = quantize_u8(in[(n * C + c) * HW + p]);
+  }
+}
+
 int ew_grid(size_t total) {
   size_t blocks = (total + 255) / 256;
   size_t cap = (size_t)sm_count() * 16;
@@ -757,6 +778,20 @@ int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st, in
 template int launch_nhwc_to_act<float>(const float*, ActView<float>, cudaStream_t, int);
 template int launch_nhwc_to_act<__nv_bfloat16>(const float*, ActView<__nv_bfloat16>, cudaStream_t, int);
 template int launch_nhwc_to_act<__half>(const float*, ActView<__half>, cudaStream_t, int);
+
+int launch_u8_nhwc_to_f32_nchw(const uint8_t* in, int N, int C, int H, int W, float* out, cudaStream_t st) {
+  const size_t hw = (size_t)H * W, total = (size_t)N * hw;
+  u8_nhwc_to_f32_nchw_kernel<<<ew_grid(total), 256, 0, st>>>(in, C, hw, total, out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+int launch_quantize_nchw_to_u8_nhwc(const float* in, int N, int C, int H, int W, uint8_t* out, cudaStream_t st) {
+  const size_t hw = (size_t)H * W, total = (size_t)N * hw;
+  quantize_nchw_to_u8_nhwc_kernel<<<ew_grid(total), 256, 0, st>>>(in, C, hw, total, out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
 
 template <typename T>
 int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st) {

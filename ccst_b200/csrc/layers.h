@@ -45,6 +45,12 @@ int merge_raw_into_state(const float2* raw, int N, int C, int64_t hw, double* d_
 
 template <typename T>
 int launch_act_to_nchw(ActView<T> in, float* out_nchw, cudaStream_t st);
+
+// Image I/O around the path: ToTensor of a uint8 HWC batch (cjm_util/data_helper.py:45,
+// torchvision to_tensor: float(u) / 255) -> NCHW fp32, and save_image's quantisation of an NCHW fp32
+// batch (torchvision utils.save_image: mul(255).add(0.5).clamp(0,255).to(uint8)) -> NHWC uint8.
+int launch_u8_nhwc_to_f32_nchw(const uint8_t* in, int N, int C, int H, int W, float* out, cudaStream_t st);
+int launch_quantize_nchw_to_u8_nhwc(const float* in, int N, int C, int H, int W, uint8_t* out, cudaStream_t st);
 template <typename T>
 int launch_nchw_to_act(const float* in_nchw, ActView<T> out, cudaStream_t st);
 // halo_edge: 1 = reflection halo, 0 = replicate halo (see for_each_halo_alias)
@@ -57,12 +63,13 @@ int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st);
 // accumulation in TMEM.  wk: [CoutPad][9*Cin] T16 K-major, bias fp32.
 // wk_sm (optional, Cout == 64 only): the same weights packed [192 = (s, co)][3*Cin = (r, c)] for the
 // s-merged kernel.
+// out_u8 (EPI_NCHW_F32 only, may be NULL): store NHWC uint8 quantised like save_image instead.
 // wk_up (EPI_UPS only): phase weights [4 = (a, b)][Cout][4*Cin], k = (dy*2 + dx)*Cin + c.
 // halo_edge: halo the epilogue writes around `out` (1 reflection, 0 replicate; EPI_ACT only).
 template <typename T16>
 int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16* wk_up,
                      const float* bias, int Cout, int CoutPad, int relu, int epi, ActView<T16> out,
-                     float* out_nchw, int halo_edge, cudaStream_t st);
+                     float* out_nchw, uint8_t* out_u8, int halo_edge, cudaStream_t st);
 
 // conv1_1 (+ folded 1x1) on tcgen05: thread-built im2col rows (K = 27 padded to 32).
 // wk: [64][32] T16 K-major, bias fp32 [64].

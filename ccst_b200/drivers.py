@@ -31,10 +31,14 @@ from .transfer import DEFAULT_PRECISION, Engine
 class TransferPipeline:
     """Pinned-host batches in, pinned-host stylised batches out, three streams, two slots."""
 
-    def __init__(self, engine: Engine, precision: str = DEFAULT_PRECISION, slots: int = 2):
+    def __init__(self, engine: Engine, precision: str = DEFAULT_PRECISION, slots: int = 2, u8: bool = False):
+        """u8 = True: batches are the loader's uint8 HWC images [N,H,W,3] (before ToTensor) and the
+        results the uint8 HWC images `save_image` encodes (Engine.transfer_u8): 4x fewer PCIe bytes."""
         self.engine = engine
         self.precision = precision
         self.slots = slots
+        self.u8 = u8
+        self.dtype = torch.uint8 if u8 else torch.float32
         dev = engine.device
         self.s_in = torch.cuda.Stream(dev)
         self.s_cmp = torch.cuda.Stream(dev)
@@ -51,10 +55,10 @@ class TransferPipeline:
     def _buffers(self, slot: int, shape, out_shape):
         dev = self.engine.device
         if self._in[slot] is None or tuple(self._in[slot].shape) != tuple(shape):
-            self._in[slot] = torch.empty(shape, dtype=torch.float32, device=dev)
+            self._in[slot] = torch.empty(shape, dtype=self.dtype, device=dev)
         if self._out[slot] is None or tuple(self._out[slot].shape) != tuple(out_shape):
-            self._out[slot] = torch.empty(out_shape, dtype=torch.float32, device=dev)
-            self._host[slot] = torch.empty(out_shape, dtype=torch.float32).pin_memory()
+            self._out[slot] = torch.empty(out_shape, dtype=self.dtype, device=dev)
+            self._host[slot] = torch.empty(out_shape, dtype=self.dtype).pin_memory()
         return self._in[slot], self._out[slot], self._host[slot]
 
     def run(self, host_batches: Iterable[torch.Tensor],
@@ -73,29 +77,36 @@ class TransferPipeline:
             st.wait_stream(cur)  # whatever prepared the inputs / statistics on the caller's stream
         for i, hb in enumerate(host_batches):
             slot = i % self.slots
-            n, _, h, w = hb.shape
+            if self.u8:
+                n, h, w, _ = hb.shape
+            else:
+                n, _, h, w = hb.shape
             fh, fw = _lib.feature_hw(h, w)
+            out_shape = (n, 8 * fh, 8 * fw, 3) if self.u8 else (n, 3, 8 * fh, 8 * fw)
             if len(pending) >= self.slots:  # the slot's previous result must have been handed out
                 j, s = pending.pop(0)       # (before _buffers may re-shape the slot for a ragged batch)
                 self._ev_out[s].synchronize()
                 yield j, self._host[s]
-            d_in, d_out, h_out = self._buffers(slot, hb.shape, (n, 3, 8 * fh, 8 * fw))
+            d_in, d_out, h_out = self._buffers(slot, hb.shape, out_shape)
             with torch.cuda.stream(self.s_in):
                 self.s_in.wait_event(self._ev_cmp[slot])  # compute of batch i-slots has read d_in
                 d_in.copy_(hb, non_blocking=True)
                 self._ev_in[slot].record(self.s_in)
-            self.h2d_bytes += hb.numel() * 4
+            self.h2d_bytes += hb.numel() * hb.element_size()
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(self._ev_in[slot])
                 self.s_cmp.wait_event(self._ev_out[slot])  # download of batch i-slots has read d_out
                 stat = style_for_batch(i, d_in)
-                self.engine.transfer(d_in, stat, alpha, self.precision, out=d_out)
+                if self.u8:
+                    self.engine.transfer_u8(d_in, stat, alpha, self.precision, out=d_out)
+                else:
+                    self.engine.transfer(d_in, stat, alpha, self.precision, out=d_out)
                 self._ev_cmp[slot].record(self.s_cmp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self._ev_cmp[slot])
                 h_out.copy_(d_out, non_blocking=True)
                 self._ev_out[slot].record(self.s_out)
-            self.d2h_bytes += d_out.numel() * 4
+            self.d2h_bytes += d_out.numel() * d_out.element_size()
             pending.append((i, slot))
         for j, s in pending:
             self._ev_out[s].synchronize()
@@ -103,9 +114,10 @@ class TransferPipeline:
 
 
 def overall_transfer(engine: Engine, host_batches: Iterable[torch.Tensor], style_stat, alpha: float = 1.0,
-                     precision: str = DEFAULT_PRECISION):
-    """Inner loop of CCST_OverallStyleTransfer.py:149-167 for one (content domain, style) pair."""
-    pipe = TransferPipeline(engine, precision)
+                     precision: str = DEFAULT_PRECISION, u8: bool = False):
+    """Inner loop of CCST_OverallStyleTransfer.py:149-167 for one (content domain, style) pair.
+    u8 = True: uint8 HWC batches in and out (ToTensor / save_image's quantisation on the GPU)."""
+    pipe = TransferPipeline(engine, precision, u8=u8)
     stat = [t.to(engine.device) for t in style_stat]
     return pipe.run(host_batches, lambda i, x: stat, alpha)
 

@@ -178,6 +178,31 @@ class Engine:
                 out.data_ptr(), PRECISIONS[precision], self._stream()))
         return out
 
+    def transfer_u8(self, content_u8, style_stat, alpha=1.0, precision=DEFAULT_PRECISION, out=None):
+        """`transfer` with the batch loop's image I/O fused around it: `content_u8` is the
+        loader's uint8 HWC batch [N,H,W,3] before `ToTensor` (cjm_util/data_helper.py:45), the result
+        the uint8 HWC batch [N,8h,8w,3] that `save_image` encodes
+        (CCST_OverallStyleTransfer.py:167) -- a quarter of the fp32 bytes each way over PCIe."""
+        assert (0.0 <= alpha <= 1.0)
+        x = content_u8
+        if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.uint8:
+            raise RuntimeError("content_u8 must be a CUDA uint8 tensor: ccst_b200 has no CPU fallback")
+        if x.device != self.device:
+            raise RuntimeError(f"content_u8 is on {x.device}, engine on {self.device}")
+        if x.dim() != 4 or x.shape[3] != 3:
+            raise RuntimeError(f"content_u8 must be [N,H,W,3], got {tuple(x.shape)}")
+        x = x.contiguous()
+        n, h, w, _ = x.shape
+        mu, sg, stride = F_._style_stat_args(style_stat, n, 512, self.device)
+        fh, fw = _lib.feature_hw(h, w)
+        if out is None:
+            out = torch.empty((n, 8 * fh, 8 * fw, 3), dtype=torch.uint8, device=self.device)
+        with _lib.on_device(self.device):
+            _lib.check(_lib.lib().ccst_style_transfer_u8(
+                self._h, x.data_ptr(), n, h, w, mu.data_ptr(), sg.data_ptr(), stride, float(alpha),
+                out.data_ptr(), PRECISIONS[precision], self._stream()))
+        return out
+
     # -- profiling -----------------------------------------------------------
     def profile(self, on: bool):
         _lib.check(_lib.lib().ccst_profile_enable(self._h, 1 if on else 0))
@@ -213,6 +238,36 @@ class Engine:
         return out
 
 
+def to_tensor_u8(images_u8: torch.Tensor) -> torch.Tensor:
+    """`transforms.ToTensor()` of a uint8 HWC batch on the device (cjm_util/data_helper.py:45):
+    [N,H,W,C] uint8 -> [N,C,H,W] fp32 = float(u) / 255."""
+    x = images_u8
+    if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.uint8 or x.dim() != 4:
+        raise RuntimeError("images_u8 must be a CUDA uint8 [N,H,W,C] tensor: ccst_b200 has no CPU fallback")
+    x = x.contiguous()
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    with _lib.on_device(x.device):
+        _lib.check(_lib.lib().ccst_u8_to_tensor(x.data_ptr(), n, c, h, w, out.data_ptr(),
+                                                torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
+def save_image_quantize(images: torch.Tensor) -> torch.Tensor:
+    """The tensor -> uint8 step of `save_image` (CCST_OverallStyleTransfer.py:167; torchvision
+    utils.save_image: mul(255).add_(0.5).clamp_(0,255).permute(1,2,0).to(uint8)) for a batch:
+    [N,C,H,W] fp32 -> [N,H,W,C] uint8."""
+    x = F_._prep(images, "images")
+    if x.dim() != 4:
+        raise RuntimeError(f"images must be [N,C,H,W], got {tuple(x.shape)}")
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, c), dtype=torch.uint8, device=x.device)
+    with _lib.on_device(x.device):
+        _lib.check(_lib.lib().ccst_quantize_u8(x.data_ptr(), n, c, h, w, out.data_ptr(),
+                                               torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
 _ENGINES = {}
 
 
@@ -230,6 +285,16 @@ def engine_for(vgg: nn.Module, decoder: nn.Module, device) -> Engine:
     eng.set_encoder(vgg)
     eng.set_decoder(decoder)
     return eng
+
+
+def style_transfer_u8(vgg, decoder, content_u8, style_stat, alpha=1.0, *, precision=None):
+    """`style_transfer` on the loader's uint8 HWC batch, returning the uint8 HWC batch `save_image`
+    would encode (see Engine.transfer_u8)."""
+    assert (0.0 <= alpha <= 1.0)
+    if not isinstance(content_u8, torch.Tensor) or not content_u8.is_cuda:
+        raise RuntimeError("content_u8 must be a CUDA tensor: ccst_b200 has no CPU fallback")
+    eng = engine_for(vgg, decoder, content_u8.device)
+    return eng.transfer_u8(content_u8, style_stat, alpha, precision or DEFAULT_PRECISION)
 
 
 def style_transfer(vgg, decoder, content, style, alpha=1.0, interpolation_weights=None, *,

@@ -142,6 +142,24 @@ int ccst_style_transfer(ccst_handle* h, const float* d_img, int N, int H, int W,
                         const float* d_mu_s, const float* d_sigma_s, int64_t stat_batch_stride,
                         float alpha, float* d_out, int precision, void* stream);
 
+/* The same call with the image I/O of the batch loop fused around it:
+ *   d_img  [N,H,W,3] uint8 HWC -- the loader's PIL image before `ToTensor`
+ *          (cjm_util/data_helper.py:45; torchvision to_tensor: float(u) / 255);
+ *   d_out  [N,8h,8w,3] uint8 HWC -- what `save_image(out_img, out_name)` hands to the encoder
+ *          (CCST_OverallStyleTransfer.py:167; torchvision utils.save_image:
+ *          mul(255).add(0.5).clamp(0,255).to(uint8)), quantised in the last conv's store.
+ * 4x fewer bytes each way across PCIe than the fp32 tensors. */
+int ccst_style_transfer_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W,
+                           const float* d_mu_s, const float* d_sigma_s, int64_t stat_batch_stride,
+                           float alpha, uint8_t* d_out, int precision, void* stream);
+
+/* The two conversions on their own: ToTensor ([N,H,W,C] uint8 -> [N,C,H,W] fp32 in [0,1]) and
+ * save_image's quantisation ([N,C,H,W] fp32 -> [N,H,W,C] uint8). */
+int ccst_u8_to_tensor(const uint8_t* d_img_nhwc, int N, int C, int H, int W, float* d_out_nchw,
+                      void* stream);
+int ccst_quantize_u8(const float* d_img_nchw, int N, int C, int H, int W, uint8_t* d_out_nhwc,
+                     void* stream);
+
 /* one iteration of the overall-statistics loop: vgg(data) + calc_sum + accumulate
  * [mean_std_computation_effcientMem.py:121-131], encoder output never leaves the arena. */
 int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N, int H, int W,

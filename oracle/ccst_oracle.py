@@ -194,3 +194,18 @@ def save_image_quantize(img: torch.Tensor) -> torch.Tensor:
     """torchvision.utils.save_image's tensor->uint8 step
     (CCST_OverallStyleTransfer.py:167): mul(255).add(0.5).clamp(0,255).to(uint8)."""
     return img.mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8)
+
+
+def to_tensor_u8(images_u8: torch.Tensor) -> torch.Tensor:
+    """`transforms.ToTensor()` on the loader's uint8 HWC image (cjm_util/data_helper.py:45;
+    torchvision 0.26 functional.to_tensor: `img.permute(2,0,1).to(float32).div(255)`), batched:
+    [N,H,W,C] uint8 -> [N,C,H,W] fp32."""
+    return images_u8.permute(0, 3, 1, 2).contiguous().to(torch.float32).div(255)
+
+
+def save_image_batch_u8(images: torch.Tensor) -> torch.Tensor:
+    """What `for out_img in output: save_image(out_img, name)` hands to the image encoder
+    (CCST_OverallStyleTransfer.py:158-167; torchvision 0.26 utils.save_image:
+    `grid.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to("cpu", torch.uint8)`; make_grid of a
+    single 3-channel image is the image itself): [N,C,H,W] fp32 -> [N,H,W,C] uint8."""
+    return save_image_quantize(images.clone()).permute(0, 2, 3, 1).contiguous()

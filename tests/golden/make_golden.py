@@ -201,5 +201,62 @@ def main():
         print(fn, os.path.getsize(p) // 1024, "KiB")
 
 
+def make_io():
+    """Image I/O either side of style_transfer: the loader transform of
+    cjm_util/data_helper.py:45-49 (`Resize((S,S))` + `ToTensor()`) applied by the REAL torchvision to
+    PIL images, the reference `style_transfer`, then the REAL `save_image` of
+    CCST_OverallStyleTransfer.py:158-167 (PNG in memory, decoded back: lossless) -> io_u8.npz."""
+    import io
+
+    from PIL import Image
+    from torchvision import transforms
+    from torchvision.utils import save_image
+
+    torch.set_num_threads(1)
+    overall_py = os.path.join(REF, "CCST_OverallStyleTransfer.py")
+    ns = {"torch": torch, "device": torch.device("cpu"),
+          "adaIN_StyleStat_ContentFeat": ref_function.adaIN_StyleStat_ContentFeat}
+    _extract_funcs(overall_py, {"style_transfer"}, ns)
+    vgg, dec = ref_models(0)
+    out = {"weights_sha256": np.frombuffer(weights_digest(vgg, dec).encode(), dtype=np.uint8)}
+    n, h, w = 2, 40, 48
+    g = torch.Generator().manual_seed(4242)
+    # smooth-ish uint8 images covering the full 0..255 range
+    base = torch.rand((n, h // 4, w // 4, 3), generator=g)
+    img = torch.nn.functional.interpolate(base.permute(0, 3, 1, 2), size=(h, w), mode="bilinear",
+                                          align_corners=False).permute(0, 2, 3, 1)
+    img = (img + 0.15 * torch.rand((n, h, w, 3), generator=g)).clamp(0, 1)
+    x_u8 = (img * 255).round().to(torch.uint8).numpy()
+    x_u8[0, 0, 0] = (0, 255, 128)
+    tr = transforms.Compose([transforms.Resize((h, w)), transforms.ToTensor()])
+    x = torch.stack([tr(Image.fromarray(x_u8[i])) for i in range(n)])
+    sm = torch.rand((1, 512, 1, 1), generator=g) * 2.0
+    ss = torch.rand((1, 512, 1, 1), generator=g) * 1.5 + 0.1
+    out["x_u8"] = x_u8
+    out["x_tensor"] = x.numpy()
+    out["style_mean"] = sm.numpy()
+    out["style_std"] = ss.numpy()
+    with torch.no_grad():
+        for alpha in (1.0, 0.5):
+            o = ns["style_transfer"](vgg, dec, x, [sm, ss], alpha)
+            # stretch so that both clamps of save_image are exercised
+            o = (o - 0.5) * 3.0 + 0.5 if alpha == 0.5 else o
+            saved = []
+            for out_img in o:
+                buf = io.BytesIO()
+                save_image(out_img, buf, format="png")
+                buf.seek(0)
+                saved.append(np.asarray(Image.open(buf).convert("RGB")))
+            out[f"out_f32_a{alpha}"] = o.numpy()
+            out[f"out_u8_a{alpha}"] = np.stack(saved)
+    np.savez_compressed(os.path.join(HERE, "io_u8.npz"), **out)
+    print("io_u8", os.path.getsize(os.path.join(HERE, "io_u8.npz")) // 1024, "KiB",
+          "clamped lo/hi:", int((out["out_u8_a0.5"] == 0).sum()), int((out["out_u8_a0.5"] == 255).sum()))
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-io" in sys.argv:
+        make_io()
+    else:
+        main()
+        make_io()

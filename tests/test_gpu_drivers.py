@@ -66,3 +66,66 @@ def test_overall_statistics_loop_with_uploads(models, engine):
     assert seen == imgs
     assert (mean.cpu().double() - mean64).abs().max().item() < 1e-4 * max(1.0, mean64.abs().max().item())
     assert (std.cpu().double() - std64).abs().max().item() < 1e-4 * max(1.0, std64.abs().max().item())
+
+
+def test_to_tensor_and_quantize_operators_bit_exact(golden):
+    """ToTensor (float(u)/255) and save_image's quantisation on the GPU: bit-exact vs torchvision."""
+    g = golden["io_u8"]
+    x = ccst_b200.to_tensor_u8(torch.from_numpy(g["x_u8"]).to(DEV))
+    assert torch.equal(x.cpu(), torch.from_numpy(g["x_tensor"]))
+    for a in ("1.0", "0.5"):
+        q = ccst_b200.save_image_quantize(torch.from_numpy(g[f"out_f32_a{a}"]).to(DEV))
+        assert torch.equal(q.cpu(), torch.from_numpy(g[f"out_u8_a{a}"]))
+    # every uint8 value and the rounding boundaries k/255 - tiny .. k/255 + tiny
+    u = torch.arange(256, dtype=torch.uint8).view(1, 16, 16, 1).to(DEV)
+    t = ccst_b200.to_tensor_u8(u)
+    assert torch.equal(t.cpu(), O.to_tensor_u8(u.cpu()))
+    assert torch.equal(ccst_b200.save_image_quantize(t).cpu(), u.cpu())
+    v = torch.cat([t - 0.5 / 255, t - 0.4999 / 255, t + 0.4999 / 255, t * 3 - 1])
+    assert torch.equal(ccst_b200.save_image_quantize(v).cpu(), O.save_image_batch_u8(v.cpu()))
+
+
+def test_style_transfer_u8_golden(models, golden):
+    """uint8 in -> uint8 out against the reference pipeline (ToTensor, style_transfer, save_image):
+    fp32 engine within one grey level (and almost always exact), tensor-core engines within the
+    1e-2 image tolerance (3 grey levels) with f16 operands; bf16 operands (documented deviation, see
+    DESIGN.md "Numerics") only to ~2.5e-2 of this vector's output range (about 4 units)."""
+    vgg, dec = models
+    g = golden["io_u8"]
+    x_u8 = torch.from_numpy(g["x_u8"]).to(DEV)
+    stat = [torch.from_numpy(g["style_mean"]).to(DEV), torch.from_numpy(g["style_std"]).to(DEV)]
+    ref = torch.from_numpy(g["out_u8_a1.0"]).int()
+    for prec, max_lv, min_exact in (("fp32", 1, 0.995), ("fp16", 3, 0.6), ("bf16", 26, 0.05)):
+        out = ccst_b200.style_transfer_u8(vgg, dec, x_u8, stat, 1.0, precision=prec)
+        assert out.dtype == torch.uint8 and tuple(out.shape) == tuple(ref.shape)
+        d = (out.cpu().int() - ref).abs()
+        assert d.max().item() <= max_lv, (prec, d.max().item())
+        assert (d == 0).float().mean().item() >= min_exact, (prec, (d == 0).float().mean().item())
+
+
+def test_style_transfer_u8_equals_float_path_quantised(models):
+    """Integer work is bit-exact: the fused uint8 path == ToTensor -> style_transfer -> quantise,
+    all on the same engine, for every precision, on a ragged non-multiple-of-8 size."""
+    vgg, dec = models
+    g = torch.Generator().manual_seed(9)
+    x_u8 = torch.randint(0, 256, (3, 52, 70, 3), generator=g, dtype=torch.uint8).to(DEV)
+    stat = [torch.randn((1, 512, 1, 1), generator=g).abs().to(DEV), (torch.rand((1, 512, 1, 1), generator=g) + 0.2).to(DEV)]
+    for prec in ("fp32", "fp16", "bf16"):
+        a = ccst_b200.style_transfer_u8(vgg, dec, x_u8, stat, 0.8, precision=prec)
+        f = ccst_b200.style_transfer(vgg, dec, ccst_b200.to_tensor_u8(x_u8), stat, 0.8, precision=prec)
+        assert tuple(a.shape) == (3, 56, 72, 3)
+        assert torch.equal(a, ccst_b200.save_image_quantize(f))
+        assert torch.equal(a.cpu(), O.save_image_batch_u8(f.cpu()))
+
+
+def test_overall_transfer_u8_pipeline(models, engine):
+    """The overlapped batch loop with uint8 batches equals per-batch calls."""
+    vgg, dec = models
+    g = torch.Generator().manual_seed(10)
+    batches = [torch.randint(0, 256, (n, 64, 48, 3), generator=g, dtype=torch.uint8).pin_memory() for n in (3, 3, 2)]
+    stat = [torch.randn((1, 512, 1, 1), generator=g).abs(), torch.rand((1, 512, 1, 1), generator=g) + 0.2]
+    sd = [t.to(DEV) for t in stat]
+    got = {i: out.clone() for i, out in drivers.overall_transfer(engine, iter(batches), stat, 1.0, u8=True)}
+    assert sorted(got) == [0, 1, 2]
+    for i, b in enumerate(batches):
+        assert torch.equal(got[i], ccst_b200.style_transfer_u8(vgg, dec, b.to(DEV), sd, 1.0).cpu())

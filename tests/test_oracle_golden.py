@@ -102,3 +102,22 @@ def test_image_style_form_equals_stat_form(models):
         stat = O.calc_mean_std(O.encode_relu4_1(vgg, s))
         b = O.style_transfer(vgg, dec, x, stat, 0.7)
     assert torch.allclose(a, b, atol=1e-6)
+
+
+def test_image_io_matches_torchvision_and_reference(golden, models):
+    """ToTensor of the loader's uint8 image and save_image's quantisation, pinned to the
+    REAL torchvision transforms / save_image (PNG round trip) run on the reference's outputs."""
+    g = golden["io_u8"]
+    x_u8 = T(g["x_u8"])
+    np.testing.assert_array_equal(O.to_tensor_u8(x_u8).numpy(), g["x_tensor"])
+    assert g["x_u8"].min() == 0 and g["x_u8"].max() == 255
+    for a in ("1.0", "0.5"):
+        q = O.save_image_batch_u8(T(g[f"out_f32_a{a}"]))
+        np.testing.assert_array_equal(q.numpy(), g[f"out_u8_a{a}"])
+    # both clamps of save_image are exercised by the stretched alpha = 0.5 vector
+    assert (g["out_u8_a0.5"] == 0).sum() > 100 and (g["out_u8_a0.5"] == 255).sum() > 100
+    # and the float vectors are the reference's style_transfer on the ToTensor'd input
+    vgg, dec = models
+    with torch.no_grad():
+        o = O.style_transfer(vgg, dec, O.to_tensor_u8(x_u8), [T(g["style_mean"]), T(g["style_std"])], 1.0)
+    np.testing.assert_allclose(o.numpy(), g["out_f32_a1.0"], rtol=0, atol=1e-6)
