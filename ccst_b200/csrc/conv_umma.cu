@@ -51,12 +51,34 @@ constexpr int kEpiWarp0 = 4;
 //            slab shifted by r tile rows = r * 2048 bytes, which keeps the 1024-byte swizzle phase.
 //            (A bytes per tile: 3 slabs instead of 9 tiles per channel chunk -> 2.4x less L2->SM traffic.)
 //   B      : BRES = false: ring of kBStages weight tiles {64 k, BN}, one per tap and channel chunk;
-//            BRES = true (9*Cin*BN*2 bytes fit): all weights loaded once per CTA and kept resident.
+//            BRES = number of 64-channel input chunks whose weights are RESIDENT (0 = stream): when
+//            taps * Cin * BN * 2 bytes fit (Cin = 64 at N <= 128, the phase weights of the Cin = 128
+//            upsample-fused layer) they are loaded once per CTA and never re-fetched.
 //   store  : kStoreBufs x 16 KiB staging tiles for the TMA store of the epilogue.
-template <int BN, bool BRES, int CG, bool UPS = false>
+// Tile geometry of the main kernel.
+//   GEO 0: 8 x 16 output pixels; one slab {64 ch, 16 px, 10 rows} PER FILTER COLUMN s (the operand of
+//          tap (r, s) is slab s shifted by r rows = r * 2048 B).
+//   GEO 1/2 ("linear slab"): ONE slab per channel chunk serves all taps.  The slab is read as a linear
+//          run of pixels with row pitch kBoxW: accumulator row i <-> slab position i, and the operand of
+//          tap (r, s) is the same slab starting (r * kBoxW + s) * 128 B later (the 128-byte swizzle is a
+//          function of the shared-memory address, so any 128-byte-multiple start keeps the pattern).
+//          Positions whose column is >= kBoxW - 2 wrap into the next row and are discarded: 14 of 16
+//          (GEO 1, 8 rows) or 30 of 32 (GEO 2, 4 rows) accumulator rows are outputs.  3x less L2 -> SM
+//          and TMA -> shared-memory traffic for the activations, paid with 12.5 % / 6.25 % idle MMA rows.
+template <int GEO>
+struct Geo {
+  static constexpr bool kLin = GEO != 0;
+  static constexpr int kBoxW = GEO == 2 ? 32 : 16;
+  static constexpr int kRows = kBlockM / kBoxW;             // output rows per tile
+  static constexpr int kOutW = kLin ? kBoxW - 2 : kBoxW;    // output columns per tile
+  static constexpr int kSlabRows = kRows + 2;
+  static constexpr int kSlabBytes = kSlabRows * kBoxW * 128;  // 20480 / 24576
+};
+
+template <int BN, int BRES, int CG, bool UPS = false, int GEO = 0>
 struct UmmaCfg {
-  static constexpr int kSlabRows = kTileH + 2;
-  static constexpr int kASlabBytes = kSlabRows * kTileW * 128;  // 20480
+  static constexpr int kSlabRows = Geo<GEO>::kSlabRows;
+  static constexpr int kASlabBytes = Geo<GEO>::kSlabBytes;
   // CG = 2 (CTA pair, tcgen05 cta_group::2): the pair computes M = 256 pixels x BN channels per MMA;
   // each CTA stages the A slab of its own 128-pixel tile and HALF of the weight tile (BN/2 rows),
   // so the per-SM shared-memory traffic of the B operand (TMA writes and tensor-core reads) halves.
@@ -64,11 +86,20 @@ struct UmmaCfg {
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kBStride = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kTaps = UPS ? 4 : 9;  // UPS: 2x2 phase convolution (see EPI_UPS)
+  // (a linear slab carries a whole channel chunk -- all taps -- so fewer stages cover the same work)
   static constexpr int kAStages =
-      CG == 2 ? (BRES ? 6 : (BN >= 256 ? 4 : 5)) : (BRES ? (BN >= 64 ? (UPS ? 6 : 5) : 6) : (BN >= 256 ? 3 : 4));
-  static constexpr int kBStages = BRES ? kTaps /* resident: all taps x (Cin == 64) */
-                                  : CG == 2 ? (BN >= 256 ? 6 : 9)
-                                            : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 9));
+      GEO != 0 ? (BN >= 128 ? 3 : 4)
+      : CG == 2 ? (BRES ? (BN >= 128 && !UPS ? 5 : 6) : (BN >= 256 ? 4 : 5))
+                : (BRES ? (BN >= 128 ? 3 : (BN >= 64 ? (UPS ? 6 : 5) : 6)) : (BN >= 256 ? 3 : 4));
+  // BRES = false: the weight tiles of the kTR filter rows of one (chunk, filter column) step travel
+  // as ONE group -- one full/empty barrier pair, one wait per step in the producer and in the MMA
+  // warp (a wait + elect + issue round per single tile costs ~300 cycles of serial scalar code in
+  // each of those warps, more than the 256 cycles of math a tile feeds at N = 128).
+  static constexpr int kBGroup = BRES ? 1 : (UPS ? 2 : 3);
+  static constexpr int kBStagesRaw = BRES ? kTaps * BRES /* resident: all taps x BRES chunks */
+                                     : CG == 2 ? (BN >= 256 ? 6 : 9)
+                                               : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 9));
+  static constexpr int kBStages = kBStagesRaw / kBGroup * kBGroup;
   static constexpr int kStoreBufs = 2;  // one staging tile per epilogue group
   static constexpr int kStoreStageBytes = (BN >= 64) ? kStoreBufs * kBlockM * 128 : 0;
   static constexpr int kBiasBytes = 2048;  // up to 512 fp32 biases
@@ -80,7 +111,7 @@ struct UmmaCfg {
   static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4 + 1;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024 /*align slack*/;
-  static_assert(kSmemBytes <= 232448, "shared memory plan exceeds 227 KiB");
+  static constexpr bool kFits = kSmemBytes <= 232448;  // 227 KiB; launch_cfg refuses plans that do not fit
   static_assert(CG == 1 || (BN >= 32 && BN % 32 == 0), "cta_group::2 needs N % 32 == 0");
 };
 
@@ -90,7 +121,10 @@ struct ConvParams {
   int Cout, CoutPad;
   int tiles_x, tiles_y, n_tiles, m_tiles;  // m_tiles = pixel tiles (N * tiles_y * tiles_x)
   int total_tiles;                        // work units: (pixel tile | pair of pixel tiles) x n_tiles
+  const T16* in_ptr;  // host side only (tensor maps of the non-default tile geometries)
   int relu;
+  int desc_mode;  // linear slabs: see make_kmajor_sw128_desc_off
+  int ablate;     // measurement only (CCST_ABLATE): 1 skip the epilogue's work, 2 skip the MMAs, 4 skip the A loads
   int halo_edge;  // halo written around `out`: 1 reflection, 0 replicate (for_each_halo_alias)
   const float* bias;
   ActView<T16> out;
@@ -242,14 +276,18 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// (default .release.cta semantics: these arrivals hand over TMEM / shared-memory stages whose accesses
+// are ordered by tcgen05 fences and wait::ld, no global data is published through them -- the
+// .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR + an L1 invalidate per arrival, which cost
+// the pair kernels ~15 % of their epilogue time)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -353,6 +391,13 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
+// Same for a start address that is a 128-byte multiple but not 1024-byte aligned (linear slabs).
+// mode 0: address only; mode 1: also the descriptor's base-offset field [49,52) = (addr >> 7) & 7.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_addr, int mode) {
+  uint64_t d = make_kmajor_sw128_desc(smem_addr);
+  if (mode == 1) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+  return d;
+}
 // kind::f16 instruction descriptor: D = fp32, A = B = bf16 or f16, both K-major, M = 128, N = BN
 template <typename T16, int BN, int CG = 1>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
@@ -368,7 +413,7 @@ struct TileCoord {
 // index n = N: its TMA loads are out of bounds (zero fill) and its stores are clipped away.
 // UPS: the four output phases (a, b) of one pixel tile are consecutive units, so the CTAs that run
 // them concurrently share the tile's input slabs in L2.
-template <int CG, bool UPS = false, typename P>
+template <int CG, bool UPS = false, int GEO = 0, typename P>
 __device__ __forceinline__ TileCoord decode_tile(const P& p, int unit, int rank) {
   TileCoord t;
   t.nt = unit % p.n_tiles;
@@ -380,9 +425,9 @@ __device__ __forceinline__ TileCoord decode_tile(const P& p, int unit, int rank)
     t.x0 = 0, t.y0 = 0, t.n = p.N;
     return t;
   }
-  t.x0 = (m % p.tiles_x) * kTileW;
+  t.x0 = (m % p.tiles_x) * Geo<GEO>::kOutW;
   m /= p.tiles_x;
-  t.y0 = (m % p.tiles_y) * kTileH;
+  t.y0 = (m % p.tiles_y) * Geo<GEO>::kRows;
   t.n = m / p.tiles_y;
   return t;
 }
@@ -444,7 +489,7 @@ __device__ __forceinline__ void store_aliases(const ActView<T16>& out, int n, in
   }, edge);
 }
 
-template <typename T16, int BN, int EPI, bool BRES, int CG>
+template <typename T16, int BN, int EPI, int BRES, int CG, int GEO = 0>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_b,
@@ -454,7 +499,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   // with the 3x3 taps that fall on the same source pixel pre-summed (api.cu pack_layer).
   constexpr bool UPS = (EPI == EPI_UPS);
   constexpr int kTR = UPS ? 2 : 3, kTS = UPS ? 2 : 3;
-  using Cfg = UmmaCfg<BN, BRES, CG, UPS>;
+  using G = Geo<GEO>;
+  constexpr bool LIN = G::kLin;
+  using Cfg = UmmaCfg<BN, BRES, CG, UPS, GEO>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte aligned bases (the dynamic shared window starts at the same
   // offset in both CTAs of a pair, so the carve-up below is identical in both)
@@ -522,44 +569,53 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       // all weight tiles of this (Cin == 64) layer, once.  UPS: the grid is a multiple of 4 (or has
       // one unit per CTA), so every unit of this CTA has the same phase and only its taps are kept.
       if (elect_one()) {
-        if (leader) mbar_expect_tx(bres_bar, CG * Cfg::kTaps * Cfg::kBBytes);
+        if (leader) mbar_expect_tx(bres_bar, CG * Cfg::kBStages * Cfg::kBBytes);
         const uint32_t bar = lead(bres_bar);
         const int row_ph = UPS ? (unit0 & 3) * p.CoutPad : 0;
-        for (int tap = 0; tap < Cfg::kTaps; ++tap)
-          tma_load_2d_cg<CG>(b_smem(tap), &tmap_b, bar, tap * p.Cin, row_ph + b_row0);
+        for (int kc = 0; kc < BRES; ++kc)
+          for (int tap = 0; tap < Cfg::kTaps; ++tap)
+            tma_load_2d_cg<CG>(b_smem(kc * Cfg::kTaps + tap), &tmap_b, bar, tap * p.Cin + kc * kBlockK,
+                               row_ph + b_row0);
       }
       __syncwarp();
     }
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     for (int unit = unit0; unit < p.total_tiles; unit += unit_step) {
-      const TileCoord t = decode_tile<CG, UPS>(p, unit, (int)cta_rank);
-      const int xs0 = t.x0 + (UPS ? (t.ph & 1) : 0);
+      const TileCoord t = decode_tile<CG, UPS, GEO>(p, unit, (int)cta_rank);
+      const int xs0 = t.x0 + ((UPS && !LIN) ? (t.ph & 1) : 0);
       const int b_row = (UPS ? t.ph * p.CoutPad : 0) + t.nt * BN + b_row0;
       for (int kc = 0; kc < kchunks; ++kc) {
         for (int s = 0; s < kTS; ++s) {
-          mbar_wait(a_empty(as), aph ^ 1, 100 + as);
-          if (elect_one()) {
-            if (leader) mbar_expect_tx(a_full(as), CG * Cfg::kASlabBytes);
-            // interior pixel (y, x) is stored at (y+1, x+1): the slab for filter column s starts at
-            // padded (y0, x0 + s) and spans the 10 rows needed by r = 0..2 (UPS: source column
-            // x + b - 1 + s, rows a + r of the slab)
-            tma_load_4d_cg<CG>(a_smem(as), &tmap_a, lead(a_full(as)), kc * kBlockK, xs0 + s, t.y0,
-                               t.n);
-          }
-          __syncwarp();
-          if (++as == Cfg::kAStages) as = 0, aph ^= 1;
-          if (!BRES) {
-            for (int r = 0; r < kTR; ++r) {
-              mbar_wait(b_empty(bs), bph ^ 1, 150 + bs);
+          if (!LIN || s == 0) {
+            mbar_wait(a_empty(as), aph ^ 1, 100 + as);
+            if (p.ablate & 4) {
               if (elect_one()) {
-                if (leader) mbar_expect_tx(b_full(bs), CG * Cfg::kBBytes);
-                tma_load_2d_cg<CG>(b_smem(bs), &tmap_b, lead(b_full(bs)),
-                                   (r * kTS + s) * p.Cin + kc * kBlockK, b_row);
+                if (leader) mbar_arrive(a_full(as));
               }
-              __syncwarp();
-              if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
+            } else if (elect_one()) {
+              if (leader) mbar_expect_tx(a_full(as), CG * Cfg::kASlabBytes);
+              // interior pixel (y, x) is stored at (y+1, x+1): the slab for filter column s starts at
+              // padded (y0, x0 + s) and spans the rows needed by r = 0..2 (UPS: source column
+              // x + b - 1 + s, rows a + r of the slab).  LIN: one slab at (y0, x0) for every tap.
+              tma_load_4d_cg<CG>(a_smem(as), &tmap_a, lead(a_full(as)), kc * kBlockK, xs0 + s, t.y0,
+                                 t.n);
             }
+            __syncwarp();
+            if (++as == Cfg::kAStages) as = 0, aph ^= 1;
+          }
+          if (!BRES) {
+            // the kTR weight tiles of this step: one barrier (that of the group's first slot)
+            mbar_wait(b_empty(bs), bph ^ 1, 150 + bs);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(b_full(bs), CG * kTR * Cfg::kBBytes);
+              const uint32_t bar = lead(b_full(bs));
+#pragma unroll
+              for (int r = 0; r < kTR; ++r)
+                tma_load_2d_cg<CG>(b_smem(bs + r), &tmap_b, bar, (r * kTS + s) * p.Cin + kc * kBlockK, b_row);
+            }
+            __syncwarp();
+            if ((bs += kTR) == Cfg::kBStages) bs = 0, bph ^= 1;
           }
         }
       }
@@ -584,42 +640,76 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         const uint32_t tmem_d = tmem_base + (uint32_t)(acs * BN);
         // UPS: row phase a of this unit shifts the slab rows of the two taps to a + r
         const int row_shift = UPS ? (((unit / p.n_tiles) & 3) >> 1) : 0;
-        for (int kc = 0; kc < kchunks; ++kc) {
-          for (int s = 0; s < kTS; ++s) {
-            mbar_wait(a_full(as), aph, 300 + as);
-            tc_fence_after();
-            for (int r = 0; r < kTR; ++r) {
-              uint32_t bsm;
-              if (BRES) {
-                bsm = b_smem(r * kTS + s);
-              } else {
-                mbar_wait(b_full(bs), bph, 350 + bs);
-                tc_fence_after();
-                bsm = b_smem(bs);
-              }
-              if (elect_one()) {
-                // tap (r,s): slab shifted by r tile rows (16 px * 128 B = 2048 B, swizzle-phase neutral)
-                const uint64_t adesc =
-                    make_kmajor_sw128_desc(a_smem(as) + (r + row_shift) * (kTileW * 128));
-                const uint64_t bdesc = make_kmajor_sw128_desc(bsm);
+        const int col_shift = (UPS && LIN) ? ((unit / p.n_tiles) & 1) : 0;
+        if (LIN && BRES == 1) {
+          // linear slab + resident weights: the whole tile (all taps x 4 K steps) in ONE region
+          mbar_wait(a_full(as), aph, 300 + as);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t adesc0 =
+                make_kmajor_sw128_desc(a_smem(as) + (uint32_t)(row_shift * G::kBoxW + col_shift) * 128u);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                  // +16 elements (32 bytes) along K inside the swizzle atom = +2 in the start field
-                  umma_f16_cg<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc,
-                                  (kc | s | r | k) ? 1u : 0u);
-                }
-                if (!BRES) umma_commit_cg<CG>(b_empty(bs));  // frees the weight tile when these MMAs retire
-                if (r == kTR - 1) {
-                  umma_commit_cg<CG>(a_empty(as));  // ... and the slab after its last tap
-                  if (kc == kchunks - 1 && s == kTS - 1) umma_commit_cg<CG>(tmem_full_bar(acs));
+            for (int s = 0; s < kTS; ++s)
+#pragma unroll
+              for (int r = 0; r < kTR; ++r) {
+                const uint64_t adesc = adesc0 + (uint64_t)((r * G::kBoxW + s) * 128 >> 4);
+                const uint64_t bdesc = make_kmajor_sw128_desc(b_smem(r * kTS + s));
+                if (!(p.ablate & 2)) {
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma_f16_cg<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (s | r | k) ? 1u : 0u);
                 }
               }
-              __syncwarp();
-              if (!BRES) {
-                if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
-              }
+            umma_commit_cg<CG>(a_empty(as));
+            umma_commit_cg<CG>(tmem_full_bar(acs));
+          }
+          __syncwarp();
+          if (++as == Cfg::kAStages) as = 0, aph ^= 1;
+          continue;
+        }
+        for (int kc = 0; kc < kchunks; ++kc) {
+#pragma unroll
+          for (int s = 0; s < kTS; ++s) {
+            // One elected-lane region per (chunk, filter column): all kTR filter rows x 4 K steps are
+            // issued back to back.  (Electing per tap cost ~40 scalar/uniform instructions around
+            // every 4 MMAs -- ~200 issue cycles against 128 cycles of math at N = 64 -- which made
+            // the issuing warp, not the tensor pipe, the bound of the 64-channel layers.)
+            if (!LIN || s == 0) {
+              mbar_wait(a_full(as), aph, 300 + as);
             }
-            if (++as == Cfg::kAStages) as = 0, aph ^= 1;
+            const int bs0 = bs;
+            if (!BRES) {
+              mbar_wait(b_full(bs), bph, 350 + bs);
+              if ((bs += kTR) == Cfg::kBStages) bs = 0, bph ^= 1;
+            }
+            tc_fence_after();
+            if (elect_one()) {
+              // tap (r, s): slab shifted by r rows (kBoxW px * 128 B, swizzle-phase neutral for the
+              // 16-px box); LIN: and by s pixels inside the same slab
+              const uint32_t a0 =
+                  a_smem(as) + (uint32_t)(row_shift * G::kBoxW + (LIN ? s + col_shift : 0)) * 128u;
+              const uint64_t adesc0 = make_kmajor_sw128_desc(a0);
+#pragma unroll
+              for (int r = 0; r < kTR; ++r) {
+                const uint64_t adesc = adesc0 + (uint64_t)(r * (G::kBoxW * 128 >> 4));
+                const uint64_t bdesc = make_kmajor_sw128_desc(BRES ? b_smem(kc * Cfg::kTaps + r * kTS + s) : b_smem(bs0 + r));
+                if (!(p.ablate & 2)) {
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k) {
+                    // +16 elements (32 bytes) along K inside the swizzle atom = +2 in the start field
+                    umma_f16_cg<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc,
+                                    (kc | s | r | k) ? 1u : 0u);
+                  }
+                }
+              }
+              if (!BRES) umma_commit_cg<CG>(b_empty(bs0));  // frees the weight tiles when these MMAs retire
+              if (!LIN || s == kTS - 1) umma_commit_cg<CG>(a_empty(as));  // ... and the slab after its last tap
+              if (kc == kchunks - 1 && s == kTS - 1) umma_commit_cg<CG>(tmem_full_bar(acs));
+            }
+            __syncwarp();
+            if (!LIN || s == kTS - 1) {
+              if (++as == Cfg::kAStages) as = 0, aph ^= 1;
+            }
           }
         }
       }
@@ -630,7 +720,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     const int grp = (warp - kEpiWarp0) >> 2;
     const int quad = warp & 3;           // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;    // accumulator row = pixel inside the tile
-    const int py = row / kTileW, px = row % kTileW;
+    const int py = row / G::kBoxW, px = row % G::kBoxW;
+    const bool col_ok = !LIN || px < G::kOutW;  // LIN: the last two columns wrap into the next row
     // warp 4 owns the bulk-store async groups: all its lanes execute the waits (a no-op for lanes
     // without groups), one elected lane -- always the same one -- issues and commits the stores
     const bool issuer_warp = (quad == 0);
@@ -638,15 +729,17 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     for (int it = grp;; it += 2) {
       const long long unit_ll = (long long)unit0 + (long long)it * unit_step;
       if (unit_ll >= p.total_tiles) break;
-      const TileCoord t = decode_tile<CG, UPS>(p, (int)unit_ll, (int)cta_rank);
+      const TileCoord t = decode_tile<CG, UPS, GEO>(p, (int)unit_ll, (int)cta_rank);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int y = t.y0 + py, x = t.x0 + px;
-      const bool valid = (y < p.H) && (x < p.W) && (CG == 1 || t.n < p.N);
+      const bool valid = col_ok && (y < p.H) && (x < p.W) && (CG == 1 || t.n < p.N);
       mbar_wait(tmem_full_bar(as), aphase, 400 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-      if (EPI == EPI_NCHW_F32) {
+      if (p.ablate & 1) {
+        // measurement only: hand the accumulator back untouched
+      } else if (EPI == EPI_NCHW_F32) {
         uint32_t r[16];
         tmem_ld16(taddr, r);
         tmem_ld_wait();
@@ -674,6 +767,16 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           // the staging buffer about to be rewritten must have been read out by its TMA store
           if (issuer_warp) bulk_wait_read<0>();
           tmem_ld_wait();
+          if (ch == BN / 64 - 1) {
+            // the accumulator stage is in registers: hand it back to the MMA warp before the
+            // pack / stage / store work of this last chunk
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(lead(tmem_empty_bar(as)));
+              else mbar_arrive(tmem_empty_bar(as));
+            }
+          }
           epi_barrier(grp);
           const int co = t.nt * BN + ch * 64;
           uint32_t pk[32];
@@ -693,11 +796,12 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
             }
           }
           // stage the row (128 bytes = 8 chunks) with the 128-byte swizzle the TMA store expects
-          int srow = row;
-          bool writer = true;
+          int srow = LIN ? py * G::kOutW + px : row;
+          bool writer = col_ok;
           if (EPI == EPI_ACT_POOL) {
-            writer = !(lane & 1) && lane < 16;  // anchor of a 2x2 window
-            srow = (py >> 1) * (kTileW / 2) + (px >> 1);
+            static_assert(EPI != EPI_ACT_POOL || G::kBoxW == 16, "fused pooling needs 2 tile rows per warp");
+            writer = col_ok && !(lane & 1) && lane < 16;  // anchor of a 2x2 window
+            srow = (py >> 1) * (G::kOutW / 2) + (px >> 1);
           }
           if (writer) {
 #pragma unroll
@@ -743,12 +847,14 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           }
         }
       }
-      // all TMEM reads of this accumulator stage are complete (wait::ld above)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster(lead(tmem_empty_bar(as)));
-        else mbar_arrive(tmem_empty_bar(as));
+      if (EPI == EPI_NCHW_F32 || (p.ablate & 1)) {
+        // all TMEM reads of this accumulator stage are complete (wait::ld above)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(lead(tmem_empty_bar(as)));
+          else mbar_arrive(tmem_empty_bar(as));
+        }
       }
     }
     if (issuer_warp) bulk_wait_all();
@@ -1768,26 +1874,56 @@ int make_weight_map(CUtensorMap* m, const T16* wk, int K, int CoutPad, int BN) {
   return CCST_OK;
 }
 
-template <typename T16, int BN, int EPI, bool BRES, int CG>
-int launch_cfg(const CUtensorMap& ma, const T16* wk, ConvParams<T16> p, cudaStream_t st) {
+int lin_desc_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CCST_LIN_DESC");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+template <typename T16, int BN, int EPI, int BRES, int CG, int GEO = 0>
+int launch_cfg(const CUtensorMap& ma0, const T16* wk, ConvParams<T16> p, cudaStream_t st) {
   constexpr bool UPS = (EPI == EPI_UPS);
-  using Cfg = UmmaCfg<BN, BRES, CG, UPS>;
+  using Cfg = UmmaCfg<BN, BRES, CG, UPS, GEO>;
+  if constexpr (!Cfg::kFits) {
+    set_error("conv_umma: configuration BN=%d resident=%d pair=%d geo=%d does not fit shared memory", BN,
+              BRES, CG, GEO);
+    return CCST_EINVAL;
+  } else {
+  using G = Geo<GEO>;
+  CUtensorMap ma = ma0;
+  if (GEO != 0) {
+    ActView<T16> in{const_cast<T16*>(p.in_ptr), p.N, p.H, p.W, p.Cin};
+    if (int e = make_act_map(&ma, in, G::kBoxW, G::kSlabRows)) return e;
+    p.tiles_x = (p.W + G::kOutW - 1) / G::kOutW;
+    p.tiles_y = (p.H + G::kRows - 1) / G::kRows;
+    const int64_t m_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
+    CCST_CHECK_ARG(m_tiles * p.n_tiles * (UPS ? 4 : 1) < (1ll << 31), "conv_umma: too many tiles");
+    p.m_tiles = (int)m_tiles;
+    p.desc_mode = lin_desc_mode();
+  }
+  {
+    static const int ablate = [] { const char* e = getenv("CCST_ABLATE"); return e ? atoi(e) : 0; }();
+    p.ablate = ablate;
+  }
   CUtensorMap mb;
   if (int e = make_weight_map(&mb, wk, Cfg::kTaps * p.Cin, (UPS ? 4 : 1) * p.CoutPad, Cfg::kBRows)) return e;
   OutMaps mo;
   memset(&mo, 0, sizeof(mo));
   if (EPI == EPI_ACT) {
-    if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kTileW, kTileH)) return e;
+    if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, G::kOutW, G::kRows)) return e;
   } else if (EPI == EPI_ACT_POOL) {
-    if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kTileW / 2, kTileH / 2)) return e;
+    if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, G::kOutW / 2, G::kRows / 2)) return e;
   } else if (EPI == EPI_ACT_UP2 || EPI == EPI_UPS) {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
-        if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, kTileW, kTileH)) return e;
+        if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, G::kOutW, G::kRows)) return e;
   }
   static bool attr_done = false;
   if (!attr_done) {
-    CCST_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T16, BN, EPI, BRES, CG>,
+    CCST_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T16, BN, EPI, BRES, CG, GEO>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
@@ -1798,7 +1934,7 @@ int launch_cfg(const CUtensorMap& ma, const T16* wk, ConvParams<T16> p, cudaStre
   if (UPS && BRES) slots &= ~3;  // resident weights of ONE phase per CTA: unit stride % 4 == 0
   const int grid = (int)(units < slots ? units : slots) * CG;
   if (CG == 1) {
-    conv_umma_kernel<T16, BN, EPI, BRES, CG><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, mo, p);
+    conv_umma_kernel<T16, BN, EPI, BRES, CG, GEO><<<grid, kThreadsUmma, Cfg::kSmemBytes, st>>>(ma, mb, mo, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreadsUmma);
@@ -1807,15 +1943,46 @@ int launch_cfg(const CUtensorMap& ma, const T16* wk, ConvParams<T16> p, cudaStre
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    CCST_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T16, BN, EPI, BRES, CG>, ma, mb, mo, p));
+    CCST_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T16, BN, EPI, BRES, CG, GEO>, ma, mb, mo, p));
   }
   CCST_LAUNCHED();
   return CCST_OK;
+  }
 }
 
-template <typename T16, int BN, bool BRES, int CG>
+// tile geometry per N (see Geo): CCST_GEO64 / CCST_GEO128 = 0, 1 or 2
+int geo_mode(int bn) {
+  static int v64 = -1, v128 = -1;
+  if (v64 < 0) {
+    const char* e = getenv("CCST_GEO64");
+    v64 = e ? atoi(e) : 0;
+    e = getenv("CCST_GEO128");
+    v128 = e ? atoi(e) : 0;
+  }
+  return bn == 64 ? v64 : (bn == 128 ? v128 : 0);
+}
+
+template <typename T16, int BN, int BRES, int CG>
 int launch_bn(const CUtensorMap& ma, const T16* wk, const ConvParams<T16>& p, int epi,
               cudaStream_t st) {
+  if (BN == 64 || BN == 128) {
+    constexpr int BNL = (BN == 64 || BN == 128) ? BN : 64;  // only these are instantiated
+    const int geo = geo_mode(BN);
+    if (geo == 1) {
+      switch (epi) {
+        case EPI_ACT: return launch_cfg<T16, BNL, EPI_ACT, BRES, CG, 1>(ma, wk, p, st);
+        case EPI_ACT_POOL: return launch_cfg<T16, BNL, EPI_ACT_POOL, BRES, CG, 1>(ma, wk, p, st);
+        case EPI_UPS: return launch_cfg<T16, BNL, EPI_UPS, BRES, CG, 1>(ma, wk, p, st);
+        default: break;
+      }
+    } else if (geo == 2) {
+      switch (epi) {
+        case EPI_ACT: return launch_cfg<T16, BNL, EPI_ACT, BRES, CG, 2>(ma, wk, p, st);
+        case EPI_UPS: return launch_cfg<T16, BNL, EPI_UPS, BRES, CG, 2>(ma, wk, p, st);
+        default: break;
+      }
+    }
+  }
   switch (epi) {
     case EPI_ACT:
       return launch_cfg<T16, BN, EPI_ACT, BRES, CG>(ma, wk, p, st);
@@ -1844,7 +2011,13 @@ int cta_pair_mode() {
   return v;
 }
 
-template <typename T16, int BN, bool BRES>
+bool bres128_on() {
+  // (the 16 KiB tiles of a single-CTA N = 128 kernel do not fit resident: CTA pairs only)
+  static const bool on = [] { const char* e = getenv("CCST_BRES128"); return !(e && e[0] == '0'); }();
+  return on && cta_pair_mode() != 0;
+}
+
+template <typename T16, int BN, int BRES>
 int launch_cg(const CUtensorMap& ma, const T16* wk, const ConvParams<T16>& p, int epi,
               cudaStream_t st) {
   const int mode = cta_pair_mode();
@@ -1965,6 +2138,8 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
   p.m_tiles = (int)m_tiles;
   p.total_tiles = 0;  // set per kernel variant (tiles or tile pairs)
   p.relu = relu;
+  p.in_ptr = in.p;
+  p.desc_mode = 0;
   p.halo_edge = halo_edge;
   p.bias = bias;
   p.out = out;
@@ -1985,7 +2160,9 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
         return in.C == kBlockK ? launch_cg<T16, 64, true>(ma, wk_up, p, epi, st)
                                : launch_cg<T16, 64, false>(ma, wk_up, p, epi, st);
       case 128:
-        return launch_cg<T16, 128, false>(ma, wk_up, p, epi, st);
+        // the 8 phase tiles (4 taps x 2 chunks) of the Cin = 128 layer stay resident
+        return (in.C == 2 * kBlockK && bres128_on()) ? launch_cg<T16, 128, 2>(ma, wk_up, p, epi, st)
+                                                     : launch_cg<T16, 128, 0>(ma, wk_up, p, epi, st);
       default:
         return launch_cg<T16, 256, false>(ma, wk_up, p, epi, st);
     }
@@ -2016,13 +2193,15 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
       // 0.446 -> 0.422); with the fused max-pool its epilogue needs 4 shuffles per value and is
       // slower than the tap-by-tap kernel (conv1_2 0.613 vs 0.672 ms), so that layer stays there
       // unless CCST_SMERGE=3
-      if (wk_sm && smerge_mode() != 0 && (epi != EPI_ACT_POOL || smerge_mode() == 3))
+      if (wk_sm && smerge_mode() != 0 && geo_mode(64) == 0 && (epi != EPI_ACT_POOL || smerge_mode() == 3))
         return launch_smerge<T16>(ma, wk_sm, p, epi, st);
       // 64 -> 64 layers keep all 9 weight tiles resident in shared memory
       return in.C == kBlockK ? launch_cg<T16, 64, true>(ma, wk, p, epi, st)
                              : launch_cg<T16, 64, false>(ma, wk, p, epi, st);
     case 128:
-      return launch_cg<T16, 128, false>(ma, wk, p, epi, st);
+      // 64 -> 128 (conv2_1): the 9 weight tiles stay resident
+      return (in.C == kBlockK && bres128_on()) ? launch_cg<T16, 128, 1>(ma, wk, p, epi, st)
+                                               : launch_cg<T16, 128, 0>(ma, wk, p, epi, st);
     default:
       return launch_cg<T16, 256, false>(ma, wk, p, epi, st);
   }
