@@ -259,6 +259,29 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * args.batch * args.steps / t.item()
 
+    # the same loop with the image I/O fused around the path: uint8 HWC batches in (the
+    # loader's images before ToTensor), uint8 HWC batches out (what save_image encodes)
+    host_u8 = [(h.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().pin_memory() for h in host]
+
+    def e2e_u8_run(nsteps):
+        seen = 0
+        batches = (host_u8[i & 1] for i in range(nsteps))
+        for _, out_host in drivers.overall_transfer(eng, batches, stat, 1.0, precision, u8=True):
+            seen += out_host.shape[0]
+        return seen
+
+    e2e_u8_run(3)
+    barrier()
+    t0 = time.perf_counter()
+    seen = e2e_u8_run(args.steps)
+    barrier()
+    e2e_u8_s = time.perf_counter() - t0
+    assert seen == args.batch * args.steps
+    t = torch.tensor([e2e_u8_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_u8_value = world * args.batch * args.steps / t.item()
+
     # same loop without overlap: the reference's own structure, one blocking call per step
     def e2e_step_serial(i):
         x = host[i & 1].to(dev, non_blocking=True)
@@ -296,8 +319,16 @@ def run_ours(args, rank, world, local_rank):
         step_ms_prof = sum(a["ms"] for a in agg.values()) / psteps
         conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
         peak_tf = peaks["tf_sust"]
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_conv_traffic.json")
+        if precision != "fp32" and os.path.exists(tp):
+            td = json.load(open(tp))
+            if td.get("batch") == args.batch:
+                traffic = td["dram_bytes_per_launch_avg"]
+                traffic_src = td["source"]
         roofline = {
-            "kernel": "conv_umma_kernel (tcgen05.mma + TMA implicit-GEMM 3x3 conv, 17 launches/step)"
+            "kernel": "tcgen05.mma + TMA implicit-GEMM 3x3 convs (conv_umma_kernel / conv_smerge_kernel / "
+                      "conv_last_umma_kernel, 18 launches/step)"
             if precision != "fp32" else "conv_ffma_kernel (fp32 validation mode)",
             "bound": "tensor", "achieved": round(conv_tflops, 2), "peak": peak_tf, "unit": "TFLOP/s",
             "frac": round(conv_tflops / peak_tf, 4),
@@ -305,7 +336,11 @@ def run_ours(args, rank, world, local_rank):
             "frac_of_burst_peak": round(conv_tflops / peaks["tf_burst"], 4),
             "flops_per_launch_avg": conv["flops"] / max(conv["n"], 1),
             "ms_per_launch_avg": round(conv["ms"] / max(conv["n"], 1), 4),
-            "share_of_step": round(conv["ms"] / psteps / step_ms_prof, 4), "traffic": None,
+            "share_of_step": round(conv["ms"] / psteps / step_ms_prof, 4), "traffic": traffic,
+            "traffic_source": traffic_src,
+            "flops_basis": "EXECUTED flops: the three convs that follow a nearest-x2 upsample run as four 2x2 "
+                           "phase convolutions (16 instead of 36 tap-GEMMs per source pixel), so a step executes "
+                           "220.9 of the 253.07 algorithmic GFLOP/image; tflops_per_gpu uses the algorithmic count",
             "timing": f"cudaEvent pair around every launch on the launch stream, {psteps}-step pass after the timed region",
             "per_kind_ms_per_step": {str(k): round(a["ms"] / psteps, 4) for k, a in sorted(agg.items())},
         }
@@ -372,6 +407,10 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": img_bytes,
                     "api": "ccst_b200.drivers.overall_transfer(engine, pinned host batches, style_stat): the batch "
                            "loop of CCST_OverallStyleTransfer.py:149-167, H2D/compute/D2H double-buffered on 3 streams",
+                    "u8_io": {"value": round(e2e_u8_value, 2), "h2d_bytes_per_step": img_bytes // 4,
+                              "d2h_bytes_per_step": img_bytes // 4,
+                              "api": "drivers.overall_transfer(..., u8=True): uint8 HWC batches in/out, ToTensor and "
+                                     "save_image's quantisation on the GPU (ccst_style_transfer_u8)"},
                     "serial_per_gpu": round(e2e_serial_value, 2),
                     "serial_api": "x.to(device); ccst_b200.style_transfer(vgg, decoder, x, style_stat, alpha); out.cpu() "
                                   "per step, no overlap (rank 0)"},
