@@ -364,12 +364,15 @@ def run_ours(args, rank, world, local_rank):
         nbytes = feat.numel() * 4
         b_stats = nbytes + 8 * BATCH * 512
         b_adain = 2 * nbytes + 8 * 512
-        roofline_stats = {"kernel": "stats_regs_kernel<256,4> (calc_mean_std [32,512,64,64] fp32)", "bound": "hbm",
+        roofline_stats = {"kernel": "plane_bulk_kernel<stats> (TMA bulk-staged single-pass Welford; calc_mean_std [32,512,64,64] fp32)", "bound": "hbm",
                           "achieved": round(b_stats / ms_stats / 1e6, 1), "peak": peaks["hbm"], "unit": "GB/s",
-                          "frac": round(b_stats / ms_stats / 1e6 / peaks["hbm"], 4), "traffic": None,
+                          "frac": round(b_stats / ms_stats / 1e6 / peaks["hbm"], 4),
+                          "traffic": 274583552 if BATCH == 32 else None,
+                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum "
+                                            "(profiles/r01_ncu_ops_summary.txt); algorithmic bytes 268.5 MB",
                           "ms": round(ms_stats, 5), "peak_source": peaks["src"] + " copy bandwidth",
                           "note": "includes torch.empty of the outputs and the ctypes call per launch"}
-        roofline_adain = {"kernel": "adain_regs_kernel<256,4> (adaIN_StyleStat_ContentFeat [32,512,64,64] fp32)",
+        roofline_adain = {"kernel": "plane_bulk_kernel<adain> (statistics + re-normalisation in one HBM pass; adaIN_StyleStat_ContentFeat [32,512,64,64] fp32)",
                           "bound": "hbm", "achieved": round(b_adain / ms_adain / 1e6, 1), "peak": peaks["hbm"],
                           "unit": "GB/s", "frac": round(b_adain / ms_adain / 1e6 / peaks["hbm"], 4), "traffic": None,
                           "ms": round(ms_adain, 5), "peak_source": peaks["src"] + " copy bandwidth"}
