@@ -347,7 +347,8 @@ struct Pipe {
                                : 2.0 * 9 * L.cin * L.cout * (double)N * H * W;
       const double bytes = (double)cur.elems() * sizeof(T) + (double)out.elems() * sizeof(T);
       ProfScope ps(h, st, sizeof(T) == 2 ? 1 : 2, flops, bytes);
-      if (int e = conv(L, 1, epi, out, nullptr, !(pool_after && !fused_pool), halo_edge)) return e;
+      // (the un-fused pool path runs the same conv kernel as the fused one, so both give the same bits)
+      if (int e = conv(L, 1, epi, out, nullptr, true, halo_edge)) return e;
     }
     cur = out, cur_slot ^= 1;
     up_pending = defer_up;
@@ -732,6 +733,14 @@ extern "C" int ccst_quantize_u8(const float* d_img_nchw, int N, int C, int H, in
   CCST_CHECK_ARG(d_img_nchw && d_out_nhwc && N >= 1 && C >= 1 && H >= 1 && W >= 1,
                  "ccst_quantize_u8: bad argument");
   return launch_quantize_nchw_to_u8_nhwc(d_img_nchw, N, C, H, W, d_out_nhwc, (cudaStream_t)stream);
+}
+
+extern "C" int ccst_resize_bilinear_aa_f32(const float* d_in, int64_t planes, int H, int W, int OH, int OW,
+                                           float* d_out, void* stream) {
+  if (int e = require_sm100()) return e;
+  CCST_CHECK_ARG(d_in && d_out && planes >= 1 && H >= 1 && W >= 1 && OH >= 1 && OW >= 1,
+                 "ccst_resize_bilinear_aa_f32: bad argument");
+  return launch_resize_aa(d_in, planes, H, W, OH, OW, d_out, (cudaStream_t)stream);
 }
 
 extern "C" int ccst_profile_enable(ccst_handle* h, int on) {

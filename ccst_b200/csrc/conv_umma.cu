@@ -888,8 +888,10 @@ struct SmergeCfg {
   static constexpr int kASlabBytes = (kTileH + 2) * kTileW * 128;  // 20480
   static constexpr int kBRows = kSmN / CG;
   static constexpr int kBBytes = kBRows * kBlockK * 2;             // 24576 / CG
-  static constexpr int kAStages = BRES ? 5 : 4;
-  static constexpr int kBStages = BRES ? 3 : (CG == 2 ? 6 : 4);    // resident: 3 filter rows x (Cin == 64)
+  // streamed weights: the 3 filter-row tiles of a chunk travel as one group (one barrier pair, one
+  // wait per chunk in the producer and the MMA warp); two groups in flight
+  static constexpr int kAStages = BRES ? 5 : (CG == 2 ? 4 : 2);
+  static constexpr int kBStages = BRES ? 3 : 6;                    // resident: 3 filter rows x (Cin == 64)
   static constexpr int kAOff = 0;
   static constexpr int kBOff = kAStages * kASlabBytes;
   static constexpr int kStoreOff = kBOff + kBStages * kBBytes;
@@ -1004,15 +1006,16 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         __syncwarp();
         if (++as == Cfg::kAStages) as = 0, aph ^= 1;
         if (!BRES) {
-          for (int r = 0; r < 3; ++r) {
-            mbar_wait(b_empty(bs), bph ^ 1, 550 + bs);
-            if (elect_one()) {
-              if (leader) mbar_expect_tx(b_full(bs), CG * Cfg::kBBytes);
-              tma_load_2d_cg<CG>(b_smem(bs), &tmap_b, lead(b_full(bs)), r * p.Cin + kc * kBlockK, b_row0);
-            }
-            __syncwarp();
-            if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
+          mbar_wait(b_empty(bs), bph ^ 1, 550 + bs);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(b_full(bs), CG * 3 * Cfg::kBBytes);
+            const uint32_t bar = lead(b_full(bs));
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              tma_load_2d_cg<CG>(b_smem(bs + r), &tmap_b, bar, r * p.Cin + kc * kBlockK, b_row0);
           }
+          __syncwarp();
+          if ((bs += 3) == Cfg::kBStages) bs = 0, bph ^= 1;
         }
       }
     }
@@ -1036,33 +1039,28 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         const uint32_t tmem_d = tmem_base + (uint32_t)(acs * kSmN);
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(a_full(as), aph, 580 + as);
+          const int bs0 = bs;
+          if (!BRES) {
+            mbar_wait(b_full(bs), bph, 590 + bs);
+            if ((bs += 3) == Cfg::kBStages) bs = 0, bph ^= 1;
+          }
           tc_fence_after();
-          for (int r = 0; r < 3; ++r) {
-            uint32_t bsm;
-            if (BRES) {
-              bsm = b_smem(r);
-            } else {
-              mbar_wait(b_full(bs), bph, 590 + bs);
-              tc_fence_after();
-              bsm = b_smem(bs);
-            }
-            if (elect_one()) {
-              const uint64_t adesc = make_kmajor_sw128_desc(a_smem(as) + r * (kTileW * 128));
-              const uint64_t bdesc = make_kmajor_sw128_desc(bsm);
+          if (elect_one()) {
+            // one issue region per chunk: 3 filter rows x 4 K steps of N = 192
+            const uint64_t adesc0 = make_kmajor_sw128_desc(a_smem(as));
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const uint64_t adesc = adesc0 + (uint64_t)(r * (kTileW * 128 >> 4));
+              const uint64_t bdesc = make_kmajor_sw128_desc(BRES ? b_smem(r) : b_smem(bs0 + r));
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k)
                 umma_f16_cg<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | r | k) ? 1u : 0u);
-              if (!BRES) umma_commit_cg<CG>(b_empty(bs));
-              if (r == 2) {
-                umma_commit_cg<CG>(a_empty(as));
-                if (kc == kchunks - 1) umma_commit_cg<CG>(tmem_full_bar(acs));
-              }
             }
-            __syncwarp();
-            if (!BRES) {
-              if (++bs == Cfg::kBStages) bs = 0, bph ^= 1;
-            }
+            if (!BRES) umma_commit_cg<CG>(b_empty(bs0));
+            umma_commit_cg<CG>(a_empty(as));
+            if (kc == kchunks - 1) umma_commit_cg<CG>(tmem_full_bar(acs));
           }
+          __syncwarp();
           if (++as == Cfg::kAStages) as = 0, aph ^= 1;
         }
       }
@@ -2464,7 +2462,10 @@ int launch_smerge_epi(const CUtensorMap& ma, const T16* wk_sm, const ConvParams<
 template <typename T16>
 int launch_smerge(const CUtensorMap& ma, const T16* wk_sm, const ConvParams<T16>& p, int epi,
                   cudaStream_t st) {
-  const bool pair = smerge_mode() == 2;
+  // CTA pairs for the streamed-weight layers (dec7: 0.30 -> 0.26 ms; each CTA stages half of every
+  // weight tile); CCST_SMERGE_PAIR=0/1 forces singles / pairs everywhere
+  static const int pair_env = [] { const char* e = getenv("CCST_SMERGE_PAIR"); return e ? atoi(e) : -1; }();
+  const bool pair = pair_env >= 0 ? pair_env != 0 : true;
   if (p.Cin == kBlockK)
     return pair ? launch_smerge_epi<T16, true, 2>(ma, wk_sm, p, epi, st)
                 : launch_smerge_epi<T16, true, 1>(ma, wk_sm, p, epi, st);
@@ -2599,11 +2600,11 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
       return CCST_OK;
     }
     case 64:
-      // s-merged kernel for the plain / upsampling 64-channel layers (dec8 0.606 -> 0.591 ms, dec7
-      // 0.446 -> 0.422); with the fused max-pool its epilogue needs 4 shuffles per value and is
-      // slower than the tap-by-tap kernel (conv1_2 0.613 vs 0.672 ms), so that layer stays there
-      // unless CCST_SMERGE=3
-      if (wk_sm && smerge_mode() != 0 && geo_mode(64) == 0 && (epi != EPI_ACT_POOL || smerge_mode() == 3))
+      // s-merged kernel (N = 192 per operand view instead of 64) for every 64-channel layer: at N = 64
+      // the tap-by-tap kernel is capped at 50 % of the tensor peak by the A-operand fetch.  Measured
+      // batch 32 @512^2: conv1_2 (fused pool, pair) 0.635 -> 0.58 ms, dec7 (pair) 0.32 -> 0.25 ms.
+      // CCST_SMERGE=0 disables it, =4 keeps the pooled layer on the tap-by-tap kernel.
+      if (wk_sm && smerge_mode() != 0 && geo_mode(64) == 0 && (epi != EPI_ACT_POOL || smerge_mode() != 4))
         return launch_smerge<T16>(ma, wk_sm, p, epi, st);
       // 64 -> 64 layers keep all 9 weight tiles resident in shared memory
       return in.C == kBlockK ? launch_cg<T16, 64, true>(ma, wk, p, epi, st)

@@ -614,6 +614,64 @@ __global__ void __launch_bounds__(256) quantize_nchw_to_u8_nhwc_kernel(const flo
   }
 }
 
+// `transforms.Resize(output_size)` on the output tensor (CCST_OverallStyleTransfer.py:134-135,154-155):
+// torch's anti-aliased bilinear interpolation (aten UpSampleKernel / UpSampleBilinear2d antialias,
+// align_corners = false), restated: separable triangle filter of support max(scale, 1), weights
+// normalised per output index, horizontal pass first, everything in fp32.
+struct AaAxis {
+  float scale, support, invscale;
+  int in_size;
+};
+__device__ __forceinline__ AaAxis aa_axis(int in_size, int out_size) {
+  AaAxis a;
+  a.in_size = in_size;
+  a.scale = __fdiv_rn((float)in_size, (float)out_size);
+  a.support = a.scale >= 1.f ? a.scale : 1.f;
+  a.invscale = a.scale >= 1.f ? __fdiv_rn(1.f, a.scale) : 1.f;
+  return a;
+}
+__device__ __forceinline__ void aa_window(const AaAxis& a, int i, int& lo, int& n, float& center) {
+  center = __fmul_rn(a.scale, __fadd_rn((float)i, 0.5f));
+  lo = max((int)__fadd_rn(__fsub_rn(center, a.support), 0.5f), 0);
+  n = min((int)__fadd_rn(__fadd_rn(center, a.support), 0.5f), a.in_size) - lo;
+}
+__device__ __forceinline__ float aa_weight(const AaAxis& a, int j, int lo, float center) {
+  const float x = fabsf(__fmul_rn(__fadd_rn(__fsub_rn((float)(j + lo), center), 0.5f), a.invscale));
+  return x < 1.f ? __fsub_rn(1.f, x) : 0.f;
+}
+
+__global__ void __launch_bounds__(256) resize_aa_kernel(const float* __restrict__ in, size_t planes, int H,
+                                                        int W, int OH, int OW, float* __restrict__ out) {
+  const AaAxis ax = aa_axis(W, OW), ay = aa_axis(H, OH);
+  const size_t total = planes * (size_t)OH * OW;
+  for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
+    const int ox = (int)(idx % OW);
+    const int oy = (int)((idx / OW) % OH);
+    const float* src = in + (idx / ((size_t)OW * OH)) * (size_t)H * W;
+    int x0, nx, y0, ny;
+    float cx, cy;
+    aa_window(ax, ox, x0, nx, cx);
+    aa_window(ay, oy, y0, ny, cy);
+    float tx = 0.f, ty = 0.f;
+    for (int j = 0; j < nx; ++j) tx = __fadd_rn(tx, aa_weight(ax, j, x0, cx));
+    for (int j = 0; j < ny; ++j) ty = __fadd_rn(ty, aa_weight(ay, j, y0, cy));
+    float acc = 0.f;
+    for (int r = 0; r < ny; ++r) {
+      const float* row = src + (size_t)(y0 + r) * W + x0;
+      float h = 0.f;  // horizontal pass of this input row
+      for (int j = 0; j < nx; ++j) {
+        float w = aa_weight(ax, j, x0, cx);
+        if (tx != 0.f) w = __fdiv_rn(w, tx);
+        h = __fadd_rn(h, __fmul_rn(w, row[j]));
+      }
+      float wy = aa_weight(ay, r, y0, cy);
+      if (ty != 0.f) wy = __fdiv_rn(wy, ty);
+      acc = __fadd_rn(acc, __fmul_rn(wy, h));
+    }
+    out[idx] = acc;
+  }
+}
+
 int ew_grid(size_t total) {
   size_t blocks = (total + 255) / 256;
   size_t cap = (size_t)sm_count() * 16;
@@ -789,6 +847,13 @@ int launch_u8_nhwc_to_f32_nchw(const uint8_t* in, int N, int C, int H, int W, fl
 int launch_quantize_nchw_to_u8_nhwc(const float* in, int N, int C, int H, int W, uint8_t* out, cudaStream_t st) {
   const size_t hw = (size_t)H * W, total = (size_t)N * hw;
   quantize_nchw_to_u8_nhwc_kernel<<<ew_grid(total), 256, 0, st>>>(in, C, hw, total, out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+int launch_resize_aa(const float* in, int64_t planes, int H, int W, int OH, int OW, float* out, cudaStream_t st) {
+  const size_t total = (size_t)planes * OH * OW;
+  resize_aa_kernel<<<ew_grid(total), 256, 0, st>>>(in, (size_t)planes, H, W, OH, OW, out);
   CCST_LAUNCHED();
   return CCST_OK;
 }

@@ -51,6 +51,8 @@ int launch_act_to_nchw(ActView<T> in, float* out_nchw, cudaStream_t st);
 // batch (torchvision utils.save_image: mul(255).add(0.5).clamp(0,255).to(uint8)) -> NHWC uint8.
 int launch_u8_nhwc_to_f32_nchw(const uint8_t* in, int N, int C, int H, int W, float* out, cudaStream_t st);
 int launch_quantize_nchw_to_u8_nhwc(const float* in, int N, int C, int H, int W, uint8_t* out, cudaStream_t st);
+// torch's anti-aliased bilinear resize of `planes` H x W fp32 planes to OH x OW (transforms.Resize on a tensor)
+int launch_resize_aa(const float* in, int64_t planes, int H, int W, int OH, int OW, float* out, cudaStream_t st);
 template <typename T>
 int launch_nchw_to_act(const float* in_nchw, ActView<T> out, cudaStream_t st);
 // halo_edge: 1 = reflection halo, 0 = replicate halo (see for_each_halo_alias)

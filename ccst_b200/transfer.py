@@ -268,6 +268,35 @@ def save_image_quantize(images: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def resized_output_size(h: int, w: int, size):
+    """torchvision `_compute_resized_output_size` (no max_size): an int matches the SMALLER edge."""
+    if isinstance(size, (tuple, list)):
+        if len(size) == 2:
+            return int(size[0]), int(size[1])
+        size = size[0]
+    size = int(size)
+    if h <= w:
+        return size, int(size * w / h)
+    return int(size * h / w), size
+
+
+def resize(images: torch.Tensor, size) -> torch.Tensor:
+    """`transforms.Resize(size)(images)` for a float tensor [N,C,H,W]
+    (CCST_OverallStyleTransfer.py:134-135,154-155): anti-aliased bilinear, on the device."""
+    x = F_._prep(images, "images")
+    if x.dim() != 4:
+        raise RuntimeError(f"images must be [N,C,H,W], got {tuple(x.shape)}")
+    n, c, h, w = x.shape
+    oh, ow = resized_output_size(h, w, size)
+    if (oh, ow) == (h, w):
+        return x  # torchvision returns the image itself
+    out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+    with _lib.on_device(x.device):
+        _lib.check(_lib.lib().ccst_resize_bilinear_aa_f32(x.data_ptr(), n * c, h, w, oh, ow, out.data_ptr(),
+                                                          torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
 _ENGINES = {}
 
 

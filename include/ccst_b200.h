@@ -160,6 +160,13 @@ int ccst_u8_to_tensor(const uint8_t* d_img_nhwc, int N, int C, int H, int W, flo
 int ccst_quantize_u8(const float* d_img_nchw, int N, int C, int H, int W, uint8_t* d_out_nhwc,
                      void* stream);
 
+/* `resize = transforms.Resize(args.output_size); output = resize(output)`
+ * [CCST_OverallStyleTransfer.py:134-135,154-155] on the device tensor: torchvision's Resize of a float
+ * tensor = torch's anti-aliased bilinear interpolation (align_corners = false).  d_in is `planes`
+ * contiguous H x W fp32 planes (planes = N*C), d_out `planes` OH x OW planes. */
+int ccst_resize_bilinear_aa_f32(const float* d_in, int64_t planes, int H, int W, int OH, int OW,
+                                float* d_out, void* stream);
+
 /* one iteration of the overall-statistics loop: vgg(data) + calc_sum + accumulate
  * [mean_std_computation_effcientMem.py:121-131], encoder output never leaves the arena. */
 int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N, int H, int W,

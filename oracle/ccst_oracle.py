@@ -209,3 +209,20 @@ def save_image_batch_u8(images: torch.Tensor) -> torch.Tensor:
     `grid.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to("cpu", torch.uint8)`; make_grid of a
     single 3-channel image is the image itself): [N,C,H,W] fp32 -> [N,H,W,C] uint8."""
     return save_image_quantize(images.clone()).permute(0, 2, 3, 1).contiguous()
+
+
+def resize_output(images: torch.Tensor, size) -> torch.Tensor:
+    """`transforms.Resize(args.output_size)` applied to the stylised batch
+    (CCST_OverallStyleTransfer.py:134-135,154-155).  torchvision 0.26 `F.resize` of a float tensor is
+    `torch.nn.functional.interpolate(mode="bilinear", align_corners=False, antialias=True)` at the
+    size `_compute_resized_output_size` gives (an int matches the smaller edge)."""
+    n, c, h, w = images.shape
+    if isinstance(size, (tuple, list)) and len(size) == 2:
+        oh, ow = int(size[0]), int(size[1])
+    else:
+        s = int(size[0] if isinstance(size, (tuple, list)) else size)
+        oh, ow = (s, int(s * w / h)) if h <= w else (int(s * h / w), s)
+    if (oh, ow) == (h, w):
+        return images
+    return torch.nn.functional.interpolate(images, size=(oh, ow), mode="bilinear", align_corners=False,
+                                           antialias=True)

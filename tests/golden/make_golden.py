@@ -249,6 +249,23 @@ def make_io():
                 saved.append(np.asarray(Image.open(buf).convert("RGB")))
             out[f"out_f32_a{alpha}"] = o.numpy()
             out[f"out_u8_a{alpha}"] = np.stack(saved)
+        # `resize = transforms.Resize(args.output_size); output = resize(output)` (:134-135,154-155),
+        # the real torchvision transform on the reference's output, then save_image
+        o = ns["style_transfer"](vgg, dec, x, [sm, ss], 1.0)
+        for tag, size in (("s24", 24), ("s17", 17), ("s64", 64), ("hw", (20, 31))):
+            r = transforms.Resize(size)(o)
+            out[f"resize_{tag}"] = r.numpy()
+            saved = []
+            for out_img in r:
+                buf = io.BytesIO()
+                save_image(out_img, buf, format="png")
+                buf.seek(0)
+                saved.append(np.asarray(Image.open(buf).convert("RGB")))
+            out[f"resize_{tag}_u8"] = np.stack(saved)
+        # the Camelyon command line: --image_size 512 --output_size 96 (:187-191), on a synthetic image
+        # (input regenerated by the tests from the same seed; only the 96x96 result is stored)
+        big = torch.rand((1, 3, 512, 512), generator=torch.Generator().manual_seed(77))
+        out["resize_512_to_96"] = transforms.Resize(96)(big).numpy()
     np.savez_compressed(os.path.join(HERE, "io_u8.npz"), **out)
     print("io_u8", os.path.getsize(os.path.join(HERE, "io_u8.npz")) // 1024, "KiB",
           "clamped lo/hi:", int((out["out_u8_a0.5"] == 0).sum()), int((out["out_u8_a0.5"] == 255).sum()))

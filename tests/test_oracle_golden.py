@@ -121,3 +121,14 @@ def test_image_io_matches_torchvision_and_reference(golden, models):
     with torch.no_grad():
         o = O.style_transfer(vgg, dec, O.to_tensor_u8(x_u8), [T(g["style_mean"]), T(g["style_std"])], 1.0)
     np.testing.assert_allclose(o.numpy(), g["out_f32_a1.0"], rtol=0, atol=1e-6)
+
+
+def test_resize_output_matches_torchvision(golden):
+    """`transforms.Resize(args.output_size)` on the stylised batch (CCST_OverallStyleTransfer.py:154-155)."""
+    g = golden["io_u8"]
+    o = T(g["out_f32_a1.0"])
+    for tag, size in (("s24", 24), ("s17", 17), ("s64", 64), ("hw", (20, 31))):
+        r = O.resize_output(o, size)
+        np.testing.assert_array_equal(r.numpy(), g[f"resize_{tag}"])
+        np.testing.assert_array_equal(O.save_image_batch_u8(r).numpy(), g[f"resize_{tag}_u8"])
+    np.testing.assert_array_equal(O.resize_output(torch.rand((1, 3, 512, 512), generator=torch.Generator().manual_seed(77)), 96).numpy(), g["resize_512_to_96"])
