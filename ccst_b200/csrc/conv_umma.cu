@@ -764,8 +764,6 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
             tmem_ld32(taddr + ch * 64, r0);
             tmem_ld32(taddr + ch * 64 + 32, r1);
           }
-          // the staging buffer about to be rewritten must have been read out by its TMA store
-          if (issuer_warp) bulk_wait_read<0>();
           tmem_ld_wait();
           if (ch == BN / 64 - 1) {
             // the accumulator stage is in registers: hand it back to the MMA warp before the
@@ -777,7 +775,6 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
               else mbar_arrive(tmem_empty_bar(as));
             }
           }
-          epi_barrier(grp);
           const int co = t.nt * BN + ch * 64;
           uint32_t pk[32];
 #pragma unroll
@@ -795,6 +792,10 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
               pk[j] = w;
             }
           }
+          // the staging buffer about to be rewritten must have been read out by its TMA store (waited
+          // for only now, so that the bias / ReLU / pack work above overlaps that read-out)
+          if (issuer_warp) bulk_wait_read<0>();
+          epi_barrier(grp);
           // stage the row (128 bytes = 8 chunks) with the 128-byte swizzle the TMA store expects
           int srow = LIN ? py * G::kOutW + px : row;
           bool writer = col_ok;
@@ -1946,14 +1947,12 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           tmem_ld32(taddr + ch * 64, r0);
           tmem_ld32(taddr + ch * 64 + 32, r1);
         }
-        if (issuer_warp) bulk_wait_read<0>();  // the staging buffer has been read out by its TMA store
         tmem_ld_wait();
         if (ch == 3) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(t_empty(acs));
         }
-        epi_barrier(grp);
         uint32_t pk[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -1961,6 +1960,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           const float v1 = __uint_as_float(r[2 * j + 1]) + s_bias[2 * j + 1];
           pk[j] = p.relu ? pack16x2_relu<T16>(v0, v1) : pack16x2<T16>(v0, v1);
         }
+        if (issuer_warp) bulk_wait_read<0>();  // the staging buffer has been read out by its TMA store
+        epi_barrier(grp);
         if (col_ok) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {

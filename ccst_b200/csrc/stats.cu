@@ -11,6 +11,8 @@
 // local (count, mean, M2) triple, the triples are merged with Chan's formula by warp shuffles and
 // (for CTA groups) a shared-memory combine.  Planes that do not fit in registers, or whose size /
 // alignment rules out 128-bit access, take a streaming variant of the same algorithm.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ccst {
@@ -336,15 +338,14 @@ __global__ void from_moments_kernel(const double* __restrict__ mom, int C,
 // warp shuffles combine the lanes of a plane), then -- for AdaIN -- makes a third pass that applies
 // the affine and writes 128-bit coalesced stores.  HBM sees exactly one read (+ one write).
 // =====================================================================================
-constexpr int kSlotBytes = 16384;
-constexpr int kSlots = 8;
-constexpr int kBulkThreads = 32 * (1 + kSlots);
+constexpr int kRingBytes = 131072;
+constexpr int kSlotBytesMax = 16384;
 
 struct BulkArgs {
   const float* x;
   float* out;      // AdaIN only
   int64_t planes;
-  int hw;          // elements per plane, hw % 4 == 0, hw * 4 <= kSlotBytes
+  int hw;          // elements per plane, hw % 4 == 0, hw * 4 <= kSlotBytesMax
   int ppc;         // planes per chunk
   int64_t chunks;
   float eps;
@@ -393,8 +394,12 @@ __device__ __forceinline__ float group_sum(float v) {
 }
 
 // MODE 0: mean/std, 1: raw {mean, M2}, 2: AdaIN
-template <int MODE, int G>
-__global__ void __launch_bounds__(kBulkThreads, 1) plane_bulk_kernel(BulkArgs a) {
+// SLOTS ring slots of kRingBytes / SLOTS bytes, one consumer warp per slot: 8 x 16 KiB by default,
+// 16 x 8 KiB for planes <= 1 KiB (the per-plane latency chain -- two shared-memory passes, shuffles,
+// sqrt -- bounds small planes, so twice the warps are put on it)
+template <int MODE, int G, int SLOTS>
+__global__ void __launch_bounds__(32 * (1 + SLOTS), 1) plane_bulk_kernel(BulkArgs a) {
+  constexpr int kSlots = SLOTS, kSlotBytes = kRingBytes / SLOTS;
   extern __shared__ __align__(128) uint8_t ring[];  // kSlots * kSlotBytes, then the barriers
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kSlots * kSlotBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -528,31 +533,38 @@ __global__ void __launch_bounds__(kBulkThreads, 1) plane_bulk_kernel(BulkArgs a)
   }
 }
 
-constexpr int kBulkSmem = kSlots * kSlotBytes + 2 * kSlots * 8;
+constexpr int kBulkSmem = kRingBytes + 2 * 16 * 8;
 
 bool bulk_ok(const void* p, int64_t hw) {
-  return hw % 4 == 0 && hw * 4 <= kSlotBytes && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+  return hw % 4 == 0 && hw * 4 <= kSlotBytesMax && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
 }
 
-template <int MODE>
-int launch_bulk(BulkArgs a, cudaStream_t st) {
-  a.ppc = (int)(kSlotBytes / ((int64_t)a.hw * 4));
+template <int MODE, int G, int SLOTS>
+int launch_bulk_cfg(BulkArgs a, cudaStream_t st) {
+  a.ppc = (int)((kRingBytes / SLOTS) / ((int64_t)a.hw * 4));
   a.chunks = ceil_div64(a.planes, a.ppc);
   const int grid = (int)(a.chunks < sm_count() ? a.chunks : sm_count());
   static bool attr_done = false;
   if (!attr_done) {
-    CCST_CUDA(cudaFuncSetAttribute(plane_bulk_kernel<MODE, 8>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSmem));
-    CCST_CUDA(cudaFuncSetAttribute(plane_bulk_kernel<MODE, 32>,
+    CCST_CUDA(cudaFuncSetAttribute(plane_bulk_kernel<MODE, G, SLOTS>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSmem));
     attr_done = true;
   }
-  if (a.hw <= 1024)  // up to 4 KiB planes: 8 lanes per plane, 4 planes in flight per warp
-    plane_bulk_kernel<MODE, 8><<<grid, kBulkThreads, kBulkSmem, st>>>(a);
-  else
-    plane_bulk_kernel<MODE, 32><<<grid, kBulkThreads, kBulkSmem, st>>>(a);
+  plane_bulk_kernel<MODE, G, SLOTS><<<grid, 32 * (1 + SLOTS), kBulkSmem, st>>>(a);
   CCST_LAUNCHED();
   return CCST_OK;
+}
+
+template <int MODE>
+int launch_bulk(BulkArgs a, cudaStream_t st) {
+  static const int g_env = [] { const char* e = getenv("CCST_BULK_G"); return e ? atoi(e) : 0; }();
+  if ((a.hw <= 256 && g_env == 0) || g_env == 4)  // up to 1 KiB planes (12x12 .. 16x16): 4 lanes per plane, 16 warps
+    return launch_bulk_cfg<MODE, 4, 16>(a, st);
+  if (g_env == 44) return launch_bulk_cfg<MODE, 4, 8>(a, st);
+  if ((a.hw <= 1024 && g_env == 0) || g_env == 16)  // up to 4 KiB planes: 16 lanes per plane, 16 warps
+    return launch_bulk_cfg<MODE, 16, 16>(a, st);
+  if (g_env == 8) return launch_bulk_cfg<MODE, 8, 8>(a, st);
+  return launch_bulk_cfg<MODE, 32, 8>(a, st);
 }
 
 int grid_for(int64_t groups) {
