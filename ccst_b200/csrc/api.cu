@@ -116,6 +116,7 @@ struct ccst_handle {
   size_t io_elems = 0;
   bool fuse_pool = true;
   bool fuse_up = true;  // nearest-x2 upsample folded into the NEXT conv (EPI_UPS) instead of the store
+  bool fuse_stats = true;  // relu4_1 statistics taken in conv4_1's epilogue (EPI_ACT_STATS)
   bool profiling = false;
   int prof_n = 0;
   ProfSlot prof[kMaxProf];
@@ -301,6 +302,7 @@ struct Pipe {
   ActView<T> cur;
   bool up_pending = false;  // `cur` is a low-resolution map (replicate halo) awaiting its x2 upsample
   uint8_t* out_u8 = nullptr;  // decoder(): store NHWC uint8 (save_image quantisation) instead of NCHW fp32
+  bool stats_in_tiles = false;  // the last encoder conv left tile statistics of `cur` in h->raw
 
   ActView<T> view(int slot, int N, int H, int W, int C) {
     ActView<T> v;
@@ -312,7 +314,7 @@ struct Pipe {
   // smerge_ok = false keeps a 64-channel layer on the tap-by-tap kernel (the un-fused pool path must
   // produce the same bits as the fused one, which always uses that kernel)
   int conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* out_nchw, bool smerge_ok = true,
-           int halo_edge = 1);
+           int halo_edge = 1, float2* tile_stats = nullptr);
 
   int first_launch(const float* img, int N, int H, int W);
   int first(const float* img, int N, int H, int W) {
@@ -324,7 +326,7 @@ struct Pipe {
   }
 
   // conv (+ fused or separate pool / fused upsample); result becomes `cur`
-  int step(const ConvLayer& L, bool pool_after, bool up_after) {
+  int step(const ConvLayer& L, bool pool_after, bool up_after, bool want_stats = false) {
     const int N = cur.N, H = cur.H, W = cur.W;
     const bool fused_pool = pool_after && h->fuse_pool && sizeof(T) == 2;
     // tcgen05 path: a layer followed by `Upsample` stores its low-resolution output with a replicate
@@ -339,6 +341,14 @@ struct Pipe {
     else if (defer_up) halo_edge = 0;
     else if (up_after) oh = 2 * H, ow = 2 * W, epi = EPI_ACT_UP2;
     if (fused_pool) oh = (H + 1) / 2, ow = (W + 1) / 2, epi = EPI_ACT_POOL;
+    // relu4_1 statistics in the epilogue of the conv that produces it (tcgen05 path, N = 256 tiles)
+    float2* tile_stats = nullptr;
+    if (want_stats && h->fuse_stats && sizeof(T) == 2 && epi == EPI_ACT && halo_edge == 1 &&
+        L.cout % 256 == 0 && N <= 65535) {
+      if (int e = ensure_raw(h, nhwc_tile_scratch_elems(N, L.cout, H, W))) return e;
+      tile_stats = h->raw + 2 * (size_t)N * L.cout;
+      epi = EPI_ACT_STATS;
+    }
     ActView<T> out = view(cur_slot ^ 1, N, oh, ow, L.cout);
     {
       // executed FLOPs: the phase form runs 4 phases x 4 taps per SOURCE pixel (= 4 taps per output
@@ -348,10 +358,11 @@ struct Pipe {
       const double bytes = (double)cur.elems() * sizeof(T) + (double)out.elems() * sizeof(T);
       ProfScope ps(h, st, sizeof(T) == 2 ? 1 : 2, flops, bytes);
       // (the un-fused pool path runs the same conv kernel as the fused one, so both give the same bits)
-      if (int e = conv(L, 1, epi, out, nullptr, true, halo_edge)) return e;
+      if (int e = conv(L, 1, epi, out, nullptr, true, halo_edge, tile_stats)) return e;
     }
     cur = out, cur_slot ^= 1;
     up_pending = defer_up;
+    stats_in_tiles = tile_stats != nullptr;
     if (pool_after && !fused_pool) {
       ActView<T> po = view(cur_slot ^ 1, N, (H + 1) / 2, (W + 1) / 2, L.cout);
       ProfScope ps(h, st, 3, 0, (double)(cur.elems() + po.elems()) * sizeof(T));
@@ -364,18 +375,20 @@ struct Pipe {
   int encoder(const float* img, int N, int H, int W) {
     if (int e = first(img, N, H, W)) return e;
     for (int i = 0; i < kEncLayers; ++i)
-      if (int e = step(h->enc[i], kEncPoolAfter[i], false)) return e;
+      if (int e = step(h->enc[i], kEncPoolAfter[i], false, i == kEncLayers - 1)) return e;
     return CCST_OK;
   }
 
   int adain(const float* mu_s, const float* sigma_s, int64_t stride, float alpha) {
     ActView<T> out = view(cur_slot ^ 1, cur.N, cur.H, cur.W, cur.C);
-    if (int e = ensure_raw(h, nhwc_scratch_elems(cur.N, cur.C, cur.H * cur.W))) return e;
     ProfScope ps(h, st, 4, 0, 2.0 * (double)cur.N * cur.H * cur.W * cur.C * sizeof(T));
-    if (int e = launch_adain_nhwc<T>(cur, out, mu_s, sigma_s, stride, alpha, 1e-5f, h->raw, st)) return e;
+    if (int e = adain_launch(out, mu_s, sigma_s, stride, alpha)) return e;
     cur = out, cur_slot ^= 1;
+    stats_in_tiles = false;
     return CCST_OK;
   }
+
+  int adain_launch(ActView<T> out, const float* mu_s, const float* sigma_s, int64_t stride, float alpha);
 
   int decoder(float* out_nchw) {
     for (int i = 0; i < kDecLayers - 1; ++i)
@@ -388,6 +401,21 @@ struct Pipe {
     return conv(L, 0, EPI_NCHW_F32, cur /*unused*/, out_nchw);
   }
 };
+
+template <>
+int Pipe<float>::adain_launch(ActView<float> out, const float* mu_s, const float* sigma_s, int64_t stride,
+                              float alpha) {
+  if (int e = ensure_raw(h, nhwc_scratch_elems(cur.N, cur.C, cur.H * cur.W))) return e;
+  return launch_adain_nhwc<float>(cur, out, mu_s, sigma_s, stride, alpha, 1e-5f, h->raw, st);
+}
+template <typename T>
+int Pipe<T>::adain_launch(ActView<T> out, const float* mu_s, const float* sigma_s, int64_t stride,
+                          float alpha) {
+  if (stats_in_tiles)  // statistics already taken by the producing conv's epilogue
+    return launch_adain_nhwc_tiles<T>(cur, out, mu_s, sigma_s, stride, alpha, 1e-5f, h->raw, st);
+  if (int e = ensure_raw(h, nhwc_scratch_elems(cur.N, cur.C, cur.H * cur.W))) return e;
+  return launch_adain_nhwc<T>(cur, out, mu_s, sigma_s, stride, alpha, 1e-5f, h->raw, st);
+}
 
 template <>
 int Pipe<float>::first_launch(const float* img, int N, int H, int W) {
@@ -403,22 +431,22 @@ int Pipe<__half>::first_launch(const float* img, int N, int H, int W) {
 }
 template <>
 int Pipe<float>::conv(const ConvLayer& L, int relu, int epi, ActView<float> out, float* out_nchw,
-                      bool, int) {
+                      bool, int, float2*) {
   return launch_conv_ffma(cur, L.w_ffma, L.bias, L.cout, L.pad64, relu, epi, out, out_nchw, st);
 }
 template <>
 int Pipe<bf16>::conv(const ConvLayer& L, int relu, int epi, ActView<bf16> out, float* out_nchw,
-                     bool smerge_ok, int halo_edge) {
+                     bool smerge_ok, int halo_edge, float2* tile_stats) {
   return launch_conv_umma<bf16>(cur, L.w_umma, smerge_ok ? L.w_sm : nullptr, L.w_up, L.bias, L.cout,
                                 L.pad_umma, relu, epi, out, out_nchw,
-                                epi == EPI_NCHW_F32 ? out_u8 : nullptr, halo_edge, st);
+                                epi == EPI_NCHW_F32 ? out_u8 : nullptr, halo_edge, st, tile_stats);
 }
 template <>
 int Pipe<__half>::conv(const ConvLayer& L, int relu, int epi, ActView<__half> out,
-                       float* out_nchw, bool smerge_ok, int halo_edge) {
+                       float* out_nchw, bool smerge_ok, int halo_edge, float2* tile_stats) {
   return launch_conv_umma<__half>(cur, L.w_umma_h, smerge_ok ? L.w_sm_h : nullptr, L.w_up_h, L.bias,
                                   L.cout, L.pad_umma, relu, epi, out, out_nchw,
-                                  epi == EPI_NCHW_F32 ? out_u8 : nullptr, halo_edge, st);
+                                  epi == EPI_NCHW_F32 ? out_u8 : nullptr, halo_edge, st, tile_stats);
 }
 
 int check_common(ccst_handle* h, int precision) {
@@ -494,9 +522,13 @@ int run_encoder(ccst_handle* h, const float* d_img, int N, int H, int W, float* 
     if (int e = launch_act_to_nchw<T>(p.cur, d_feat, st)) return e;
   }
   if (d_state) {
-    if (int e = ensure_raw(h, nhwc_scratch_elems(N, 512, fh * fw))) return e;
     ProfScope ps(h, st, 4, 0, (double)N * fh * fw * 512 * sizeof(T));
-    if (int e = launch_stats_nhwc<T>(p.cur, h->raw, st)) return e;
+    if (p.stats_in_tiles) {
+      if (int e = launch_stats_from_tiles(N, 512, fh, fw, h->raw, st)) return e;
+    } else {
+      if (int e = ensure_raw(h, nhwc_scratch_elems(N, 512, fh * fw))) return e;
+      if (int e = launch_stats_nhwc<T>(p.cur, h->raw, st)) return e;
+    }
     if (int e = merge_raw_into_state(h->raw, N, 512, (int64_t)fh * fw, d_state, st)) return e;
   }
   return CCST_OK;
@@ -558,6 +590,8 @@ extern "C" ccst_handle* ccst_create(int device) {
   if (fp && fp[0] == '0') h->fuse_pool = false;
   const char* fu = getenv("CCST_FUSE_UP");
   if (fu && fu[0] == '0') h->fuse_up = false;
+  const char* fs = getenv("CCST_FUSE_STATS");
+  if (fs && fs[0] == '0') h->fuse_stats = false;
   return h;
 }
 

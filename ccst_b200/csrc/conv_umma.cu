@@ -130,6 +130,7 @@ struct ConvParams {
   ActView<T16> out;
   float* out_nchw;
   uint8_t* out_u8;  // last conv only: NHWC uint8 store quantised like torchvision's save_image
+  float2* tile_stats;  // EPI_ACT_STATS: [(pixel tile * 4 + row quarter) * Cout + channel] {mean, M2}
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -249,6 +250,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <typename T16>
+__device__ __forceinline__ float2 unpack16x2(uint32_t w);
+template <>
+__device__ __forceinline__ float2 unpack16x2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+template <>
+__device__ __forceinline__ float2 unpack16x2<__nv_bfloat16>(uint32_t w) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
 }
 
 // ---- CTA-pair (cta_group::2) variants.  CG = 1 forwards to the single-CTA forms above.
@@ -814,7 +831,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
             }
           }
           if (valid) {
-            if (EPI == EPI_ACT) {
+            if (EPI == EPI_ACT || EPI == EPI_ACT_STATS) {
               store_aliases(p.out, t.n, y, x, co, pk, p.halo_edge);
             } else if (EPI == EPI_UPS) {
               store_aliases(p.out, t.n, 2 * y + (t.ph >> 1), 2 * x + (t.ph & 1), co, pk);
@@ -845,6 +862,34 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
               }
             }
             bulk_commit();
+          }
+          if (EPI == EPI_ACT_STATS && (CG == 1 || t.n < p.N)) {
+            // statistics of the STORED (rounded) values, read back from the staged tile: thread =
+            // (channel pair = lane, quarter of the tile = two tile rows = warp); exact two-pass over
+            // the quarter's valid pixels, conflict-free (a warp reads one 128-byte staged row at a time)
+            const int wv = min(kTileW, p.W - t.x0);
+            const int rows = max(0, min(2, p.H - (t.y0 + 2 * quad)));
+            const int cnt = rows * wv;
+            float s0 = 0.f, s1 = 0.f;
+            for (int rr = 0; rr < rows; ++rr)
+              for (int xx = 0; xx < wv; ++xx) {
+                const int r2 = (2 * quad + rr) * kTileW + xx;
+                const float2 f = unpack16x2<T16>(lds_u32(sbuf + r2 * 128 + ((((lane >> 2) ^ (r2 & 7))) << 4) + ((lane & 3) << 2)));
+                s0 += f.x, s1 += f.y;
+              }
+            const float inv = cnt > 0 ? 1.f / (float)cnt : 0.f;
+            const float m0 = s0 * inv, m1 = s1 * inv;
+            float q0 = 0.f, q1 = 0.f;
+            for (int rr = 0; rr < rows; ++rr)
+              for (int xx = 0; xx < wv; ++xx) {
+                const int r2 = (2 * quad + rr) * kTileW + xx;
+                const float2 f = unpack16x2<T16>(lds_u32(sbuf + r2 * 128 + ((((lane >> 2) ^ (r2 & 7))) << 4) + ((lane & 3) << 2)));
+                const float d0 = f.x - m0, d1 = f.y - m1;
+                q0 = fmaf(d0, d0, q0), q1 = fmaf(d1, d1, q1);
+              }
+            const size_t tile = ((size_t)t.n * p.tiles_y + t.y0 / kTileH) * p.tiles_x + t.x0 / kTileW;
+            float4* dst = reinterpret_cast<float4*>(p.tile_stats + (tile * 4 + quad) * p.Cout + co + 2 * lane);
+            *dst = make_float4(m0, q0, m1, q1);
           }
         }
       }
@@ -2273,7 +2318,7 @@ int launch_cfg(const CUtensorMap& ma0, const T16* wk, ConvParams<T16> p, cudaStr
   if (int e = make_weight_map(&mb, wk, Cfg::kTaps * p.Cin, (UPS ? 4 : 1) * p.CoutPad, Cfg::kBRows)) return e;
   OutMaps mo;
   memset(&mo, 0, sizeof(mo));
-  if (EPI == EPI_ACT) {
+  if (EPI == EPI_ACT || EPI == EPI_ACT_STATS) {
     if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, G::kOutW, G::kRows)) return e;
   } else if (EPI == EPI_ACT_POOL) {
     if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, G::kOutW / 2, G::kRows / 2)) return e;
@@ -2353,6 +2398,10 @@ int launch_bn(const CUtensorMap& ma, const T16* wk, const ConvParams<T16>& p, in
       return launch_cfg<T16, BN, EPI_ACT_POOL, BRES, CG>(ma, wk, p, st);
     case EPI_UPS:
       return launch_cfg<T16, BN, EPI_UPS, BRES, CG>(ma, wk, p, st);
+    case EPI_ACT_STATS:
+      if constexpr (BN == 256 && BRES == 0) return launch_cfg<T16, BN, EPI_ACT_STATS, BRES, CG>(ma, wk, p, st);
+      set_error("conv_umma: tile statistics are available for the N = 256 tiles only");
+      return CCST_EINVAL;
     default:
       set_error("conv_umma: epilogue %d not available for BN=%d", epi, BN);
       return CCST_EINVAL;
@@ -2479,7 +2528,7 @@ int launch_smerge(const CUtensorMap& ma, const T16* wk_sm, const ConvParams<T16>
 template <typename T16>
 int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16* wk_up,
                      const float* bias, int Cout, int CoutPad, int relu, int epi, ActView<T16> out,
-                     float* out_nchw, uint8_t* out_u8, int halo_edge, cudaStream_t st) {
+                     float* out_nchw, uint8_t* out_u8, int halo_edge, cudaStream_t st, float2* tile_stats) {
   CCST_CHECK_ARG(in.C % kBlockK == 0, "conv_umma: Cin=%d must be a multiple of 64", in.C);
   int BN;
   if (epi == EPI_NCHW_F32) {
@@ -2509,6 +2558,8 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
   p.out = out;
   p.out_nchw = out_nchw;
   p.out_u8 = out_u8;
+  p.tile_stats = tile_stats;
+  CCST_CHECK_ARG((epi == EPI_ACT_STATS) == (tile_stats != nullptr), "conv_umma: tile_stats goes with EPI_ACT_STATS");
   CCST_CHECK_ARG(out_u8 == nullptr || epi == EPI_NCHW_F32, "conv_umma: uint8 store is the last conv's");
   CCST_CHECK_ARG(halo_edge == 1 || (halo_edge == 0 && epi == EPI_ACT),
                  "conv_umma: a replicate halo is only written by the plain epilogue");
@@ -2621,10 +2672,10 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
 template int launch_conv_umma<__nv_bfloat16>(ActView<__nv_bfloat16>, const __nv_bfloat16*,
                                              const __nv_bfloat16*, const __nv_bfloat16*, const float*,
                                              int, int, int, int, ActView<__nv_bfloat16>, float*,
-                                             uint8_t*, int, cudaStream_t);
+                                             uint8_t*, int, cudaStream_t, float2*);
 template int launch_conv_umma<__half>(ActView<__half>, const __half*, const __half*, const __half*,
                                       const float*, int, int, int, int, ActView<__half>, float*,
-                                      uint8_t*, int, cudaStream_t);
+                                      uint8_t*, int, cudaStream_t, float2*);
 
 template <typename T16>
 int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk, const float* bias,

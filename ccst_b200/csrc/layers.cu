@@ -350,7 +350,7 @@ struct NhwcGeom {
 // read 128-byte pieces at a 1 KiB stride from eight different SMs and reached 2.3 TB/s).  Every
 // chunk CTA writes its {mean, M2} partials (the count follows from the geometry); consumers merge
 // the partials of a plane with Chan's formula in fixed chunk order (deterministic).
-constexpr int kNhwcChunk = 256;
+constexpr int kNhwcChunk = 128;
 constexpr int kNhwcBatch = 8;  // 16-byte loads in flight per thread
 
 __host__ __device__ inline int nhwc_chunks(int HW) { return (HW + kNhwcChunk - 1) / kNhwcChunk; }
@@ -445,6 +445,64 @@ __global__ void __launch_bounds__(256)
   if (i >= NC) return;
   const Wf acc = nhwc_merge_partials(part, i / C, i % C, C, HW);
   raw[i] = make_float2(acc.mean, acc.m2);
+}
+
+// Chan merge, in fixed order, of the statistics the conv epilogue wrote per (8x16 pixel tile, quarter
+// of the tile = two tile rows): tile_part[((n * tiles_y + ty) * tiles_x + tx) * 4 + q][c].
+// Block = (image n, 32 channels) x 8 tile groups: group g merges tiles g, g + 8, ... (independent
+// loads, 8x shorter dependency chains), then lanes of group 0 merge the 8 group results in order.
+__device__ __forceinline__ Wf nhwc_merge_tiles_block(const float2* __restrict__ tp, int n, int c, int C, int H,
+                                                     int W, Wf* s_grp /* [8][32] */) {
+  const int tiles_x = (W + 15) / 16, tiles_y = (H + 7) / 8, tiles = tiles_x * tiles_y;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Wf acc{0.f, 0.f, 0.f};
+  for (int t = g; t < tiles; t += 8) {
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int wv = min(16, W - tx * 16);
+    const size_t base = ((size_t)n * tiles + t) * 4;
+    float2 o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = tp[(base + q) * C + c];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int rows = max(0, min(2, H - (ty * 8 + 2 * q)));
+      if (rows > 0) acc = wf_merge(acc, Wf{(float)(rows * wv), o[q].x, o[q].y});
+    }
+  }
+  s_grp[g * 32 + lane] = acc;
+  __syncthreads();
+  Wf r = s_grp[lane];
+  if (g == 0) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r = wf_merge(r, s_grp[k * 32 + lane]);
+  }
+  return r;  // valid in group 0
+}
+
+// grid = N * C / 32 blocks of 256 threads
+__global__ void __launch_bounds__(256)
+    nhwc_tiles_merge_kernel(const float2* __restrict__ tp, float2* __restrict__ raw, int C, int H, int W) {
+  __shared__ Wf s_grp[8 * 32];
+  const int blocks_per_n = C / 32;
+  const int n = blockIdx.x / blocks_per_n, c = (blockIdx.x % blocks_per_n) * 32 + (threadIdx.x & 31);
+  const Wf acc = nhwc_merge_tiles_block(tp, n, c, C, H, W, s_grp);
+  if (threadIdx.x < 32) raw[(size_t)n * C + c] = make_float2(acc.mean, acc.m2);
+}
+
+__global__ void __launch_bounds__(256)
+    adain_nhwc_coef_tiles_kernel(const float2* __restrict__ tp, float4* __restrict__ coef, int C, int H, int W,
+                                 const float* __restrict__ mu_s, const float* __restrict__ sigma_s,
+                                 int64_t stat_batch_stride, float alpha, float eps) {
+  __shared__ Wf s_grp[8 * 32];
+  const int blocks_per_n = C / 32;
+  const int n = blockIdx.x / blocks_per_n, c = (blockIdx.x % blocks_per_n) * 32 + (threadIdx.x & 31);
+  const Wf st = nhwc_merge_tiles_block(tp, n, c, C, H, W, s_grp);
+  if (threadIdx.x >= 32) return;
+  const float sg_c = sqrtf(st.m2 / ((float)(H * W) - 1.f) + eps);
+  const int64_t si = (int64_t)n * stat_batch_stride + c;
+  const float ms = mu_s[si], ss = sigma_s[si];
+  coef[(size_t)n * C + c] = make_float4(st.mean, alpha * (ss / sg_c) + (1.f - alpha),
+                                        alpha * ms + (1.f - alpha) * st.mean, 0.f);
 }
 
 // coef[n * C + c] = {mu_c, A, B}:  out = (x - mu_c) * A + B,
@@ -786,6 +844,90 @@ template int launch_adain_nhwc<__nv_bfloat16>(ActView<__nv_bfloat16>, ActView<__
                                               float2*, cudaStream_t);
 template int launch_adain_nhwc<__half>(ActView<__half>, ActView<__half>, const float*, const float*,
                                        int64_t, float, float, float2*, cudaStream_t);
+
+// Row-wise apply: CTA = (image n, row y), thread = (VEC channels, every PX_LANES-th pixel of the row).
+// No per-pixel index arithmetic, the row's halo aliases are decided once per CTA / per x.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    adain_nhwc_apply_rows_kernel(ActView<T> in, ActView<T> out, const float4* __restrict__ coef) {
+  constexpr int VEC = VecOf<T>::value;
+  constexpr int kB = 8;
+  const int C = in.C, ch_lanes = C / VEC, px_lanes = 256 / ch_lanes;
+  const int y = blockIdx.x, n = blockIdx.y;
+  const int cl = threadIdx.x % ch_lanes, pl = threadIdx.x / ch_lanes;
+  const size_t coff = (size_t)cl * VEC;
+  const T* src = in.px(n, y, 0) + coff;
+  T* dst = out.px(n, y, 0) + coff;
+  // rows that alias this one in the reflection halo: -1 for y == 1, H for y == H - 2
+  T* dst_up = (y == 1) ? out.px(n, -1, 0) + coff : nullptr;
+  T* dst_dn = (y == in.H - 2) ? out.px(n, in.H, 0) + coff : nullptr;
+  float A[VEC], B[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const float4 q = coef[(size_t)n * C + coff + k];
+    A[k] = q.y, B[k] = fmaf(-q.x, q.y, q.z);
+  }
+  for (int xb = pl; xb < in.W; xb += kB * px_lanes) {
+    Pack<T, VEC> v[kB];
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+      const int x = xb + i * px_lanes;
+      if (x < in.W) v[i].v = *reinterpret_cast<const decltype(v[i].v)*>(src + (size_t)x * C);
+    }
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+      const int x = xb + i * px_lanes;
+      if (x < in.W) {
+        float f[VEC];
+        unpack_vec(v[i], f);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) f[k] = fmaf(f[k], A[k], B[k]);
+        Pack<T, VEC> o;
+        pack_vec(o, f);
+        const int xa = (x == 1) ? -1 : ((x == in.W - 2) ? in.W : x);  // x's halo alias (or x itself)
+        auto put = [&](T* row) {
+          *reinterpret_cast<decltype(o.v)*>(row + (ptrdiff_t)x * C) = o.v;
+          if (xa != x) *reinterpret_cast<decltype(o.v)*>(row + (ptrdiff_t)xa * C) = o.v;
+        };
+        put(dst);
+        if (dst_up) put(dst_up);
+        if (dst_dn) put(dst_dn);
+      }
+    }
+  }
+}
+
+size_t nhwc_tile_scratch_elems(int N, int C, int H, int W) {
+  return (size_t)N * C * 2 + (size_t)N * ((H + 7) / 8) * ((W + 15) / 16) * 4 * C;
+}
+
+template <typename T>
+int launch_adain_nhwc_tiles(ActView<T> in, ActView<T> out, const float* mu_s, const float* sigma_s,
+                            int64_t stat_batch_stride, float alpha, float eps, float2* scratch,
+                            cudaStream_t st) {
+  if (int e = nhwc_geometry_ok(in, "adain_nhwc")) return e;
+  const int NC = in.N * in.C;
+  float4* coef = reinterpret_cast<float4*>(scratch);
+  adain_nhwc_coef_tiles_kernel<<<NC / 32, 256, 0, st>>>(scratch + 2 * (size_t)NC, coef, in.C, in.H, in.W, mu_s,
+                                                        sigma_s, stat_batch_stride, alpha, eps);
+  CCST_LAUNCHED();
+  dim3 grid(in.H, in.N);
+  adain_nhwc_apply_rows_kernel<T><<<grid, 256, 0, st>>>(in, out, coef);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_adain_nhwc_tiles<__nv_bfloat16>(ActView<__nv_bfloat16>, ActView<__nv_bfloat16>,
+                                                    const float*, const float*, int64_t, float, float,
+                                                    float2*, cudaStream_t);
+template int launch_adain_nhwc_tiles<__half>(ActView<__half>, ActView<__half>, const float*, const float*,
+                                             int64_t, float, float, float2*, cudaStream_t);
+
+int launch_stats_from_tiles(int N, int C, int H, int W, float2* scratch, cudaStream_t st) {
+  const int NC = N * C;
+  nhwc_tiles_merge_kernel<<<NC / 32, 256, 0, st>>>(scratch + 2 * (size_t)NC, scratch, C, H, W);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
 
 // scratch: nhwc_scratch_elems() float2; the merged per-plane {mean, M2} land in its first N*C entries
 template <typename T>

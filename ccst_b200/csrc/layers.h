@@ -9,6 +9,9 @@ enum Epilogue {
   EPI_ACT_UP2 = 1,  // same, every pixel replicated 2x2 (nearest upsample fused into the store)
   EPI_NCHW_F32 = 2, // bias (+ReLU) -> caller's NCHW fp32 tensor (last decoder conv)
   EPI_ACT_POOL = 3, // bias + ReLU + 2x2 ceil-mode max-pool fused into the store (tcgen05 path)
+  EPI_ACT_STATS = 5,  // tcgen05 path, EPI_ACT + per-(8x16 pixel tile, row quarter, channel) {mean, M2} of the
+                      // stored values written to `tile_stats` (relu4_1 statistics for AdaIN / the
+                      // overall-style accumulation without another pass over the feature map)
   EPI_UPS = 4,      // tcgen05 path: the INPUT is the low-resolution activation (replicate halo) of a
                     // nearest-x2 upsample; conv(reflect_pad(upsample(S))) is computed as four 2x2
                     // phase convolutions with pre-summed weights (16 instead of 36 tap-GEMMs per source
@@ -35,6 +38,15 @@ template <typename T>
 int launch_adain_nhwc(ActView<T> in, ActView<T> out, const float* mu_s, const float* sigma_s,
                       int64_t stat_batch_stride, float alpha, float eps, float2* scratch,
                       cudaStream_t st);
+
+// Variants fed by the tile statistics a conv wrote with EPI_ACT_STATS: scratch = [2*N*C float2 coef / raw]
+// [tile_part: tiles*4*C float2], tiles = N * ceil(H/8) * ceil(W/16); the conv is given scratch + 2*N*C.
+size_t nhwc_tile_scratch_elems(int N, int C, int H, int W);
+template <typename T>
+int launch_adain_nhwc_tiles(ActView<T> in, ActView<T> out, const float* mu_s, const float* sigma_s,
+                            int64_t stat_batch_stride, float alpha, float eps, float2* scratch,
+                            cudaStream_t st);
+int launch_stats_from_tiles(int N, int C, int H, int W, float2* scratch, cudaStream_t st);
 
 // per-(n,c) {mean, M2} of an activation -> scratch[0 .. N*C)
 template <typename T>
@@ -71,7 +83,8 @@ int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st);
 template <typename T16>
 int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16* wk_up,
                      const float* bias, int Cout, int CoutPad, int relu, int epi, ActView<T16> out,
-                     float* out_nchw, uint8_t* out_u8, int halo_edge, cudaStream_t st);
+                     float* out_nchw, uint8_t* out_u8, int halo_edge, cudaStream_t st,
+                     float2* tile_stats = nullptr);
 
 // conv1_1 (+ folded 1x1) on tcgen05: thread-built im2col rows (K = 27 padded to 32).
 // wk: [64][32] T16 K-major, bias fp32 [64].
