@@ -18,7 +18,7 @@ python tools/ncu_traffic.py gpurun_out/prof_conv_$TAG.ncu-rep 32 > gpurun_out/nc
 $NCU --set full --import-source on -k regex:'plane_bulk_kernel|stats_regs_kernel|adain_regs_kernel|merge_planes' -s 8 -c 4 -f -o gpurun_out/prof_ops_$TAG \
     python tools/op_bench.py --iters 1 > gpurun_out/ncu_ops_$TAG.log 2>&1
 python tools/ncu_summary.py gpurun_out/prof_ops_$TAG.ncu-rep > gpurun_out/ncu_ops_summary_$TAG.txt 2>&1
-$NCU --set full --import-source on -k regex:'nhwc_stats_partial|adain_nhwc|stats_nhwc' -s 9 -c 3 -f -o gpurun_out/prof_nhwc_$TAG \
+$NCU --set full --import-source on -k regex:'nhwc_stats_partial|adain_nhwc|stats_nhwc|nhwc_tiles' -s 6 -c 2 -f -o gpurun_out/prof_nhwc_$TAG \
     python tools/layer_report.py --iters 1 --batch 32 > gpurun_out/ncu_nhwc_$TAG.log 2>&1
 python tools/ncu_summary.py gpurun_out/prof_nhwc_$TAG.ncu-rep > gpurun_out/ncu_nhwc_summary_$TAG.txt 2>&1
 du -sh gpurun_out
