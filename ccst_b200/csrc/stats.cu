@@ -251,41 +251,48 @@ __global__ void __launch_bounds__(kThreads) adain_stream_kernel(AdainArgs a) {
 // ---- per-channel merge over the batch and into the running state (fp64) ----
 // state = {count, mean[C], M2[C]}.  Block = 32 channels x 8 batch lanes; each thread Chan-merges its
 // strided share of the N per-plane results, the 8 partials are combined through shared memory.
+// Folds the per-plane {mean, M2} of a batch over n and into the running fp64 state (Chan), fixed
+// order.  Block = 8 channels (one per warp) x 32 lanes over n: lane l merges planes l, l + 32, ...,
+// the lanes are combined by a shuffle butterfly, lane 0 merges the result into the state.
+__device__ __forceinline__ void chan_merge(double& n, double& mean, double& m2, double nb, double mb,
+                                           double m2b) {
+  if (nb == 0.0) return;
+  const double nn = n + nb, d = mb - mean;
+  mean += d * (nb / nn);
+  m2 += m2b + d * d * (n * nb / nn);
+  n = nn;
+}
+
 __global__ void __launch_bounds__(256) merge_planes_kernel(const float2* __restrict__ raw, int N,
                                                             int C, double hw,
                                                             double* __restrict__ state) {
-  __shared__ double s_n[8][32], s_mean[8][32], s_m2[8][32];
-  const int cl = threadIdx.x & 31, nl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  const double n0 = state[0];
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;
   double n = 0.0, mean = 0.0, m2 = 0.0;
-  if (c < C)
-    for (int i = nl; i < N; i += 8) {
-      const float2 r = raw[(size_t)i * C + c];
-      const double nn = n + hw, d = (double)r.x - mean;
-      mean += d * (hw / nn);
-      m2 += (double)r.y + d * d * (n * hw / nn);
-      n = nn;
-    }
-  s_n[nl][cl] = n, s_mean[nl][cl] = mean, s_m2[nl][cl] = m2;
-  __syncthreads();
-  if (nl == 0 && c < C) {
-    n = n0, mean = state[1 + c], m2 = state[1 + C + c];
-    for (int l = 0; l < 8; ++l) {
-      const double nb = s_n[l][cl];
-      if (nb == 0.0) continue;
-      const double nn = n + nb, d = s_mean[l][cl] - mean;
-      mean += d * (nb / nn);
-      m2 += s_m2[l][cl] + d * d * (n * nb / nn);
-      n = nn;
-    }
-    state[1 + c] = mean;
-    state[1 + C + c] = m2;
+  for (int i = lane; i < N; i += 32) {
+    const float2 r = raw[(size_t)i * C + c];
+    chan_merge(n, mean, m2, hw, (double)r.x, (double)r.y);
   }
-  // every thread has read state[0] before anyone may overwrite it
-  __syncthreads();
-  if (gridDim.x == 1 && threadIdx.x == 0) state[0] = n0 + hw * N;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double nb = __shfl_xor_sync(0xffffffffu, n, off);
+    const double mb = __shfl_xor_sync(0xffffffffu, mean, off);
+    const double qb = __shfl_xor_sync(0xffffffffu, m2, off);
+    // both partners must compute the same bits: merge (lower lane's value) <- (upper lane's value)
+    double an = n, am = mean, aq = m2, bn = nb, bm = mb, bq = qb;
+    if (lane & off) an = nb, am = mb, aq = qb, bn = n, bm = mean, bq = m2;
+    chan_merge(an, am, aq, bn, bm, bq);
+    n = an, mean = am, m2 = aq;
+  }
+  if (lane == 0) {
+    double sn = state[0], sm = state[1 + c], sq = state[1 + C + c];
+    chan_merge(sn, sm, sq, n, mean, m2);
+    state[1 + c] = sm;
+    state[1 + C + c] = sq;
+  }
 }
+
 __global__ void bump_count_kernel(double* state, double add) { state[0] += add; }
 
 __global__ void finalize_kernel(const double* __restrict__ state, int C, float eps,
@@ -629,13 +636,12 @@ int launch_adain(const AdainArgs& a, cudaStream_t st) {
 
 int merge_raw_into_state(const float2* raw, int N, int C, int64_t hw, double* d_state,
                          cudaStream_t st) {
-  const int blocks = (C + 31) / 32;
+  const int blocks = (C + 7) / 8;
   merge_planes_kernel<<<blocks, 256, 0, st>>>(raw, N, C, (double)hw, d_state);
   CCST_LAUNCHED();
-  if (blocks > 1) {
-    bump_count_kernel<<<1, 1, 0, st>>>(d_state, (double)hw * N);
-    CCST_LAUNCHED();
-  }
+  // state[0] (the count) is read by every block above and bumped afterwards, in stream order
+  bump_count_kernel<<<1, 1, 0, st>>>(d_state, (double)hw * N);
+  CCST_LAUNCHED();
   return CCST_OK;
 }
 
