@@ -46,6 +46,7 @@ PROTOTYPES = {
     "ccst_quantize_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "ccst_resize_bilinear_aa_f32": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "ccst_encoder_accumulate": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "ccst_encoder_accumulate_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "ccst_feature_hw": (None, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "ccst_launch_count": (_i64, []),
     "ccst_profile_enable": (_i, [_vp, _i]),

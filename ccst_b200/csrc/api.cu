@@ -713,6 +713,27 @@ extern "C" int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N
   CCST_DISPATCH(precision, run_encoder<T>(h, d_img, N, H, W, nullptr, d_state, (cudaStream_t)stream));
 }
 
+namespace {
+template <typename T>
+int run_encoder_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W, double* d_state, cudaStream_t st) {
+  if (int e = ensure_io(h, (size_t)N * 3 * H * W)) return e;
+  {
+    ProfScope ps(h, st, 5, 0, (double)N * 3 * H * W * 5.0);
+    if (int e = launch_u8_nhwc_to_f32_nchw(d_img, N, 3, H, W, h->io_f32, st)) return e;
+  }
+  return run_encoder<T>(h, h->io_f32, N, H, W, nullptr, d_state, st);
+}
+}  // namespace
+
+extern "C" int ccst_encoder_accumulate_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W,
+                                          double* d_state, int precision, void* stream) {
+  if (int e = check_common(h, precision)) return e;
+  CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_accumulate_u8: encoder weights not set");
+  CCST_CHECK_ARG(d_img && d_state && N >= 1 && H >= 8 && W >= 8,
+                 "ccst_encoder_accumulate_u8: bad argument");
+  CCST_DISPATCH(precision, run_encoder_u8<T>(h, d_img, N, H, W, d_state, (cudaStream_t)stream));
+}
+
 extern "C" int ccst_decoder_fwd(ccst_handle* h, const float* d_feat, int N, int fh, int fw,
                                 float* d_img, int precision, void* stream) {
   if (int e = check_common(h, precision)) return e;

@@ -158,8 +158,8 @@ def overall_statistics(engine: Engine, host_batches: Iterable[torch.Tensor], pre
     s_cmp.wait_stream(torch.cuda.current_stream(dev))  # the zeroed Welford state
     for i, hb in enumerate(host_batches):
         s = i & 1
-        if bufs[s] is None or bufs[s].shape != hb.shape:
-            bufs[s] = torch.empty(hb.shape, dtype=torch.float32, device=dev)
+        if bufs[s] is None or bufs[s].shape != hb.shape or bufs[s].dtype != hb.dtype:
+            bufs[s] = torch.empty(hb.shape, dtype=hb.dtype, device=dev)  # fp32 NCHW or uint8 NHWC batches
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_cmp[s])
             bufs[s].copy_(hb, non_blocking=True)

@@ -58,7 +58,10 @@ class OverallStyleAccumulator:
 
     def add_images(self, images: torch.Tensor):
         """`feat = vgg(data); calc_sum(feat); all_* += ...` (:121-131)."""
-        self.engine.accumulate(images, self.state, self.precision)
+        if images.dtype == torch.uint8:  # the loader's HWC images before ToTensor
+            self.engine.accumulate_u8(images, self.state, self.precision)
+        else:
+            self.engine.accumulate(images, self.state, self.precision)
         self.img_count += int(images.shape[0])
         return self
 

@@ -163,6 +163,24 @@ class Engine:
                                                           self._stream()))
         return state
 
+    def accumulate_u8(self, images_u8, state: "F_.WelfordState", precision=DEFAULT_PRECISION):
+        """`accumulate` on the loader's uint8 HWC batch [N,H,W,3] (ToTensor on the GPU)."""
+        x = images_u8
+        if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.uint8 or x.dim() != 4 \
+                or x.shape[3] != 3:
+            raise RuntimeError("images_u8 must be a CUDA uint8 [N,H,W,3] tensor: ccst_b200 has no CPU fallback")
+        if x.device != self.device:
+            raise RuntimeError(f"images_u8 is on {x.device}, engine on {self.device}")
+        x = x.contiguous()
+        n, h, w, _ = x.shape
+        if state.C != 512 or state.device != self.device:
+            raise RuntimeError("state must be a 512-channel WelfordState on the engine's device")
+        with _lib.on_device(self.device):
+            _lib.check(_lib.lib().ccst_encoder_accumulate_u8(self._h, x.data_ptr(), n, h, w,
+                                                             state.buf.data_ptr(), PRECISIONS[precision],
+                                                             self._stream()))
+        return state
+
     def transfer(self, content, style_stat, alpha=1.0, precision=DEFAULT_PRECISION, out=None):
         """Fused encoder -> AdaIN(+alpha) -> decoder; activations never leave the arena."""
         assert (0.0 <= alpha <= 1.0)

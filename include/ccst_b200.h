@@ -172,6 +172,10 @@ int ccst_resize_bilinear_aa_f32(const float* d_in, int64_t planes, int H, int W,
 int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N, int H, int W,
                             double* d_state, int precision, void* stream);
 
+/* the same on the loader's uint8 HWC batch [N,H,W,3] (ToTensor on the GPU, a quarter of the upload) */
+int ccst_encoder_accumulate_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W,
+                               double* d_state, int precision, void* stream);
+
 /* shape helper: relu4_1 spatial size for an input of H x W */
 void ccst_feature_hw(int H, int W, int* fh, int* fw);
 

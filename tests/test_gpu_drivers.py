@@ -160,3 +160,15 @@ def test_resize_output_golden(golden):
     assert tuple(a.shape) == (32, 3, 96, 96)
     assert (b - (a * 0.5 + 0.25)).abs().max().item() < 1e-5
     assert (a.cpu() - O.resize_output(x.cpu(), 96)).abs().max().item() < 1e-5
+
+
+def test_overall_statistics_u8_equals_float_path(models, engine):
+    """mean_std_computation_effcientMem.py:117-137 fed with the loader's uint8 images: same bits as
+    feeding ToTensor'd floats (the conversion is exact), through the double-buffered loop."""
+    g = torch.Generator().manual_seed(12)
+    b8 = [torch.randint(0, 256, (n, 64, 72, 3), generator=g, dtype=torch.uint8).pin_memory() for n in (3, 2, 3)]
+    bf = [O.to_tensor_u8(b).pin_memory() for b in b8]
+    m8, s8, c8 = drivers.overall_statistics(engine, iter(b8))
+    mf, sf, cf = drivers.overall_statistics(engine, iter(bf))
+    assert c8 == cf == 8
+    assert torch.equal(m8, mf) and torch.equal(s8, sf)
