@@ -18,8 +18,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(PKG, "libccst_b200.so")
-SOURCES = ["api.cu", "stats.cu", "layers.cu", "conv_umma.cu"]
-HEADERS = ["common.cuh", "layers.h", os.path.join("..", "..", "include", "ccst_b200.h")]
+SOURCES = ["api.cu", "stats.cu", "layers.cu", "conv_umma_bf16.cu", "conv_umma_f16.cu"]
+HEADERS = ["common.cuh", "layers.h", "conv_umma_impl.cuh", os.path.join("..", "..", "include", "ccst_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

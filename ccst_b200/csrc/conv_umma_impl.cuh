@@ -2701,13 +2701,19 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
       return launch_cg<T16, 256, false>(ma, wk, p, epi, st);
   }
 }
+// (one operand type per translation unit -- conv_umma_bf16.cu / conv_umma_f16.cu -- so that the two
+// halves of the template instantiations compile in parallel)
+#if CCST_INST_BF16
 template int launch_conv_umma<__nv_bfloat16>(ActView<__nv_bfloat16>, const __nv_bfloat16*,
                                              const __nv_bfloat16*, const __nv_bfloat16*, const float*,
                                              int, int, int, int, ActView<__nv_bfloat16>, float*,
                                              uint8_t*, int, cudaStream_t, float2*);
+#endif
+#if CCST_INST_F16
 template int launch_conv_umma<__half>(ActView<__half>, const __half*, const __half*, const __half*,
                                       const float*, int, int, int, int, ActView<__half>, float*,
                                       uint8_t*, int, cudaStream_t, float2*);
+#endif
 
 template <typename T16>
 int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk, const float* bias,
@@ -2764,10 +2770,14 @@ int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk,
   CCST_LAUNCHED();
   return CCST_OK;
 }
+#if CCST_INST_BF16
 template int launch_conv_first_umma<__nv_bfloat16>(const float*, int, int, int,
                                                    const __nv_bfloat16*, const float*,
                                                    ActView<__nv_bfloat16>, cudaStream_t);
+#endif
+#if CCST_INST_F16
 template int launch_conv_first_umma<__half>(const float*, int, int, int, const __half*,
                                             const float*, ActView<__half>, cudaStream_t);
+#endif
 
 }  // namespace ccst

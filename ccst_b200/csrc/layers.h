@@ -1,4 +1,4 @@
-// Internal (non-ABI) launch wrappers shared by api.cu / layers.cu / conv_umma.cu.
+// Internal (non-ABI) launch wrappers shared by api.cu / layers.cu / conv_umma_impl.cuh.
 #pragma once
 #include "common.cuh"
 
@@ -73,7 +73,7 @@ int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st, in
 template <typename T>
 int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st);
 
-// tcgen05 / TMA implicit GEMM (conv_umma.cu), T16 = __nv_bfloat16 or __half operands, fp32
+// tcgen05 / TMA implicit GEMM (conv_umma_impl.cuh, instantiated per operand type in conv_umma_{bf16,f16}.cu), T16 = __nv_bfloat16 or __half operands, fp32
 // accumulation in TMEM.  wk: [CoutPad][9*Cin] T16 K-major, bias fp32.
 // wk_sm (optional, Cout == 64 only): the same weights packed [192 = (s, co)][3*Cin = (r, c)] for the
 // s-merged kernel.
