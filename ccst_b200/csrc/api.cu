@@ -357,8 +357,11 @@ struct Pipe {
                                : 2.0 * 9 * L.cin * L.cout * (double)N * H * W;
       const double bytes = (double)cur.elems() * sizeof(T) + (double)out.elems() * sizeof(T);
       ProfScope ps(h, st, sizeof(T) == 2 ? 1 : 2, flops, bytes);
-      // (the un-fused pool path runs the same conv kernel as the fused one, so both give the same bits)
-      if (int e = conv(L, 1, epi, out, nullptr, true, halo_edge, tile_stats)) return e;
+      // the un-fused pool path runs the same conv kernel as the fused one, so both give the same bits
+      // (with CCST_SMERGE=4 the pooled layer stays on the tap-by-tap kernel in both)
+      static const bool smerge_pooled = [] { const char* e = getenv("CCST_SMERGE"); return !(e && atoi(e) == 4); }();
+      const bool smerge_ok = smerge_pooled || !(pool_after && !fused_pool);
+      if (int e = conv(L, 1, epi, out, nullptr, smerge_ok, halo_edge, tile_stats)) return e;
     }
     cur = out, cur_slot ^= 1;
     up_pending = defer_up;
