@@ -329,7 +329,7 @@ def run_ours(args, rank, world, local_rank):
                 traffic_src = td["source"]
         roofline = {
             "kernel": "tcgen05.mma + TMA implicit-GEMM 3x3 convs (conv_umma_kernel / conv_smerge_kernel / "
-                      "conv_last_umma_kernel, 18 launches/step)"
+                      "conv_ups4_kernel / conv_last_rows_kernel, 18 launches/step)"
             if precision != "fp32" else "conv_ffma_kernel (fp32 validation mode)",
             "bound": "tensor", "achieved": round(conv_tflops, 2), "peak": peak_tf, "unit": "TFLOP/s",
             "frac": round(conv_tflops / peak_tf, 4),
