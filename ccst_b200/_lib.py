@@ -29,6 +29,7 @@ PROTOTYPES = {
     "ccst_stats_nchw_f32": (_i, [_vp, _i64, _i64, _f, _i, _vp, _vp, _vp]),
     "ccst_welford_accumulate_nchw_f32": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp]),
     "ccst_welford_finalize": (_i, [_vp, _i, _f, _vp, _vp, _vp]),
+    "ccst_welford_finalize_unbiased": (_i, [_vp, _i, _f, _vp, _vp, _vp]),
     "ccst_welford_to_sums": (_i, [_vp, _i, _vp, _vp, _vp]),
     "ccst_welford_to_moments": (_i, [_vp, _i, _vp, _vp]),
     "ccst_welford_from_moments": (_i, [_vp, _i, _vp, _vp]),

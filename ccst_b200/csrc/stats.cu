@@ -295,11 +295,11 @@ __global__ void __launch_bounds__(256) merge_planes_kernel(const float2* __restr
 
 __global__ void bump_count_kernel(double* state, double add) { state[0] += add; }
 
-__global__ void finalize_kernel(const double* __restrict__ state, int C, float eps,
+__global__ void finalize_kernel(const double* __restrict__ state, int C, float eps, int unbiased,
                                 float* __restrict__ mean, float* __restrict__ stdv) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double n = state[0];
+  const double n = state[0] - (unbiased ? 1.0 : 0.0);  // n == 1, unbiased: 0/0 = NaN as torch.var
   if (mean) mean[c] = (float)state[1 + c];
   if (stdv) stdv[c] = (float)sqrt(state[1 + C + c] / n + (double)eps);
 }
@@ -676,7 +676,16 @@ extern "C" int ccst_welford_finalize(const double* d_state, int C, float eps, fl
                                      float* d_std, void* stream) {
   CCST_CHECK_ARG(d_state && C >= 1, "ccst_welford_finalize: bad argument");
   if (int e = require_sm100()) return e;
-  finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_state, C, eps, d_mean, d_std);
+  finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_state, C, eps, 0, d_mean, d_std);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+extern "C" int ccst_welford_finalize_unbiased(const double* d_state, int C, float eps, float* d_mean,
+                                              float* d_std, void* stream) {
+  CCST_CHECK_ARG(d_state && C >= 1, "ccst_welford_finalize_unbiased: bad argument");
+  if (int e = require_sm100()) return e;
+  finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_state, C, eps, 1, d_mean, d_std);
   CCST_LAUNCHED();
   return CCST_OK;
 }

@@ -51,6 +51,22 @@ def calc_mean_std(feat, eps=EPS):
     return mean, std
 
 
+def calc_mean_std_batch(feat, eps=EPS):
+    """The second `calc_mean_std` of the reference (mean_std_computation_effcientMem.py:89-101, defined
+    but never called): per CHANNEL over the whole batch N*H*W, unbiased variance -> each [1,C,1,1]."""
+    size = feat.shape
+    assert (len(size) == 4)
+    state = WelfordState(size[1], feat.device)
+    state.add_features(feat)
+    mean = torch.empty((1, state.C, 1, 1), dtype=torch.float32, device=state.device)
+    std = torch.empty_like(mean)
+    with _lib.on_device(state.device):
+        _lib.check(_lib.lib().ccst_welford_finalize_unbiased(
+            state.buf.data_ptr(), state.C, float(eps), mean.data_ptr(), std.data_ptr(),
+            torch.cuda.current_stream(state.device).cuda_stream))
+    return mean, std
+
+
 def calc_mean_std_vector(feat, eps=EPS):
     """`calc_mean_std` variant of reconstruct_img/test.py:36-46: cat(mean, std) -> [N, 2C]."""
     mean, std = calc_mean_std(feat, eps)

@@ -83,6 +83,11 @@ int ccst_welford_accumulate_nchw_f32(const float* d_x, int N, int C, int64_t hw,
 int ccst_welford_finalize(const double* d_state, int C, float eps, float* d_mean, float* d_std,
                           void* stream);
 
+/* the batch-wide `calc_mean_std` of mean_std_computation_effcientMem.py:89-101 (defined there, never
+ * called): per channel over N*H*W, torch's default UNBIASED variance: std = sqrt(M2/(count-1) + eps). */
+int ccst_welford_finalize_unbiased(const double* d_state, int C, float eps, float* d_mean,
+                                   float* d_std, void* stream);
+
 /* calc_sum's return values from a state: sum = n*mean, sqsum = M2 + n*mean^2 (fp32 [C]). */
 int ccst_welford_to_sums(const double* d_state, int C, float* d_sum, float* d_sqsum, void* stream);
 

@@ -226,3 +226,13 @@ def resize_output(images: torch.Tensor, size) -> torch.Tensor:
         return images
     return torch.nn.functional.interpolate(images, size=(oh, ow), mode="bilinear", align_corners=False,
                                            antialias=True)
+
+
+def calc_mean_std_batch(feat: torch.Tensor, eps: float = EPS):
+    """The batch-wide `calc_mean_std` of mean_std_computation_effcientMem.py:89-101 (defined, never
+    called): per channel over N*H*W with torch's default unbiased `var`."""
+    assert feat.dim() == 4
+    c = feat.shape[1]
+    flat = feat.swapaxes(1, 0).reshape(c, -1)
+    var = flat.var(dim=1) + eps
+    return flat.mean(dim=1).reshape(1, c, 1, 1), torch.sqrt(var.reshape(1, c, 1, 1))

@@ -262,6 +262,14 @@ def make_io():
                 buf.seek(0)
                 saved.append(np.asarray(Image.open(buf).convert("RGB")))
             out[f"resize_{tag}_u8"] = np.stack(saved)
+        # the batch-wide calc_mean_std of mean_std_computation_effcientMem.py:89-101 (AST-extracted, as is)
+        ns_stats = {"torch": torch}
+        _extract_funcs(os.path.join(REF, "mean_std_computation_effcientMem.py"), {"calc_mean_std"}, ns_stats)
+        bf = synth.features((3, 24, 9, 11), 91)
+        bm, bs = ns_stats["calc_mean_std"](bf)
+        bm64, bs64 = ns_stats["calc_mean_std"](bf.double())
+        out["batchstat/x"], out["batchstat/mean"], out["batchstat/std"] = bf.numpy(), bm.numpy(), bs.numpy()
+        out["batchstat/mean64"], out["batchstat/std64"] = bm64.numpy(), bs64.numpy()
         # the Camelyon command line: --image_size 512 --output_size 96 (:187-191), on a synthetic image
         # (input regenerated by the tests from the same seed; only the 96x96 result is stored)
         big = torch.rand((1, 3, 512, 512), generator=torch.Generator().manual_seed(77))

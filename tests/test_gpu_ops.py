@@ -181,3 +181,13 @@ def test_ops_reject_cpu_and_bad_dtype():
         ccst_b200.calc_mean_std(torch.zeros(1, 2, 4, 4, device=DEV, dtype=torch.float16))
     with pytest.raises(AssertionError):
         ccst_b200.adain_blend(torch.zeros(1, 2, 4, 4, device=DEV), [torch.zeros(2, device=DEV)] * 2, alpha=2.0)
+
+
+def test_calc_mean_std_batch_golden(golden):
+    """SURVEY 8 a10 (mean_std_computation_effcientMem.py:89-101): per channel over N*H*W, unbiased."""
+    g = golden["io_u8"]
+    x = torch.from_numpy(g["batchstat/x"]).to("cuda:0")
+    m, s = ccst_b200.calc_mean_std_batch(x)
+    assert tuple(m.shape) == tuple(s.shape) == (1, 24, 1, 1)
+    assert torch.allclose(m.cpu().double(), torch.from_numpy(g["batchstat/mean64"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(s.cpu().double(), torch.from_numpy(g["batchstat/std64"]), rtol=1e-5, atol=1e-6)

@@ -132,3 +132,11 @@ def test_resize_output_matches_torchvision(golden):
         np.testing.assert_array_equal(r.numpy(), g[f"resize_{tag}"])
         np.testing.assert_array_equal(O.save_image_batch_u8(r).numpy(), g[f"resize_{tag}_u8"])
     np.testing.assert_array_equal(O.resize_output(torch.rand((1, 3, 512, 512), generator=torch.Generator().manual_seed(77)), 96).numpy(), g["resize_512_to_96"])
+
+
+def test_batch_calc_mean_std_matches_reference(golden):
+    """the second calc_mean_std of mean_std_computation_effcientMem.py:89-101."""
+    g = golden["io_u8"]
+    m, s = O.calc_mean_std_batch(T(g["batchstat/x"]))
+    np.testing.assert_array_equal(m.numpy(), g["batchstat/mean"])
+    np.testing.assert_array_equal(s.numpy(), g["batchstat/std"])
