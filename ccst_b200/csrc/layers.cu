@@ -884,10 +884,11 @@ __global__ void __launch_bounds__(256)
         for (int k = 0; k < VEC; ++k) f[k] = fmaf(f[k], A[k], B[k]);
         Pack<T, VEC> o;
         pack_vec(o, f);
-        const int xa = (x == 1) ? -1 : ((x == in.W - 2) ? in.W : x);  // x's halo alias (or x itself)
+        // x's reflection-halo aliases: -1 for x == 1, W for x == W - 2 (both when W == 3)
         auto put = [&](T* row) {
           *reinterpret_cast<decltype(o.v)*>(row + (ptrdiff_t)x * C) = o.v;
-          if (xa != x) *reinterpret_cast<decltype(o.v)*>(row + (ptrdiff_t)xa * C) = o.v;
+          if (x == 1) *reinterpret_cast<decltype(o.v)*>(row - (ptrdiff_t)C) = o.v;
+          if (x == in.W - 2) *reinterpret_cast<decltype(o.v)*>(row + (ptrdiff_t)in.W * C) = o.v;
         };
         put(dst);
         if (dst_up) put(dst_up);

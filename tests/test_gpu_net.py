@@ -260,3 +260,20 @@ def test_pipelines_are_bit_reproducible_over_many_runs(models):
         assert all(torch.equal(f, feats[0]) for f in feats[1:]), precision
         imgs = [eng.decode(feats[0], precision).clone() for _ in range(20)]
         assert all(torch.equal(f, imgs[0]) for f in imgs[1:]), precision
+
+
+@pytest.mark.parametrize("hw", [(24, 24), (17, 40), (16, 16)])
+def test_style_transfer_smallest_feature_maps(models, hw):
+    """relu4_1 maps of 3x3 / 3x5 / 2x2: every pixel is on a border, rows and columns alias both halos."""
+    vgg, dec = models
+    h, w = hw
+    x = synth.images(2, h, w, 60 + h)
+    with torch.no_grad():
+        stat = O.single_style_stats(O.encode_relu4_1(vgg, synth.images(1, 32, 32, 61)))
+        ref = O.style_transfer(vgg, dec, x, stat, 0.9)
+    sd = [t.to(DEV) for t in stat]
+    out32 = ccst_b200.style_transfer(vgg, dec, x.to(DEV), sd, 0.9, precision="fp32")
+    out16 = ccst_b200.style_transfer(vgg, dec, x.to(DEV), sd, 0.9, precision="fp16")
+    assert out32.shape == ref.shape
+    assert (out32.cpu() - ref).abs().max().item() < TOL_FP32
+    assert (out16.cpu() - ref).abs().max().item() < TOL_TC
