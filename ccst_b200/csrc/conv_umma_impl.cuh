@@ -941,7 +941,10 @@ constexpr int kSmOutW = kTileW - 2;                 // 14 output columns per til
 constexpr int kSmN = 192;
 constexpr int kSmStoreBytes = kTileH * kSmOutW * 128;  // 14336 = 14 x 1024
 
-template <bool BRES, int CG>
+// NG = number of 4-warp epilogue groups (tile i is drained by group i % NG from accumulator stage
+// i % 2): the s-merged epilogue (192 accumulator columns, shuffles, pooling) is latency-bound with two
+// epilogue warps per scheduler, a third group adds issue capacity.
+template <bool BRES, int CG, int NG = 2>
 struct SmergeCfg {
   static constexpr int kASlabBytes = (kTileH + 2) * kTileW * 128;  // 20480
   static constexpr int kBRows = kSmN / CG;
@@ -953,9 +956,14 @@ struct SmergeCfg {
   static constexpr int kAOff = 0;
   static constexpr int kBOff = kAStages * kASlabBytes;
   static constexpr int kStoreOff = kBOff + kBStages * kBBytes;
-  static constexpr int kBiasOff = kStoreOff + 2 * kSmStoreBytes;
+  static constexpr int kThreads = 128 + NG * 128;                  // 4 control warps + NG epilogue groups
+  // "accumulator ready" barriers: one per residue of the tile counter mod lcm(2 stages, NG groups), so
+  // that each barrier is waited on by ONE group and that group sees every one of its phases (a parity
+  // wait cannot tell a phase from the one two earlier)
+  static constexpr int kFullBars = NG == 2 ? 2 : 2 * NG;
+  static constexpr int kBiasOff = kStoreOff + NG * kSmStoreBytes;
   static constexpr int kBarOff = kBiasOff + 256;
-  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4 + 1;
+  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + kFullBars + 2 + 1;
   static constexpr int kTmemCols = 512;                            // 2 stages x 192 columns
   static constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024;
   static_assert(kSmemBytes <= 232448, "shared memory plan exceeds 227 KiB");
@@ -978,12 +986,12 @@ __device__ __forceinline__ TileCoord decode_tile_sm(const P& p, int unit, int ra
   return t;
 }
 
-template <typename T16, int EPI, bool BRES, int CG>
-__global__ void __launch_bounds__(kThreadsUmma, 1)
+template <typename T16, int EPI, bool BRES, int CG, int NG = 2>
+__global__ void __launch_bounds__(128 + NG * 128, 1)
     conv_smerge_kernel(const __grid_constant__ CUtensorMap tmap_a,
                        const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ OutMaps tmap_out, ConvParams<T16> p) {
-  using Cfg = SmergeCfg<BRES, CG>;
+  using Cfg = SmergeCfg<BRES, CG, NG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -997,9 +1005,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   auto b_full = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + s); };
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + Cfg::kBStages + s); };
   constexpr int kBar2 = 2 * Cfg::kAStages + 2 * Cfg::kBStages;
-  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (kBar2 + s); };
-  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (kBar2 + 2 + s); };
-  const uint32_t bres_bar = bar_base + 8u * (kBar2 + 4);
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (kBar2 + s); };  // s = tile counter % kFullBars
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (kBar2 + Cfg::kFullBars + s); };
+  const uint32_t bres_bar = bar_base + 8u * (kBar2 + Cfg::kFullBars + 2);
   const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1024,10 +1032,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       mbar_init(b_full(s), 1);
       mbar_init(b_empty(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tmem_full_bar(s), 1);
-      mbar_init(tmem_empty_bar(s), 4 * CG);
-    }
+    for (int s = 0; s < Cfg::kFullBars; ++s) mbar_init(tmem_full_bar(s), 1);
+    for (int s = 0; s < 2; ++s) mbar_init(tmem_empty_bar(s), 4 * CG);
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
@@ -1119,7 +1125,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
             }
             if (!BRES) umma_commit_cg<CG>(b_empty(bs0));
             umma_commit_cg<CG>(a_empty(as));
-            if (kc == kchunks - 1) umma_commit_cg<CG>(tmem_full_bar(acs));
+            if (kc == kchunks - 1) umma_commit_cg<CG>(tmem_full_bar(it % Cfg::kFullBars));
           }
           __syncwarp();
           if (++as == Cfg::kAStages) as = 0, aph ^= 1;
@@ -1139,7 +1145,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     const bool col_ok = jx >= 1 && jx <= kSmOutW;
     const bool issuer_warp = (quad == 0);
     const uint32_t sbuf = store_base + grp * kSmStoreBytes;
-    for (int it = grp;; it += 2) {
+    for (int it = grp;; it += NG) {
       const long long unit_ll = (long long)unit0 + (long long)it * unit_step;
       if (unit_ll >= p.total_tiles) break;
       const TileCoord t = decode_tile_sm<CG>(p, (int)unit_ll, (int)cta_rank);
@@ -1147,7 +1153,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       const uint32_t aphase = (it >> 1) & 1;
       const int y = t.y0 + jy, x = t.x0 + ox;
       const bool valid = col_ok && (y < p.H) && (x < p.W) && (CG == 1 || t.n < p.N);
-      mbar_wait(tmem_full_bar(as), aphase, 600 + as);
+      mbar_wait(tmem_full_bar(it % Cfg::kFullBars), (uint32_t)(it / Cfg::kFullBars) & 1u, 600 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kSmN);
       uint32_t pk[32];
@@ -2488,9 +2494,9 @@ int smerge_mode() {
   return v;
 }
 
-template <typename T16, int EPI, bool BRES, int CG>
+template <typename T16, int EPI, bool BRES, int CG, int NG = 2>
 int launch_smerge_cfg(const CUtensorMap& ma, const T16* wk_sm, ConvParams<T16> p, cudaStream_t st) {
-  using Cfg = SmergeCfg<BRES, CG>;
+  using Cfg = SmergeCfg<BRES, CG, NG>;
   CUtensorMap mb;
   if (int e = make_weight_map(&mb, wk_sm, 3 * p.Cin, kSmN, Cfg::kBRows)) return e;
   OutMaps mo;
@@ -2506,7 +2512,7 @@ int launch_smerge_cfg(const CUtensorMap& ma, const T16* wk_sm, ConvParams<T16> p
   }
   static bool attr_done = false;
   if (!attr_done) {
-    CCST_CUDA(cudaFuncSetAttribute(conv_smerge_kernel<T16, EPI, BRES, CG>,
+    CCST_CUDA(cudaFuncSetAttribute(conv_smerge_kernel<T16, EPI, BRES, CG, NG>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
@@ -2519,8 +2525,8 @@ int launch_smerge_cfg(const CUtensorMap& ma, const T16* wk_sm, ConvParams<T16> p
   p.total_tiles = (int)units;
   const int slots = sm_count() / CG;
   const int grid = (int)(units < slots ? units : slots) * CG;
-  CCST_CUDA(launch_conv(conv_smerge_kernel<T16, EPI, BRES, CG>, grid, kThreadsUmma, Cfg::kSmemBytes, st, CG, ma, mb,
-                        mo, p));
+  CCST_CUDA(launch_conv(conv_smerge_kernel<T16, EPI, BRES, CG, NG>, grid, Cfg::kThreads, Cfg::kSmemBytes, st, CG, ma,
+                        mb, mo, p));
   CCST_LAUNCHED();
   return CCST_OK;
 }
@@ -2528,6 +2534,13 @@ int launch_smerge_cfg(const CUtensorMap& ma, const T16* wk_sm, ConvParams<T16> p
 template <typename T16, bool BRES, int CG>
 int launch_smerge_epi(const CUtensorMap& ma, const T16* wk_sm, const ConvParams<T16>& p, int epi,
                       cudaStream_t st) {
+  static const int groups = [] { const char* e = getenv("CCST_SMERGE_GROUPS"); return e ? atoi(e) : 2; }();
+  if constexpr (CG == 2) {
+    if (groups == 3) {
+      if (epi == EPI_ACT) return launch_smerge_cfg<T16, EPI_ACT, BRES, CG, 3>(ma, wk_sm, p, st);
+      if (epi == EPI_ACT_POOL) return launch_smerge_cfg<T16, EPI_ACT_POOL, BRES, CG, 3>(ma, wk_sm, p, st);
+    }
+  }
   switch (epi) {
     case EPI_ACT:
       return launch_smerge_cfg<T16, EPI_ACT, BRES, CG>(ma, wk_sm, p, st);
