@@ -1119,9 +1119,11 @@ __global__ void __launch_bounds__(128 + NG * 128, 1)
             for (int r = 0; r < 3; ++r) {
               const uint64_t adesc = adesc0 + (uint64_t)(r * (kTileW * 128 >> 4));
               const uint64_t bdesc = make_kmajor_sw128_desc(BRES ? b_smem(r) : b_smem(bs0 + r));
+              if (!(p.ablate & 2)) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_f16_cg<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | r | k) ? 1u : 0u);
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_f16_cg<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | r | k) ? 1u : 0u);
+              }
             }
             if (!BRES) umma_commit_cg<CG>(b_empty(bs0));
             umma_commit_cg<CG>(a_empty(as));
@@ -1156,6 +1158,15 @@ __global__ void __launch_bounds__(128 + NG * 128, 1)
       mbar_wait(tmem_full_bar(it % Cfg::kFullBars), (uint32_t)(it / Cfg::kFullBars) & 1u, 600 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kSmN);
+      if (p.ablate & 1) {  // measurement only: hand the accumulator back untouched
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(lead(tmem_empty_bar(as)));
+          else mbar_arrive(tmem_empty_bar(as));
+        }
+        continue;
+      }
       uint32_t pk[32];
 #pragma unroll
       for (int cq = 0; cq < 4; ++cq) {
@@ -2516,6 +2527,10 @@ int launch_smerge_cfg(const CUtensorMap& ma, const T16* wk_sm, ConvParams<T16> p
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
+  {
+    static const int ablate = [] { const char* e = getenv("CCST_ABLATE"); return e ? atoi(e) : 0; }();
+    p.ablate = ablate;
+  }
   p.tiles_x = (p.W + kSmOutW - 1) / kSmOutW;
   p.n_tiles = 1;
   const int64_t m_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
@@ -2598,6 +2613,7 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
   p.relu = relu;
   p.in_ptr = in.p;
   p.desc_mode = 0;
+  p.ablate = 0;
   p.halo_edge = halo_edge;
   p.bias = bias;
   p.out = out;
