@@ -161,6 +161,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifndef CCST_RELAXED_WAITS
+#define CCST_RELAXED_WAITS 1
+#endif
+#if CCST_RELAXED_WAITS
+#define MBAR_WAIT_RELAXED mbar_wait_relaxed
+#else
+#define MBAR_WAIT_RELAXED mbar_wait
+#endif
+// The same for the waits that are NOT on the tensor pipe's critical path (producer waiting for a free
+// stage, epilogue waiting for an accumulator): back off between polls instead of spinning, so the
+// pollers leave the issue slots (and the power budget -- long runs are power-capped) to the MMA warp.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("ccst conv_umma: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag,
+             (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
 // Bounded wait: a pipeline bug must trap (reported as a CUDA error), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
@@ -617,7 +640,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       for (int kc = 0; kc < kchunks; ++kc) {
         for (int s = 0; s < kTS; ++s) {
           if (!LIN || s == 0) {
-            mbar_wait(a_empty(as), aph ^ 1, 100 + as);
+            MBAR_WAIT_RELAXED(a_empty(as), aph ^ 1, 100 + as);
             if (p.ablate & 4) {
               if (elect_one()) {
                 if (leader) mbar_arrive(a_full(as));
@@ -635,7 +658,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           }
           if (!BRES) {
             // the kTR weight tiles of this step: one barrier (that of the group's first slot)
-            mbar_wait(b_empty(bs), bph ^ 1, 150 + bs);
+            MBAR_WAIT_RELAXED(b_empty(bs), bph ^ 1, 150 + bs);
             if (elect_one()) {
               if (leader) mbar_expect_tx(b_full(bs), CG * kTR * Cfg::kBBytes);
               const uint32_t bar = lead(b_full(bs));
@@ -763,7 +786,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       const uint32_t aphase = (it >> 1) & 1;
       const int y = t.y0 + py, x = t.x0 + px;
       const bool valid = col_ok && (y < p.H) && (x < p.W) && (CG == 1 || t.n < p.N);
-      mbar_wait(tmem_full_bar(as), aphase, 400 + as);
+      MBAR_WAIT_RELAXED(tmem_full_bar(as), aphase, 400 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
       if (p.ablate & 1) {
@@ -1064,7 +1087,7 @@ __global__ void __launch_bounds__(128 + NG * 128, 1)
     for (int unit = unit0; unit < p.total_tiles; unit += unit_step) {
       const TileCoord t = decode_tile_sm<CG>(p, unit, (int)cta_rank);
       for (int kc = 0; kc < kchunks; ++kc) {
-        mbar_wait(a_empty(as), aph ^ 1, 500 + as);
+        MBAR_WAIT_RELAXED(a_empty(as), aph ^ 1, 500 + as);
         if (elect_one()) {
           if (leader) mbar_expect_tx(a_full(as), CG * Cfg::kASlabBytes);
           // slab column jx <-> interior x0 - 1 + jx <-> padded x0 + jx; rows y0 - 1 .. y0 + 8
@@ -1073,7 +1096,7 @@ __global__ void __launch_bounds__(128 + NG * 128, 1)
         __syncwarp();
         if (++as == Cfg::kAStages) as = 0, aph ^= 1;
         if (!BRES) {
-          mbar_wait(b_empty(bs), bph ^ 1, 550 + bs);
+          MBAR_WAIT_RELAXED(b_empty(bs), bph ^ 1, 550 + bs);
           if (elect_one()) {
             if (leader) mbar_expect_tx(b_full(bs), CG * 3 * Cfg::kBBytes);
             const uint32_t bar = lead(b_full(bs));
@@ -1155,7 +1178,7 @@ __global__ void __launch_bounds__(128 + NG * 128, 1)
       const uint32_t aphase = (it >> 1) & 1;
       const int y = t.y0 + jy, x = t.x0 + ox;
       const bool valid = col_ok && (y < p.H) && (x < p.W) && (CG == 1 || t.n < p.N);
-      mbar_wait(tmem_full_bar(it % Cfg::kFullBars), (uint32_t)(it / Cfg::kFullBars) & 1u, 600 + as);
+      MBAR_WAIT_RELAXED(tmem_full_bar(it % Cfg::kFullBars), (uint32_t)(it / Cfg::kFullBars) & 1u, 600 + as);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kSmN);
       if (p.ablate & 1) {  // measurement only: hand the accumulator back untouched
@@ -1602,7 +1625,7 @@ __global__ void __launch_bounds__(kF2Threads, 2)
 #pragma unroll
       for (int k2 = 0; k2 < 14; ++k2) pk[k2] = pack16x2<T16>(v[2 * k2], v[2 * k2 + 1]);
       pk[14] = 0u, pk[15] = 0u;
-      mbar_wait(a_empty(as), ((it >> 1) & 1) ^ 1, 930);
+      MBAR_WAIT_RELAXED(a_empty(as), ((it >> 1) & 1) ^ 1, 930);
       const uint32_t sA = base + kF2OffA + as * kF2ABytes;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -1644,7 +1667,7 @@ __global__ void __launch_bounds__(kF2Threads, 2)
       const int as = it & 1;
       int n, y, x0;
       tile_coord(tile, n, y, x0);
-      mbar_wait(t_full(as), (it >> 1) & 1, 950);
+      MBAR_WAIT_RELAXED(t_full(as), (it >> 1) & 1, 950);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 64);
       uint32_t r0[32], r1[32];
@@ -1766,7 +1789,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile<1>(p, tile, 0);
       const int s = it % kLStages;
-      mbar_wait(a_empty(s), ((it / kLStages) & 1) ^ 1, 700 + s);
+      MBAR_WAIT_RELAXED(a_empty(s), ((it / kLStages) & 1) ^ 1, 700 + s);
       if (elect_one()) {
         mbar_expect_tx(a_full(s), kLSlabBytes);
         tma_load_4d(base + s * kLStageStride, &tmap_a, a_full(s), 0, t.x0, t.y0, t.n);
@@ -1811,7 +1834,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       if (tile_ll >= p.total_tiles) break;
       const TileCoord t = decode_tile<1>(p, (int)tile_ll, 0);
       const int acs = it & 1;
-      mbar_wait(t_full(acs), (it >> 1) & 1, 730 + acs);
+      MBAR_WAIT_RELAXED(t_full(acs), (it >> 1) & 1, 730 + acs);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acs * 64);
       uint32_t r0[32], r1[32];
@@ -1957,7 +1980,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int n, y0, x0;
       tile_of(tile, n, y0, x0);
-      mbar_wait(a_empty(s), ph ^ 1, 900 + s);
+      MBAR_WAIT_RELAXED(a_empty(s), ph ^ 1, 900 + s);
       if (elect_one()) {
         mbar_expect_tx(a_full(s), kU4SlabBytes);
         // slab position (jy, jx) = padded pixel (y0 + jy, x0 + jx) = source (y0 - 1 + jy, x0 - 1 + jx)
@@ -2016,7 +2039,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       const int y = y0 + quad, x = x0 + lane;
       const bool col_ok = lane < kU4OutW;
       const bool valid = col_ok && y < p.H && x < p.W;
-      mbar_wait(t_full(acs), (it >> 1) & 1, 930 + acs);
+      MBAR_WAIT_RELAXED(t_full(acs), (it >> 1) & 1, 930 + acs);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acs * 256);
 #pragma unroll 1
@@ -2148,7 +2171,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int n, y0, x0;
       tile_of(tile, n, y0, x0);
-      mbar_wait(a_empty(s), ph ^ 1, 800 + s);
+      MBAR_WAIT_RELAXED(a_empty(s), ph ^ 1, 800 + s);
       if (elect_one()) {
         mbar_expect_tx(a_full(s), kRSlabBytes);
         tma_load_4d(base + s * kRSlabBytes, &tmap_a, a_full(s), 0, x0, y0, n);
@@ -2195,7 +2218,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       int n, y0, x0;
       tile_of((int)tile_ll, n, y0, x0);
       const int acs = it & 1;
-      mbar_wait(t_full(acs), (it >> 1) & 1, 830 + acs);
+      MBAR_WAIT_RELAXED(t_full(acs), (it >> 1) & 1, 830 + acs);
       tc_fence_after();
       uint32_t v[16];
       tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acs * 16), v);
