@@ -5,6 +5,9 @@
 // the only NCHW fp32 tensors are the caller's image / feature / output tensors.
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <vector>
 
 #include "layers.h"
@@ -56,6 +59,19 @@ int require_sm100() {
     return CCST_EARCH;
   }
   return CCST_OK;
+}
+
+cudaError_t ensure_dyn_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({kernel, dev})) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.insert({kernel, dev});
+  return e;
 }
 
 int sm_count() {

@@ -49,6 +49,9 @@ extern int64_t g_launches;
 
 int require_sm100();  // 0 or CCST_EARCH for the current device
 int sm_count();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is
+// per device, and a process may own handles on several GPUs.
+cudaError_t ensure_dyn_smem(const void* kernel, int bytes);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -2419,12 +2419,7 @@ int launch_cfg(const CUtensorMap& ma0, const T16* wk, ConvParams<T16> p, cudaStr
       for (int b = 0; b < 2; ++b)
         if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, G::kOutW, G::kRows)) return e;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    CCST_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T16, BN, EPI, BRES, CG, GEO>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_umma_kernel<T16, BN, EPI, BRES, CG, GEO>), Cfg::kSmemBytes));
   const int64_t units = ((int64_t)p.m_tiles + CG - 1) / CG * p.n_tiles * (UPS ? 4 : 1);
   CCST_CHECK_ARG(units < (1ll << 31), "conv_umma: too many tiles");
   p.total_tiles = (int)units;
@@ -2544,12 +2539,7 @@ int launch_smerge_cfg(const CUtensorMap& ma, const T16* wk_sm, ConvParams<T16> p
       for (int b = 0; b < 2; ++b)
         if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, kSmOutW, kTileH)) return e;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    CCST_CUDA(cudaFuncSetAttribute(conv_smerge_kernel<T16, EPI, BRES, CG, NG>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_smerge_kernel<T16, EPI, BRES, CG, NG>), Cfg::kSmemBytes));
   {
     static const int ablate = [] { const char* e = getenv("CCST_ABLATE"); return e ? atoi(e) : 0; }();
     p.ablate = ablate;
@@ -2665,12 +2655,7 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b)
           if (int e = make_out_map(&mo.m[a * 2 + b], out, a, b, 2, 2, kU4OutW, kU4Rows)) return e;
-      static bool attr4 = false;
-      if (!attr4) {
-        CCST_CUDA(cudaFuncSetAttribute(conv_ups4_kernel<T16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kU4Smem));
-        attr4 = true;
-      }
+      CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_ups4_kernel<T16>), kU4Smem));
       p.tiles_x = (in.W + kU4OutW - 1) / kU4OutW;
       p.tiles_y = (in.H + kU4Rows - 1) / kU4Rows;
       const int64_t tiles = (int64_t)in.N * p.tiles_x * p.tiles_y;
@@ -2704,12 +2689,7 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
         // filter rows by operand shifts, filter columns in N + two shuffles (see conv_last_rows_kernel)
         CUtensorMap mr;
         if (int e = make_act_map(&mr, in, kRBoxW, kRRows + 2)) return e;
-        static bool attr_r = false;
-        if (!attr_r) {
-          CCST_CUDA(cudaFuncSetAttribute(conv_last_rows_kernel<T16>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmem));
-          attr_r = true;
-        }
+        CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_last_rows_kernel<T16>), kRSmem));
         p.tiles_x = (in.W + kROutW - 1) / kROutW;
         p.tiles_y = (in.H + kRRows - 1) / kRRows;
         const int64_t tiles = (int64_t)in.N * p.tiles_x * p.tiles_y;
@@ -2723,12 +2703,7 @@ int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16
       // taps in the N dimension + 9-point gather (see conv_last_umma_kernel)
       CUtensorMap ml;
       if (int e = make_act_map(&ml, in, kLSlabW, kLSlabH)) return e;
-      static bool attr_done = false;
-      if (!attr_done) {
-        CCST_CUDA(cudaFuncSetAttribute(conv_last_umma_kernel<T16>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kLSmem));
-        attr_done = true;
-      }
+      CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_last_umma_kernel<T16>), kLSmem));
       p.total_tiles = p.m_tiles;
       const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
       conv_last_umma_kernel<T16><<<grid, kThreadsUmma, kLSmem, st>>>(ml, wk, p);
@@ -2798,24 +2773,14 @@ int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk,
       set_error("cuTensorMapEncodeTiled(image %dx3x%dx%d) failed: CUresult %d", N, H, W, (int)r);
       return CCST_ECUDA;
     }
-    static bool attr2_done = false;
-    if (!attr2_done) {
-      CCST_CUDA(cudaFuncSetAttribute(conv_first_umma_ws_kernel<T16>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kF2Smem));
-      attr2_done = true;
-    }
+    CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_first_umma_ws_kernel<T16>), kF2Smem));
     const int64_t cap2 = (int64_t)sm_count() * 2;
     const int grid2 = (int)(total < cap2 ? total : cap2);
     CCST_CUDA(launch_conv(conv_first_umma_ws_kernel<T16>, grid2, kF2Threads, kF2Smem, st, 1, mi, mo, p));
     CCST_LAUNCHED();
     return CCST_OK;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    CCST_CUDA(cudaFuncSetAttribute(conv_first_umma_kernel<T16>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kFirstSmem));
-    attr_done = true;
-  }
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_first_umma_kernel<T16>), kFirstSmem));
   const int64_t cap = (int64_t)sm_count() * 4;
   const int grid = (int)(total < cap ? total : cap);
   conv_first_umma_kernel<T16><<<grid, kFirstPx, kFirstSmem, st>>>(mo, p);

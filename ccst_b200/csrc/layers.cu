@@ -764,16 +764,9 @@ int launch_conv_ffma(ActView<float> in, const float* w, const float* bias, int C
   CCST_CHECK_ARG(blocks < (1ull << 31), "conv_ffma: grid too large");
   const size_t smem =
       ((size_t)(kFT_H + 2) * (kFT_W + 2) * kFT_K + (size_t)9 * kFT_K * kFT_N) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CCST_CUDA(cudaFuncSetAttribute(conv_ffma_kernel<EPI_ACT>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CCST_CUDA(cudaFuncSetAttribute(conv_ffma_kernel<EPI_ACT_UP2>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CCST_CUDA(cudaFuncSetAttribute(conv_ffma_kernel<EPI_NCHW_F32>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_ffma_kernel<EPI_ACT>), (int)smem));
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_ffma_kernel<EPI_ACT_UP2>), (int)smem));
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_ffma_kernel<EPI_NCHW_F32>), (int)smem));
   if (epi == EPI_ACT)
     conv_ffma_kernel<EPI_ACT><<<(unsigned)blocks, 256, smem, st>>>(in, w, bias, Cout, CoutPad, relu,
                                                                    out, out_nchw);

@@ -551,12 +551,7 @@ int launch_bulk_cfg(BulkArgs a, cudaStream_t st) {
   a.ppc = (int)((kRingBytes / SLOTS) / ((int64_t)a.hw * 4));
   a.chunks = ceil_div64(a.planes, a.ppc);
   const int grid = (int)(a.chunks < sm_count() ? a.chunks : sm_count());
-  static bool attr_done = false;
-  if (!attr_done) {
-    CCST_CUDA(cudaFuncSetAttribute(plane_bulk_kernel<MODE, G, SLOTS>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kBulkSmem));
-    attr_done = true;
-  }
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(plane_bulk_kernel<MODE, G, SLOTS>), kBulkSmem));
   plane_bulk_kernel<MODE, G, SLOTS><<<grid, 32 * (1 + SLOTS), kBulkSmem, st>>>(a);
   CCST_LAUNCHED();
   return CCST_OK;
