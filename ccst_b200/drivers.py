@@ -145,6 +145,30 @@ def single_transfer(engine: Engine, host_batches: Iterable[torch.Tensor], style_
     return pipe.run(host_batches, stat_for, alpha)
 
 
+def single_transfer_per_image(engine: Engine, host_batches: Iterable[torch.Tensor],
+                              style_images: Sequence[torch.Tensor], alpha: float = 1.0,
+                              precision: str = DEFAULT_PRECISION, seed: int = 1):
+    """BASELINE.json's config 4 as worded ("per-image style sampling"): every IMAGE of a batch gets
+    its own randomly drawn style image (the reference draws one per batch,
+    CCST_SingleStyleTransfer.py:195).  The drawn style images of a batch (same size) are encoded as
+    one batch, their per-image statistics (:199-203, biased variance) come from one pass of the
+    statistics kernel, and AdaIN takes them as [N,512,1,1] (`stat_batch_stride = C`)."""
+    rng = random.Random(seed)
+    pipe = TransferPipeline(engine, precision)
+
+    def stat_for(i, x):
+        n = x.shape[0]
+        imgs = [rng.choice(style_images) for _ in range(n)]
+        shapes = {tuple(im.shape[1:]) for im in imgs}
+        if len(shapes) == 1:
+            feats = engine.encode(torch.cat(imgs).to(engine.device, non_blocking=True), precision)
+            return list(F_.calc_mean_std_biased(feats))
+        stats = [single_style_stat(engine, im.to(engine.device, non_blocking=True), precision) for im in imgs]
+        return [torch.cat([s[0] for s in stats]), torch.cat([s[1] for s in stats])]
+
+    return pipe.run(host_batches, stat_for, alpha)
+
+
 def overall_statistics(engine: Engine, host_batches: Iterable[torch.Tensor], precision: str = DEFAULT_PRECISION,
                        group=None):
     """Loop of mean_std_computation_effcientMem.py:117-137 over this rank's share of one client;

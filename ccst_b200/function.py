@@ -51,6 +51,23 @@ def calc_mean_std(feat, eps=EPS):
     return mean, std
 
 
+def calc_mean_std_biased(feat, eps=EPS):
+    """Per-(n,c) mean and sqrt(BIASED var + eps), each [N,C,1,1]: the single-style statistic of
+    CCST_SingleStyleTransfer.py:199-203 (`calc_sum` + `var = E[x^2] - mean^2`) for every image of a
+    batch of style features at once."""
+    size = feat.size()
+    assert (len(size) == 4)
+    feat = _prep(feat, "feat")
+    n, c = size[:2]
+    mean = torch.empty((n, c, 1, 1), dtype=torch.float32, device=feat.device)
+    std = torch.empty_like(mean)
+    with _lib.on_device(feat.device):
+        _lib.check(_lib.lib().ccst_stats_nchw_f32(
+            feat.data_ptr(), n * c, size[2] * size[3], float(eps), 0, mean.data_ptr(), std.data_ptr(),
+            _stream(feat)))
+    return mean, std
+
+
 def calc_mean_std_batch(feat, eps=EPS):
     """The second `calc_mean_std` of the reference (mean_std_computation_effcientMem.py:89-101, defined
     but never called): per CHANNEL over the whole batch N*H*W, unbiased variance -> each [1,C,1,1]."""

@@ -172,3 +172,22 @@ def test_overall_statistics_u8_equals_float_path(models, engine):
     mf, sf, cf = drivers.overall_statistics(engine, iter(bf))
     assert c8 == cf == 8
     assert torch.equal(m8, mf) and torch.equal(s8, sf)
+
+
+def test_single_transfer_per_image_sampling(models, engine):
+    """Config 4 as BASELINE.json words it: one style image drawn per IMAGE; equals running the
+    reference's statistic (CCST_SingleStyleTransfer.py:199-203) and style_transfer image by image."""
+    vgg, dec = models
+    batches = [synth.images(3, 48, 48, 700 + i).pin_memory() for i in range(2)]
+    for styles in ([synth.images(1, 56, 56, 800 + k) for k in range(4)],                 # same size: batched
+                   [synth.images(1, 56, 40 + 8 * k, 810 + k) for k in range(4)]):       # ragged: one by one
+        rng = random.Random(3)
+        outs = {}
+        for i, o in drivers.single_transfer_per_image(engine, iter(batches), styles, 1.0, "fp32", seed=3):
+            outs[i] = o.clone()
+        with torch.no_grad():
+            for i, b in enumerate(batches):
+                for j in range(b.shape[0]):
+                    stat = O.single_style_stats(O.encode_relu4_1(vgg, rng.choice(styles)))
+                    ref = O.style_transfer(vgg, dec, b[j:j + 1], stat, 1.0)
+                    assert (outs[i][j:j + 1] - ref).abs().max().item() < 1e-4
