@@ -399,8 +399,10 @@ def run_ours(args, rank, world, local_rank):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[precision], "data": "synthetic",
-            "dtype_note": "tcgen05 kind::f16 MMA, f16 operands, fp32 accumulation in TMEM (same tensor peak as "
-                          "bf16; meets the 1e-2 image tolerance, bf16 operands do not -- see DESIGN.md Numerics)",
+            "dtype_note": ("fp32 FFMA validation mode (CUDA cores), not the product path" if precision == "fp32" else
+                           "tcgen05 kind::f16 MMA, %s operands, fp32 accumulation in TMEM (f16 and bf16 run at the same "
+                           "tensor peak; f16 meets the 1e-2 image tolerance, bf16 operands do not -- see DESIGN.md "
+                           "Numerics)" % ("f16" if precision == "fp16" else "bf16")),
             "other_precisions": other,
             "config": {"workload": "CCST Overall K=3 transfer step (config 3): style_transfer batch 32 @512x512, "
                                    "random-init VGG-19 relu4_1 encoder + decoder, overall style stats, alpha=1",
