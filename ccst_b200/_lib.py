@@ -16,6 +16,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "ccst_b200.h")
 
 OK, EINVAL, EARCH, ECUDA, ESTATE = 0, -1, -2, -3, -4
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2
+ABI_VERSION = 2
+FUSE_POOL, FUSE_UPSAMPLE, FUSE_STATS, FUSE_ADAIN, FUSE_ALL = 1, 2, 4, 8, 15
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pp = C.POINTER(C.c_void_p)
@@ -48,6 +50,9 @@ PROTOTYPES = {
     "ccst_resize_bilinear_aa_f32": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "ccst_encoder_accumulate": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "ccst_encoder_accumulate_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "ccst_saturation_snapshot": (_i, [_vp, _vp, _vp]),
+    "ccst_saturation_reset": (_i, [_vp, _vp]),
+    "ccst_set_fusion": (_i, [_vp, _i]),
     "ccst_feature_hw": (None, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "ccst_launch_count": (_i64, []),
     "ccst_profile_enable": (_i, [_vp, _i]),
@@ -85,7 +90,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.ccst_abi_version() != 1:
+        if handle.ccst_abi_version() != ABI_VERSION:
             raise RuntimeError("libccst_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

@@ -101,6 +101,10 @@ struct ConvLayer {
   bf16* w_up = nullptr;     // layer after a nearest-x2 upsample: phase weights [4][cout][4*cin] (EPI_UPS)
   __half* w_up_h = nullptr;
   float* bias = nullptr;    // [pad64]
+  // first decoder conv only (AdaIN folded into it): fp32 K-major master weights [cout][9*cin] and the
+  // per-(cout, cin) sums over the 9 taps
+  float* w_k32 = nullptr;
+  float* w_tapsum = nullptr;
 };
 
 constexpr int kEncLayers = 8;  // conv1_2 .. conv4_1 (conv1_1 is the fused first conv)
@@ -133,6 +137,12 @@ struct ccst_handle {
   bool fuse_pool = true;
   bool fuse_up = true;  // nearest-x2 upsample folded into the NEXT conv (EPI_UPS) instead of the store
   bool fuse_stats = true;  // relu4_1 statistics taken in conv4_1's epilogue (EPI_ACT_STATS)
+  bool fuse_adain = true;  // AdaIN folded into dec1's weights / bias per image (maps >= kFoldMinHW pixels)
+  void* w_fold = nullptr;  // per-image dec1 weights [N][256][9*512] (16-bit) of the folded AdaIN
+  size_t w_fold_bytes = 0;
+  float* b_fold = nullptr; // per-image dec1 bias [N][256]
+  size_t b_fold_elems = 0;
+  unsigned int* sat_count = nullptr;  // f16 stores that hit the +-65504 clamp since the last reset
   bool profiling = false;
   int prof_n = 0;
   ProfSlot prof[kMaxProf];
@@ -166,11 +176,14 @@ void free_layer(ConvLayer& L) {
   cudaFree(L.w_up);
   cudaFree(L.w_up_h);
   cudaFree(L.bias);
+  cudaFree(L.w_k32);
+  cudaFree(L.w_tapsum);
   L = ConvLayer();
 }
 
 // OIHW fp32 host weights -> device packs
-int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b, bool up_before = false) {
+int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b, bool up_before = false,
+               bool fold_src = false) {
   free_layer(L);
   L.cin = cin, L.cout = cout;
   L.pad64 = (cout + 63) / 64 * 64;
@@ -200,6 +213,23 @@ int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b, 
   CCST_CUDA(cudaMemcpy(L.w_ffma, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(L.w_umma, wu.data(), wu.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (fold_src) {
+    std::vector<float> wk((size_t)cout * K), ws((size_t)cout * cin);
+    for (int o = 0; o < cout; ++o)
+      for (int c = 0; c < cin; ++c) {
+        double acc = 0;
+        for (int t = 0; t < 9; ++t) {
+          const float v = w[((size_t)o * cin + c) * 9 + t];
+          wk[(size_t)o * K + (size_t)t * cin + c] = v;
+          acc += (double)v;
+        }
+        ws[(size_t)o * cin + c] = (float)acc;
+      }
+    CCST_CUDA(cudaMalloc(&L.w_k32, wk.size() * sizeof(float)));
+    CCST_CUDA(cudaMalloc(&L.w_tapsum, ws.size() * sizeof(float)));
+    CCST_CUDA(cudaMemcpy(L.w_k32, wk.data(), wk.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CCST_CUDA(cudaMemcpy(L.w_tapsum, ws.data(), ws.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   if (cout == 64) {
     const int K3 = 3 * cin;
     std::vector<bf16> sb((size_t)192 * K3);
@@ -310,6 +340,43 @@ size_t plan_bytes(int N, int H, int W, int fh, int fw, size_t esz, bool enc, boo
   return m;
 }
 
+// maps with at least this many pixels fold AdaIN into dec1 (per-image weights: 2.4 MB written per
+// image); below it the affine pass over the feature map (2 KiB per pixel) is cheaper
+constexpr int kFoldMinHW = 2048;
+
+int ensure_fold(ccst_handle* h, size_t w_bytes, size_t b_elems) {
+  if (h->w_fold_bytes < w_bytes) {
+    if (h->w_fold) CCST_CUDA(cudaFree(h->w_fold));
+    h->w_fold = nullptr, h->w_fold_bytes = 0;
+    CCST_CUDA(cudaMalloc(&h->w_fold, w_bytes));
+    h->w_fold_bytes = w_bytes;
+  }
+  if (h->b_fold_elems < b_elems) {
+    if (h->b_fold) CCST_CUDA(cudaFree(h->b_fold));
+    h->b_fold = nullptr, h->b_fold_elems = 0;
+    CCST_CUDA(cudaMalloc(&h->b_fold, b_elems * sizeof(float)));
+    h->b_fold_elems = b_elems;
+  }
+  return CCST_OK;
+}
+
+template <typename T>
+struct Weights16;  // the operand-type view of a layer's 16-bit packs
+template <>
+struct Weights16<bf16> {
+  static const bf16* wk(const ConvLayer& L) { return L.w_umma; }
+  static const bf16* sm(const ConvLayer& L) { return L.w_sm; }
+  static const bf16* up(const ConvLayer& L) { return L.w_up; }
+  static const bf16* first(const ccst_handle* h) { return h->first_wk_b; }
+};
+template <>
+struct Weights16<__half> {
+  static const __half* wk(const ConvLayer& L) { return L.w_umma_h; }
+  static const __half* sm(const ConvLayer& L) { return L.w_sm_h; }
+  static const __half* up(const ConvLayer& L) { return L.w_up_h; }
+  static const __half* first(const ccst_handle* h) { return h->first_wk_h; }
+};
+
 template <typename T>
 struct Pipe {
   ccst_handle* h;
@@ -319,6 +386,7 @@ struct Pipe {
   bool up_pending = false;  // `cur` is a low-resolution map (replicate halo) awaiting its x2 upsample
   uint8_t* out_u8 = nullptr;  // decoder(): store NHWC uint8 (save_image quantisation) instead of NCHW fp32
   bool stats_in_tiles = false;  // the last encoder conv left tile statistics of `cur` in h->raw
+  bool fold_pending = false;  // AdaIN of `cur` lives in h->w_fold / h->b_fold: the next conv applies it
 
   ActView<T> view(int slot, int N, int H, int W, int C) {
     ActView<T> v;
@@ -327,10 +395,8 @@ struct Pipe {
     return v;
   }
 
-  // smerge_ok = false keeps a 64-channel layer on the tap-by-tap kernel (the un-fused pool path must
-  // produce the same bits as the fused one, which always uses that kernel)
-  int conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* out_nchw, bool smerge_ok = true,
-           int halo_edge = 1, float2* tile_stats = nullptr);
+  int conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* out_nchw, int halo_edge = 1,
+           float2* tile_stats = nullptr, bool per_sample = false);
 
   int first_launch(const float* img, int N, int H, int W);
   int first(const float* img, int N, int H, int W) {
@@ -365,6 +431,8 @@ struct Pipe {
       tile_stats = h->raw + 2 * (size_t)N * L.cout;
       epi = EPI_ACT_STATS;
     }
+    const bool per_sample = fold_pending;
+    CCST_CHECK_ARG(!per_sample || epi == EPI_ACT, "folded AdaIN needs the plain epilogue");
     ActView<T> out = view(cur_slot ^ 1, N, oh, ow, L.cout);
     {
       // executed FLOPs: the phase form runs 4 phases x 4 taps per SOURCE pixel (= 4 taps per output
@@ -373,14 +441,11 @@ struct Pipe {
                                : 2.0 * 9 * L.cin * L.cout * (double)N * H * W;
       const double bytes = (double)cur.elems() * sizeof(T) + (double)out.elems() * sizeof(T);
       ProfScope ps(h, st, sizeof(T) == 2 ? 1 : 2, flops, bytes);
-      // the un-fused pool path runs the same conv kernel as the fused one, so both give the same bits
-      // (with CCST_SMERGE=4 the pooled layer stays on the tap-by-tap kernel in both)
-      static const bool smerge_pooled = [] { const char* e = getenv("CCST_SMERGE"); return !(e && atoi(e) == 4); }();
-      const bool smerge_ok = smerge_pooled || !(pool_after && !fused_pool);
-      if (int e = conv(L, 1, epi, out, nullptr, smerge_ok, halo_edge, tile_stats)) return e;
+      if (int e = conv(L, 1, epi, out, nullptr, halo_edge, tile_stats, per_sample)) return e;
     }
     cur = out, cur_slot ^= 1;
     up_pending = defer_up;
+    fold_pending = false;
     stats_in_tiles = tile_stats != nullptr;
     if (pool_after && !fused_pool) {
       ActView<T> po = view(cur_slot ^ 1, N, (H + 1) / 2, (W + 1) / 2, L.cout);
@@ -398,7 +463,12 @@ struct Pipe {
     return CCST_OK;
   }
 
+  // AdaIN (+ alpha blend) of `cur` = relu4_1.  tcgen05 path with tile statistics and a map of at least
+  // kFoldMinHW pixels: nothing touches the feature map -- the per-(n, c) affine goes into per-image
+  // copies of dec1's weights and bias (conv(W, x*A + B') = conv(W*diag(A), x) + tapsum(W) . B', exact
+  // under reflection padding) and the decoder's first conv reads relu4_1 as conv4_1 left it.
   int adain(const float* mu_s, const float* sigma_s, int64_t stride, float alpha) {
+    if (try_fold(mu_s, sigma_s, stride, alpha)) return fold_rc;
     ActView<T> out = view(cur_slot ^ 1, cur.N, cur.H, cur.W, cur.C);
     ProfScope ps(h, st, 4, 0, 2.0 * (double)cur.N * cur.H * cur.W * cur.C * sizeof(T));
     if (int e = adain_launch(out, mu_s, sigma_s, stride, alpha)) return e;
@@ -407,6 +477,8 @@ struct Pipe {
     return CCST_OK;
   }
 
+  int fold_rc = CCST_OK;
+  bool try_fold(const float* mu_s, const float* sigma_s, int64_t stride, float alpha);
   int adain_launch(ActView<T> out, const float* mu_s, const float* sigma_s, int64_t stride, float alpha);
 
   int decoder(float* out_nchw) {
@@ -420,6 +492,27 @@ struct Pipe {
     return conv(L, 0, EPI_NCHW_F32, cur /*unused*/, out_nchw);
   }
 };
+
+template <>
+bool Pipe<float>::try_fold(const float*, const float*, int64_t, float) {
+  return false;
+}
+template <typename T>
+bool Pipe<T>::try_fold(const float* mu_s, const float* sigma_s, int64_t stride, float alpha) {
+  const ConvLayer& L = h->dec[0];
+  const size_t w_bytes = (size_t)cur.N * L.cout * 9 * L.cin * sizeof(T);
+  if (!(stats_in_tiles && h->fuse_adain && h->fuse_up && L.w_k32 && cur.C == L.cin && L.cout == 256 &&
+        cur.H * cur.W >= kFoldMinHW && w_bytes <= ((size_t)1 << 30)))
+    return false;
+  fold_rc = CCST_OK;
+  ProfScope ps(h, st, 6, 0, (double)w_bytes + (double)L.cout * 9 * L.cin * 4.0);
+  if ((fold_rc = ensure_fold(h, w_bytes, (size_t)cur.N * L.cout))) return true;
+  fold_rc = launch_adain_fold<T>(cur.N, cur.C, cur.H, cur.W, L.cout, h->raw, mu_s, sigma_s, stride, alpha, 1e-5f,
+                                 L.w_k32, L.w_tapsum, L.bias, reinterpret_cast<T*>(h->w_fold), h->b_fold,
+                                 h->sat_count, st);
+  if (fold_rc == CCST_OK) fold_pending = true, stats_in_tiles = false;
+  return true;
+}
 
 template <>
 int Pipe<float>::adain_launch(ActView<float> out, const float* mu_s, const float* sigma_s, int64_t stride,
@@ -440,32 +533,30 @@ template <>
 int Pipe<float>::first_launch(const float* img, int N, int H, int W) {
   return launch_conv_first<float>(img, N, H, W, h->first_w27, h->first_b64, cur, st);
 }
-template <>
-int Pipe<bf16>::first_launch(const float* img, int N, int H, int W) {
-  return launch_conv_first_umma<bf16>(img, N, H, W, h->first_wk_b, h->first_b64, cur, st);
+template <typename T>
+int Pipe<T>::first_launch(const float* img, int N, int H, int W) {
+  return launch_conv_first_umma<T>(img, N, H, W, Weights16<T>::first(h), h->first_b64, cur, st, h->sat_count);
 }
 template <>
-int Pipe<__half>::first_launch(const float* img, int N, int H, int W) {
-  return launch_conv_first_umma<__half>(img, N, H, W, h->first_wk_h, h->first_b64, cur, st);
-}
-template <>
-int Pipe<float>::conv(const ConvLayer& L, int relu, int epi, ActView<float> out, float* out_nchw,
-                      bool, int, float2*) {
+int Pipe<float>::conv(const ConvLayer& L, int relu, int epi, ActView<float> out, float* out_nchw, int,
+                      float2*, bool) {
   return launch_conv_ffma(cur, L.w_ffma, L.bias, L.cout, L.pad64, relu, epi, out, out_nchw, st);
 }
-template <>
-int Pipe<bf16>::conv(const ConvLayer& L, int relu, int epi, ActView<bf16> out, float* out_nchw,
-                     bool smerge_ok, int halo_edge, float2* tile_stats) {
-  return launch_conv_umma<bf16>(cur, L.w_umma, smerge_ok ? L.w_sm : nullptr, L.w_up, L.bias, L.cout,
-                                L.pad_umma, relu, epi, out, out_nchw,
-                                epi == EPI_NCHW_F32 ? out_u8 : nullptr, halo_edge, st, tile_stats);
-}
-template <>
-int Pipe<__half>::conv(const ConvLayer& L, int relu, int epi, ActView<__half> out,
-                       float* out_nchw, bool smerge_ok, int halo_edge, float2* tile_stats) {
-  return launch_conv_umma<__half>(cur, L.w_umma_h, smerge_ok ? L.w_sm_h : nullptr, L.w_up_h, L.bias,
-                                  L.cout, L.pad_umma, relu, epi, out, out_nchw,
-                                  epi == EPI_NCHW_F32 ? out_u8 : nullptr, halo_edge, st, tile_stats);
+template <typename T>
+int Pipe<T>::conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* out_nchw, int halo_edge,
+                  float2* tile_stats, bool per_sample) {
+  UmmaConvArgs<T> a;
+  a.in = cur, a.out = out;
+  a.wk = per_sample ? reinterpret_cast<const T*>(h->w_fold) : Weights16<T>::wk(L);
+  a.wk_sm = Weights16<T>::sm(L), a.wk_up = Weights16<T>::up(L);
+  a.bias = per_sample ? h->b_fold : L.bias;
+  a.Cout = L.cout, a.CoutPad = L.pad_umma;
+  a.relu = relu, a.epi = epi, a.halo_edge = halo_edge;
+  a.out_nchw = out_nchw, a.out_u8 = epi == EPI_NCHW_F32 ? out_u8 : nullptr;
+  a.tile_stats = tile_stats;
+  a.sat_count = h->sat_count;
+  a.per_sample = per_sample;
+  return launch_conv_umma<T>(a, st);
 }
 
 int check_common(ccst_handle* h, int precision) {
@@ -605,12 +696,12 @@ extern "C" ccst_handle* ccst_create(int device) {
   }
   ccst_handle* h = new ccst_handle();
   h->device = device;
-  const char* fp = getenv("CCST_FUSE_POOL");
-  if (fp && fp[0] == '0') h->fuse_pool = false;
-  const char* fu = getenv("CCST_FUSE_UP");
-  if (fu && fu[0] == '0') h->fuse_up = false;
-  const char* fs = getenv("CCST_FUSE_STATS");
-  if (fs && fs[0] == '0') h->fuse_stats = false;
+  if (cudaMalloc(&h->sat_count, sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(h->sat_count, 0, sizeof(unsigned int)) != cudaSuccess) {
+    set_error("ccst_create: cannot allocate the saturation counter: %s", cudaGetErrorString(cudaGetLastError()));
+    delete h;
+    return nullptr;
+  }
   return h;
 }
 
@@ -627,6 +718,9 @@ extern "C" void ccst_destroy(ccst_handle* h) {
   cudaFree(h->arena[1]);
   cudaFree(h->raw);
   cudaFree(h->io_f32);
+  cudaFree(h->w_fold);
+  cudaFree(h->b_fold);
+  cudaFree(h->sat_count);
   for (auto& s : h->prof) {
     if (s.a) cudaEventDestroy(s.a);
     if (s.b) cudaEventDestroy(s.b);
@@ -685,7 +779,8 @@ extern "C" int ccst_set_decoder_weights(ccst_handle* h, const float* const* w,
   CCST_CUDA(cudaSetDevice(h->device));
   for (int i = 0; i < kDecLayers; ++i) {
     CCST_CHECK_ARG(w[i] && b[i], "ccst_set_decoder_weights: null tensor %d", i);
-    if (int e = pack_layer(h->dec[i], kDecCh[i][0], kDecCh[i][1], w[i], b[i], i > 0 && kDecUpAfter[i - 1]))
+    if (int e = pack_layer(h->dec[i], kDecCh[i][0], kDecCh[i][1], w[i], b[i], i > 0 && kDecUpAfter[i - 1],
+                           /*fold_src=*/i == 0))
       return e;
   }
   h->dec_ready = true;
@@ -817,6 +912,30 @@ extern "C" int ccst_resize_bilinear_aa_f32(const float* d_in, int64_t planes, in
   return launch_resize_aa(d_in, planes, H, W, OH, OW, d_out, (cudaStream_t)stream);
 }
 
+extern "C" int ccst_set_fusion(ccst_handle* h, int mask) {
+  CCST_CHECK_ARG(h != nullptr, "null handle");
+  CCST_CHECK_ARG(mask >= 0 && mask <= CCST_FUSE_ALL, "ccst_set_fusion: bad mask %d", mask);
+  h->fuse_pool = (mask & CCST_FUSE_POOL) != 0;
+  h->fuse_up = (mask & CCST_FUSE_UPSAMPLE) != 0;
+  h->fuse_stats = (mask & CCST_FUSE_STATS) != 0;
+  h->fuse_adain = (mask & CCST_FUSE_ADAIN) != 0;
+  return CCST_OK;
+}
+
+extern "C" int ccst_saturation_snapshot(ccst_handle* h, uint32_t* h_count, void* stream) {
+  CCST_CHECK_ARG(h != nullptr && h_count != nullptr, "ccst_saturation_snapshot: null argument");
+  CCST_CUDA(cudaSetDevice(h->device));
+  CCST_CUDA(cudaMemcpyAsync(h_count, h->sat_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return CCST_OK;
+}
+
+extern "C" int ccst_saturation_reset(ccst_handle* h, void* stream) {
+  CCST_CHECK_ARG(h != nullptr, "null handle");
+  CCST_CUDA(cudaSetDevice(h->device));
+  CCST_CUDA(cudaMemsetAsync(h->sat_count, 0, sizeof(unsigned int), (cudaStream_t)stream));
+  return CCST_OK;
+}
+
 extern "C" int ccst_profile_enable(ccst_handle* h, int on) {
   CCST_CHECK_ARG(h != nullptr, "null handle");
   h->profiling = on != 0;
@@ -899,7 +1018,8 @@ extern "C" int ccst_debug_conv3x3(ccst_handle* h, const float* d_in, int N, int 
                  "ccst_debug_conv3x3: bad shape/mode");
   CCST_CHECK_ARG(mode != 4 || precision != CCST_PREC_FP32,
                  "ccst_debug_conv3x3: the upsample-fused conv exists on the tcgen05 path only");
-  CCST_CHECK_ARG(mode == 3 ? Cout <= 16 : Cout % 64 == 0, "ccst_debug_conv3x3: bad Cout");
+  CCST_CHECK_ARG(mode == 3 ? Cout <= (precision == CCST_PREC_FP32 ? 16 : 3) : Cout % 64 == 0,
+                 "ccst_debug_conv3x3: bad Cout");
   CCST_CHECK_ARG(mode != 2 || relu, "ccst_debug_conv3x3: pool mode requires relu");
   ConvLayer L;
   int rc = pack_layer(L, Cin, Cout, h_weight, h_bias, mode == 4);

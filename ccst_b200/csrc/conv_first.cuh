@@ -1,0 +1,448 @@
+// conv1_1 (+ folded 1x1 colour conv) on tcgen05: thread-built im2col rows (K = 27 padded to 32).
+#pragma once
+#include "umma_common.cuh"
+
+namespace ccst {
+namespace {
+
+// =====================================================================================
+// conv1_1 (+ folded 1x1 colour conv, net.py:39-42) on the tensor cores.
+// K = 27 is too thin for TMA-fed tiles, so the 128 threads of a CTA build the im2col rows
+// themselves: CTA tile = 128 consecutive pixels of one image row; thread p gathers the 27 taps of
+// pixel p from a staged fp32 window of the NCHW image (reflection applied while staging), converts
+// to T16 and writes one 64-byte K-major row (K padded to 32) into shared memory with the 128-byte
+// swizzle applied by hand (16-byte chunk j of row r lives at chunk j ^ (r & 7)).  One thread then
+// issues two tcgen05.mma (M=128, N=64, K=16), the accumulator comes back through tcgen05.ld and is
+// stored as NHWC (the tile is one contiguous 16 KiB span of the activation).
+// =====================================================================================
+constexpr int kFirstPx = 128;
+
+template <typename T16>
+struct FirstParams {
+  const float* img;  // [N,3,H,W]
+  int N, H, W;
+  const T16* wk;     // [64][32] K-major (k = (r*3+s)*3 + ci, 27..31 zero)
+  const float* bias; // [64]
+  ActView<T16> out;
+  int total_tiles, tiles_x;
+  unsigned int* sat_count;  // see SatTracker
+};
+
+constexpr int kFirstWin = 9 * (kFirstPx + 2);         // 3 channels x 3 rows x 130 columns
+constexpr int kFirstWinBytes = (kFirstWin * 4 + 127) / 128 * 128;
+constexpr int kFirstSmem = 1024 /*align*/ + kFirstPx * 128 * 2 + 64 * 128 + 2 * kFirstWinBytes + 256 + 64;
+
+template <typename T16>
+__global__ void __launch_bounds__(kFirstPx)
+    conv_first_umma_kernel(const __grid_constant__ CUtensorMap tmap_out, FirstParams<T16> p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base;                              // im2col rows, 128 x 128 B (swizzled)
+  const uint32_t sOut = base + kFirstPx * 128;           // staged output tile for the TMA store
+  uint8_t* sB_gen = gen + 2 * kFirstPx * 128;            // weights, 64 x 128 B (swizzled)
+  const uint32_t sB = base + 2 * kFirstPx * 128;
+  const uint32_t win_off = 2 * kFirstPx * 128 + 64 * 128;
+  float* sbias = reinterpret_cast<float*>(gen + win_off + 2 * kFirstWinBytes);
+  const uint32_t bar = base + win_off + 2 * kFirstWinBytes + 256;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(gen + win_off + 2 * kFirstWinBytes + 256 + 16);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  // one-time: weights -> swizzled K-major B tile, barrier, TMEM
+  for (int i = tid; i < 64 * 4; i += kFirstPx) {
+    const int o = i >> 2, j = i & 3;
+    const uint4 v = reinterpret_cast<const uint4*>(p.wk)[o * 4 + j];
+    *reinterpret_cast<uint4*>(sB_gen + o * 128 + ((j ^ (o & 7)) << 4)) = v;
+  }
+  if (tid < 64) sbias[tid] = p.bias[tid];
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmap_out);
+  }
+  if (warp == 0) tmem_alloc<64>(base + win_off + 2 * kFirstWinBytes + 256 + 16);
+
+  // Input window of one tile: 3 ch x 3 rows x 130 cols of the NCHW fp32 image, reflection resolved
+  // per element, fetched with 4-byte cp.async one tile AHEAD of its use (the loads are the only
+  // DRAM-latency-bound part of this kernel).
+  auto stage_window = [&](int tile, int buf) {
+    int b = tile;
+    const int x0 = (b % p.tiles_x) * kFirstPx;
+    b /= p.tiles_x;
+    const int y = b % p.H;
+    const int n = b / p.H;
+    const uint32_t dst0 = base + win_off + buf * kFirstWinBytes;
+    for (int i = tid; i < kFirstWin; i += kFirstPx) {
+      const int col = i % (kFirstPx + 2);
+      const int rc = i / (kFirstPx + 2);  // ci*3 + row
+      const int row = rc % 3, ci = rc / 3;
+      int yy = y + row - 1;
+      yy = yy < 0 ? -yy : (yy >= p.H ? 2 * p.H - 2 - yy : yy);
+      int xx = x0 + col - 1;
+      if (xx <= p.W) {
+        xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
+        const float* src = p.img + (((size_t)n * 3 + ci) * p.H + yy) * p.W + xx;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + 4 * i), "l"(src)
+                     : "memory");
+      } else {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst0 + 4 * i), "r"(0u) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if ((int)blockIdx.x < p.total_tiles) stage_window(blockIdx.x, 0);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  const uint64_t adesc = make_kmajor_sw128_desc(sA);
+  const uint64_t bdesc = make_kmajor_sw128_desc(sB);
+  constexpr uint32_t idesc = make_idesc<T16, 64>();
+  uint32_t phase = 0;
+  int buf = 0;
+  SatTracker<T16> sat;
+
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, buf ^= 1) {
+    int b = tile;
+    const int x0 = (b % p.tiles_x) * kFirstPx;
+    b /= p.tiles_x;
+    const int y = b % p.H;
+    const int n = b / p.H;
+    // (1) prefetch the next tile's window, then wait for this tile's
+    const int next = tile + gridDim.x;
+    if (next < p.total_tiles) {
+      stage_window(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* win = reinterpret_cast<const float*>(gen + win_off + buf * kFirstWinBytes);
+    // (2) im2col row of pixel tid -> swizzled K-major A tile
+    {
+      uint32_t pk[16];
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = 2 * k2 + e;
+          if (k < 27) {
+            const int tap = k / 3, ci = k - 3 * tap;
+            const int r = tap / 3, s = tap - 3 * r;
+            v[e] = win[(ci * 3 + r) * (kFirstPx + 2) + tid + s];
+          } else {
+            v[e] = 0.f;
+          }
+        }
+        pk[k2] = pack16x2<T16>(v[0], v[1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t dst = sA + tid * 128 + ((j ^ (tid & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                     "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                     : "memory");
+      }
+    }
+    fence_async_smem();  // generic smem writes -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    // (3) two K=16 steps, issued by one elected lane of the converged warp 0
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        umma_bf16(tmem_base, adesc, bdesc, idesc, 0u);
+        umma_bf16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
+        umma_commit(bar);
+      }
+      __syncwarp();
+    }
+    // (4) accumulator ready
+    mbar_wait(bar, phase, 900);
+    phase ^= 1;
+    tc_fence_after();
+    // (5) epilogue: row tid of the accumulator = pixel x0 + tid
+    const int x = x0 + tid;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t r0[32], r1[32];
+    tmem_ld32(taddr, r0);
+    tmem_ld32(taddr + 32, r1);
+    tmem_ld_wait();
+    uint32_t pk[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      pk[j] = pack16x2_relu<T16>(__uint_as_float(r0[2 * j]) + sbias[2 * j],
+                                 __uint_as_float(r0[2 * j + 1]) + sbias[2 * j + 1]);
+      pk[16 + j] = pack16x2_relu<T16>(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j],
+                                      __uint_as_float(r1[2 * j + 1]) + sbias[33 + 2 * j]);
+      sat.track(pk[j]);
+      sat.track(pk[16 + j]);
+    }
+    // TMEM reads are complete (wait::ld); every thread passes two more block barriers before warp 0
+    // overwrites the accumulator with the next tile
+    tc_fence_before();
+    // each warp stages and stores its own 32-pixel quarter of the row segment, so only its own
+    // previous TMA store has to have drained (no block-wide barrier on the store path)
+    bulk_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t dst = sOut + tid * 128 + ((j ^ (tid & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                   "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                   : "memory");
+    }
+    if (x < p.W) store_aliases(p.out, n, y, x, 0, pk);
+    fence_async_smem();
+    __syncwarp();
+    if (elect_one()) {
+      tma_store_4d(&tmap_out, sOut + warp * (32 * 128), 0, x0 + warp * 32, y, n);  // clipped at W
+      bulk_commit();
+    }
+    __syncwarp();
+  }
+  bulk_wait_all();
+  sat.flush(p.sat_count);
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem_base);
+}
+
+// =====================================================================================
+// conv1_1, warp-specialised persistent variant (used when W % 4 == 0, i.e. the image rows are
+// 16-byte aligned and TMA can fetch the input window).  Same math as conv_first_umma_kernel; the
+// per-tile chain  window -> im2col rows -> MMA -> epilogue -> store  is cut into four roles that
+// run on different tiles at the same time, so the kernel is bound by its HBM writes (128 B per
+// pixel) instead of by the latency of the chain:
+//   warp 0      TMA producer: {136 col, 3 row, 3 ch} fp32 window of the NCHW image per tile, ring
+//               of kF2WinStages (out-of-image rows / columns arrive as zeros and are never read:
+//               reflection is an index remap in the builders)
+//   warps 1-4   builders: thread p gathers the 27 taps of pixel p, converts to T16 and writes the
+//               swizzled K-major row p of the A tile (ring of 2)
+//   warp 5      MMA issuer: 2 x tcgen05.mma (M=128, N=64, K=16) per tile into one of 2 TMEM stages
+//   warps 6-9   epilogue: tcgen05.ld -> bias + ReLU -> T16 -> per-warp staging -> TMA store
+// =====================================================================================
+constexpr int kF2Threads = 320;
+constexpr int kF2WinCols = 136;  // columns x0-4 .. x0+131: a non-swizzled TMA box must start 16-byte aligned
+constexpr int kF2WinX0 = 4;     // window column of pixel x0
+constexpr int kF2WinElems = 9 * kF2WinCols;
+constexpr int kF2WinTx = kF2WinElems * 4;                      // 4896 bytes per TMA box
+constexpr int kF2WinBytes = (kF2WinTx + 127) / 128 * 128;      // 4992
+constexpr int kF2WinStages = 4;
+constexpr int kF2ABytes = kFirstPx * 128;                      // 16 KiB
+constexpr int kF2OffA = 0;                                     // 2 A tiles
+constexpr int kF2OffOut = 2 * kF2ABytes;                       // 2 staging tiles
+constexpr int kF2OffB = 4 * kF2ABytes;                         // weights 64 x 128 B
+constexpr int kF2OffWin = kF2OffB + 64 * 128;
+constexpr int kF2OffBias = kF2OffWin + kF2WinStages * kF2WinBytes;
+constexpr int kF2OffBar = kF2OffBias + 256;
+constexpr int kF2NumBars = 2 * kF2WinStages + 8;
+constexpr int kF2Smem = 1024 + kF2OffBar + 8 * kF2NumBars + 16;
+
+template <typename T16>
+__global__ void __launch_bounds__(kF2Threads, 2)
+    conv_first_umma_ws_kernel(const __grid_constant__ CUtensorMap tmap_img,
+                              const __grid_constant__ CUtensorMap tmap_out, FirstParams<T16> p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + kF2OffBar;
+  auto win_full = [&](int s) { return bar0 + 8u * s; };
+  auto win_empty = [&](int s) { return bar0 + 8u * (kF2WinStages + s); };
+  auto a_full = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + s); };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + 2 + s); };
+  auto t_full = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + 4 + s); };
+  auto t_empty = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + 6 + s); };
+  const uint32_t tmem_slot = bar0 + 8u * kF2NumBars;
+  float* sbias = reinterpret_cast<float*>(gen + kF2OffBias);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // one-time: weights -> swizzled K-major B tile, bias, barriers, TMEM (2 stages x 64 columns)
+  for (int i = tid; i < 64 * 4; i += kF2Threads) {
+    const int o = i >> 2, j = i & 3;
+    const uint4 v = reinterpret_cast<const uint4*>(p.wk)[o * 4 + j];
+    *reinterpret_cast<uint4*>(gen + kF2OffB + o * 128 + ((j ^ (o & 7)) << 4)) = v;
+  }
+  if (tid < 64) sbias[tid] = p.bias[tid];
+  if (tid == 0) {
+    for (int s = 0; s < kF2WinStages; ++s) {
+      mbar_init(win_full(s), 1);
+      mbar_init(win_empty(s), 128);  // every builder thread arrives for itself
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_full(s), 128);
+      mbar_init(a_empty(s), 1);
+      mbar_init(t_full(s), 1);
+      mbar_init(t_empty(s), 4);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmap_img);
+    prefetch_tmap(&tmap_out);
+  }
+  if (warp == 5) tmem_alloc<128>(tmem_slot);
+  fence_async_smem();  // the weight tile is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + kF2OffBar + 8 * kF2NumBars);
+  pdl_launch_dependents();
+  pdl_wait();
+
+  auto tile_coord = [&](int tile, int& n, int& y, int& x0) {
+    x0 = (tile % p.tiles_x) * kFirstPx;
+    const int b = tile / p.tiles_x;
+    y = b % p.H;
+    n = b / p.H;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int ws = it % kF2WinStages;
+      const uint32_t ph = (it / kF2WinStages) & 1;
+      int n, y, x0;
+      tile_coord(tile, n, y, x0);
+      mbar_wait(win_empty(ws), ph ^ 1, 910);
+      if (elect_one()) {
+        mbar_expect_tx(win_full(ws), kF2WinTx);
+        tma_load_4d(base + kF2OffWin + ws * kF2WinBytes, &tmap_img, win_full(ws), x0 - kF2WinX0, y - 1, 0, n);
+      }
+      __syncwarp();
+    }
+  } else if (warp <= 4) {
+    // ===================== builders: im2col row of pixel px of the tile
+    const int px = tid - 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int ws = it % kF2WinStages, as = it & 1;
+      int n, y, x0;
+      tile_coord(tile, n, y, x0);
+      // reflection = index remap inside the window (rows y-1..y+1 at 0..2, columns from x0-4)
+      int ridx[3] = {0, 1, 2};
+      if (y == 0) ridx[0] = 2;
+      if (y == p.H - 1) ridx[2] = 0;
+      int cidx[3];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int xx = x0 + px + s - 1;
+        xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
+        int c = xx - (x0 - kF2WinX0);
+        cidx[s] = c < 0 ? 0 : (c > kF2WinCols - 1 ? kF2WinCols - 1 : c);  // only for pixels past W
+      }
+      mbar_wait(win_full(ws), (it / kF2WinStages) & 1, 920);
+      const float* win = reinterpret_cast<const float*>(gen + kF2OffWin + ws * kF2WinBytes);
+      float v[28];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        const int tap = k / 3, ci = k - 3 * tap;
+        const int r = tap / 3, s = tap - 3 * r;
+        v[k] = win[(ci * 3 + ridx[r]) * kF2WinCols + cidx[s]];
+      }
+      v[27] = 0.f;
+      // The window is rewritten by TMA (async proxy): this thread's generic-proxy reads must be
+      // ordered before that write, which takes a proxy fence before the release (without it a
+      // 32-pixel quarter of a tile came out wrong about once per 10^5 tiles).
+      fence_async_smem();
+      mbar_arrive(win_empty(ws));
+      uint32_t pk[16];
+#pragma unroll
+      for (int k2 = 0; k2 < 14; ++k2) pk[k2] = pack16x2<T16>(v[2 * k2], v[2 * k2 + 1]);
+      pk[14] = 0u, pk[15] = 0u;
+      MBAR_WAIT_RELAXED(a_empty(as), ((it >> 1) & 1) ^ 1, 930);
+      const uint32_t sA = base + kF2OffA + as * kF2ABytes;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t dst = sA + px * 128 + ((j ^ (px & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                     "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                     : "memory");
+      }
+      fence_async_smem();  // this thread's generic writes -> visible to the tensor core
+      mbar_arrive(a_full(as));
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer
+    constexpr uint32_t idesc = make_idesc<T16, 64>();
+    const uint64_t bdesc = make_kmajor_sw128_desc(base + kF2OffB);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(t_empty(as), ph ^ 1, 940);
+      mbar_wait(a_full(as), ph, 941);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = make_kmajor_sw128_desc(base + kF2OffA + as * kF2ABytes);
+        const uint32_t d = tmem_base + (uint32_t)(as * 64);
+        umma_bf16(d, adesc, bdesc, idesc, 0u);
+        umma_bf16(d, adesc + 2, bdesc + 2, idesc, 1u);
+        umma_commit(a_empty(as));
+        umma_commit(t_full(as));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: warp q owns TMEM lanes 32q..32q+31 = pixels 32q.. of the tile
+    const int q = warp & 3;  // warps 6,7,8,9 -> lane quadrants 2,3,0,1
+    const int px = q * 32 + lane;
+    int it = 0;
+    SatTracker<T16> sat;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      int n, y, x0;
+      tile_coord(tile, n, y, x0);
+      MBAR_WAIT_RELAXED(t_full(as), (it >> 1) & 1, 950);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 64);
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr, r0);
+      tmem_ld32(taddr + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty(as));
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        pk[j] = pack16x2_relu<T16>(__uint_as_float(r0[2 * j]) + sbias[2 * j],
+                                   __uint_as_float(r0[2 * j + 1]) + sbias[2 * j + 1]);
+        pk[16 + j] = pack16x2_relu<T16>(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j],
+                                        __uint_as_float(r1[2 * j + 1]) + sbias[33 + 2 * j]);
+        sat.track(pk[j]);
+        sat.track(pk[16 + j]);
+      }
+      // per-warp staging (two buffers): the store issued two tiles ago must have read its buffer
+      bulk_wait_read<1>();
+      __syncwarp();
+      const uint32_t sOut = base + kF2OffOut + as * kF2ABytes;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t dst = sOut + px * 128 + ((j ^ (px & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                     "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                     : "memory");
+      }
+      const int x = x0 + px;
+      if (x < p.W) store_aliases(p.out, n, y, x, 0, pk);
+      fence_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        tma_store_4d(&tmap_out, sOut + q * (32 * 128), 0, x0 + q * 32, y, n);  // clipped at W
+        bulk_commit();
+      }
+      __syncwarp();
+    }
+    bulk_wait_all();
+    sat.flush(p.sat_count);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<128>(tmem_base);
+}
+
+}  // namespace
+}  // namespace ccst

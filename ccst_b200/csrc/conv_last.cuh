@@ -1,0 +1,179 @@
+// Last decoder conv (64 -> 3 channels, HBM-bound) on tcgen05.
+#pragma once
+#include "umma_common.cuh"
+
+namespace ccst {
+namespace {
+
+// =====================================================================================
+// Last decoder conv (net.py:34-35, 64 -> 3 channels, no ReLU, fp32 NCHW or uint8 NHWC result):
+// filter ROWS by operand shifts, filter COLUMNS in N.  HBM-bound (reads 128 B, writes 12 B or 3 B per
+// pixel).  The tile is 4 rows x 32 columns of a linear slab {64 ch, 32 px, 6 rows} (one TMA load):
+//   P[(jy, jx), (s, co)] = sum_{r, c} X[(jy + r, jx), c] * W[co][c][r][s]     3 MMAs chains (r), N = 16
+//   out[(y, x), co]      = bias[co] + P[(y, x), (0, co)] + P[(y, x+1), (1, co)] + P[(y, x+2), (2, co)]
+// The row shift r is a start-address offset of r * 32 * 128 B into the slab; the column shift s
+// is two warp shuffles in the epilogue (one tile row = one warp = one TMEM lane quadrant), so a
+// thread reads 16 accumulator columns and writes its pixel: no shared-memory staging at all.
+// 30 of the 32 columns are outputs (the last two would need the next tile's pixels).
+// =====================================================================================
+constexpr int kRBoxW = 32, kRRows = 4, kROutW = kRBoxW - 2;
+constexpr int kRSlabBytes = (kRRows + 2) * kRBoxW * 128;  // 24576
+constexpr int kRStages = 6;
+constexpr int kROffB = kRStages * kRSlabBytes;            // 3 weight tiles of 16 rows x 128 B
+constexpr int kROffBar = kROffB + 3 * 2048 + 1024;        // (+ slack: the last MMA rows read 256 B past a slab)
+constexpr int kRNumBars = 2 * kRStages + 4;
+constexpr int kRSmem = 1024 + kROffBar + 8 * kRNumBars + 16;
+
+template <typename T16>
+__global__ void __launch_bounds__(kThreadsUmma, 1)
+    conv_last_rows_kernel(const __grid_constant__ CUtensorMap tmap_a, const T16* __restrict__ wk,
+                          ConvParams<T16> p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + kROffBar;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (kRStages + s); };
+  auto t_full = [&](int s) { return bar0 + 8u * (2 * kRStages + s); };
+  auto t_empty = [&](int s) { return bar0 + 8u * (2 * kRStages + 2 + s); };
+  const uint32_t tmem_slot = bar0 + 8u * kRNumBars;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto tile_of = [&](int tile, int& n, int& y0, int& x0) {
+    x0 = (tile % p.tiles_x) * kROutW;
+    tile /= p.tiles_x;
+    y0 = (tile % p.tiles_y) * kRRows;
+    n = tile / p.tiles_y;
+  };
+
+  // B_r[n = s*4 + co][k = c] = W[co][c][r][s] from the packed weights wk[co][(r*3+s)*64 + c]; K-major
+  // rows of 128 B with the 128-byte swizzle; unused rows are zero
+  for (int i = threadIdx.x; i < 3 * 16 * 8; i += kThreadsUmma) {
+    const int r = i / 128, n = (i >> 3) & 15, j = i & 7;
+    const int sc = n >> 2, co = n & 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (sc < 3 && co < p.Cout && co < 3)
+      v = *reinterpret_cast<const uint4*>(wk + (size_t)co * (9 * kBlockK) + (r * 3 + sc) * kBlockK + j * 8);
+    *reinterpret_cast<uint4*>(gen + kROffB + r * 2048 + n * 128 + ((j ^ (n & 7)) << 4)) = v;
+  }
+  if (warp == 0 && lane == 0) prefetch_tmap(&tmap_a);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kRStages; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(t_full(s), 1);
+      mbar_init(t_empty(s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<32>(tmem_slot);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + kROffBar + 8 * kRNumBars);
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer: one slab per tile
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int n, y0, x0;
+      tile_of(tile, n, y0, x0);
+      MBAR_WAIT_RELAXED(a_empty(s), ph ^ 1, 800 + s);
+      if (elect_one()) {
+        mbar_expect_tx(a_full(s), kRSlabBytes);
+        tma_load_4d(base + s * kRSlabBytes, &tmap_a, a_full(s), 0, x0, y0, n);
+      }
+      __syncwarp();
+      if (++s == kRStages) s = 0, ph ^= 1;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: 3 filter rows x 4 K steps, M = 128, N = 16
+    constexpr uint32_t idesc = make_idesc<T16, 16>();
+    const uint64_t bdesc0 = make_kmajor_sw128_desc(base + kROffB);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acs = it & 1;
+      mbar_wait(t_empty(acs), ((it >> 1) & 1) ^ 1, 810 + acs);
+      mbar_wait(a_full(s), ph, 820 + s);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc0 = make_kmajor_sw128_desc(base + s * kRSlabBytes);
+        const uint32_t d = tmem_base + (uint32_t)(acs * 16);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(d, adesc0 + (uint64_t)(r * (kRBoxW * 128 >> 4) + 2 * k), bdesc0 + (uint64_t)(r * (2048 >> 4) + 2 * k),
+                      idesc, (r | k) ? 1u : 0u);
+        umma_commit(a_empty(s));
+        umma_commit(t_full(acs));
+      }
+      __syncwarp();
+      if (++s == kRStages) s = 0, ph ^= 1;
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue: group g takes tiles g, g+2, ...; warp <-> tile row, lane <-> column
+    const int grp = (warp - kEpiWarp0) >> 2;
+    const int quad = warp & 3;
+    float bias[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) bias[c] = c < p.Cout ? p.bias[c] : 0.f;
+    for (int it = grp;; it += 2) {
+      const long long tile_ll = (long long)blockIdx.x + (long long)it * gridDim.x;
+      if (tile_ll >= p.total_tiles) break;
+      int n, y0, x0;
+      tile_of((int)tile_ll, n, y0, x0);
+      const int acs = it & 1;
+      MBAR_WAIT_RELAXED(t_full(acs), (it >> 1) & 1, 830 + acs);
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acs * 16), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty(acs));
+      const int y = y0 + quad, x = x0 + lane;
+      const bool ok = lane < kROutW && y < p.H && x < p.W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float p1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[4 + c]), 1);
+        const float p2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[8 + c]), 2);
+        float o = ((bias[c] + __uint_as_float(v[c])) + p1) + p2;
+        if (p.relu) o = fmaxf(o, 0.f);
+        if (ok && c < p.Cout) {
+          if (p.out_u8) p.out_u8[(((size_t)n * p.H + y) * p.W + x) * p.Cout + c] = quantize_u8(o);
+          else p.out_nchw[(((size_t)n * p.Cout + c) * p.H + y) * p.W + x] = o;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<32>(tmem_base);
+}
+
+template <typename T16>
+int launch_last_rows(ActView<T16> in, const T16* wk, ConvParams<T16> p, cudaStream_t st) {
+  CUtensorMap mr;
+  if (int e = make_act_map(&mr, in, kRBoxW, kRRows + 2)) return e;
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_last_rows_kernel<T16>), kRSmem));
+  p.tiles_x = (in.W + kROutW - 1) / kROutW;
+  p.tiles_y = (in.H + kRRows - 1) / kRRows;
+  const int64_t tiles = (int64_t)in.N * p.tiles_x * p.tiles_y;
+  CCST_CHECK_ARG(tiles < (1ll << 31), "conv_last_rows: too many tiles");
+  p.m_tiles = p.total_tiles = (int)tiles;
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  CCST_CUDA(launch_conv(conv_last_rows_kernel<T16>, grid, kThreadsUmma, kRSmem, st, 1, mr, wk, p));
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+}  // namespace
+}  // namespace ccst

@@ -1,0 +1,247 @@
+// dec8 (upsample-fused 64 -> 64 conv): all four output phases per tile over one linear slab.
+#pragma once
+#include "umma_common.cuh"
+
+namespace ccst {
+namespace {
+
+// =====================================================================================
+// Upsample-fused 64 -> 64 conv (dec8, net.py:30-32), all four output phases per tile.
+// At N = 64 a tcgen05.mma is bound by the shared-memory fetch of its A operand (128 x 32 B at
+// 64 B/clk = 64 cycles for 32 cycles of math), and the per-phase kernel issues 16 such MMAs per
+// K step and source tile.  Here one linear slab {64 ch, 32 px, 6 rows} of the low-resolution map
+// feeds all four phases: the operand view (R, S) = slab shifted by R rows and S pixels is shared
+// by every (phase, tap) with a + dy = R, b + dx = S, so their weight tiles are stacked in N:
+//   view (1,1): 4 phases, N = 256;  (0,1) (1,0) (1,2): 2 phases, N = 128;  (2,1): 2 x N = 64 (its two
+//   phases are not adjacent in TMEM);  corners: N = 64       -> 10 MMAs per K step instead of 16,
+// with accumulator columns ordered [phase 10 | 00 | 01 | 11].  The N = 256 view is issued first and
+// initialises all four accumulators.  All 16 weight tiles (128 KiB) stay resident in shared memory.
+// =====================================================================================
+constexpr int kU4BoxW = 32, kU4Rows = 4, kU4OutW = kU4BoxW - 2;
+constexpr int kU4SlabBytes = (kU4Rows + 2) * kU4BoxW * 128;  // 24576
+constexpr int kU4AStages = 2;
+constexpr int kU4OffB = kU4AStages * kU4SlabBytes;           // 16 tiles x 8 KiB
+constexpr int kU4OffStore = kU4OffB + 16 * 8192;
+constexpr int kU4StoreBytes = 16384;                          // 120 rows x 128 B, rounded
+constexpr int kU4OffBias = kU4OffStore + 2 * kU4StoreBytes;
+constexpr int kU4OffBar = kU4OffBias + 256;
+constexpr int kU4NumBars = 2 * kU4AStages + 4 + 1;
+constexpr int kU4Smem = 1024 + kU4OffBar + 8 * kU4NumBars + 16;
+static_assert(kU4Smem <= 232448, "ups4 shared memory plan exceeds 227 KiB");
+
+struct U4Op {
+  int R, S, first, ntiles, slot;
+};
+// issue order: the 4-phase view first (accumulate = 0), then the rest
+__device__ constexpr U4Op kU4Ops[10] = {{1, 1, 6, 4, 0}, {0, 0, 0, 1, 1}, {0, 1, 1, 2, 1}, {0, 2, 3, 1, 2},
+                                        {1, 0, 4, 2, 0}, {1, 2, 10, 2, 2}, {2, 0, 12, 1, 0}, {2, 1, 13, 1, 0},
+                                        {2, 1, 14, 1, 3}, {2, 2, 15, 1, 3}};
+// resident slot -> (phase = a*2+b, tap = dy*2+dx) of the packed phase weights
+__device__ constexpr int kU4TilePh[16] = {0, 0, 1, 1, 2, 0, 2, 0, 1, 3, 1, 3, 2, 2, 3, 3};
+__device__ constexpr int kU4TileTap[16] = {0, 1, 0, 1, 0, 2, 1, 3, 2, 0, 3, 1, 2, 3, 2, 3};
+__device__ constexpr int kU4SlotPh[4] = {2, 0, 1, 3};  // accumulator column slot -> phase
+
+template <typename T16>
+__global__ void __launch_bounds__(kThreadsUmma, 1)
+    conv_ups4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ OutMaps tmap_out, ConvParams<T16> p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + kU4OffBar;
+  float* s_bias = reinterpret_cast<float*>(gen + kU4OffBias);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (kU4AStages + s); };
+  auto t_full = [&](int s) { return bar0 + 8u * (2 * kU4AStages + s); };
+  auto t_empty = [&](int s) { return bar0 + 8u * (2 * kU4AStages + 2 + s); };
+  const uint32_t bres_bar = bar0 + 8u * (2 * kU4AStages + 4);
+  const uint32_t tmem_slot = bar0 + 8u * kU4NumBars;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto tile_of = [&](int tile, int& n, int& y0, int& x0) {
+    x0 = (tile % p.tiles_x) * kU4OutW;
+    tile /= p.tiles_x;
+    y0 = (tile % p.tiles_y) * kU4Rows;
+    n = tile / p.tiles_y;
+  };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_out.m[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kU4AStages; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(t_full(s), 1);
+      mbar_init(t_empty(s), 4);
+    }
+    mbar_init(bres_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + kU4OffBar + 8 * kU4NumBars);
+  pdl_launch_dependents();
+  if (warp != 0) pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer: resident phase weights once, then one slab per tile
+    if (elect_one()) {
+      mbar_expect_tx(bres_bar, 16 * 8192);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        tma_load_2d(base + kU4OffB + i * 8192, &tmap_b, bres_bar, kU4TileTap[i] * kBlockK, kU4TilePh[i] * 64);
+    }
+    __syncwarp();
+    pdl_wait();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int n, y0, x0;
+      tile_of(tile, n, y0, x0);
+      MBAR_WAIT_RELAXED(a_empty(s), ph ^ 1, 900 + s);
+      if (elect_one()) {
+        mbar_expect_tx(a_full(s), kU4SlabBytes);
+        // slab position (jy, jx) = padded pixel (y0 + jy, x0 + jx) = source (y0 - 1 + jy, x0 - 1 + jx)
+        tma_load_4d(base + s * kU4SlabBytes, &tmap_a, a_full(s), 0, x0, y0, n);
+      }
+      __syncwarp();
+      if (++s == kU4AStages) s = 0, ph ^= 1;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: 10 operand views x 4 K steps per tile
+    mbar_wait(bres_bar, 0, 905);
+    tc_fence_after();
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acs = it & 1;
+      mbar_wait(t_empty(acs), ((it >> 1) & 1) ^ 1, 910 + acs);
+      mbar_wait(a_full(s), ph, 920 + s);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc0 = make_kmajor_sw128_desc(base + s * kU4SlabBytes);
+        const uint64_t bdesc0 = make_kmajor_sw128_desc(base + kU4OffB);
+        const uint32_t d0 = tmem_base + (uint32_t)(acs * 256);
+#pragma unroll
+        for (int o = 0; o < 10; ++o) {
+          const uint64_t adesc = adesc0 + (uint64_t)((kU4Ops[o].R * kU4BoxW + kU4Ops[o].S) * 128 >> 4);
+          const uint64_t bdesc = bdesc0 + (uint64_t)(kU4Ops[o].first * (8192 >> 4));
+          const uint32_t d = d0 + (uint32_t)(kU4Ops[o].slot * 64);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint32_t acc = (o | k) ? 1u : 0u;
+            if (kU4Ops[o].ntiles == 4) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 256>(), acc);
+            else if (kU4Ops[o].ntiles == 2) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 128>(), acc);
+            else umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 64>(), acc);
+          }
+        }
+        umma_commit(a_empty(s));
+        umma_commit(t_full(acs));
+      }
+      __syncwarp();
+      if (++s == kU4AStages) s = 0, ph ^= 1;
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue: group g drains accumulator stage g; warp <-> tile row, lane <-> column
+    const int grp = (warp - kEpiWarp0) >> 2;
+    const int quad = warp & 3;
+    const bool issuer_warp = (quad == 0);
+    const uint32_t sbuf = base + kU4OffStore + grp * kU4StoreBytes;
+    const int srow = quad * kU4OutW + lane;
+    SatTracker<T16> sat;
+    for (int it = grp;; it += 2) {
+      const long long tile_ll = (long long)blockIdx.x + (long long)it * gridDim.x;
+      if (tile_ll >= p.total_tiles) break;
+      int n, y0, x0;
+      tile_of((int)tile_ll, n, y0, x0);
+      const int acs = it & 1;
+      const int y = y0 + quad, x = x0 + lane;
+      const bool col_ok = lane < kU4OutW;
+      const bool valid = col_ok && y < p.H && x < p.W;
+      MBAR_WAIT_RELAXED(t_full(acs), (it >> 1) & 1, 930 + acs);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acs * 256);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int phs = kU4SlotPh[ch], a = phs >> 1, b = phs & 1;
+        uint32_t r[64];
+        {
+          uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+          uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+          tmem_ld32(taddr + ch * 64, r0);
+          tmem_ld32(taddr + ch * 64 + 32, r1);
+        }
+        tmem_ld_wait();
+        if (ch == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty(acs));
+        }
+        uint32_t pk[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v0 = __uint_as_float(r[2 * j]) + s_bias[2 * j];
+          const float v1 = __uint_as_float(r[2 * j + 1]) + s_bias[2 * j + 1];
+          pk[j] = p.relu ? pack16x2_relu<T16>(v0, v1) : pack16x2<T16>(v0, v1);
+          sat.track(pk[j]);
+        }
+        if (issuer_warp) bulk_wait_read<0>();  // the staging buffer has been read out by its TMA store
+        epi_barrier(grp);
+        if (col_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t dst = sbuf + srow * 128 + ((j ^ (srow & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                         "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                         : "memory");
+          }
+        }
+        if (valid) store_aliases(p.out, n, 2 * y + a, 2 * x + b, 0, pk);
+        fence_async_smem();
+        epi_barrier(grp);
+        if (issuer_warp && elect_one()) {
+          tma_store_4d(&tmap_out.m[phs], sbuf, 0, x0, y0, n);
+          bulk_commit();
+        }
+      }
+    }
+    if (issuer_warp) bulk_wait_all();
+    sat.flush(p.sat_count);
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+template <typename T16>
+int launch_ups4(ActView<T16> in, const T16* wk_up, ConvParams<T16> p, cudaStream_t st) {
+  CUtensorMap m4, mb;
+  if (int e = make_act_map(&m4, in, kU4BoxW, kU4Rows + 2)) return e;
+  if (int e = make_weight_map(&mb, wk_up, 4 * in.C, 4 * p.Cout, 64)) return e;
+  OutMaps mo;
+  memset(&mo, 0, sizeof(mo));
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b)
+      if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, kU4OutW, kU4Rows)) return e;
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_ups4_kernel<T16>), kU4Smem));
+  p.tiles_x = (in.W + kU4OutW - 1) / kU4OutW;
+  p.tiles_y = (in.H + kU4Rows - 1) / kU4Rows;
+  const int64_t tiles = (int64_t)in.N * p.tiles_x * p.tiles_y;
+  CCST_CHECK_ARG(tiles < (1ll << 31), "conv_ups4: too many tiles");
+  p.m_tiles = p.total_tiles = (int)tiles;
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  CCST_CUDA(launch_conv(conv_ups4_kernel<T16>, grid, kThreadsUmma, kU4Smem, st, 1, m4, mb, mo, p));
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+}  // namespace
+}  // namespace ccst

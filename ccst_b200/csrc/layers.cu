@@ -10,6 +10,8 @@
 //  * stats_nhwc      : per-(n,c) Welford partials of relu4_1 for the overall-style loop
 //                      (mean_std_computation_effcientMem.py:103-131)
 //  * layout converters between the reference's NCHW fp32 tensors and the arena layout.
+#include <type_traits>
+
 #include "layers.h"
 
 namespace ccst {
@@ -505,6 +507,69 @@ __global__ void __launch_bounds__(256)
                                         alpha * ms + (1.f - alpha) * st.mean, 0.f);
 }
 
+// The same statistics -> {A, B - mu_c * A} as two float arrays (folded AdaIN: out = x * A + B').
+__global__ void __launch_bounds__(256)
+    adain_fold_coef_tiles_kernel(const float2* __restrict__ tp, float* __restrict__ fold_a, float* __restrict__ fold_b,
+                                 int C, int H, int W, const float* __restrict__ mu_s,
+                                 const float* __restrict__ sigma_s, int64_t stat_batch_stride, float alpha, float eps) {
+  __shared__ Wf s_grp[8 * 32];
+  const int blocks_per_n = C / 32;
+  const int n = blockIdx.x / blocks_per_n, c = (blockIdx.x % blocks_per_n) * 32 + (threadIdx.x & 31);
+  const Wf st = nhwc_merge_tiles_block(tp, n, c, C, H, W, s_grp);
+  if (threadIdx.x >= 32) return;
+  const float sg_c = sqrtf(st.m2 / ((float)(H * W) - 1.f) + eps);
+  const int64_t si = (int64_t)n * stat_batch_stride + c;
+  const float A = alpha * (sigma_s[si] / sg_c) + (1.f - alpha);
+  const float B = alpha * mu_s[si] + (1.f - alpha) * st.mean;
+  fold_a[(size_t)n * C + c] = A;
+  fold_b[(size_t)n * C + c] = fmaf(-st.mean, A, B);
+}
+
+// w_out[n][co][tap*Cin + c] = T16(w_k32[co][tap*Cin + c] * A[n][c]); thread = 8 consecutive k, grid (K*Cout/2048, N)
+template <typename T16>
+__global__ void __launch_bounds__(256)
+    adain_fold_weights_kernel(const float* __restrict__ w_k32, const float* __restrict__ fold_a, int Cin, int K,
+                              int Cout, T16* __restrict__ w_out, unsigned int* sat_count) {
+  const int n = blockIdx.y;
+  const size_t i8 = ((size_t)blockIdx.x * 256 + threadIdx.x) * 8;  // first of 8 elements of [Cout][K]
+  uint32_t absmax = 0u;
+  if (i8 < (size_t)Cout * K) {
+    const int k = (int)(i8 % K);
+    const int c = k % Cin;  // Cin % 8 == 0: the 8 elements share the tap and have consecutive channels
+    const float4 w0 = *reinterpret_cast<const float4*>(w_k32 + i8), w1 = *reinterpret_cast<const float4*>(w_k32 + i8 + 4);
+    const float4 a0 = *reinterpret_cast<const float4*>(fold_a + (size_t)n * Cin + c);
+    const float4 a1 = *reinterpret_cast<const float4*>(fold_a + (size_t)n * Cin + c + 4);
+    uint4 o;
+    o.x = pack16x2<T16>(w0.x * a0.x, w0.y * a0.y);
+    o.y = pack16x2<T16>(w0.z * a0.z, w0.w * a0.w);
+    o.z = pack16x2<T16>(w1.x * a1.x, w1.y * a1.y);
+    o.w = pack16x2<T16>(w1.z * a1.z, w1.w * a1.w);
+    *reinterpret_cast<uint4*>(w_out + (size_t)n * Cout * K + i8) = o;
+    if (sizeof(T16) == 2 && std::is_same<T16, __half>::value) {
+      absmax = max16x2<__half>(max16x2<__half>(o.x & 0x7fff7fffu, o.y & 0x7fff7fffu),
+                               max16x2<__half>(o.z & 0x7fff7fffu, o.w & 0x7fff7fffu));
+    }
+  }
+  if (std::is_same<T16, __half>::value) {
+    const bool hit = (absmax & 0xffffu) >= 0x7bffu || (absmax >> 16) >= 0x7bffu;
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    if (ballot != 0u && sat_count != nullptr && (threadIdx.x & 31) == 0) atomicAdd(sat_count, (unsigned)__popc(ballot));
+  }
+}
+
+// b_out[n][co] = bias[co] + sum_c w_tapsum[co][c] * fold_b[n][c]; one warp per (n, co), fixed order
+__global__ void __launch_bounds__(256)
+    adain_fold_bias_kernel(const float* __restrict__ w_tapsum, const float* __restrict__ fold_b,
+                           const float* __restrict__ bias, int Cin, int Cout, float* __restrict__ b_out) {
+  const int n = blockIdx.y, co = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (co >= Cout) return;
+  float acc = 0.f;
+  for (int c = lane; c < Cin; c += 32) acc = fmaf(w_tapsum[(size_t)co * Cin + c], fold_b[(size_t)n * Cin + c], acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) b_out[(size_t)n * Cout + co] = bias[co] + acc;
+}
+
 // coef[n * C + c] = {mu_c, A, B}:  out = (x - mu_c) * A + B,
 //   A = alpha * sigma_s / sigma_c + (1 - alpha),  B = alpha * mu_s + (1 - alpha) * mu_c
 __global__ void __launch_bounds__(256)
@@ -915,6 +980,33 @@ template int launch_adain_nhwc_tiles<__nv_bfloat16>(ActView<__nv_bfloat16>, ActV
                                                     float2*, cudaStream_t);
 template int launch_adain_nhwc_tiles<__half>(ActView<__half>, ActView<__half>, const float*, const float*,
                                              int64_t, float, float, float2*, cudaStream_t);
+
+template <typename T16>
+int launch_adain_fold(int N, int C, int H, int W, int Cout, float2* scratch, const float* mu_s, const float* sigma_s,
+                      int64_t stat_batch_stride, float alpha, float eps, const float* w_k32, const float* w_tapsum,
+                      const float* bias, T16* w_out, float* b_out, unsigned int* sat_count, cudaStream_t st) {
+  CCST_CHECK_ARG(C % 32 == 0 && N <= 65535 && Cout % 8 == 0, "adain_fold: C=%d N=%d Cout=%d", C, N, Cout);
+  const int NC = N * C, K = 9 * C;
+  float* fold_a = reinterpret_cast<float*>(scratch);  // the coefficient area of the tile scratch: 4*NC floats
+  float* fold_b = fold_a + NC;
+  adain_fold_coef_tiles_kernel<<<NC / 32, 256, 0, st>>>(scratch + 2 * (size_t)NC, fold_a, fold_b, C, H, W, mu_s,
+                                                        sigma_s, stat_batch_stride, alpha, eps);
+  CCST_LAUNCHED();
+  const size_t per_img = (size_t)Cout * K;
+  dim3 gw((unsigned)((per_img / 8 + 255) / 256), N);
+  adain_fold_weights_kernel<T16><<<gw, 256, 0, st>>>(w_k32, fold_a, C, K, Cout, w_out, sat_count);
+  CCST_LAUNCHED();
+  dim3 gb((Cout + 7) / 8, N);
+  adain_fold_bias_kernel<<<gb, 256, 0, st>>>(w_tapsum, fold_b, bias, C, Cout, b_out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_adain_fold<__nv_bfloat16>(int, int, int, int, int, float2*, const float*, const float*, int64_t,
+                                              float, float, const float*, const float*, const float*,
+                                              __nv_bfloat16*, float*, unsigned int*, cudaStream_t);
+template int launch_adain_fold<__half>(int, int, int, int, int, float2*, const float*, const float*, int64_t, float,
+                                       float, const float*, const float*, const float*, __half*, float*,
+                                       unsigned int*, cudaStream_t);
 
 int launch_stats_from_tiles(int N, int C, int H, int W, float2* scratch, cudaStream_t st) {
   const int NC = N * C;

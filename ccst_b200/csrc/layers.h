@@ -48,6 +48,17 @@ int launch_adain_nhwc_tiles(ActView<T> in, ActView<T> out, const float* mu_s, co
                             cudaStream_t st);
 int launch_stats_from_tiles(int N, int C, int H, int W, float2* scratch, cudaStream_t st);
 
+// AdaIN folded into the conv that consumes it (dec1): from the tile statistics in `scratch` (layout of
+// nhwc_tile_scratch_elems) and the style statistics, per image n
+//   w_out[n][co][k = tap*Cin + c] = w_k32[co][k] * A[n][c]                       (rounded once to T16)
+//   b_out[n][co] = bias[co] + sum_c w_tapsum[co][c] * (B[n][c] - mu_c[n][c] * A[n][c])
+// with out = (x - mu_c) * A + B the AdaIN + alpha-blend affine of function.py:26-33 /
+// CCST_OverallStyleTransfer.py:44-45.  The first 2*N*C floats of `scratch` are overwritten.
+template <typename T16>
+int launch_adain_fold(int N, int C, int H, int W, int Cout, float2* scratch, const float* mu_s, const float* sigma_s,
+                      int64_t stat_batch_stride, float alpha, float eps, const float* w_k32, const float* w_tapsum,
+                      const float* bias, T16* w_out, float* b_out, unsigned int* sat_count, cudaStream_t st);
+
 // per-(n,c) {mean, M2} of an activation -> scratch[0 .. N*C)
 template <typename T>
 int launch_stats_nhwc(ActView<T> in, float2* scratch, cudaStream_t st);
@@ -73,23 +84,32 @@ int launch_nhwc_to_act(const float* in_nhwc, ActView<T> out, cudaStream_t st, in
 template <typename T>
 int launch_act_to_nhwc(ActView<T> in, float* out_nhwc, cudaStream_t st);
 
-// tcgen05 / TMA implicit GEMM (conv_umma_impl.cuh, instantiated per operand type in conv_umma_{bf16,f16}.cu), T16 = __nv_bfloat16 or __half operands, fp32
-// accumulation in TMEM.  wk: [CoutPad][9*Cin] T16 K-major, bias fp32.
-// wk_sm (optional, Cout == 64 only): the same weights packed [192 = (s, co)][3*Cin = (r, c)] for the
-// s-merged kernel.
-// out_u8 (EPI_NCHW_F32 only, may be NULL): store NHWC uint8 quantised like save_image instead.
-// wk_up (EPI_UPS only): phase weights [4 = (a, b)][Cout][4*Cin], k = (dy*2 + dx)*Cin + c.
-// halo_edge: halo the epilogue writes around `out` (1 reflection, 0 replicate; EPI_ACT only).
+// tcgen05 / TMA implicit GEMM (conv_umma_impl.cuh, instantiated per operand type in
+// conv_umma_{bf16,f16}.cu), T16 = __nv_bfloat16 or __half operands, fp32 accumulation in TMEM.
 template <typename T16>
-int launch_conv_umma(ActView<T16> in, const T16* wk, const T16* wk_sm, const T16* wk_up,
-                     const float* bias, int Cout, int CoutPad, int relu, int epi, ActView<T16> out,
-                     float* out_nchw, uint8_t* out_u8, int halo_edge, cudaStream_t st,
-                     float2* tile_stats = nullptr);
+struct UmmaConvArgs {
+  ActView<T16> in{}, out{};
+  const T16* wk = nullptr;     // [CoutPad][9*Cin] K-major (k = tap*Cin + c); per_sample: [N][Cout][9*Cin]
+  const T16* wk_sm = nullptr;  // Cout == 64 only: the same weights packed [192 = (s, co)][3*Cin = (r, c)]
+  const T16* wk_up = nullptr;  // EPI_UPS only: phase weights [4 = (a, b)][Cout][4*Cin], k = (dy*2 + dx)*Cin + c
+  const float* bias = nullptr; // fp32 [CoutPad]; per_sample: [N][Cout]
+  int Cout = 0, CoutPad = 0;
+  int relu = 1;
+  int epi = EPI_ACT;
+  int halo_edge = 1;           // halo the epilogue writes around `out` (1 reflection, 0 replicate; EPI_ACT only)
+  float* out_nchw = nullptr;   // EPI_NCHW_F32 (last conv)
+  uint8_t* out_u8 = nullptr;   // EPI_NCHW_F32 only, may be NULL: store NHWC uint8 quantised like save_image instead
+  float2* tile_stats = nullptr;       // EPI_ACT_STATS
+  unsigned int* sat_count = nullptr;  // device counter of f16 stores that hit the +-65504 clamp (may be NULL)
+  bool per_sample = false;     // image n uses weights wk[n] / bias[n] (AdaIN folded into dec1)
+};
+template <typename T16>
+int launch_conv_umma(const UmmaConvArgs<T16>& a, cudaStream_t st);
 
 // conv1_1 (+ folded 1x1) on tcgen05: thread-built im2col rows (K = 27 padded to 32).
 // wk: [64][32] T16 K-major, bias fp32 [64].
 template <typename T16>
 int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk, const float* bias,
-                           ActView<T16> out, cudaStream_t st);
+                           ActView<T16> out, cudaStream_t st, unsigned int* sat_count = nullptr);
 
 }  // namespace ccst

@@ -11,8 +11,6 @@
 // local (count, mean, M2) triple, the triples are merged with Chan's formula by warp shuffles and
 // (for CTA groups) a shared-memory combine.  Planes that do not fit in registers, or whose size /
 // alignment rules out 128-bit access, take a streaming variant of the same algorithm.
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace ccst {
@@ -549,6 +547,8 @@ bool bulk_ok(const void* p, int64_t hw) {
 template <int MODE, int G, int SLOTS>
 int launch_bulk_cfg(BulkArgs a, cudaStream_t st) {
   a.ppc = (int)((kRingBytes / SLOTS) / ((int64_t)a.hw * 4));
+  CCST_CHECK_ARG(a.ppc >= 1, "plane_bulk: a plane of %d floats does not fit a %d-byte ring slot", a.hw,
+                 kRingBytes / SLOTS);
   a.chunks = ceil_div64(a.planes, a.ppc);
   const int grid = (int)(a.chunks < sm_count() ? a.chunks : sm_count());
   CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(plane_bulk_kernel<MODE, G, SLOTS>), kBulkSmem));
@@ -559,13 +559,10 @@ int launch_bulk_cfg(BulkArgs a, cudaStream_t st) {
 
 template <int MODE>
 int launch_bulk(BulkArgs a, cudaStream_t st) {
-  static const int g_env = [] { const char* e = getenv("CCST_BULK_G"); return e ? atoi(e) : 0; }();
-  if ((a.hw <= 256 && g_env == 0) || g_env == 4)  // up to 1 KiB planes (12x12 .. 16x16): 4 lanes per plane, 16 warps
+  if (a.hw <= 256)  // up to 1 KiB planes (12x12 .. 16x16): 4 lanes per plane, 16 warps
     return launch_bulk_cfg<MODE, 4, 16>(a, st);
-  if (g_env == 44) return launch_bulk_cfg<MODE, 4, 8>(a, st);
-  if ((a.hw <= 1024 && g_env == 0) || g_env == 16)  // up to 4 KiB planes: 16 lanes per plane, 16 warps
+  if (a.hw <= 1024)  // up to 4 KiB planes: 16 lanes per plane, 16 warps
     return launch_bulk_cfg<MODE, 16, 16>(a, st);
-  if (g_env == 8) return launch_bulk_cfg<MODE, 8, 8>(a, st);
   return launch_bulk_cfg<MODE, 32, 8>(a, st);
 }
 

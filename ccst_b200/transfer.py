@@ -33,6 +33,10 @@ PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_
 DEFAULT_PRECISION = "fp16"
 
 
+class F16SaturationError(RuntimeError):
+    """Activations left the f16 range on the precision="fp16" path (stores clamp at +-65504)."""
+
+
 def _conv_params(seq: nn.Module, count: int, what: str):
     convs = [m for m in seq.modules() if isinstance(m, nn.Conv2d)]
     if len(convs) < count:
@@ -220,6 +224,38 @@ class Engine:
                 self._h, x.data_ptr(), n, h, w, mu.data_ptr(), sg.data_ptr(), stride, float(alpha),
                 out.data_ptr(), PRECISIONS[precision], self._stream()))
         return out
+
+    # -- f16 range guard -------------------------------------------------------
+    def saturation_count(self, reset: bool = False) -> int:
+        """Number of epilogue threads whose f16 stores hit the +-65504 clamp since the last reset
+        (synchronises the current stream).  Non-zero means the weights drive activations outside the
+        f16 range: use precision="bf16" (or "fp32") for them."""
+        if not hasattr(self, "_sat_host"):
+            self._sat_host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        st = torch.cuda.current_stream(self.device)
+        with _lib.on_device(self.device):
+            _lib.check(_lib.lib().ccst_saturation_snapshot(self._h, self._sat_host.data_ptr(), st.cuda_stream))
+            if reset:
+                _lib.check(_lib.lib().ccst_saturation_reset(self._h, st.cuda_stream))
+        st.synchronize()
+        return int(self._sat_host.item()) & 0xFFFFFFFF
+
+    def check_saturation(self):
+        """Raise if any f16 store saturated since the last check (and reset the counter)."""
+        n = self.saturation_count(reset=True)
+        if n:
+            raise F16SaturationError(
+                f"{n} epilogue threads stored activations clamped to +-65504: these weights exceed the f16 "
+                "range of precision='fp16'; re-run with precision='bf16' (same speed, wider range) or 'fp32'")
+
+    def saturation_snapshot_async(self, host_i32: torch.Tensor, stream: "torch.cuda.Stream"):
+        """Enqueue a copy of the counter into pinned `host_i32[0]` on `stream` (valid after it syncs)."""
+        with _lib.on_device(self.device):
+            _lib.check(_lib.lib().ccst_saturation_snapshot(self._h, host_i32.data_ptr(), stream.cuda_stream))
+
+    def set_fusion(self, mask: int = _lib.FUSE_ALL):
+        """Tests only: switch individual kernel fusions off (see CCST_FUSE_* in the header)."""
+        _lib.check(_lib.lib().ccst_set_fusion(self._h, int(mask)))
 
     # -- profiling -----------------------------------------------------------
     def profile(self, on: bool):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CCST_ABI_VERSION 1
+#define CCST_ABI_VERSION 2
 
 #define CCST_OK 0
 #define CCST_EINVAL (-1)  /* bad shape / null pointer / bad argument          */
@@ -181,6 +181,15 @@ int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N, int H, in
 int ccst_encoder_accumulate_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W,
                                double* d_state, int precision, void* stream);
 
+/* f16 operands (CCST_PREC_FP16) store activations with saturation at +-65504 instead of overflowing to
+ * inf.  Every epilogue counts the threads whose stores hit the clamp in a device counter owned by the
+ * handle; weights whose activations exceed the f16 range (the synthetic and the published VGG weights do
+ * not) show up here instead of silently producing a wrong image.  `snapshot` enqueues an asynchronous
+ * copy of the counter to *h_count (pinned host memory recommended; valid once `stream` has reached this
+ * point), `reset` zeroes it in stream order. */
+int ccst_saturation_snapshot(ccst_handle* h, uint32_t* h_count, void* stream);
+int ccst_saturation_reset(ccst_handle* h, void* stream);
+
 /* shape helper: relu4_1 spatial size for an input of H x W */
 void ccst_feature_hw(int H, int W, int* fh, int* fw);
 
@@ -194,13 +203,22 @@ int64_t ccst_launch_count(void);
 /* One reflect-pad 3x3 convolution through the selected engine on caller data:
  * d_in  [N,H,W,Cin]  NHWC fp32 (unpadded), h_weight OIHW fp32 [Cout,Cin,3,3], h_bias [Cout].
  * mode 0: d_out [N,H,W,Cout]; mode 1: nearest x2 fused, d_out [N,2H,2W,Cout]; mode 2: 2x2 ceil-mode
- * max-pool fused (requires relu), d_out [N,ceil(H/2),ceil(W/2),Cout]; mode 3: Cout <= 16, d_out is
- * NCHW [N,Cout,H,W] (the last decoder conv's store); mode 4 (16-bit precisions only): the input is
+ * max-pool fused (requires relu), d_out [N,ceil(H/2),ceil(W/2),Cout]; mode 3: Cout <= 3 (fp32 engine: <= 16),
+ * d_out is NCHW [N,Cout,H,W] (the last decoder conv's store); mode 4 (16-bit precisions only): the input is
  * nearest-x2 upsampled BEFORE the reflect-pad conv (net.py:10-11), computed by the phase-decomposed
  * kernel straight from the low-resolution map, d_out [N,2H,2W,Cout].  d_out is fp32. Synchronous. */
 int ccst_debug_conv3x3(ccst_handle* h, const float* d_in, int N, int H, int W, int Cin, int Cout,
                        const float* h_weight, const float* h_bias, int relu, int mode,
                        float* d_out, int precision, void* stream);
+
+/* Fusions of the tcgen05 path, all on by default; the tests switch them off one at a time to compare
+ * each fused kernel with its un-fused form (bit-exact for the pool, within one 16-bit rounding else). */
+#define CCST_FUSE_POOL 1      /* ceil-mode 2x2 max-pool in the producing conv's epilogue            */
+#define CCST_FUSE_UPSAMPLE 2  /* nearest x2 upsample folded into the NEXT conv (4 phase convolutions) */
+#define CCST_FUSE_STATS 4     /* relu4_1 statistics taken in conv4_1's epilogue                      */
+#define CCST_FUSE_ADAIN 8     /* AdaIN folded into dec1's per-image weights / bias (maps >= 2048 px)  */
+#define CCST_FUSE_ALL 15
+int ccst_set_fusion(ccst_handle* h, int mask);
 
 /* Per-launch device timing of the encoder/decoder entry points (CUDA events recorded on the
  * caller's stream around every kernel the entry point enqueues).  Off by default. */
@@ -208,7 +226,8 @@ int ccst_profile_enable(ccst_handle* h, int on);
 /* Synchronises the recorded events of the LAST encoder/decoder/style_transfer call and returns
  * the number of launches; for launch i: ms[i] device time, flops[i] algorithmic FLOPs (convs,
  * else 0), bytes[i] algorithmic HBM bytes, kind[i]: 0 conv_first, 1 tcgen05 conv, 2 ffma conv,
- * 3 pool, 4 adain/stats, 5 layout convert.  Arrays hold `max` entries. */
+ * 3 pool, 4 adain/stats, 5 layout convert, 6 AdaIN fold (coefficients + per-image dec1 weights).  Arrays hold
+ * `max` entries. */
 int ccst_profile_read(ccst_handle* h, int max, float* ms, double* flops, double* bytes, int* kind);
 
 #ifdef __cplusplus

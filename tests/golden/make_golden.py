@@ -230,8 +230,20 @@ def make_io():
     x_u8[0, 0, 0] = (0, 255, 128)
     tr = transforms.Compose([transforms.Resize((h, w)), transforms.ToTensor()])
     x = torch.stack([tr(Image.fromarray(x_u8[i])) for i in range(n)])
-    sm = torch.rand((1, 512, 1, 1), generator=g) * 2.0
-    ss = torch.rand((1, 512, 1, 1), generator=g) * 1.5 + 0.1
+    # style statistics of an encoded style image through the reference's own single-style lines
+    # (CCST_SingleStyleTransfer.py:55-67 calc_sum, :201-203): relu4_1-like statistics keep the decoder's
+    # output inside [0, 1], the range the image tolerance of BASELINE.json is stated for
+    single_py = os.path.join(REF, "CCST_SingleStyleTransfer.py")
+    ns_single = {"torch": torch}
+    _extract_funcs(single_py, {"calc_sum"}, ns_single)
+    single_final_src = _source_lines(single_py, 201, 203)
+    assert "feat_std = torch.sqrt(feat_var + 1e-5)" in single_final_src
+    with torch.no_grad():
+        sf = vgg(synth.images(1, h + 8, w - 8, 4243))
+    fs, fss, cnt = ns_single["calc_sum"](sf)
+    env = {"torch": torch, "feat_sum": fs, "feat_square_sum": fss, "count": cnt, "feat_mean": fs / float(cnt)}
+    exec(single_final_src, env)
+    sm, ss = env["feat_mean"], env["feat_std"]
     out["x_u8"] = x_u8
     out["x_tensor"] = x.numpy()
     out["style_mean"] = sm.numpy()
@@ -276,6 +288,7 @@ def make_io():
         out["resize_512_to_96"] = transforms.Resize(96)(big).numpy()
     np.savez_compressed(os.path.join(HERE, "io_u8.npz"), **out)
     print("io_u8", os.path.getsize(os.path.join(HERE, "io_u8.npz")) // 1024, "KiB",
+          "a=1 range [%.3f, %.3f]" % (out["out_f32_a1.0"].min(), out["out_f32_a1.0"].max()),
           "clamped lo/hi:", int((out["out_u8_a0.5"] == 0).sum()), int((out["out_u8_a0.5"] == 255).sum()))
 
 

@@ -19,7 +19,7 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in ccst_b200.h but not exported"
     assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes out of sync with the header"
-    assert handle.ccst_abi_version() == 1
+    assert handle.ccst_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_library_has_no_torch_or_python_dependency():

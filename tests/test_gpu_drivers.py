@@ -43,12 +43,9 @@ def test_single_transfer_matches_reference_loop(models, engine):
     batches = [synth.images(2, 48, 48, 400 + i).pin_memory() for i in range(3)]
     styles = [synth.images(1, 56, 40 + 8 * k, 500 + k) for k in range(4)]
     rng = random.Random(1)
-    outs = dict(drivers.single_transfer(engine, iter(batches), styles, 1.0, "fp32", seed=1))
-    outs = {i: o.clone() for i, o in outs.items()}  # only 3 batches > 2 slots: clone after the fact is too late
-    # redo with cloning inside the loop (pipeline buffers are reused)
     outs = {}
     for i, o in drivers.single_transfer(engine, iter(batches), styles, 1.0, "fp32", seed=1):
-        outs[i] = o.clone()
+        outs[i] = o.clone()  # pipeline buffers are reused: keep a copy
     with torch.no_grad():
         for i, b in enumerate(batches):
             img = rng.choice(styles)
@@ -86,26 +83,44 @@ def test_to_tensor_and_quantize_operators_bit_exact(golden):
     assert torch.equal(ccst_b200.save_image_quantize(v).cpu(), O.save_image_batch_u8(v.cpu()))
 
 
-def test_style_transfer_u8_golden(models, golden):
-    """uint8 in -> uint8 out against the reference pipeline (ToTensor, style_transfer, save_image):
-    fp32 engine within one grey level (and almost always exact), tensor-core engines within the
-    1e-2 image tolerance (3 grey levels) with f16 operands; bf16 operands (documented deviation, see
-    DESIGN.md "Numerics") only to ~2.5e-2 of this vector's output range (about 4 units)."""
+BF16_MISS = pytest.mark.xfail(strict=True, reason="bf16 operands miss the 1e-2 image bar (DESIGN.md Numerics)")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", pytest.param("bf16", marks=BF16_MISS)])
+def test_style_transfer_u8_golden(models, golden, precision):
+    """uint8 in -> uint8 out against the reference pipeline (ToTensor, style_transfer, save_image; the
+    vector's float output lies inside [0,1]): fp32 engine within one grey level (rounding ties) and
+    almost always exact; tensor-core engines within the 1e-2 image tolerance = 3 grey levels."""
     vgg, dec = models
     g = golden["io_u8"]
+    assert 0.0 <= g["out_f32_a1.0"].min() and g["out_f32_a1.0"].max() <= 1.0
     x_u8 = torch.from_numpy(g["x_u8"]).to(DEV)
     stat = [torch.from_numpy(g["style_mean"]).to(DEV), torch.from_numpy(g["style_std"]).to(DEV)]
     ref = torch.from_numpy(g["out_u8_a1.0"]).int()
-    # this vector's style statistics are larger than a trained model's: its float output spans
-    # [-1.0, 1.6] (2.5x the [0,1] range the 1e-2 bar is stated for), so the bar scales with it
-    span = float(g["out_f32_a1.0"].max() - g["out_f32_a1.0"].min())
-    lv16 = int(np.ceil(1e-2 * span * 255))
-    for prec, max_lv, min_exact in (("fp32", 1, 0.995), ("fp16", lv16, 0.6), ("bf16", 4 * lv16, 0.05)):
-        out = ccst_b200.style_transfer_u8(vgg, dec, x_u8, stat, 1.0, precision=prec)
-        assert out.dtype == torch.uint8 and tuple(out.shape) == tuple(ref.shape)
-        d = (out.cpu().int() - ref).abs()
-        assert d.max().item() <= max_lv, (prec, d.max().item())
-        assert (d == 0).float().mean().item() >= min_exact, (prec, (d == 0).float().mean().item())
+    max_lv, min_exact = {"fp32": (1, 0.995), "fp16": (3, 0.6), "bf16": (3, 0.0)}[precision]
+    out = ccst_b200.style_transfer_u8(vgg, dec, x_u8, stat, 1.0, precision=precision)
+    assert out.dtype == torch.uint8 and tuple(out.shape) == tuple(ref.shape)
+    d = (out.cpu().int() - ref).abs()
+    print(f"[measured] u8 golden {precision}: max {d.max().item()} grey levels, exact {(d == 0).float().mean().item():.3f}")
+    assert d.max().item() <= max_lv, (precision, d.max().item())
+    assert (d == 0).float().mean().item() >= min_exact, (precision, (d == 0).float().mean().item())
+
+
+def test_pipeline_result_survives_one_more_step(models, engine):
+    """A yielded pinned buffer stays valid while the NEXT result is produced and handed out (slots + 1
+    host buffers): materialising pairs of consecutive results needs no clone."""
+    vgg, dec = models
+    batches = [synth.images(2, 48, 64, 900 + i).pin_memory() for i in range(5)]
+    g = torch.Generator().manual_seed(5)
+    stat = [torch.randn((1, 512, 1, 1), generator=g).abs(), torch.rand((1, 512, 1, 1), generator=g) + 0.2]
+    sd = [t.to(DEV) for t in stat]
+    refs = [ccst_b200.style_transfer(vgg, dec, b.to(DEV), sd, 1.0).cpu() for b in batches]
+    prev = None
+    for i, out in drivers.overall_transfer(engine, iter(batches), stat, 1.0):
+        if prev is not None:
+            assert torch.equal(prev[1], refs[prev[0]])  # still intact after the next hand-out
+        assert torch.equal(out, refs[i])
+        prev = (i, out)
 
 
 def test_style_transfer_u8_equals_float_path_quantised(models):

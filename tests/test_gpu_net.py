@@ -2,12 +2,15 @@
 reference's golden vectors.
 
 Tolerances (BASELINE.json north_star): fp32 mode 1e-4 max-abs; tensor-core path 1e-2 max-abs on
-images in [0,1].  The tcgen05 kernels run with f16 or bf16 operands (fp32 accumulation in TMEM):
-  * "fp16" (default) meets the 1e-2 bar (measured ~2e-3);
+images in [0,1]; style statistics 1e-5 relative.  No assert in this file is looser than those bars.
+The tcgen05 kernels run with f16 or bf16 operands (fp32 accumulation in TMEM):
+  * "fp16" (default) meets the 1e-2 image bar (measured ~2e-3);
   * "bf16" does NOT on the synthetic He-init weights: its 8-bit significand gives ~1.3 % rms relative
-    error after 19 layers (max-abs 1.4e-2 on these cases, reproduced by a CPU emulation that rounds
-    activations/weights to bf16, see DESIGN.md "Numerics").  It is checked against TOL_BF16 = 2.5e-2
-    and reported as a deviation, not hidden.
+    error after 19 layers (max-abs 1.3e-2 .. 1.6e-2, reproduced by a CPU emulation that rounds
+    activations/weights to bf16, see DESIGN.md "Numerics").  Every bf16 image comparison is asserted
+    at the SAME 1e-2 bar and marked xfail(strict=True): a documented miss, not a widened pass.
+  * statistics taken through a 16-bit encoder (either operand type) cannot meet 1e-5; those cases are
+    strict xfails too and the measured error is printed.  The fp32 engine meets both bars.
 """
 import numpy as np
 import pytest
@@ -21,10 +24,20 @@ from oracle import ccst_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL_FP32 = 1e-4
-TOL_TC = 1e-2      # north_star bar for the tensor-core path, met by f16 operands
-TOL_BF16 = 2.5e-2  # documented deviation of bf16 operands (see module docstring)
+TOL_TC = 1e-2      # north_star bar for the tensor-core path (f16 and bf16 operands alike)
+TOL_STATS = 1e-5   # north_star bar for style statistics (relative)
 T = torch.from_numpy
 DEV = "cuda:0"
+BF16_MISS = pytest.mark.xfail(strict=True, reason="bf16 operands: 1.3e-2..1.6e-2 max-abs on these weights, above the "
+                                                  "1e-2 bar of BASELINE.json (DESIGN.md Numerics); f16 is the default")
+STATS16_MISS = pytest.mark.xfail(strict=True, reason="style statistics through a 16-bit encoder are ~1e-3 relative, above "
+                                                     "the 1e-5 bar; the statistics drivers default to the fp32 engine")
+PREC_IMG = ["fp32", "fp16", pytest.param("bf16", marks=BF16_MISS)]
+IMG_TOL = {"fp32": TOL_FP32, "fp16": TOL_TC, "bf16": TOL_TC}
+
+
+def report(name, **kv):
+    print("[measured] " + name + ": " + ", ".join(f"{k}={v:.3e}" if isinstance(v, float) else f"{k}={v}" for k, v in kv.items()))
 
 
 @pytest.fixture(scope="module")
@@ -111,54 +124,63 @@ def test_encoder_decoder_golden_fp32(engine, golden, tag):
 
 
 @pytest.mark.parametrize("tag", ["sq40", "odd37x45", "r96"])
-@pytest.mark.parametrize("precision", ["fp16", "bf16"])
-def test_encoder_decoder_golden_tensor_core(engine, golden, tag, precision):
-    """tcgen05 path per stage (catches halo / border errors that a loose image tolerance hides)."""
+def test_encoder_decoder_golden_tensor_core(engine, golden, tag):
+    """tcgen05 path per stage (catches halo / border errors that a loose image tolerance hides): f16
+    operands within 4e-3 of each stage's range; the bf16 figures are printed, not asserted (the image-
+    level bf16 comparisons below carry the strict xfail)."""
     g = golden["net"]
-    rel = 4e-3 if precision == "fp16" else 3e-2
-    feat = engine.encode(T(g[tag + "/x"]).to(DEV), precision).cpu().numpy()
-    assert np.abs(feat - g[tag + "/feat"]).max() < rel * np.abs(g[tag + "/feat"]).max()
-    img = engine.decode(T(g[tag + "/feat"]).to(DEV), precision).cpu().numpy()
-    assert np.abs(img - g[tag + "/dec_of_feat"]).max() < rel * np.abs(g[tag + "/dec_of_feat"]).max()
+    for precision in ("fp16", "bf16"):
+        feat = engine.encode(T(g[tag + "/x"]).to(DEV), precision).cpu().numpy()
+        e_enc = np.abs(feat - g[tag + "/feat"]).max() / np.abs(g[tag + "/feat"]).max()
+        img = engine.decode(T(g[tag + "/feat"]).to(DEV), precision).cpu().numpy()
+        e_dec = np.abs(img - g[tag + "/dec_of_feat"]).max() / np.abs(g[tag + "/dec_of_feat"]).max()
+        report(f"per-stage {tag} {precision}", encoder_rel=float(e_enc), decoder_rel=float(e_dec))
+        if precision == "fp16":
+            assert e_enc < 4e-3 and e_dec < 4e-3
 
 
 @pytest.mark.parametrize("tag", ["sq40", "odd37x45", "r96"])
 @pytest.mark.parametrize("alpha", [1.0, 0.6])
-def test_style_transfer_golden(models, golden, tag, alpha):
+@pytest.mark.parametrize("precision", PREC_IMG)
+def test_style_transfer_golden(models, golden, tag, alpha, precision):
     g = golden["net"]
     vgg, dec = models
     x = T(g[tag + "/x"]).to(DEV)
     stat = [T(g[tag + "/style_mean"]).to(DEV), T(g[tag + "/style_std"]).to(DEV)]
     ref = g[f"{tag}/out_a{alpha}"]
-    out32 = ccst_b200.style_transfer(vgg, dec, x, stat, alpha, precision="fp32")
-    assert out32.shape == ref.shape and out32.dtype == torch.float32 and out32.is_cuda
-    assert np.abs(out32.cpu().numpy() - ref).max() < TOL_FP32
-    out16 = ccst_b200.style_transfer(vgg, dec, x, stat, alpha)  # default: tcgen05 path, f16 operands
-    assert np.abs(out16.cpu().numpy() - ref).max() < TOL_TC
-    outb = ccst_b200.style_transfer(vgg, dec, x, stat, alpha, precision="bf16")
-    assert np.abs(outb.cpu().numpy() - ref).max() < TOL_BF16
+    kw = {} if precision == "fp16" else {"precision": precision}  # fp16 = the default tcgen05 path
+    out = ccst_b200.style_transfer(vgg, dec, x, stat, alpha, **kw)
+    assert out.shape == ref.shape and out.dtype == torch.float32 and out.is_cuda
+    err = float(np.abs(out.cpu().numpy() - ref).max())
+    report(f"style_transfer {tag} a={alpha} {precision}", max_abs=err)
+    assert err < IMG_TOL[precision]
 
 
-def test_style_transfer_interpolation_and_image_style(models, golden):
+def test_style_transfer_interpolation_branch(models, golden):
     g = golden["net"]
     vgg, dec = models
     x = T(g["sq40/x"]).to(DEV)
     stat = [T(g["sq40/style_mean"]).to(DEV), T(g["sq40/style_std"]).to(DEV)]
     out = ccst_b200.style_transfer(vgg, dec, x, stat, 1.0, [0.25, 0.75], precision="fp32")
     assert np.abs(out.cpu().numpy() - g["sq40/out_interp"]).max() < 1e-4
-    # upstream form: style given as an image batch (per-sample statistics)
+
+
+@pytest.mark.parametrize("precision", PREC_IMG)
+def test_style_transfer_image_style(models, golden, precision):
+    """upstream form: style given as an image batch (per-sample statistics)"""
+    vgg, dec = models
+    x = T(golden["net"]["sq40/x"]).to(DEV)
     s = synth.images(2, 48, 40, 3)
     with torch.no_grad():
         ref = O.style_transfer_image_style(vgg, dec, x.cpu(), s, 0.8)
-    out = ccst_b200.style_transfer(vgg, dec, x, s.to(DEV), 0.8, precision="fp32")
-    assert (out.cpu() - ref).abs().max().item() < TOL_FP32
-    out = ccst_b200.style_transfer(vgg, dec, x, s.to(DEV), 0.8, precision="fp16")
-    assert (out.cpu() - ref).abs().max().item() < TOL_TC
-    out = ccst_b200.style_transfer(vgg, dec, x, s.to(DEV), 0.8, precision="bf16")
-    assert (out.cpu() - ref).abs().max().item() < TOL_BF16
+    out = ccst_b200.style_transfer(vgg, dec, x, s.to(DEV), 0.8, precision=precision)
+    err = (out.cpu() - ref).abs().max().item()
+    report(f"image-style {precision}", max_abs=err)
+    assert err < IMG_TOL[precision]
 
 
-def test_style_transfer_reference_default_size_222(models):
+@pytest.mark.parametrize("precision", PREC_IMG)
+def test_style_transfer_reference_default_size_222(models, precision):
     """--image_size default 222 (mean_std_computation_effcientMem.py:51): 222 -> 28 -> 224."""
     vgg, dec = models
     x = synth.images(1, 222, 222, 8)
@@ -168,68 +190,160 @@ def test_style_transfer_reference_default_size_222(models):
         ref = O.style_transfer(vgg, dec, x, stat, 1.0)
     assert f.shape[-2:] == (28, 28) and ref.shape[-2:] == (224, 224)
     sd = [t.to(DEV) for t in stat]
-    out32 = ccst_b200.style_transfer(vgg, dec, x.to(DEV), sd, 1.0, precision="fp32")
-    out16 = ccst_b200.style_transfer(vgg, dec, x.to(DEV), sd, 1.0, precision="fp16")
-    outb = ccst_b200.style_transfer(vgg, dec, x.to(DEV), sd, 1.0, precision="bf16")
-    assert (out32.cpu() - ref).abs().max().item() < TOL_FP32
-    assert (out16.cpu() - ref).abs().max().item() < TOL_TC
-    assert (outb.cpu() - ref).abs().max().item() < TOL_BF16
+    out = ccst_b200.style_transfer(vgg, dec, x.to(DEV), sd, 1.0, precision=precision)
+    err = (out.cpu() - ref).abs().max().item()
+    report(f"222^2 {precision}", max_abs=err)
+    assert err < IMG_TOL[precision]
 
 
-def test_fused_pool_equals_separate_pool(models, monkeypatch):
+def test_fused_pool_equals_separate_pool(models):
+    from ccst_b200 import _lib
     vgg, dec = models
     x = synth.images(2, 72, 56, 4).to(DEV)
+    eng = ccst_b200.Engine(vgg, dec, DEV)
     for prec in ("bf16", "fp16"):
-        monkeypatch.setenv("CCST_FUSE_POOL", "1")
-        a = ccst_b200.Engine(vgg, dec, DEV).encode(x, prec)
-        monkeypatch.setenv("CCST_FUSE_POOL", "0")
-        b = ccst_b200.Engine(vgg, dec, DEV).encode(x, prec)
+        eng.set_fusion(_lib.FUSE_ALL)
+        a = eng.encode(x, prec)
+        eng.set_fusion(_lib.FUSE_ALL & ~_lib.FUSE_POOL)
+        b = eng.encode(x, prec)
         assert torch.equal(a, b)
 
 
-def test_fused_upsample_matches_unfused_decoder(models, monkeypatch):
+def test_fused_upsample_matches_unfused_decoder(models):
     """Upsample folded into the next conv (phase-decomposed 2x2 kernels) vs the 4x-replicating store:
-    same function, weights pre-summed and rounded once more, so equal within the 16-bit rounding."""
+    same function, weights pre-summed and rounded once more, so equal within the 16-bit rounding
+    (an implementation-equivalence bound, not a parity bar: both sides are this library)."""
+    from ccst_b200 import _lib
     vgg, dec = models
     feat = synth.features((2, 512, 9, 13), 11).to(DEV)
+    eng = ccst_b200.Engine(vgg, dec, DEV)
     for prec, tol in (("fp16", 2e-3), ("bf16", 1.6e-2)):
-        monkeypatch.setenv("CCST_FUSE_UP", "1")
-        a = ccst_b200.Engine(vgg, dec, DEV).decode(feat, prec)
-        monkeypatch.setenv("CCST_FUSE_UP", "0")
-        b = ccst_b200.Engine(vgg, dec, DEV).decode(feat, prec)
+        eng.set_fusion(_lib.FUSE_ALL)
+        a = eng.decode(feat, prec)
+        eng.set_fusion(_lib.FUSE_ALL & ~_lib.FUSE_UPSAMPLE)
+        b = eng.decode(feat, prec)
         assert a.shape == b.shape == (2, 3, 72, 104)
         assert (a - b).abs().max().item() < tol
 
 
-def test_overall_statistics_loop(models):
-    """mean_std_computation_effcientMem.py:117-137 on 3 batches of images, fp32 and bf16 engines."""
+def test_folded_adain_matches_affine_pass(models):
+    """AdaIN folded into dec1's per-image weights / bias (maps >= 2048 px) vs the affine pass over the
+    feature map: the same function up to one 16-bit rounding (of W*A instead of x*A + B); both within
+    the image bar of the oracle, the folded form usually closer (the feature map is not re-rounded)."""
+    from ccst_b200 import _lib
+    vgg, dec = models
+    x = synth.images(3, 448, 320, 31)  # relu4_1 56 x 40 = 2240 px, 7 x 3 = 21 tiles per image: odd (pair padding)
+    with torch.no_grad():
+        stat = O.single_style_stats(O.encode_relu4_1(vgg, synth.images(1, 200, 180, 32)))
+        ref = O.style_transfer(vgg, dec, x, stat, 0.7)
+    sd = [t.to(DEV) for t in stat]
+    per = [torch.cat([t] * 3).to(DEV) * torch.tensor([1.0, 0.9, 1.1], device=DEV).view(3, 1, 1, 1) for t in stat]
+    eng = ccst_b200.Engine(vgg, dec, DEV)
+    for prec in ("fp16", "bf16"):
+        eng.set_fusion(_lib.FUSE_ALL)
+        a = eng.transfer(x.to(DEV), sd, 0.7, prec)
+        ap = eng.transfer(x.to(DEV), per, 0.7, prec)  # per-image style statistics ([N,512,1,1])
+        eng.set_fusion(_lib.FUSE_ALL & ~_lib.FUSE_ADAIN)
+        b = eng.transfer(x.to(DEV), sd, 0.7, prec)
+        bp = eng.transfer(x.to(DEV), per, 0.7, prec)
+        d, dp = (a - b).abs().max().item(), (ap - bp).abs().max().item()
+        ea, eb = (a.cpu() - ref).abs().max().item(), (b.cpu() - ref).abs().max().item()
+        report(f"folded AdaIN {prec}", fold_vs_pass=d, per_image=dp, fold_vs_oracle=ea, pass_vs_oracle=eb)
+        assert d < (4e-3 if prec == "fp16" else 2.5e-2) and dp < (4e-3 if prec == "fp16" else 2.5e-2)
+        if prec == "fp16":
+            assert ea < TOL_TC and eb < TOL_TC
+
+
+def _stat_rel(a, b):
+    """max |a - b| relative to the statistic's scale (its largest magnitude over the channels)."""
+    b = b.double().flatten()
+    return ((a.cpu().double().flatten() - b).abs().max() / b.abs().max()).item()
+
+
+@pytest.mark.parametrize("precision", ["fp32", pytest.param("fp16", marks=STATS16_MISS),
+                                       pytest.param("bf16", marks=STATS16_MISS)])
+def test_overall_statistics_loop(models, precision):
+    """mean_std_computation_effcientMem.py:117-137 on 3 batches of images against the reference formula
+    evaluated in fp64: 1e-5 relative, per engine."""
     vgg, dec = models
     batches = [synth.images(n, 64, 64, 50 + i) for i, n in enumerate((3, 3, 2))]
     with torch.no_grad():
         feats = [O.encode_relu4_1(vgg, b) for b in batches]
     mean64, std64, count, imgs = O.overall_style_stats(feats, dtype=torch.float64)
     eng = ccst_b200.engine_for(vgg, dec, torch.device(DEV))
-    for prec, tol in (("fp32", 1e-4), ("fp16", 5e-3), ("bf16", 3e-2)):
-        acc = OverallStyleAccumulator(eng, prec)
-        for b in batches:
-            acc.add_images(b.to(DEV))
-        mean, std = acc.finalize()
-        assert acc.state.count == count and acc.img_count == imgs
-        assert (mean.cpu().double() - mean64).abs().max().item() < tol * max(1.0, mean64.abs().max().item())
-        assert (std.cpu().double() - std64).abs().max().item() < tol * max(1.0, std64.abs().max().item())
-    # given identical features, the accumulator meets the 1e-5 bar
+    acc = OverallStyleAccumulator(eng, precision)
+    for b in batches:
+        acc.add_images(b.to(DEV))
+    mean, std = acc.finalize()
+    assert acc.state.count == count and acc.img_count == imgs
+    em, es = _stat_rel(mean, mean64), _stat_rel(std, std64)
+    report(f"overall statistics {precision}", mean_rel=em, std_rel=es)
+    assert em < TOL_STATS and es < TOL_STATS
+
+
+def test_overall_statistics_default_engine_and_identical_features(models):
+    """The statistics drivers default to the engine that meets 1e-5 (fp32); and given identical
+    features the accumulator itself meets the bar per element."""
+    from ccst_b200 import overall
+    vgg, dec = models
+    assert overall.STATS_PRECISION == "fp32"
+    batches = [synth.images(n, 64, 64, 50 + i) for i, n in enumerate((3, 3, 2))]
+    with torch.no_grad():
+        feats = [O.encode_relu4_1(vgg, b) for b in batches]
+    mean64, std64, count, imgs = O.overall_style_stats(feats, dtype=torch.float64)
+    eng = ccst_b200.engine_for(vgg, dec, torch.device(DEV))
     acc = OverallStyleAccumulator(eng)
+    assert acc.precision == "fp32"
     for f in feats:
         acc.add_features(f.to(DEV))
     mean, std = acc.finalize()
     rel = lambda a, b: ((a.cpu().double() - b).abs() / (b.abs() + 1e-4)).max().item()
-    assert rel(mean, mean64) < 1e-5 and rel(std, std64) < 1e-5
+    assert rel(mean, mean64) < TOL_STATS and rel(std, std64) < TOL_STATS
+
+
+@pytest.mark.parametrize("precision", PREC_IMG)
+def test_config1_batch6_512_vs_oracle(models, precision):
+    """BASELINE config 1 at its full shape: style_transfer, batch 6 @512x512, against the ORACLE (the
+    reference's own PyTorch path on the CPU), every precision at the north_star bar."""
+    vgg, dec = models
+    x = synth.images(6, 512, 512, 1)
+    with torch.no_grad():
+        stat = O.single_style_stats(O.encode_relu4_1(vgg, synth.images(1, 512, 512, 2)))
+        ref = O.style_transfer(vgg, dec, x, stat, 1.0)
+    sd = [t.to(DEV) for t in stat]
+    out = ccst_b200.style_transfer(vgg, dec, x.to(DEV), sd, 1.0, precision=precision)
+    assert tuple(out.shape) == (6, 3, 512, 512)
+    err = (out.cpu() - ref).abs().max().item()
+    report(f"config 1 (6 x 512^2) {precision}", max_abs=err, ref_min=ref.min().item(), ref_max=ref.max().item())
+    assert err < IMG_TOL[precision]
+
+
+@pytest.mark.parametrize("precision", PREC_IMG)
+def test_config5_batch1024_96_vs_oracle(models, precision):
+    """BASELINE config 5 (Camelyon17-like): 96x96 patches, ONE batch of 1024 through the library; the
+    oracle is run on every 32nd image (images are independent; the whole batch costs the CPU minutes)
+    and the full batch is checked against sub-batches bit for bit."""
+    vgg, dec = models
+    n = 1024 if precision != "fp32" else 128  # the FFMA validation engine is ~25x slower
+    x = synth.images(n, 96, 96, 5)
+    with torch.no_grad():
+        stat = O.single_style_stats(O.encode_relu4_1(vgg, synth.images(4, 96, 96, 6)))
+        idx = torch.arange(0, n, 32)
+        ref = O.style_transfer(vgg, dec, x[idx], stat, 1.0)
+    sd = [t.to(DEV) for t in stat]
+    xd = x.to(DEV)
+    out = ccst_b200.style_transfer(vgg, dec, xd, sd, 1.0, precision=precision)
+    assert tuple(out.shape) == (n, 3, 96, 96) and torch.isfinite(out).all()
+    err = (out[idx.to(DEV)].cpu() - ref).abs().max().item()
+    report(f"config 5 ({n} x 96^2) {precision}", max_abs=err, oracle_images=len(idx))
+    part = ccst_b200.style_transfer(vgg, dec, xd[96:160].contiguous(), sd, 1.0, precision=precision)
+    assert torch.equal(part, out[96:160])
+    assert err < IMG_TOL[precision]
 
 
 def test_full_size_batch_is_deterministic_and_shards(models):
-    """512x512 (BASELINE config 3 shape, batch 4): two runs are bit-identical, a batch split in two
-    (the multi-GPU sharding unit) reproduces the unsplit result, and the tensor-core path agrees
-    with the fp32 engine at full size."""
+    """512x512 (BASELINE config 3 shape, batch 4): two runs are bit-identical and a batch split in two
+    (the multi-GPU sharding unit) reproduces the unsplit result."""
     vgg, dec = models
     eng = ccst_b200.engine_for(vgg, dec, torch.device(DEV))
     x = synth.images(4, 512, 512, 21).to(DEV)
@@ -241,10 +355,33 @@ def test_full_size_batch_is_deterministic_and_shards(models):
     c = torch.cat([ccst_b200.style_transfer(vgg, dec, x[:2], stat, 1.0),
                    ccst_b200.style_transfer(vgg, dec, x[2:], stat, 1.0)])
     assert torch.equal(a, c)
-    d = ccst_b200.style_transfer(vgg, dec, x[:1], stat, 1.0, precision="fp32")
-    assert (a[:1] - d).abs().max().item() < TOL_TC
-    e = ccst_b200.style_transfer(vgg, dec, x[:1], stat, 1.0, precision="bf16")
-    assert (e - d).abs().max().item() < 2 * TOL_BF16  # 786k pixels: heavier tail than the 96^2 cases
+
+
+def test_f16_saturation_is_reported(models):
+    """f16 stores clamp at +-65504: weights that drive activations out of the f16 range must raise,
+    not silently produce an image (the counter is kept by every epilogue, one atomic per warp)."""
+    import copy
+    from ccst_b200.transfer import F16SaturationError
+    vgg, dec = models
+    x = synth.images(2, 64, 64, 71).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    stat = [torch.randn((1, 512, 1, 1), generator=g).abs().to(DEV), (torch.rand((1, 512, 1, 1), generator=g) + 0.1).to(DEV)]
+    eng = ccst_b200.Engine(vgg, dec, DEV)
+    eng.transfer(x, stat, 1.0, "fp16")
+    assert eng.saturation_count() == 0
+    eng.check_saturation()  # in-range weights: no error
+    big = copy.deepcopy(vgg)
+    convs = [m for m in big if isinstance(m, torch.nn.Conv2d)]
+    with torch.no_grad():
+        convs[2].weight.mul_(3.0e5)  # conv1_2: activations ~1e5 > 65504
+    eng2 = ccst_b200.Engine(big, dec, DEV)
+    eng2.transfer(x, stat, 1.0, "fp16")
+    assert eng2.saturation_count() > 0
+    with pytest.raises(F16SaturationError):
+        eng2.check_saturation()
+    assert eng2.saturation_count() == 0  # reset by the check
+    eng2.transfer(x, stat, 1.0, "bf16")  # bf16 has the fp32 range: nothing to report
+    assert eng2.saturation_count() == 0
 
 
 def test_pipelines_are_bit_reproducible_over_many_runs(models):

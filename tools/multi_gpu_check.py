@@ -47,7 +47,7 @@ def main():
         for b0 in range(begin, end, a.batch):
             acc.add_images(batch_of(b0, min(a.batch, end - b0)).to(dev))
         if group_reduce:
-            return acc.finalize(None) + (acc.img_count,)
+            return acc.finalize(None) + (acc.global_img_count,)
         return acc.state.finalize() + (acc.img_count,)
 
     begin, end = overall.shard_range(a.images, rank, world)
