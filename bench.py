@@ -14,8 +14,17 @@ Printed JSON (one line, rank 0):
   e2e         same metric through the public batch loop `ccst_b200.drivers.overall_transfer` with
               pinned HOST buffers (uint8 HWC images in, uint8 HWC images out; the fp32-tensor form
               beside it): H2D of the batch and D2H of the stylised images inside the timed region
-  roofline    tcgen05 convolution kernels (dominant: ~99 % of the FLOPs) vs the measured bf16
-              peak; extra `roofline_adain` / `roofline_stats` objects for the HBM-bound operators
+  sustained   the same step in a >= 3 s loop (the headline region is a short burst; long runs are
+              power-capped), with the clocks sampled during it
+  roofline    tcgen05 convolution kernels (dominant: ~99 % of the FLOPs) vs the measured bf16 BURST
+              peak (each launch is event-timed on its own); extra `roofline_stats` / `roofline_adain`
+              objects for the HBM-bound operators
+  configs     every other configuration of BASELINE.json in the same run: config 1 (batch 6), config 2
+              (overall statistics of a 2048-image client, sharded over the ranks, ONE NCCL all-reduce of
+              the Welford moments, its cost reported), config 4 (single-style transfer, per batch and per
+              image), config 5 (96^2 patches, batch 1024 per GPU)
+  gpu_eager_baseline  the reference's own nn.Sequential forward (stock PyTorch eager / cuDNN) on the same
+              B200 with the same inputs -- informational, the comparison SURVEY section 2 names
   cpu_baseline the oracle port of the reference path (PyTorch CPU, all host cores) on a bounded
               sample of the same workload
 Weights are random-init (seeded) VGG-19/decoder, images synthetic: no dataset/checkpoint offline.
@@ -38,6 +47,17 @@ UNIT = "images/s"
 BATCH = 32
 SIZE = 512
 FLOP_PER_IMG = 253.072e9  # SURVEY.md §8d (enc 126.538 + dec 126.534 GFLOP @512^2)
+FLOP_PER_IMG_96 = 8.897e9
+ENC_FLOP_PER_IMG = 126.538e9
+CLIENT_IMAGES = 2048      # config 2: PACS art_painting-sized client
+
+
+def workload_config(batch, world):
+    """`config` of the JSON line -- identical for both arms (the reference arm runs a bounded sample of it)."""
+    return {"workload": "CCST Overall K=3 transfer step (config 3): style_transfer batch 32 @512x512, "
+                        "random-init VGG-19 relu4_1 encoder + decoder, overall style stats, alpha=1",
+            "batch_per_gpu": batch, "image": [3, SIZE, SIZE], "parallelism": f"image-sharded x{world}",
+            "l2": "two input batches alternate; per-step activations (>1 GB) exceed the 126 MB L2"}
 
 
 def load_peaks():
@@ -47,6 +67,16 @@ def load_peaks():
         return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"],
                     src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def load_profile_json(name):
+    p = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
 
 
 class ClockSampler:
@@ -88,6 +118,7 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.t = None
+        return self
 
     def stop(self):
         if self.t is None:
@@ -128,17 +159,21 @@ def run_reference(args, rank, world):
         return
     sample = 2
     ips, sec_per_step, cores = cpu_reference_throughput(args.steps, args.warmup, sample)
+    # one full batch-32 step through the same code (outside the K timed steps): the per-image rate of
+    # the CPU does not depend on the batch -- one image already saturates the cores
+    b32, _, _ = cpu_reference_throughput(1, 0, BATCH)
+    same_batch = {"batch": BATCH, "value": round(b32, 4), "unit": UNIT}
     line = {
         "impl": "reference", "metric": METRIC, "value": round(ips, 4), "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(sec_per_step * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CCST Overall K=3 transfer step (config 3): style_transfer batch @512x512, "
-                               "random-init VGG-19 relu4_1 encoder + decoder, alpha=1",
-                   "batch_per_step": sample, "image": [3, SIZE, SIZE]},
+        "config": workload_config(BATCH, world),
         "cpu_baseline": {"value": round(ips, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} images per step (batch {BATCH} of the GPU arm scaled down), "
-                                   "oracle port of the reference path on PyTorch CPU"},
+                         "sample": f"{sample} images of the batch per step (bounded sample of the batch-{BATCH} workload; "
+                                   "per-image CPU throughput is batch-independent, see same_batch_as_gpu_arm), "
+                                   "oracle port of the reference path on PyTorch CPU, all host cores",
+                         "same_batch_as_gpu_arm": same_batch},
         "e2e": {"value": round(ips, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -162,7 +197,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
 
     import ccst_b200
-    from ccst_b200 import _lib, synth
+    from ccst_b200 import _lib, drivers, overall, synth
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a B200 GPU; ccst_b200 has no CPU fallback "
@@ -195,20 +230,26 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     def step(i, prec=None):
         eng.transfer(dev_in[i & 1], stat, 1.0, prec or precision, out=out)
 
-    def timed_steps(prec):
+    def timed_steps(prec, n):
         for i in range(3):
             step(i, prec)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(args.steps):
+        for i in range(n):
             step(i, prec)
         b.record()
         torch.cuda.synchronize()
-        return a.elapsed_time(b) / args.steps
+        return a.elapsed_time(b) / n
 
     # ---------------- device-resident throughput ----------------
     for i in range(max(args.warmup, 3)):
@@ -226,62 +267,38 @@ def run_ours(args, rank, world, local_rank):
     ev1.record()
     barrier()
     launches = _lib.lib().ccst_launch_count() - l0
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = t.item()
     value = world * args.batch * args.steps / (ms_total / 1e3)
+    eng.check_saturation()  # f16 range guard: raises if any store clamped
 
     # ---------------- end to end through the public API (host buffers) ----------------
     # The user-level loop of CCST_OverallStyleTransfer.py:149-167 (`data.to(device)` ->
     # `style_transfer` -> `output.cpu()`), via ccst_b200.drivers.overall_transfer: every step uploads
     # its batch from pinned host memory and downloads the stylised batch to pinned host memory;
     # uploads/downloads of neighbouring steps overlap the compute on separate streams.
-    from ccst_b200 import drivers
+    def e2e_loop(batches_of, nsteps, **kw):
+        def run(n):
+            seen = 0
+            for _, out_host in drivers.overall_transfer(eng, (batches_of[i & 1] for i in range(n)), stat, 1.0,
+                                                        precision, **kw):
+                seen += out_host.shape[0]  # the result is in host memory here (what save_image would read)
+            return seen
 
-    def e2e_run(nsteps):
-        seen = 0
-        batches = (host[i & 1] for i in range(nsteps))
-        for _, out_host in drivers.overall_transfer(eng, batches, stat, 1.0, precision):
-            seen += out_host.shape[0]  # the result is in host memory here (what save_image would read)
-        return seen
+        run(3)
+        barrier()
+        t0 = time.perf_counter()
+        seen = run(nsteps)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        assert seen == args.batch * nsteps
+        return world * args.batch * nsteps / dt
 
-    e2e_run(3)
-    barrier()
-    t0 = time.perf_counter()
-    seen = e2e_run(args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    assert seen == args.batch * args.steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.batch * args.steps / t.item()
-
+    e2e_value = e2e_loop(host, args.steps)
     # the same loop with the image I/O fused around the path: uint8 HWC batches in (the
     # loader's images before ToTensor), uint8 HWC batches out (what save_image encodes)
     host_u8 = [(h.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().pin_memory() for h in host]
-
-    def e2e_u8_run(nsteps):
-        seen = 0
-        batches = (host_u8[i & 1] for i in range(nsteps))
-        for _, out_host in drivers.overall_transfer(eng, batches, stat, 1.0, precision, u8=True):
-            seen += out_host.shape[0]
-        return seen
-
-    e2e_u8_run(3)
-    barrier()
-    t0 = time.perf_counter()
-    seen = e2e_u8_run(args.steps)
-    barrier()
-    e2e_u8_s = time.perf_counter() - t0
-    assert seen == args.batch * args.steps
-    t = torch.tensor([e2e_u8_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_u8_value = world * args.batch * args.steps / t.item()
+    e2e_u8_value = e2e_loop(host_u8, args.steps, u8=True)
 
     # same loop without overlap: the reference's own structure, one blocking call per step
     def e2e_step_serial(i):
@@ -300,6 +317,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_serial_value = args.batch * args.steps / (time.perf_counter() - t0)
     img_bytes = args.batch * 3 * SIZE * SIZE * 4
 
+    # (rank 0, right after the timed regions: the GPU is in the same thermal / power state as for `value`)
     line = None
     if rank == 0:
         # ---------------- per-kernel roofline (separate profiled pass, events per launch) ----------
@@ -319,31 +337,36 @@ def run_ours(args, rank, world, local_rank):
         conv = agg.get(conv_kind, dict(ms=1e-9, flops=0, n=1))
         step_ms_prof = sum(a["ms"] for a in agg.values()) / psteps
         conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
-        peak_tf = peaks["tf_sust"]
+        # algorithmic FLOPs of the same launches (253.072 GFLOP/image minus conv1_1's 0.906)
+        alg_flops_step = (FLOP_PER_IMG - 0.906e9) * args.batch
+        conv_tflops_alg = alg_flops_step / (conv["ms"] / psteps * 1e-3) / 1e12
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_ncu_conv_traffic.json")
-        if precision != "fp32" and os.path.exists(tp):
-            td = json.load(open(tp))
-            if td.get("batch") == args.batch:
-                traffic = td["dram_bytes_per_launch_avg"]
-                traffic_src = td["source"]
+        td = load_profile_json("r02_ncu_conv_traffic.json") or load_profile_json("r01_ncu_conv_traffic.json")
+        if precision != "fp32" and td and td.get("batch") == args.batch:
+            traffic = td["dram_bytes_per_launch_avg"]
+            traffic_src = td["source"]
         roofline = {
             "kernel": "tcgen05.mma + TMA implicit-GEMM 3x3 convs (conv_umma_kernel / conv_smerge_kernel / "
                       "conv_ups4_kernel / conv_last_rows_kernel, 18 launches/step)"
             if precision != "fp32" else "conv_ffma_kernel (fp32 validation mode)",
-            "bound": "tensor", "achieved": round(conv_tflops, 2), "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": round(conv_tflops / peak_tf, 4),
-            "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
-            "frac_of_burst_peak": round(conv_tflops / peaks["tf_burst"], 4),
+            "bound": "tensor", "achieved": round(conv_tflops, 2), "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+            "frac": round(conv_tflops / peaks["tf_burst"], 4),
+            "peak_source": f"{peaks['src']} bf16 BURST peak (every launch is timed on its own with a CUDA-event pair)",
+            "achieved_algorithmic": round(conv_tflops_alg, 2),
+            "frac_algorithmic": round(conv_tflops_alg / peaks["tf_burst"], 4),
+            "frac_of_sustained_peak": round(conv_tflops / peaks["tf_sust"], 4),
             "flops_per_launch_avg": conv["flops"] / max(conv["n"], 1),
             "ms_per_launch_avg": round(conv["ms"] / max(conv["n"], 1), 4),
             "share_of_step": round(conv["ms"] / psteps / step_ms_prof, 4), "traffic": traffic,
             "traffic_source": traffic_src,
-            "flops_basis": "EXECUTED flops: the three convs that follow a nearest-x2 upsample run as four 2x2 "
-                           "phase convolutions (16 instead of 36 tap-GEMMs per source pixel), so a step executes "
-                           "220.9 of the 253.07 algorithmic GFLOP/image; tflops_per_gpu uses the algorithmic count",
+            "flops_basis": "`achieved` counts EXECUTED flops: the three convs that follow a nearest-x2 upsample run as "
+                           "four 2x2 phase convolutions (16 instead of 36 tap-GEMMs per source pixel), so a step "
+                           "executes 220.9 of the 253.07 algorithmic GFLOP/image; `achieved_algorithmic` divides the "
+                           "algorithmic FLOPs of the same launches by the same time",
             "timing": f"cudaEvent pair around every launch on the launch stream, {psteps}-step pass after the timed region",
             "per_kind_ms_per_step": {str(k): round(a["ms"] / psteps, 4) for k, a in sorted(agg.items())},
+            "kinds": "0 conv1_1, 1 tcgen05 convs, 2 ffma convs, 3 pool, 4 adain/stats pass, 5 layout convert, "
+                     "6 AdaIN folded into dec1 (coefficients + per-image weights)",
         }
 
         # ---------------- HBM-bound operators on [32,512,64,64] fp32 ----------------
@@ -365,17 +388,24 @@ def run_ours(args, rank, world, local_rank):
         nbytes = feat.numel() * 4
         b_stats = nbytes + 8 * BATCH * 512
         b_adain = 2 * nbytes + 8 * 512
-        roofline_stats = {"kernel": "plane_bulk_kernel<stats> (TMA bulk-staged single-pass Welford; calc_mean_std [32,512,64,64] fp32)", "bound": "hbm",
-                          "achieved": round(b_stats / ms_stats / 1e6, 1), "peak": peaks["hbm"], "unit": "GB/s",
+        ops_traffic = load_profile_json("r02_ncu_ops_traffic.json") or {}
+
+        def op_traffic(key):
+            e = ops_traffic.get(key)
+            return (e["dram_bytes"], e["source"]) if e else (None, None)
+
+        t_s, t_s_src = op_traffic("calc_mean_std")
+        t_a, t_a_src = op_traffic("adain_stat")
+        roofline_stats = {"kernel": "plane_bulk_kernel<0> (TMA bulk-staged single-pass Welford; calc_mean_std [32,512,64,64] fp32)",
+                          "bound": "hbm", "achieved": round(b_stats / ms_stats / 1e6, 1), "peak": peaks["hbm"], "unit": "GB/s",
                           "frac": round(b_stats / ms_stats / 1e6 / peaks["hbm"], 4),
-                          "traffic": 274583552 if BATCH == 32 else None,
-                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum "
-                                            "(profiles/r01_ncu_ops_summary.txt); algorithmic bytes 268.5 MB",
+                          "traffic": t_s, "traffic_source": t_s_src, "algorithmic_bytes": b_stats,
                           "ms": round(ms_stats, 5), "peak_source": peaks["src"] + " copy bandwidth",
                           "note": "includes torch.empty of the outputs and the ctypes call per launch"}
-        roofline_adain = {"kernel": "plane_bulk_kernel<adain> (statistics + re-normalisation in one HBM pass; adaIN_StyleStat_ContentFeat [32,512,64,64] fp32)",
+        roofline_adain = {"kernel": "plane_bulk_kernel<2> (statistics + re-normalisation in one HBM pass; adaIN_StyleStat_ContentFeat [32,512,64,64] fp32)",
                           "bound": "hbm", "achieved": round(b_adain / ms_adain / 1e6, 1), "peak": peaks["hbm"],
-                          "unit": "GB/s", "frac": round(b_adain / ms_adain / 1e6 / peaks["hbm"], 4), "traffic": None,
+                          "unit": "GB/s", "frac": round(b_adain / ms_adain / 1e6 / peaks["hbm"], 4),
+                          "traffic": t_a, "traffic_source": t_a_src, "algorithmic_bytes": b_adain,
                           "ms": round(ms_adain, 5), "peak_source": peaks["src"] + " copy bandwidth"}
         del feat, feat2
 
@@ -383,8 +413,41 @@ def run_ours(args, rank, world, local_rank):
         other = {}
         for alt in ("bf16", "fp16"):
             if alt != precision and precision != "fp32":
-                ms_alt = timed_steps(alt)
+                ms_alt = timed_steps(alt, args.steps)
                 other[alt] = {"ms_per_step": round(ms_alt, 4), "images_per_s_per_gpu": round(args.batch / ms_alt * 1e3, 2)}
+
+    barrier()
+
+    # ---------------- the other BASELINE.json configurations (all ranks take part) ----------------
+    configs = {}
+    if not args.no_configs:
+        configs = run_configs(args, torch, dist, dev, rank, world, eng, vgg, dec, stat, peaks, barrier, max_over_ranks)
+
+    # ---------------- sustained: the same step for >= 3 s (all ranks, power-capped regime) -------
+    sustained = None
+    if not args.no_sustained:
+        # (long loops run at lower clocks than the burst above, so this lasts longer than sustain_s)
+        n_sus = max(args.steps, int(1.25 * args.sustain_s * 1e3 / (ms_total / args.steps)) + 1)
+        sam = ClockSampler(local_rank).start() if rank == 0 else None
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n_sus):
+            step(i)
+        b.record()
+        barrier()
+        ms_sus = max_over_ranks(a.elapsed_time(b))
+        ck = sam.stop() if sam is not None else {}
+        sustained = {"steps": n_sus, "seconds": round(ms_sus / 1e3, 3),
+                     "value": round(world * args.batch * n_sus / (ms_sus / 1e3), 2), "unit": UNIT,
+                     "ms_per_step": round(ms_sus / n_sus, 4), "sm_mhz": ck.get("sm_mhz"),
+                     "reasons": ck.get("reasons"), "power_w_max": ck.get("power_w_max")}
+
+    if rank == 0:
+        # ---------------- the reference's own modules through stock PyTorch on this GPU -----------
+        eager = None
+        if not args.no_eager:
+            eager = gpu_eager_baseline(torch, vgg, dec, dev_in, stat, args, value / world)
 
         # ---------------- CPU baseline beside it (bounded sample) ----------------
         cpu = None
@@ -404,10 +467,7 @@ def run_ours(args, rank, world, local_rank):
                            "tensor peak; f16 meets the 1e-2 image tolerance, bf16 operands do not -- see DESIGN.md "
                            "Numerics)" % ("f16" if precision == "fp16" else "bf16")),
             "other_precisions": other,
-            "config": {"workload": "CCST Overall K=3 transfer step (config 3): style_transfer batch 32 @512x512, "
-                                   "random-init VGG-19 relu4_1 encoder + decoder, overall style stats, alpha=1",
-                       "batch_per_gpu": args.batch, "image": [3, SIZE, SIZE], "parallelism": f"image-sharded x{world}",
-                       "l2": "two input batches alternate; per-step activations (>1 GB) exceed the 126 MB L2"},
+            "config": workload_config(args.batch, world),
             "tflops_per_gpu": round(value / world * FLOP_PER_IMG / 1e12, 2),
             # headline e2e: the batch loop fed with what the reference's loader actually holds (uint8 HWC
             # images, before ToTensor) and returning what save_image encodes (uint8 HWC) -- ToTensor and
@@ -428,7 +488,9 @@ def run_ours(args, rank, world, local_rank):
                     "serial_api": "x.to(device); ccst_b200.style_transfer(vgg, decoder, x, style_stat, alpha); out.cpu() "
                                   "per step with fp32 tensors, no overlap (rank 0)"},
             "gpu_launches": int(launches),
+            "sustained": sustained,
             "roofline": roofline, "roofline_stats": roofline_stats, "roofline_adain": roofline_adain,
+            "configs": configs, "gpu_eager_baseline": eager,
             "cpu_baseline": cpu, "clocks": clocks,
         }
     barrier()
@@ -436,6 +498,186 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def run_configs(args, torch, dist, dev, rank, world, eng, vgg, dec, stat, peaks, barrier, max_over_ranks):
+    """Configs 1, 2, 4, 5 of BASELINE.json, each a short timed region on every rank (max over ranks)."""
+    import random
+
+    import ccst_b200
+    from ccst_b200 import drivers, overall, synth
+
+    precision = args.precision
+    res = {}
+
+    def dev_timed(fn, iters, warm=2):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            fn(i)
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / iters
+
+    # ---- config 1: AdaIN single-style transfer, batch 6 @512^2 (the reference's CPU-runnable case)
+    x6 = [synth.images(6, SIZE, SIZE, 2000 + 10 * rank + i).to(dev) for i in range(2)]
+    o6 = torch.empty((6, 3, SIZE, SIZE), dtype=torch.float32, device=dev)
+    ms = dev_timed(lambda i: eng.transfer(x6[i & 1], stat, 1.0, precision, out=o6), 20)
+    res["config1_batch6_512"] = {
+        "workload": "style_transfer batch 6 @512x512 (BASELINE config 1 on the GPU), device-resident",
+        "value": round(world * 6 / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 4),
+        "tensor_frac_algorithmic": round(6 * FLOP_PER_IMG / (ms * 1e-3) / 1e12 / peaks["tf_burst"], 4)}
+    del x6, o6
+
+    # ---- config 2: overall style statistics of one 2048-image client, sharded over the ranks ----
+    # (mean_std_computation_effcientMem.py:117-137): contiguous image ranges per rank, uint8 HWC host
+    # batches of 32 uploaded under the encoder, ONE all-reduce of the 1+2C fp64 moments (+ image count)
+    begin, end = overall.shard_range(CLIENT_IMAGES, rank, world)
+    hb = [torch.randint(0, 256, (BATCH, SIZE, SIZE, 3), dtype=torch.uint8,
+                        generator=torch.Generator().manual_seed(3000 + rank + i)).pin_memory() for i in range(2)]
+
+    def client_batches(first, last):
+        i = 0
+        for b0 in range(first, last, BATCH):
+            n = min(BATCH, last - b0)
+            yield hb[i & 1][:n]
+            i += 1
+
+    group = None  # default process group (NCCL) when world > 1
+    c2 = {"workload": f"overall style statistics of a {CLIENT_IMAGES}-image client @512x512, batch 32, images "
+                      f"sharded over {world} rank(s), uint8 host batches uploaded in the timed region, one "
+                      "all-reduce(sum) of the 1025 fp64 Welford moments + image count"}
+    for prec, n_img in ((precision, CLIENT_IMAGES), ("fp32", min(CLIENT_IMAGES, 64 * world))):
+        if prec == "fp32" and precision == "fp32":
+            continue
+        b_, e_ = overall.shard_range(n_img, rank, world)
+        drivers.overall_statistics(eng, client_batches(b_, min(e_, b_ + BATCH)), prec, group)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        mean, std, seen = drivers.overall_statistics(eng, client_batches(b_, e_), prec, group)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        assert seen == n_img, (seen, n_img)
+        key = "tensor_core_encoder" if prec != "fp32" else "fp32_engine_default"
+        c2[key] = {"precision": prec, "images": n_img, "value": round(n_img / dt, 1), "unit": UNIT,
+                   "seconds": round(dt, 4),
+                   "tensor_frac_algorithmic": round(n_img / world * ENC_FLOP_PER_IMG / dt / 1e12 / peaks["tf_burst"], 4)
+                   if prec != "fp32" else None,
+                   "statistics_vs_reference": "~1e-3 relative (16-bit encoder)" if prec != "fp32" else
+                   "< 1e-5 relative (tests/test_gpu_net.py::test_overall_statistics_loop)"}
+    # the collective on its own: all-reduce of the 1026-double payload, CUDA events, 50 repetitions
+    payload = torch.zeros((1026,), dtype=torch.float64, device=dev)
+    if dist is not None:
+        for _ in range(5):
+            dist.all_reduce(payload)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(50):
+            dist.all_reduce(payload)
+        b.record()
+        torch.cuda.synchronize()
+        c2["allreduce_us"] = round(max_over_ranks(a.elapsed_time(b)) / 50 * 1e3, 2)
+        c2["allreduce"] = "NCCL all_reduce(SUM) of 1026 fp64 (8.2 KB) per client, once; latency-bound"
+    else:
+        c2["allreduce_us"] = 0.0
+        c2["allreduce"] = "single rank: no collective"
+    res["config2_overall_stats_2048"] = c2
+    del hb
+
+    # ---- config 4: single-style transfer (CCST_SingleStyleTransfer.py:176-223), batch 32 @512^2 ----
+    # through the public batch loops with pinned host batches: per BATCH one random style image (the
+    # reference's semantics) and per IMAGE (BASELINE.json's wording); style encode + statistics included
+    hc = [synth.images(BATCH, SIZE, SIZE, 4000 + 10 * rank + i).pin_memory() for i in range(2)]
+    styles = [synth.images(1, SIZE, SIZE, 4100 + k) for k in range(8)]
+    styles_ragged = [synth.images(1, 512, 512 + 128 * (k % 3 - 1), 4200 + k) for k in range(6)]  # 4:3 / 1:1 / 3:4 mix
+    nb = max(4, min(args.steps, 10))
+
+    def run_loop(fn, sts):
+        seen = 0
+        for _, o in fn(eng, (hc[i & 1] for i in range(nb)), sts, 1.0, precision, seed=1):
+            seen += o.shape[0]
+        return seen
+
+    c4 = {"workload": "single-style transfer, batch 32 @512x512, pinned fp32 host batches in/out, style image "
+                      "encode + statistics inside the loop"}
+    for key, fn, sts in (("per_batch_style", drivers.single_transfer, styles_ragged),
+                         ("per_image_style", drivers.single_transfer_per_image, styles)):
+        run_loop(fn, sts)
+        barrier()
+        t0 = time.perf_counter()
+        seen = run_loop(fn, sts)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        c4[key] = {"value": round(world * seen / dt, 1), "unit": UNIT, "batches": nb}
+    res["config4_single_style"] = c4
+    del hc
+
+    # ---- config 5: Camelyon17-like 96x96 patches, batch 1024 per GPU, 4 target styles -----------
+    n5 = 1024
+    x5 = [synth.images(n5, 96, 96, 5000 + 10 * rank + i).to(dev) for i in range(2)]
+    o5 = torch.empty((n5, 3, 96, 96), dtype=torch.float32, device=dev)
+    gs = torch.Generator().manual_seed(11)
+    stats4 = [[torch.randn((1, 512, 1, 1), generator=gs).abs().to(dev), (torch.rand((1, 512, 1, 1), generator=gs) + 0.1).to(dev)]
+              for _ in range(4)]
+    ms = dev_timed(lambda i: eng.transfer(x5[i & 1], stats4[i & 3], 1.0, precision, out=o5), 8)
+    res["config5_camelyon_96"] = {
+        "workload": "Overall K=4 transfer at 96x96 patches, batch 1024 per GPU, 4 styles in turn, device-resident",
+        "value": round(world * n5 / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 4),
+        "tensor_frac_algorithmic": round(n5 * FLOP_PER_IMG_96 / (ms * 1e-3) / 1e12 / peaks["tf_burst"], 4),
+        "note": "24x24 / 12x12 maps fill 75 % / 56 % of the 8x16 pixel tiles"}
+    del x5, o5
+    eng.check_saturation()
+    return res
+
+
+def gpu_eager_baseline(torch, vgg, dec, dev_in, stat, args, ours_ips):
+    """The reference's nn.Sequential modules (net.py:6-92 as built by ccst_b200.net) run by stock PyTorch
+    eager (cuDNN / ATen) on this GPU + the reference AdaIN formula (function.py:26-33), same inputs."""
+    import copy
+
+    from oracle import ccst_oracle as O
+
+    dev = dev_in[0].device
+    res = {"what": "stock PyTorch eager forward of the same nn.Sequential encoder/decoder + the reference's "
+                   "AdaIN (function.py:26-33) on the same B200, batch %d @512x512, CUDA events" % args.batch}
+    try:
+        v, d = copy.deepcopy(vgg).to(dev), copy.deepcopy(dec).to(dev)
+        modes = (("fp32_tf32_off", dict(tf32=False, amp=False, cl=False)),
+                 ("fp32_tf32_on", dict(tf32=True, amp=False, cl=False)),
+                 ("bf16_autocast_channels_last", dict(tf32=True, amp=True, cl=True)))
+        for name, m in modes:
+            torch.backends.cudnn.allow_tf32 = m["tf32"]
+            torch.backends.cuda.matmul.allow_tf32 = m["tf32"]
+            torch.backends.cudnn.benchmark = True
+            vv, dd = (v.to(memory_format=torch.channels_last), d.to(memory_format=torch.channels_last)) if m["cl"] else (v, d)
+            xs = [x.contiguous(memory_format=torch.channels_last) if m["cl"] else x for x in dev_in]
+
+            def fwd(i):
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=m["amp"]):
+                    return O.style_transfer(vv, dd, xs[i & 1], stat, 1.0)
+
+            for i in range(2):
+                fwd(i)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 4
+            a.record()
+            for i in range(n):
+                fwd(i)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / n
+            ips = args.batch / ms * 1e3
+            res[name] = {"value": round(ips, 1), "unit": UNIT, "ms_per_step": round(ms, 3),
+                         "ours_over_eager": round(ours_ips / ips, 2)}
+        torch.backends.cudnn.allow_tf32 = True
+    except Exception as e:  # informational: never take the bench line down
+        res["error"] = repr(e)[:200]
+    return res
 
 
 def main():
@@ -447,6 +689,10 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-eager", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sustain-s", type=float, default=3.0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

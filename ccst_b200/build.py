@@ -45,7 +45,9 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, dev: bool = False) -> str:
+    """dev=True adds -DCCST_DEV: measurement switches (CCST_ABLATE, CCST_PDL) read from the environment.
+    The shipped library is built without it and reads nothing from the environment."""
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
@@ -56,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + (["-DCCST_DEV"] if dev else []) + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd), flush=True)
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -85,5 +87,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv,
+                 dev="--dev" in sys.argv)
     print(path)

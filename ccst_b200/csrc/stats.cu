@@ -261,37 +261,49 @@ __device__ __forceinline__ void chan_merge(double& n, double& mean, double& m2, 
   n = nn;
 }
 
+// The running state is 2 + 2C doubles: {count, mean[C], M2[C], ticket}.  Every block of an accumulating
+// kernel reads the OLD count, merges its channels, then takes a ticket (atomicInc wraps to 0 at the
+// grid size, so the word is zero again afterwards); the block that draws the last ticket -- by then
+// every block has read the old count -- stores the new count.  No second launch, no scratch counter.
+__device__ __forceinline__ void bump_count_last_block(double* state, int C, double old_count, double add) {
+  __threadfence();
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(state + 1 + 2 * C);
+  if (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1) state[0] = old_count + add;
+}
+
 __global__ void __launch_bounds__(256) merge_planes_kernel(const float2* __restrict__ raw, int N,
                                                             int C, double hw,
                                                             double* __restrict__ state) {
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c >= C) return;
-  double n = 0.0, mean = 0.0, m2 = 0.0;
-  for (int i = lane; i < N; i += 32) {
-    const float2 r = raw[(size_t)i * C + c];
-    chan_merge(n, mean, m2, hw, (double)r.x, (double)r.y);
-  }
+  const double old_count = state[0];
+  if (c < C) {
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      const float2 r = raw[(size_t)i * C + c];
+      chan_merge(n, mean, m2, hw, (double)r.x, (double)r.y);
+    }
 #pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const double nb = __shfl_xor_sync(0xffffffffu, n, off);
-    const double mb = __shfl_xor_sync(0xffffffffu, mean, off);
-    const double qb = __shfl_xor_sync(0xffffffffu, m2, off);
-    // both partners must compute the same bits: merge (lower lane's value) <- (upper lane's value)
-    double an = n, am = mean, aq = m2, bn = nb, bm = mb, bq = qb;
-    if (lane & off) an = nb, am = mb, aq = qb, bn = n, bm = mean, bq = m2;
-    chan_merge(an, am, aq, bn, bm, bq);
-    n = an, mean = am, m2 = aq;
+    for (int off = 1; off < 32; off <<= 1) {
+      const double nb = __shfl_xor_sync(0xffffffffu, n, off);
+      const double mb = __shfl_xor_sync(0xffffffffu, mean, off);
+      const double qb = __shfl_xor_sync(0xffffffffu, m2, off);
+      // both partners must compute the same bits: merge (lower lane's value) <- (upper lane's value)
+      double an = n, am = mean, aq = m2, bn = nb, bm = mb, bq = qb;
+      if (lane & off) an = nb, am = mb, aq = qb, bn = n, bm = mean, bq = m2;
+      chan_merge(an, am, aq, bn, bm, bq);
+      n = an, mean = am, m2 = aq;
+    }
+    if (lane == 0) {
+      double sn = old_count, sm = state[1 + c], sq = state[1 + C + c];
+      chan_merge(sn, sm, sq, n, mean, m2);
+      state[1 + c] = sm;
+      state[1 + C + c] = sq;
+    }
   }
-  if (lane == 0) {
-    double sn = state[0], sm = state[1 + c], sq = state[1 + C + c];
-    chan_merge(sn, sm, sq, n, mean, m2);
-    state[1 + c] = sm;
-    state[1 + C + c] = sq;
-  }
+  __syncthreads();
+  if (threadIdx.x == 0) bump_count_last_block(state, C, old_count, hw * (double)N);
 }
-
-__global__ void bump_count_kernel(double* state, double add) { state[0] += add; }
 
 __global__ void finalize_kernel(const double* __restrict__ state, int C, float eps, int unbiased,
                                 float* __restrict__ mean, float* __restrict__ stdv) {
@@ -538,11 +550,183 @@ __global__ void __launch_bounds__(32 * (1 + SLOTS), 1) plane_bulk_kernel(BulkArg
   }
 }
 
-constexpr int kBulkSmem = kRingBytes + 2 * 16 * 8;
-
+// =====================================================================================
+// Welford accumulation in ONE launch (calc_sum + `all_* += ...`, mean_std_computation_effcientMem.py:
+// 103-131): the bulk-staged ring of plane_bulk_kernel, but with the planes dealt to the CTAs so that a
+// CTA owns whole CHANNELS: chunk = PPC consecutive planes (channels j*PPC .. of one image), and CTA b
+// takes the chunk classes j = b, b + grid, ... of EVERY image (grid divides C / PPC).  The per-plane
+// {mean, M2} never leave the SM: each consumer warp keeps a running fp64 Chan state per channel over its
+// images, the warps of a CTA are merged through shared memory in fixed order, and the CTA folds its
+// channels into the global state itself (count: bump_count_last_block).  Deterministic.
+//   NSLOTS ring slots of 128 KiB / NSLOTS bytes, W = min(16, NSLOTS) consumer warps: warp w takes the CTA's
+//   chunks i = w, w + W, ...; chunk i = (image i / J, class b + (i % J) * grid), J = C / PPC / grid classes per
+//   CTA, W % J == 0 so a warp always sees the same class; G = 32 / PPC lanes work on one plane.
+// =====================================================================================
 bool bulk_ok(const void* p, int64_t hw) {
   return hw % 4 == 0 && hw * 4 <= kSlotBytesMax && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
 }
+
+struct AccArgs {
+  const float* x;
+  int N, C, hw;
+  int J;        // chunk classes per CTA
+  double* state;
+};
+
+template <int PPC, int NSLOTS>
+__global__ void __launch_bounds__(32 * (1 + (NSLOTS < 16 ? NSLOTS : 16)), 1) welford_bulk_kernel(AccArgs a) {
+  constexpr int kSlotBytes = kRingBytes / NSLOTS;
+  constexpr int W = NSLOTS < 16 ? NSLOTS : 16;
+  constexpr int G = 32 / PPC;
+  extern __shared__ __align__(128) uint8_t ring[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kRingBytes);
+  double* s_part = reinterpret_cast<double*>(ring + kRingBytes + 2 * 32 * 8);  // [W][PPC][3]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSLOTS; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[s])));           // full
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[NSLOTS + s])));  // empty
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int grid = gridDim.x, b = blockIdx.x;
+  const int cpi = a.C / PPC;                       // chunks per image
+  const int64_t chunks = (int64_t)a.N * a.J;       // chunks of this CTA
+  const uint32_t chunk_bytes = (uint32_t)PPC * a.hw * 4u;
+  auto chunk_src = [&](int64_t i) {
+    const int64_t n = i / a.J;
+    const int j = b + (int)(i % a.J) * grid;
+    return a.x + ((n * cpi + j) * PPC) * (int64_t)a.hw;
+  };
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int64_t i = 0; i < chunks; ++i) {
+        const int slot = (int)(i % NSLOTS);
+        const uint32_t use = (uint32_t)(i / NSLOTS);
+        bar_wait(smem_addr(&bars[NSLOTS + slot]), (use & 1) ^ 1);
+        const uint32_t full = smem_addr(&bars[slot]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(chunk_bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_addr(ring + slot * kSlotBytes)),
+            "l"(chunk_src(i)), "r"(chunk_bytes), "r"(full)
+            : "memory");
+      }
+    }
+    return;
+  }
+  const double old_count = a.state[0];
+  const int w = warp - 1;
+  const int grp = lane / G, sub = lane % G;  // plane of the chunk, lane inside the plane's group
+  const int n4 = a.hw >> 2;
+  double rn = 0.0, rmean = 0.0, rm2 = 0.0;   // running state of channel (class of this warp, plane grp); lane sub == 0
+  for (int64_t i = w; i < chunks; i += W) {
+    const int slot = (int)(i % NSLOTS);
+    bar_wait(smem_addr(&bars[slot]), (uint32_t)(i / NSLOTS) & 1);
+    const float4* src = reinterpret_cast<const float4*>(ring + slot * kSlotBytes) + (size_t)grp * n4;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = sub;
+    for (; k + 3 * G < n4; k += 4 * G) {
+      const float4 v0 = src[k], v1 = src[k + G], v2 = src[k + 2 * G], v3 = src[k + 3 * G];
+      s0 += (v0.x + v0.y) + (v0.z + v0.w);
+      s1 += (v1.x + v1.y) + (v1.z + v1.w);
+      s2 += (v2.x + v2.y) + (v2.z + v2.w);
+      s3 += (v3.x + v3.y) + (v3.z + v3.w);
+    }
+    for (; k < n4; k += G) {
+      const float4 v = src[k];
+      s0 += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mean = group_sum<G>((s0 + s1) + (s2 + s3)) / (float)a.hw;
+    auto sq = [mean](const float4 v) {
+      const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+      return (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    };
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    k = sub;
+    for (; k + 3 * G < n4; k += 4 * G) {
+      const float4 v0 = src[k], v1 = src[k + G], v2 = src[k + 2 * G], v3 = src[k + 3 * G];
+      q0 += sq(v0);
+      q1 += sq(v1);
+      q2 += sq(v2);
+      q3 += sq(v3);
+    }
+    for (; k < n4; k += G) q0 += sq(src[k]);
+    const float q = group_sum<G>((q0 + q1) + (q2 + q3));
+    // generic-proxy reads of the slot -> ordered before the producer's next bulk copy (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bars[NSLOTS + slot])) : "memory");
+    if (sub == 0) chan_merge(rn, rmean, rm2, (double)a.hw, (double)mean, (double)q);
+  }
+  // warps of the CTA -> shared memory -> fixed-order merge per channel -> global state
+  if (sub == 0) {
+    double* d = s_part + ((size_t)w * PPC + grp) * 3;
+    d[0] = rn, d[1] = rmean, d[2] = rm2;
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(32 * W) : "memory");  // consumer warps only (the producer warp has left)
+  if (w == 0) {
+    if (lane < a.J * PPC) {
+      const int jj = lane / PPC, pl = lane % PPC;
+      double n = 0.0, mean = 0.0, m2 = 0.0;
+      for (int ww = jj; ww < W; ww += a.J) {  // warps whose class is jj, increasing
+        const double* d = s_part + ((size_t)ww * PPC + pl) * 3;
+        chan_merge(n, mean, m2, d[0], d[1], d[2]);
+      }
+      const int c = (b + jj * grid) * PPC + pl;
+      double sn = old_count, sm = a.state[1 + c], sq2 = a.state[1 + a.C + c];
+      chan_merge(sn, sm, sq2, n, mean, m2);
+      a.state[1 + c] = sm;
+      a.state[1 + a.C + c] = sq2;
+    }
+    __syncwarp();
+    if (lane == 0) bump_count_last_block(a.state, a.C, old_count, (double)a.hw * (double)a.N);
+  }
+}
+
+constexpr int kAccSmem = kRingBytes + 2 * 32 * 8 + 16 * 8 * 3 * 8;
+
+template <int PPC, int NSLOTS>
+int launch_acc_cfg(const AccArgs& a, int grid, cudaStream_t st) {
+  constexpr int W = NSLOTS < 16 ? NSLOTS : 16;
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(welford_bulk_kernel<PPC, NSLOTS>), kAccSmem));
+  welford_bulk_kernel<PPC, NSLOTS><<<grid, 32 * (1 + W), kAccSmem, st>>>(a);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+// Picks (PPC, NSLOTS, grid) for the one-launch accumulation, or returns false (-> two-launch path).
+bool launch_acc(const float* x, int N, int C, int64_t hw, double* state, cudaStream_t st, int* rc) {
+  if (!bulk_ok(x, hw) || C % 4 != 0) return false;
+  const int sms = sm_count();
+  for (int ppc = 4; ppc >= 1; ppc >>= 1) {
+    const int64_t cb = (int64_t)ppc * hw * 4;
+    if (C % ppc != 0 || cb > kSlotBytesMax) continue;
+    const int cpi = C / ppc;
+    int grid = 0;  // largest divisor of cpi that fits the SMs
+    for (int g = (cpi < sms ? cpi : sms); g >= 1; --g)
+      if (cpi % g == 0) {
+        grid = g;
+        break;
+      }
+    const int J = cpi / grid;
+    const int nslots = cb <= 4096 ? 32 : (cb <= 8192 ? 16 : 8);
+    const int W = nslots < 16 ? nslots : 16;
+    // enough CTAs to pull the HBM bandwidth, classes a warp can own, one lane per channel in the final merge
+    if (grid * 4 < sms * 3 || W % J != 0 || J * ppc > 32) continue;
+    AccArgs a{x, N, C, (int)hw, J, state};
+    if (ppc == 4) *rc = nslots == 32 ? launch_acc_cfg<4, 32>(a, grid, st) : (nslots == 16 ? launch_acc_cfg<4, 16>(a, grid, st) : launch_acc_cfg<4, 8>(a, grid, st));
+    else if (ppc == 2) *rc = nslots == 32 ? launch_acc_cfg<2, 32>(a, grid, st) : (nslots == 16 ? launch_acc_cfg<2, 16>(a, grid, st) : launch_acc_cfg<2, 8>(a, grid, st));
+    else *rc = nslots == 32 ? launch_acc_cfg<1, 32>(a, grid, st) : (nslots == 16 ? launch_acc_cfg<1, 16>(a, grid, st) : launch_acc_cfg<1, 8>(a, grid, st));
+    return true;
+  }
+  return false;
+}
+
+constexpr int kBulkSmem = kRingBytes + 2 * 16 * 8;
 
 template <int MODE, int G, int SLOTS>
 int launch_bulk_cfg(BulkArgs a, cudaStream_t st) {
@@ -629,10 +813,8 @@ int launch_adain(const AdainArgs& a, cudaStream_t st) {
 int merge_raw_into_state(const float2* raw, int N, int C, int64_t hw, double* d_state,
                          cudaStream_t st) {
   const int blocks = (C + 7) / 8;
+  // (the block that draws the last ticket stores the new count: see bump_count_last_block)
   merge_planes_kernel<<<blocks, 256, 0, st>>>(raw, N, C, (double)hw, d_state);
-  CCST_LAUNCHED();
-  // state[0] (the count) is read by every block above and bumped afterwards, in stream order
-  bump_count_kernel<<<1, 1, 0, st>>>(d_state, (double)hw * N);
   CCST_LAUNCHED();
   return CCST_OK;
 }
@@ -657,6 +839,8 @@ extern "C" int ccst_welford_accumulate_nchw_f32(const float* d_x, int N, int C, 
   CCST_CHECK_ARG(d_x && d_state && d_scratch, "ccst_welford_accumulate_nchw_f32: null pointer");
   CCST_CHECK_ARG(N >= 1 && C >= 1 && hw >= 1, "ccst_welford_accumulate_nchw_f32: bad shape");
   if (int e = require_sm100()) return e;
+  int rc = CCST_OK;
+  if (launch_acc(d_x, N, C, hw, d_state, (cudaStream_t)stream, &rc)) return rc;  // one launch, no scratch
   StatsArgs a{d_x, (int64_t)N * C, hw, 0.f, 0, nullptr, nullptr,
               reinterpret_cast<float2*>(d_scratch)};
   if (int e = launch_stats<OUT_MEAN_M2>(a, (cudaStream_t)stream)) return e;

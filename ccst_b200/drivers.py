@@ -149,6 +149,31 @@ def single_style_stat(engine: Engine, style_image: torch.Tensor, precision: str 
     return list(acc.state.finalize())
 
 
+class _StyleSet:
+    """The loop's style images on the device (uploaded once: the reference re-opens the drawn image from
+    disk every batch, CCST_SingleStyleTransfer.py:196-198; here the set is fixed for the loop).  Sets larger
+    than `limit_bytes` stay on the host and are uploaded when drawn."""
+
+    def __init__(self, engine: Engine, style_images: Sequence[torch.Tensor], limit_bytes: int = 4 << 30):
+        self.engine = engine
+        self.host = list(style_images)
+        total = sum(im.numel() * im.element_size() for im in self.host)
+        self.dev = [im.to(engine.device) for im in self.host] if total <= limit_bytes else None
+        shapes = {tuple(im.shape[1:]) for im in self.host}
+        # same-size sets are stacked so that a per-image draw is one gather
+        self.stack = torch.cat(self.dev) if (self.dev is not None and len(shapes) == 1 and
+                                             all(im.shape[0] == 1 for im in self.host)) else None
+
+    def get(self, k: int) -> torch.Tensor:
+        return self.dev[k] if self.dev is not None else self.host[k].to(self.engine.device, non_blocking=True)
+
+    def gather(self, ks: Sequence[int]) -> Optional[torch.Tensor]:
+        if self.stack is None:
+            return None
+        idx = torch.tensor(list(ks), dtype=torch.int64).to(self.engine.device, non_blocking=True)
+        return self.stack.index_select(0, idx)
+
+
 def single_transfer(engine: Engine, host_batches: Iterable[torch.Tensor], style_images: Sequence[torch.Tensor],
                     alpha: float = 1.0, precision: str = DEFAULT_PRECISION, seed: int = 1):
     """Inner loop of CCST_SingleStyleTransfer.py:176-223: per BATCH one style image drawn with
@@ -156,10 +181,11 @@ def single_transfer(engine: Engine, host_batches: Iterable[torch.Tensor], style_
     GPU, then the transfer."""
     rng = random.Random(seed)
     pipe = TransferPipeline(engine, precision)
+    styles = _StyleSet(engine, style_images)
 
     def stat_for(i, x):
-        img = rng.choice(style_images)
-        return single_style_stat(engine, img.to(engine.device, non_blocking=True), precision)
+        k = rng.choice(range(len(style_images)))  # == rng.choice(style_images): one _randbelow(len) draw
+        return single_style_stat(engine, styles.get(k), precision)
 
     return pipe.run(host_batches, stat_for, alpha)
 
@@ -174,15 +200,17 @@ def single_transfer_per_image(engine: Engine, host_batches: Iterable[torch.Tenso
     statistics kernel, and AdaIN takes them as [N,512,1,1] (`stat_batch_stride = C`)."""
     rng = random.Random(seed)
     pipe = TransferPipeline(engine, precision)
+    styles = _StyleSet(engine, style_images)
 
     def stat_for(i, x):
         n = x.shape[0]
-        imgs = [rng.choice(style_images) for _ in range(n)]
-        shapes = {tuple(im.shape[1:]) for im in imgs}
-        if len(shapes) == 1:
-            feats = engine.encode(torch.cat(imgs).to(engine.device, non_blocking=True), precision)
-            return list(F_.calc_mean_std_biased(feats))
-        stats = [single_style_stat(engine, im.to(engine.device, non_blocking=True), precision) for im in imgs]
+        ks = [rng.choice(range(len(style_images))) for _ in range(n)]
+        batch = styles.gather(ks)
+        if batch is None and len({tuple(style_images[k].shape[1:]) for k in ks}) == 1:
+            batch = torch.cat([styles.get(k) for k in ks])
+        if batch is not None:
+            return list(F_.calc_mean_std_biased(engine.encode(batch, precision)))
+        stats = [single_style_stat(engine, styles.get(k), precision) for k in ks]
         return [torch.cat([s[0] for s in stats]), torch.cat([s[1] for s in stats])]
 
     return pipe.run(host_batches, stat_for, alpha)

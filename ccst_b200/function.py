@@ -159,12 +159,13 @@ def adaptive_instance_normalization(content_feat, style_feat, alpha=1.0):
 class WelfordState:
     """Device-resident running {count, mean[C], M2[C]} (fp64) of one client's features:
     the numerically safe replacement of `all_feat_sum, all_feat_square_sum, all_count`
-    (mean_std_computation_effcientMem.py:117)."""
+    (mean_std_computation_effcientMem.py:117).  The buffer is 2 + 2C doubles: the last word is the
+    ticket the accumulating kernels use to publish the new count (see ccst_b200.h)."""
 
     def __init__(self, channels: int, device):
         self.C = int(channels)
         self.device = torch.device(device)
-        self.buf = torch.zeros((1 + 2 * self.C,), dtype=torch.float64, device=self.device)
+        self.buf = torch.zeros((2 + 2 * self.C,), dtype=torch.float64, device=self.device)
 
     def reset(self):
         self.buf.zero_()
@@ -209,7 +210,7 @@ class WelfordState:
 
     def moments(self):
         """Exactly-summable fp64 vector {n, n*mean, M2 + n*mean^2} (the all-reduce payload)."""
-        m = torch.empty_like(self.buf)
+        m = torch.empty((1 + 2 * self.C,), dtype=torch.float64, device=self.device)
         with _lib.on_device(self.device):
             _lib.check(_lib.lib().ccst_welford_to_moments(
                 self.buf.data_ptr(), self.C, m.data_ptr(),

@@ -68,13 +68,15 @@ int ccst_stats_nchw_f32(const float* d_x, int64_t planes, int64_t hw, float eps,
 
 /* Running per-channel Welford state of one client
  * [mean_std_computation_effcientMem.py:117 `all_feat_sum, all_feat_square_sum,
- * all_count`], kept on the device as 1+2C doubles: {count, mean[C], M2[C]}.
- * Zero it (cudaMemset) to start a client. */
+ * all_count`], kept on the device as 2+2C doubles: {count, mean[C], M2[C], ticket}.  The last word is
+ * scratch of the accumulating kernels (the block that finishes last publishes the new count through it;
+ * it is zero between calls).  Zero the whole buffer (cudaMemset) to start a client. */
 
 /* calc_sum(feat) + `all_* += ...`  [mean_std_computation_effcientMem.py:103-115,129-131]
- * Folds the batch d_x = [N,C,HW] into d_state with one pass over d_x
- * (per-plane Welford, then a Chan merge over N and into the state, in fp64).
- * d_scratch must hold 2*N*C floats. */
+ * Folds the batch d_x = [N,C,HW] into d_state with one pass over d_x (per-plane two-pass statistics in
+ * fp32, Chan merges over N and into the state in fp64, fixed order).  Planes of up to 16 KiB with
+ * 16-byte alignment run as ONE launch in which every CTA owns whole channels; other shapes take a
+ * statistics launch + a merge launch through d_scratch, which must hold 2*N*C floats. */
 int ccst_welford_accumulate_nchw_f32(const float* d_x, int N, int C, int64_t hw, double* d_state,
                                      float* d_scratch, void* stream);
 

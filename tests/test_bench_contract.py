@@ -35,8 +35,11 @@ def test_reference_arm_line():
 @pytest.mark.gpu
 def test_cuda_arm_line():
     """The CUDA arm at a reduced batch (contract only; the numbers are the full bench's business)."""
-    d = _run(["--batch", "2", "--steps", "2", "--warmup", "3", "--no-cpu-baseline"], 900)
-    assert (BASE_KEYS | {"roofline", "clocks"}) <= set(d)
+    d = _run(["--batch", "2", "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--sustain-s", "1.0"], 900)
+    assert (BASE_KEYS | {"roofline", "clocks", "configs", "sustained", "gpu_eager_baseline"}) <= set(d)
+    assert {"config1_batch6_512", "config2_overall_stats_2048", "config4_single_style", "config5_camelyon_96"} <= set(d["configs"])
+    assert d["configs"]["config2_overall_stats_2048"]["allreduce_us"] == 0.0  # single rank: no collective
+    assert d["sustained"]["seconds"] >= 0.5 and d["sustained"]["value"] > 0
     assert d["value"] > 0 and d["gpu_launches"] > 0 and d["scaling"] == "weak" and d["dtype"] == "f16"
     r = d["roofline"]
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and 0 < r["frac"] and r["peak"] > 0

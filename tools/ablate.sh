@@ -1,5 +1,6 @@
 #!/bin/bash
-# pipeline-stage ablation of the tcgen05 conv kernels (timing only; outputs are garbage):
+# pipeline-stage ablation of the tcgen05 conv kernels (timing only; outputs are garbage).  The switch
+# exists only in a development build of the library:   python -m ccst_b200.build --dev --force
 # CCST_ABLATE bit 1 = epilogue does nothing, 2 = no MMAs, 4 = no activation (A) loads
 for a in 0 1 2 4 3 5 6 7; do
   echo "=== ABLATE=$a"

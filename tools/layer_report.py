@@ -13,7 +13,7 @@ import torch
 import ccst_b200
 from ccst_b200 import synth
 
-KIND = {0: "conv_first", 1: "conv_umma", 2: "conv_ffma", 3: "pool", 4: "adain/stats", 5: "convert"}
+KIND = {0: "conv_first", 1: "conv_umma", 2: "conv_ffma", 3: "pool", 4: "adain/stats", 5: "convert", 6: "adain_fold"}
 NAMES = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3", "conv3_4", "conv4_1",
          "adain", "dec1", "dec2", "dec3", "dec4", "dec5", "dec6", "dec7", "dec8", "dec9"]
 

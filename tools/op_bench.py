@@ -14,7 +14,7 @@ import torch
 
 from ccst_b200 import _lib
 
-PEAK = 6545.0
+PEAK = 6650.0  # fallback of /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
 if os.path.exists(p):
     PEAK = json.load(open(p))["hbm_gbs"]
@@ -49,7 +49,7 @@ def main():
         std = torch.empty_like(mean)
         mu = torch.randn((c,), device=dev)
         sg = torch.rand((c,), device=dev) + 0.1
-        state = torch.zeros((1 + 2 * c,), dtype=torch.float64, device=dev)
+        state = torch.zeros((2 + 2 * c,), dtype=torch.float64, device=dev)
         scratch = torch.empty((2 * n * c,), device=dev)
         nbytes = xs[0].numel() * 4
         t = timeit(lambda i: L.ccst_stats_nchw_f32(xs[i & 1].data_ptr(), n * c, h * w, 1e-5, 1, mean.data_ptr(),
@@ -62,10 +62,10 @@ def main():
                                                                 scratch.data_ptr(), st), a.iters)
         rows.append(("welford_accumulate", (n, c, h, w), t, nbytes + 16 * n * c))
         del xs, out
-    print(f"{'op':20s} {'shape':22s} {'ms':>8s} {'GB/s':>8s} {'frac of ' + str(PEAK):>14s}")
+    print(f"{'op':20s} {'shape':22s} {'MB':>7s} {'ms':>8s} {'GB/s':>8s} {'frac of ' + str(PEAK):>14s}")
     for name, shape, ms, by in rows:
         gbs = by / ms / 1e6
-        print(f"{name:20s} {str(shape):22s} {ms:8.4f} {gbs:8.1f} {gbs / PEAK:14.3f}")
+        print(f"{name:20s} {str(shape):22s} {by / 1e6:7.1f} {ms:8.4f} {gbs:8.1f} {gbs / PEAK:14.3f}")
 
 
 if __name__ == "__main__":
