@@ -21,6 +21,20 @@ constexpr int kSmOutW = kTileW - 2;                 // 14 output columns per til
 constexpr int kSmN = 192;
 constexpr int kSmStoreBytes = kTileH * kSmOutW * 128;  // 14336 = 14 x 1024
 
+// halo aliases of pixel (y, x) for a 16-channel quarter (two 16-byte stores per alias)
+template <typename T16>
+__device__ __forceinline__ void store_aliases_q(const ActView<T16>& out, int n, int y, int x, int co,
+                                                const uint32_t (&pk)[8], int edge = 1) {
+  const bool ya = (y == edge) || (y == out.H - 1 - edge), xa = (x == edge) || (x == out.W - 1 - edge);
+  if (!(ya || xa)) return;
+  for_each_halo_alias(y, x, out.H, out.W, [&](int yy, int xx) {
+    if (yy == y && xx == x) return;
+    uint4* dst = reinterpret_cast<uint4*>(out.px(n, yy, xx) + co);
+    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }, edge);
+}
+
 // Two 4-warp epilogue groups (tile i is drained by group i % 2 from accumulator stage i % 2).  A third
 // group was measured to buy nothing: the epilogue alone gets faster (0.50 -> 0.41 ms on conv1_2) but
 // not the kernel (0.59 ms), see DESIGN.md.
@@ -92,8 +106,17 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   auto lead = [&](uint32_t bar) { return CG == 2 ? mapa_rank(bar, 0) : bar; };
-  const int unit0 = CG == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
-  const int unit_step = CG == 2 ? (int)ncluster_x() : (int)gridDim.x;
+  // Work units of this CTA (pair): normally unit_id, unit_id + unit_cnt, ... (concurrent CTAs on neighbouring
+  // tiles: shared halos stay in L2).  When the stride in tiles is a multiple of tiles_x -- 148 = 4 x 37 at
+  // 512 px -- that order hands a CTA the same tile column over and over, and the CTAs that own the image-border
+  // columns, with their halo-alias stores, finish 40 % after the average (ncu sm__cycles_elapsed.max vs
+  // sm__cycles_active.avg); the launcher then asks for CONTIGUOUS ranges (p.contig_units).
+  const int unit_id = CG == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_cnt = CG == 2 ? (int)ncluster_x() : (int)gridDim.x;
+  const int units_lo = p.total_tiles / unit_cnt, units_rem = p.total_tiles % unit_cnt;
+  const int unit_begin = p.contig_units ? unit_id * units_lo + min(unit_id, units_rem) : unit_id;
+  const int unit_end = p.contig_units ? unit_begin + units_lo + (unit_id < units_rem ? 1 : 0) : p.total_tiles;
+  const int unit_inc = p.contig_units ? 1 : unit_cnt;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -138,7 +161,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     pdl_wait();
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
-    for (int unit = unit0; unit < p.total_tiles; unit += unit_step) {
+    for (int unit = unit_begin; unit < unit_end; unit += unit_inc) {
       const TileCoord t = decode_tile_sm<CG>(p, unit, (int)cta_rank);
       for (int kc = 0; kc < kchunks; ++kc) {
         MBAR_WAIT_RELAXED(a_empty(as), aph ^ 1, 500 + as);
@@ -174,7 +197,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         mbar_wait(bres_bar, 0, 560);
         tc_fence_after();
       }
-      for (int unit = unit0; unit < p.total_tiles; unit += unit_step, ++it) {
+      for (int unit = unit_begin; unit < unit_end; unit += unit_inc, ++it) {
         const int acs = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         if (CG == 2) mbar_wait_cluster(tmem_empty_bar(acs), aphase ^ 1, 570 + acs);
@@ -212,10 +235,21 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue: two groups of 4 warps, group g drains accumulator stage g.
-    // (Letting all 8 warps share every tile -- half the channels each, to halve the time an
-    // accumulator stage is held -- was measured SLOWER, 0.59 -> 0.73 ms on dec8, both with a joint
-    // 256-thread barrier per tile and with two fully independent half-channel groups.)
+    // ===================== epilogue: two groups of 4 warps, group g drains accumulator stage g (tiles g,
+    // g + 2, ...).  The group's work per tile -- 192 accumulator columns, two shuffles and three adds per
+    // output, packing, pooling -- is what bounds conv1_2 (ncu, round 1: tensor pipe 68 %, the MMA warp
+    // waiting for the accumulator stage), so:
+    //   * the stage is handed back after HALF of the columns have been worked on: channel quarters 0 and 1
+    //     are read and processed one at a time, quarters 2 and 3 are read together (96 registers) and the
+    //     stage released before their math (round 1 released it after three quarters of the epilogue);
+    //   * the three adds of two neighbouring channels run as packed FADD2 (add.rn.f32x2), same operation
+    //     order and rounding as before;
+    //   * each quarter goes to the staging tile as soon as it is packed (8 instead of 32 live registers);
+    //   * tile coordinates advance incrementally (no integer divisions per tile), ReLU / interior-tile
+    //     variants are separate instances of the loop body (no per-word selects, one-instruction range guard).
+    // (Four groups of channel quarters on every tile were measured much slower, 0.60 -> 0.86 ms: the per-tile
+    // overhead is paid by 16 warps and every scheduler is issue-bound.  Letting all 8 warps share every tile
+    // was slower as well, 0.59 -> 0.73 ms on dec8.)
     const int grp = (warp - kEpiWarp0) >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;   // TMEM lane = slab pixel (jy, jx)
@@ -224,18 +258,162 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     const bool col_ok = jx >= 1 && jx <= kSmOutW;
     const bool issuer_warp = (quad == 0);
     const uint32_t sbuf = store_base + grp * kSmStoreBytes;
+    int srow = jy * kSmOutW + ox;
+    bool writer = col_ok;
+    if (EPI == EPI_ACT_POOL) {
+      writer = col_ok && (jx & 1) && lane < 16;  // anchor of a 2x2 window
+      srow = (jy >> 1) * (kSmOutW / 2) + (ox >> 1);
+    }
+    const uint32_t srow_addr = sbuf + (uint32_t)srow * 128u;
+    const uint32_t sw = (uint32_t)(srow & 7);
+    const float2* s_bias2 = reinterpret_cast<const float2*>(s_bias);
     SatTracker<T16> sat;
-    for (int it = grp;; it += 2) {
-      const long long unit_ll = (long long)unit0 + (long long)it * unit_step;
-      if (unit_ll >= p.total_tiles) break;
-      const TileCoord t = decode_tile_sm<CG>(p, (int)unit_ll, (int)cta_rank);
+    // tile of this CTA for it = grp, advancing by two units per iteration, kept as (tx, ty, n)
+    const int per_img = p.tiles_x * p.tiles_y;
+    int tx, ty, tn;
+    {
+      const long long m0 = ((long long)unit_begin + (long long)grp * unit_inc) * CG + cta_rank;
+      tx = (int)(m0 % p.tiles_x), ty = (int)((m0 / p.tiles_x) % p.tiles_y), tn = (int)(m0 / per_img);
+    }
+    const int dm = 2 * unit_inc * CG;  // two units per iteration of a group
+    const int dx = dm % p.tiles_x, dy = (dm / p.tiles_x) % p.tiles_y, dn = dm / per_img;
+
+    // one tile; RELU / FULL (= every window of the tile lies inside the image) are compile-time here
+    auto tile_body = [&](auto relu_tag, auto full_tag, int it) {
+      constexpr bool RELU = decltype(relu_tag)::value, FULL = decltype(full_tag)::value;
       const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      const int y = t.y0 + jy, x = t.x0 + ox;
-      const bool valid = col_ok && (y < p.H) && (x < p.W) && (CG == 1 || t.n < p.N);
+      const int x0 = tx * kSmOutW, y0 = ty * kTileH;
+      const int y = y0 + jy, x = x0 + ox;
+      const bool valid = col_ok && (FULL || ((y < p.H) && (x < p.W) && (CG == 1 || tn < p.N)));
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kSmN);
+      // does this thread's pixel have halo aliases (direct stores beside the tile's TMA store)?
+      bool border;
+      if (EPI == EPI_ACT) {
+        const int e = p.halo_edge;
+        border = valid && (y == e || y == p.out.H - 1 - e || x == e || x == p.out.W - 1 - e);
+      } else if (EPI == EPI_ACT_POOL) {
+        const int yp = y >> 1, xp = x >> 1;
+        border = valid && writer && (yp == 1 || yp == p.out.H - 2 || xp == 1 || xp == p.out.W - 2);
+      } else {
+        border = valid && (y <= 1 || y >= p.H - 2 || x <= 1 || x >= p.W - 2);  // upsampled pixels 2y + a, 2x + b
+      }
+      auto release = [&]() {
+        // all TMEM reads of this accumulator stage are complete: hand it back before the math
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(lead(tmem_empty_bar(as)));
+          else mbar_arrive(tmem_empty_bar(as));
+        }
+      };
+      // the group's staging tile was read out by the TMA store of its previous tile (two tile times ago)
+      if (issuer_warp) bulk_wait_read<0>();
+      epi_barrier(grp);
+      // Shuffles are convergent operations: the compiler keeps them in program order.  Written value by
+      // value (shuffle, add, pack, pool-shuffle, max, ...) every output's ~100-cycle dependency chain ran
+      // to its end before the next one's first shuffle could issue -- 32 chains back to back per tile, which
+      // is what bounded this epilogue (ncu: one instruction per 4.2 cycles and warp, stall_wait + short
+      // scoreboard).  So each quarter is written in phases: all 32 neighbour shuffles, then all adds and
+      // packs, then the 8 + 8 pooling shuffles.
+      auto quarter = [&](int cq, const uint32_t (&a)[16], const uint32_t (&b)[16], const uint32_t (&c)[16]) {
+        uint32_t pk[8];
+        float lft[16], rgt[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) lft[q] = __shfl_up_sync(0xffffffffu, __uint_as_float(a[q]), 1);    // P[jx-1][s=0]
+#pragma unroll
+        for (int q = 0; q < 16; ++q) rgt[q] = __shfl_down_sync(0xffffffffu, __uint_as_float(c[q]), 1);  // P[jx+1][s=2]
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 mid = add2_f32(make_float2(__uint_as_float(b[2 * j]), __uint_as_float(b[2 * j + 1])),
+                                      s_bias2[cq * 8 + j]);
+          const float2 v = add2_f32(add2_f32(make_float2(lft[2 * j], lft[2 * j + 1]), mid),
+                                    make_float2(rgt[2 * j], rgt[2 * j + 1]));  // (lft + (b + bias)) + rgt
+          uint32_t w = RELU ? pack16x2_relu<T16>(v.x, v.y) : pack16x2<T16>(v.x, v.y);
+          // pooling below: pixels outside the image contribute 0 (the identity for post-ReLU values)
+          if (EPI == EPI_ACT_POOL && !FULL) w = valid ? w : 0u;
+          pk[j] = w;
+        }
+        if (EPI == EPI_ACT_POOL) {
+          // 2x2 window: columns (jx odd, jx + 1), rows (jy even, jy + 1) = lanes l, l+1, l^16, ...,
+          // pooled on the packed pairs (exact, see max16x2)
+          uint32_t t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = __shfl_down_sync(0xffffffffu, pk[j], 1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = max16x2<T16>(pk[j], t[j]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = __shfl_xor_sync(0xffffffffu, pk[j], 16);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = max16x2<T16>(pk[j], t[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (RELU) sat.track_nonneg(pk[j]); else sat.track(pk[j]);
+        }
+        if (writer) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_addr + (((uint32_t)(2 * cq) ^ sw) << 4)),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_addr + (((uint32_t)(2 * cq + 1) ^ sw) << 4)),
+                       "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                       : "memory");
+        }
+        if (border) {  // (rare: decided once per tile)
+          if (EPI == EPI_ACT) {
+            store_aliases_q(p.out, tn, y, x, cq * 16, pk, p.halo_edge);
+          } else if (EPI == EPI_ACT_UP2) {
+#pragma unroll
+            for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+              for (int bb = 0; bb < 2; ++bb) store_aliases_q(p.out, tn, 2 * y + aa, 2 * x + bb, cq * 16, pk);
+          } else if (EPI == EPI_ACT_POOL) {
+            store_aliases_q(p.out, tn, y >> 1, x >> 1, cq * 16, pk);
+          }
+        }
+      };
+#pragma unroll
+      for (int cq = 0; cq < 2; ++cq) {
+        uint32_t a[16], b[16], c[16];
+        tmem_ld16(taddr + 0 * 64 + cq * 16, a);
+        tmem_ld16(taddr + 1 * 64 + cq * 16, b);
+        tmem_ld16(taddr + 2 * 64 + cq * 16, c);
+        tmem_ld_wait();
+        quarter(cq, a, b, c);
+      }
+      {
+        uint32_t a2[16], b2[16], c2[16], a3[16], b3[16], c3[16];
+        tmem_ld16(taddr + 0 * 64 + 32, a2);
+        tmem_ld16(taddr + 1 * 64 + 32, b2);
+        tmem_ld16(taddr + 2 * 64 + 32, c2);
+        tmem_ld16(taddr + 0 * 64 + 48, a3);
+        tmem_ld16(taddr + 1 * 64 + 48, b3);
+        tmem_ld16(taddr + 2 * 64 + 48, c3);
+        tmem_ld_wait();
+        release();
+        quarter(2, a2, b2, c2);
+        quarter(3, a3, b3, c3);
+      }
+      fence_async_smem();
+      epi_barrier(grp);
+      if (issuer_warp && elect_one()) {
+        if (EPI == EPI_ACT_POOL) {
+          tma_store_4d(&tmap_out.m[0], sbuf, 0, x0 >> 1, y0 >> 1, tn);
+        } else {
+          tma_store_4d(&tmap_out.m[0], sbuf, 0, x0, y0, tn);
+          if (EPI == EPI_ACT_UP2) {
+            tma_store_4d(&tmap_out.m[1], sbuf, 0, x0, y0, tn);
+            tma_store_4d(&tmap_out.m[2], sbuf, 0, x0, y0, tn);
+            tma_store_4d(&tmap_out.m[3], sbuf, 0, x0, y0, tn);
+          }
+        }
+        bulk_commit();
+      }
+    };
+
+    for (int it = grp; (long long)unit_begin + (long long)it * unit_inc < unit_end; it += 2) {
+      const int as = it & 1;
       MBAR_WAIT_RELAXED(tmem_full_bar(it % Cfg::kFullBars), (uint32_t)(it / Cfg::kFullBars) & 1u, 600 + as);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kSmN);
       if (CCST_ABLATE_BITS(p) & 1) {  // measurement only: hand the accumulator back untouched
         tc_fence_before();
         __syncwarp();
@@ -243,92 +421,23 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           if (CG == 2) mbar_arrive_cluster(lead(tmem_empty_bar(as)));
           else mbar_arrive(tmem_empty_bar(as));
         }
-        continue;
-      }
-      uint32_t pk[32];
-#pragma unroll
-      for (int cq = 0; cq < 4; ++cq) {
-        uint32_t a[16], b[16], c[16];
-        tmem_ld16(taddr + 0 * 64 + cq * 16, a);
-        tmem_ld16(taddr + 1 * 64 + cq * 16, b);
-        tmem_ld16(taddr + 2 * 64 + cq * 16, c);
-        tmem_ld_wait();
-        if (cq == 3) {
-          // all TMEM reads of this accumulator stage are complete: hand it back before the math
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (CG == 2) mbar_arrive_cluster(lead(tmem_empty_bar(as)));
-            else mbar_arrive(tmem_empty_bar(as));
-          }
-        }
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float lft = __shfl_up_sync(0xffffffffu, __uint_as_float(a[j]), 1);    // P[jx-1][s=0]
-          const float rgt = __shfl_down_sync(0xffffffffu, __uint_as_float(c[j]), 1);  // P[jx+1][s=2]
-          v[j] = (lft + (__uint_as_float(b[j]) + s_bias[cq * 16 + j])) + rgt;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint32_t w = p.relu ? pack16x2_relu<T16>(v[2 * j], v[2 * j + 1])
-                              : pack16x2<T16>(v[2 * j], v[2 * j + 1]);
-          if (EPI == EPI_ACT_POOL) {
-            // 2x2 window: columns (jx odd, jx + 1), rows (jy even, jy + 1) = lanes l, l+1, l^16, ...,
-            // pooled on the packed pairs (exact, see max16x2); invalid pixels contribute 0
-            w = valid ? w : 0u;
-            w = max16x2<T16>(w, __shfl_down_sync(0xffffffffu, w, 1));
-            w = max16x2<T16>(w, __shfl_xor_sync(0xffffffffu, w, 16));
-          }
-          pk[cq * 8 + j] = w;
-          sat.track(w);
-        }
-      }
-      // the staging buffer about to be rewritten must have been read out by its TMA store
-      if (issuer_warp) bulk_wait_read<0>();
-      epi_barrier(grp);
-      int srow = jy * kSmOutW + ox;
-      bool writer = col_ok;
-      if (EPI == EPI_ACT_POOL) {
-        writer = col_ok && (jx & 1) && lane < 16;  // anchor of a 2x2 window
-        srow = (jy >> 1) * (kSmOutW / 2) + (ox >> 1);
-      }
-      if (writer) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t dst = sbuf + srow * 128 + ((j ^ (srow & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
-                       "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                       : "memory");
-        }
-      }
-      if (valid) {
-        if (EPI == EPI_ACT) {
-          store_aliases(p.out, t.n, y, x, 0, pk, p.halo_edge);
-        } else if (EPI == EPI_ACT_UP2) {
-#pragma unroll
-          for (int aa = 0; aa < 2; ++aa)
-#pragma unroll
-            for (int bb = 0; bb < 2; ++bb) store_aliases(p.out, t.n, 2 * y + aa, 2 * x + bb, 0, pk);
-        } else if (EPI == EPI_ACT_POOL) {
-          if (writer) store_aliases(p.out, t.n, y >> 1, x >> 1, 0, pk);
-        }
-      }
-      fence_async_smem();
-      epi_barrier(grp);
-      if (issuer_warp && elect_one()) {
-        if (EPI == EPI_ACT_POOL) {
-          tma_store_4d(&tmap_out.m[0], sbuf, 0, t.x0 >> 1, t.y0 >> 1, t.n);
+      } else {
+        const bool full = (ty * kTileH + kTileH <= p.H) && (tx * kSmOutW + kSmOutW <= p.W) && (CG == 1 || tn < p.N);
+        if (p.relu) {
+          if (full) tile_body(std::true_type{}, std::true_type{}, it);
+          else tile_body(std::true_type{}, std::false_type{}, it);
         } else {
-          tma_store_4d(&tmap_out.m[0], sbuf, 0, t.x0, t.y0, t.n);
-          if (EPI == EPI_ACT_UP2) {
-            tma_store_4d(&tmap_out.m[1], sbuf, 0, t.x0, t.y0, t.n);
-            tma_store_4d(&tmap_out.m[2], sbuf, 0, t.x0, t.y0, t.n);
-            tma_store_4d(&tmap_out.m[3], sbuf, 0, t.x0, t.y0, t.n);
-          }
+          tile_body(std::false_type{}, std::false_type{}, it);
         }
-        bulk_commit();
       }
+      // next tile of this group
+      tx += dx;
+      int carry = tx >= p.tiles_x;
+      tx -= carry ? p.tiles_x : 0;
+      ty += dy + carry;
+      carry = ty >= p.tiles_y;
+      ty -= carry ? p.tiles_y : 0;
+      tn += dn + carry;
     }
     if (issuer_warp) bulk_wait_all();
     sat.flush(p.sat_count);
@@ -366,6 +475,7 @@ int launch_smerge_cfg(const CUtensorMap& ma, const T16* wk_sm, ConvParams<T16> p
   p.total_tiles = (int)units;
   const int slots = sm_count() / CG;
   const int grid = (int)(units < slots ? units : slots) * CG;
+  p.contig_units = ((grid / CG) * CG) % p.tiles_x == 0 ? 1 : 0;  // stride resonates with the tile columns
   CCST_CUDA(launch_conv(conv_smerge_kernel<T16, EPI, BRES, CG>, grid, Cfg::kThreads, Cfg::kSmemBytes, st, CG, ma,
                         mb, mo, p));
   CCST_LAUNCHED();

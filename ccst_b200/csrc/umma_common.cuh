@@ -5,6 +5,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <utility>
 
 #include "layers.h"
@@ -53,6 +54,7 @@ struct ConvParams {
   // rows n * w_rows_per_n + ... of the weight map and the bias bias[n * bias_per_n + co]; both 0 otherwise
   int w_rows_per_n, bias_per_n;
   int m_tiles_img;  // pixel tiles per image (padded to even for CTA pairs when weights are per sample)
+  int contig_units; // s-merged kernel: every CTA takes a contiguous range of work units instead of a strided one
   const float* bias;
   ActView<T16> out;
   float* out_nchw;
@@ -378,6 +380,17 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((CG * kBlockM) >> 4) << 24);
 }
 
+// two fp32 additions in one instruction (FADD2); each half rounds like a scalar add.rn.f32
+__device__ __forceinline__ float2 add2_f32(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
 struct TileCoord {
   int n, y0, x0, nt, ph;
   int nw;  // image whose weights the tile uses (per-sample weights only)
@@ -390,12 +403,15 @@ struct TileCoord {
 template <typename T16>
 struct SatTracker {
   __device__ __forceinline__ void track(uint32_t) {}
+  __device__ __forceinline__ void track_nonneg(uint32_t) {}
   __device__ __forceinline__ void flush(unsigned int*) {}
 };
 template <>
 struct SatTracker<__half> {
   uint32_t m = 0u;
   __device__ __forceinline__ void track(uint32_t w) { m = max16x2<__half>(m, w & 0x7fff7fffu); }
+  // values known to be >= 0 (packed with ReLU): one instruction
+  __device__ __forceinline__ void track_nonneg(uint32_t w) { m = max16x2<__half>(m, w); }
   __device__ __forceinline__ void flush(unsigned int* counter) {
     // bit patterns of non-negative halves order like the values; 0x7bff = 65504, above = inf / NaN
     const bool hit = (m & 0xffffu) >= 0x7bffu || (m >> 16) >= 0x7bffu;
