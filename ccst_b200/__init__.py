@@ -13,12 +13,13 @@ an operator without one raises.
 """
 from .function import (EPS, WelfordState, adaIN_StyleStat_ContentFeat, adain_blend,
                        adaptive_instance_normalization, calc_mean_std, calc_mean_std_batch,
-                       calc_mean_std_vector, calc_sum)
-from .transfer import (Engine, engine_for, resize, save_image_quantize, style_transfer,
+                       calc_mean_std_vector, calc_sum, mixstyle, mixstyle_stats, mse_loss)
+from .transfer import (Engine, engine_for, resize, resize_input_u8, save_image_quantize, style_transfer,
                        style_transfer_u8, to_tensor_u8)
 
 __all__ = [
     "EPS", "WelfordState", "adaIN_StyleStat_ContentFeat", "adain_blend",
     "adaptive_instance_normalization", "calc_mean_std", "calc_mean_std_batch", "calc_mean_std_vector", "calc_sum",
-    "Engine", "engine_for", "style_transfer", "style_transfer_u8", "to_tensor_u8", "save_image_quantize", "resize",
+    "mse_loss", "mixstyle", "mixstyle_stats",
+    "Engine", "engine_for", "style_transfer", "style_transfer_u8", "to_tensor_u8", "save_image_quantize", "resize", "resize_input_u8",
 ]

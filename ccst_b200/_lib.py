@@ -47,7 +47,11 @@ PROTOTYPES = {
     "ccst_style_transfer_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i64, _f, _vp, _i, _vp]),
     "ccst_u8_to_tensor": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "ccst_quantize_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "ccst_resize_pil_scratch_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
+    "ccst_resize_pil_bilinear_u8": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "ccst_resize_bilinear_aa_f32": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "ccst_encoder_levels": (_i, [_vp, _vp, _i, _i, _i, _vp, _pp, _pp, _f, _i, _vp]),
+    "ccst_mse_f32": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "ccst_encoder_accumulate": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "ccst_encoder_accumulate_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "ccst_saturation_snapshot": (_i, [_vp, _vp, _vp]),

@@ -3,6 +3,7 @@
 // Pipelines follow vgg[:31] (net.py:38-69), decoder (net.py:6-36) and style_transfer
 // (CCST_OverallStyleTransfer.py:32-46).  Activations never leave the device arena between layers;
 // the only NCHW fp32 tensors are the caller's image / feature / output tensors.
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -387,6 +388,11 @@ struct Pipe {
   uint8_t* out_u8 = nullptr;  // decoder(): store NHWC uint8 (save_image quantisation) instead of NCHW fp32
   bool stats_in_tiles = false;  // the last encoder conv left tile statistics of `cur` in h->raw
   bool fold_pending = false;  // AdaIN of `cur` lives in h->w_fold / h->b_fold: the next conv applies it
+  // per-(n, c) mean / std (calc_mean_std) of relu1_1, relu2_1, relu3_1, relu4_1 while encoding
+  // (Net.encode_with_intermediate + calc_style_loss, net.py:112-136); NULL = not wanted
+  float* const* lvl_mean = nullptr;
+  float* const* lvl_std = nullptr;
+  float lvl_eps = 1e-5f;
 
   ActView<T> view(int slot, int N, int H, int W, int C) {
     ActView<T> v;
@@ -456,10 +462,26 @@ struct Pipe {
     return CCST_OK;
   }
 
+  // statistics of `cur` (one of the four relu*_1 maps) for the style losses
+  int level_stats(int level) {
+    if (!lvl_mean) return CCST_OK;
+    const int NC = cur.N * cur.C, HW = cur.H * cur.W;
+    ProfScope ps(h, st, 4, 0, (double)cur.elems() * sizeof(T));
+    if (int e = ensure_raw(h, nhwc_scratch_elems(cur.N, cur.C, HW))) return e;
+    if (int e = launch_stats_nhwc<T>(cur, h->raw, st)) return e;
+    return launch_raw_to_mean_std(h->raw, NC, HW, lvl_eps, 1, lvl_mean[level], lvl_std[level], st);
+  }
+
   int encoder(const float* img, int N, int H, int W) {
     if (int e = first(img, N, H, W)) return e;
-    for (int i = 0; i < kEncLayers; ++i)
-      if (int e = step(h->enc[i], kEncPoolAfter[i], false, i == kEncLayers - 1)) return e;
+    if (int e = level_stats(0)) return e;  // relu1_1
+    for (int i = 0; i < kEncLayers; ++i) {
+      // with level statistics on, relu4_1's come from the same pass as the other levels
+      if (int e = step(h->enc[i], kEncPoolAfter[i], false, i == kEncLayers - 1 && !lvl_mean)) return e;
+      if (i == 1) if (int e = level_stats(1)) return e;  // relu2_1 = conv2_1
+      if (i == 3) if (int e = level_stats(2)) return e;  // relu3_1 = conv3_1
+      if (i == 7) if (int e = level_stats(3)) return e;  // relu4_1 = conv4_1
+    }
     return CCST_OK;
   }
 
@@ -621,11 +643,13 @@ int run_style_transfer_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, in
 
 template <typename T>
 int run_encoder(ccst_handle* h, const float* d_img, int N, int H, int W, float* d_feat,
-                double* d_state, cudaStream_t st) {
+                double* d_state, cudaStream_t st, float* const* lvl_mean = nullptr, float* const* lvl_std = nullptr,
+                float lvl_eps = 1e-5f) {
   int fh, fw;
   ccst_feature_hw(H, W, &fh, &fw);
   if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T), true, false))) return e;
   Pipe<T> p{h, st};
+  p.lvl_mean = lvl_mean, p.lvl_std = lvl_std, p.lvl_eps = lvl_eps;
   if (int e = p.encoder(d_img, N, H, W)) return e;
   if (d_feat) {
     ProfScope ps(h, st, 5, 0, (double)N * fh * fw * 512 * (4.0 + sizeof(T)));
@@ -818,6 +842,24 @@ extern "C" int ccst_encoder_fwd(ccst_handle* h, const float* d_img, int N, int H
   CCST_DISPATCH(precision, run_encoder<T>(h, d_img, N, H, W, d_feat, nullptr, (cudaStream_t)stream));
 }
 
+extern "C" int ccst_encoder_levels(ccst_handle* h, const float* d_img, int N, int H, int W, float* d_feat,
+                                   float* const* d_mean, float* const* d_std, float eps, int precision,
+                                   void* stream) {
+  if (int e = check_common(h, precision)) return e;
+  CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_levels: encoder weights not set");
+  CCST_CHECK_ARG(d_img && d_mean && d_std && N >= 1 && H >= 8 && W >= 8, "ccst_encoder_levels: bad argument");
+  for (int l = 0; l < 4; ++l)
+    CCST_CHECK_ARG(d_mean[l] && d_std[l], "ccst_encoder_levels: null output for level %d", l);
+  CCST_DISPATCH(precision, run_encoder<T>(h, d_img, N, H, W, d_feat, nullptr, (cudaStream_t)stream, d_mean, d_std, eps));
+}
+
+extern "C" int ccst_mse_f32(const float* d_a, const float* d_b, int64_t n, double* d_scratch, float* d_out,
+                            void* stream) {
+  if (int e = require_sm100()) return e;
+  CCST_CHECK_ARG(d_a && d_b && d_scratch && d_out && n >= 1, "ccst_mse_f32: bad argument");
+  return launch_mse(d_a, d_b, n, d_scratch, d_out, (cudaStream_t)stream);
+}
+
 extern "C" int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N, int H, int W,
                                        double* d_state, int precision, void* stream) {
   if (int e = check_common(h, precision)) return e;
@@ -934,6 +976,75 @@ extern "C" int ccst_saturation_reset(ccst_handle* h, void* stream) {
   CCST_CUDA(cudaSetDevice(h->device));
   CCST_CUDA(cudaMemsetAsync(h->sat_count, 0, sizeof(unsigned int), (cudaStream_t)stream));
   return CCST_OK;
+}
+
+namespace {
+// Pillow's precompute_coeffs + normalize_coeffs_8bpc (Resample.c) for the bilinear filter (support 1),
+// in the same double arithmetic: per output index the window {first, count} and its fixed-point weights.
+int pil_bilinear_coeffs(int in_size, int out_size, std::vector<int>& kk, std::vector<int>& bounds) {
+  const double scale = (double)in_size / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * filterscale;
+  const int ksize = (int)ceil(support) * 2 + 1;
+  kk.assign((size_t)out_size * ksize, 0);
+  bounds.assign((size_t)out_size * 2, 0);
+  std::vector<double> w(ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    const double ss = 1.0 / filterscale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      double v = (x + xmin - center + 0.5) * ss;
+      if (v < 0.0) v = -v;
+      w[x] = v < 1.0 ? 1.0 - v : 0.0;
+      ww += w[x];
+    }
+    for (int x = 0; x < xmax; ++x) {
+      if (ww != 0.0) w[x] /= ww;
+      kk[(size_t)xx * ksize + x] = w[x] < 0 ? (int)(-0.5 + w[x] * (1 << 22)) : (int)(0.5 + w[x] * (1 << 22));
+    }
+    bounds[2 * xx] = xmin, bounds[2 * xx + 1] = xmax;
+  }
+  return ksize;
+}
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+}  // namespace
+
+extern "C" int64_t ccst_resize_pil_scratch_bytes(int N, int H, int W, int C, int OH, int OW) {
+  if (N < 1 || H < 1 || W < 1 || C < 1 || OH < 1 || OW < 1) return 0;
+  const int ksx = (int)ceil(W > OW ? (double)W / OW : 1.0) * 2 + 1, ksy = (int)ceil(H > OH ? (double)H / OH : 1.0) * 2 + 1;
+  return (int64_t)(align256((size_t)OW * ksx * 4) + align256((size_t)OW * 8) + align256((size_t)OH * ksy * 4) +
+                   align256((size_t)OH * 8) + align256((size_t)N * H * OW * C));
+}
+
+extern "C" int ccst_resize_pil_bilinear_u8(const uint8_t* d_in, int N, int H, int W, int C, int OH, int OW,
+                                           uint8_t* d_out, void* d_scratch, void* stream) {
+  if (int e = require_sm100()) return e;
+  CCST_CHECK_ARG(d_in && d_out && d_scratch && N >= 1 && H >= 1 && W >= 1 && C >= 1 && OH >= 1 && OW >= 1,
+                 "ccst_resize_pil_bilinear_u8: bad argument");
+  std::vector<int> kx, bx, ky, by;
+  const int ksx = pil_bilinear_coeffs(W, OW, kx, bx), ksy = pil_bilinear_coeffs(H, OH, ky, by);
+  uint8_t* sp = static_cast<uint8_t*>(d_scratch);
+  int* d_kx = reinterpret_cast<int*>(sp);
+  sp += align256(kx.size() * 4);
+  int* d_bx = reinterpret_cast<int*>(sp);
+  sp += align256(bx.size() * 4);
+  int* d_ky = reinterpret_cast<int*>(sp);
+  sp += align256(ky.size() * 4);
+  int* d_by = reinterpret_cast<int*>(sp);
+  sp += align256(by.size() * 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  // (pageable sources: the runtime stages them before returning, so the vectors may die at the end of the call)
+  CCST_CUDA(cudaMemcpyAsync(d_kx, kx.data(), kx.size() * 4, cudaMemcpyHostToDevice, st));
+  CCST_CUDA(cudaMemcpyAsync(d_bx, bx.data(), bx.size() * 4, cudaMemcpyHostToDevice, st));
+  CCST_CUDA(cudaMemcpyAsync(d_ky, ky.data(), ky.size() * 4, cudaMemcpyHostToDevice, st));
+  CCST_CUDA(cudaMemcpyAsync(d_by, by.data(), by.size() * 4, cudaMemcpyHostToDevice, st));
+  return launch_resize_pil_u8(d_in, N, H, W, C, OH, OW, d_kx, d_bx, ksx, d_ky, d_by, ksy, sp, d_out, st);
 }
 
 extern "C" int ccst_profile_enable(ccst_handle* h, int on) {

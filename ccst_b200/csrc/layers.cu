@@ -795,6 +795,66 @@ __global__ void __launch_bounds__(256) resize_aa_kernel(const float* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(256)
+    raw_to_mean_std_kernel(const float2* __restrict__ raw, int planes, float hw, float eps, int unbiased,
+                           float* __restrict__ mean, float* __restrict__ stdv) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= planes) return;
+  const float2 r = raw[i];
+  if (mean) mean[i] = r.x;
+  if (stdv) stdv[i] = sqrtf(r.y / (unbiased ? hw - 1.f : hw) + eps);  // hw == 1, unbiased: NaN as torch.var
+}
+
+// nn.MSELoss (net.py:104,124-136): mean of squared differences.  Stage 1: per-block double sums in a fixed
+// thread order; stage 2: one block adds the partials in index order -> bit-reproducible.
+constexpr int kMseBlocks = 1024;
+__global__ void __launch_bounds__(256)
+    mse_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, double* __restrict__ part) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float d = a[i] - b[i];
+    acc += (double)(d * d);  // the square in fp32 like torch's (input - target) ** 2, the sum in fp64
+  }
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = s[0];
+}
+__global__ void mse_final_kernel(const double* __restrict__ part, int blocks, double n, float* __restrict__ out) {
+  double acc = 0.0;
+  for (int i = 0; i < blocks; ++i) acc += part[i];
+  out[0] = (float)(acc / n);
+}
+
+// Pillow's ImagingResampleHorizontal_8bpc / Vertical_8bpc (src/libImaging/Resample.c): 22-bit fixed-point
+// coefficients, accumulator seeded with one half, result shifted and clamped to 0..255.  One thread per
+// output byte; `stride` = distance in bytes between successive taps of the window.
+constexpr int kPilPrecisionBits = 32 - 8 - 2;
+__global__ void __launch_bounds__(256)
+    resize_pil_pass_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t total, int out_len,
+                           size_t inner, size_t in_len, const int* __restrict__ kk, const int* __restrict__ bounds,
+                           int ks) {
+  // layout of both tensors: [outer][len][inner] with len = in_len (input) / out_len (output) along the
+  // resampled axis (inner = C for the horizontal pass, OW * C for the vertical one)
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const size_t in_idx = i % inner;
+    const size_t t = i / inner;
+    const int o = (int)(t % out_len);
+    const size_t outer = t / out_len;
+    const int first = bounds[2 * o], cnt = bounds[2 * o + 1];
+    const uint8_t* src = in + (outer * in_len + first) * inner + in_idx;
+    const int* k = kk + (size_t)o * ks;
+    int ss = 1 << (kPilPrecisionBits - 1);
+    for (int x = 0; x < cnt; ++x) ss += (int)src[(size_t)x * inner] * k[x];
+    ss >>= kPilPrecisionBits;
+    out[i] = (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+  }
+}
+
 int ew_grid(size_t total) {
   size_t blocks = (total + 255) / 256;
   size_t cap = (size_t)sm_count() * 16;
@@ -1008,6 +1068,23 @@ template int launch_adain_fold<__half>(int, int, int, int, int, float2*, const f
                                        float, const float*, const float*, const float*, __half*, float*,
                                        unsigned int*, cudaStream_t);
 
+int launch_raw_to_mean_std(const float2* raw, int planes, int64_t hw, float eps, int unbiased, float* mean,
+                           float* stdv, cudaStream_t st) {
+  raw_to_mean_std_kernel<<<(planes + 255) / 256, 256, 0, st>>>(raw, planes, (float)hw, eps, unbiased, mean, stdv);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+int launch_mse(const float* a, const float* b, int64_t n, double* scratch, float* out, cudaStream_t st) {
+  const int64_t want = (n + 255) / 256;
+  const int blocks = (int)(want < kMseBlocks ? (want > 0 ? want : 1) : kMseBlocks);
+  mse_partial_kernel<<<blocks, 256, 0, st>>>(a, b, n, scratch);
+  CCST_LAUNCHED();
+  mse_final_kernel<<<1, 1, 0, st>>>(scratch, blocks, (double)n, out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
 int launch_stats_from_tiles(int N, int C, int H, int W, float2* scratch, cudaStream_t st) {
   const int NC = N * C;
   nhwc_tiles_merge_kernel<<<NC / 32, 256, 0, st>>>(scratch + 2 * (size_t)NC, scratch, C, H, W);
@@ -1075,6 +1152,18 @@ int launch_u8_nhwc_to_f32_nchw(const uint8_t* in, int N, int C, int H, int W, fl
 int launch_quantize_nchw_to_u8_nhwc(const float* in, int N, int C, int H, int W, uint8_t* out, cudaStream_t st) {
   const size_t hw = (size_t)H * W, total = (size_t)N * hw;
   quantize_nchw_to_u8_nhwc_kernel<<<ew_grid(total), 256, 0, st>>>(in, C, hw, total, out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+int launch_resize_pil_u8(const uint8_t* in, int N, int H, int W, int C, int OH, int OW, const int* kx, const int* bx,
+                         int ksx, const int* ky, const int* by, int ksy, uint8_t* tmp, uint8_t* out, cudaStream_t st) {
+  // Pillow resamples horizontally first, then vertically (ImagingResample); a pass whose size does not
+  // change is skipped there and is the identity here (one coefficient of 1 << 22 per output index)
+  const size_t t1 = (size_t)N * H * OW * C, t2 = (size_t)N * OH * OW * C;
+  resize_pil_pass_kernel<<<ew_grid(t1), 256, 0, st>>>(in, tmp, t1, OW, (size_t)C, (size_t)W, kx, bx, ksx);
+  CCST_LAUNCHED();
+  resize_pil_pass_kernel<<<ew_grid(t2), 256, 0, st>>>(tmp, out, t2, OH, (size_t)OW * C, (size_t)H, ky, by, ksy);
   CCST_LAUNCHED();
   return CCST_OK;
 }

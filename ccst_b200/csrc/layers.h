@@ -63,6 +63,12 @@ int launch_adain_fold(int N, int C, int H, int W, int Cout, float2* scratch, con
 template <typename T>
 int launch_stats_nhwc(ActView<T> in, float2* scratch, cudaStream_t st);
 
+// raw[i] = {mean, M2} of a plane of `hw` values -> mean[i], std[i] = sqrt(M2 / (hw - unbiased) + eps)
+int launch_raw_to_mean_std(const float2* raw, int planes, int64_t hw, float eps, int unbiased, float* mean,
+                           float* stdv, cudaStream_t st);
+// out[0] = mean((a - b)^2) over n floats (nn.MSELoss), deterministic two-stage sum; scratch: 1024 doubles
+int launch_mse(const float* a, const float* b, int64_t n, double* scratch, float* out, cudaStream_t st);
+
 int merge_raw_into_state(const float2* raw, int N, int C, int64_t hw, double* d_state,
                          cudaStream_t st);
 
@@ -74,6 +80,11 @@ int launch_act_to_nchw(ActView<T> in, float* out_nchw, cudaStream_t st);
 // batch (torchvision utils.save_image: mul(255).add(0.5).clamp(0,255).to(uint8)) -> NHWC uint8.
 int launch_u8_nhwc_to_f32_nchw(const uint8_t* in, int N, int C, int H, int W, float* out, cudaStream_t st);
 int launch_quantize_nchw_to_u8_nhwc(const float* in, int N, int C, int H, int W, uint8_t* out, cudaStream_t st);
+// Pillow's 8-bit bilinear resample of a uint8 NHWC batch (the loader's `transforms.Resize((S, S))` on the PIL
+// image, cjm_util/data_helper.py:45-49): horizontal pass into `tmp` [N,H,OW,C], vertical pass into `out`
+// [N,OH,OW,C]; kx / ky: fixed-point coefficients [out][ks], bx / by: {first input index, count} per output index.
+int launch_resize_pil_u8(const uint8_t* in, int N, int H, int W, int C, int OH, int OW, const int* kx, const int* bx,
+                         int ksx, const int* ky, const int* by, int ksy, uint8_t* tmp, uint8_t* out, cudaStream_t st);
 // torch's anti-aliased bilinear resize of `planes` H x W fp32 planes to OH x OW (transforms.Resize on a tensor)
 int launch_resize_aa(const float* in, int64_t planes, int H, int W, int OH, int OW, float* out, cudaStream_t st);
 template <typename T>

@@ -705,6 +705,9 @@ bool launch_acc(const float* x, int N, int C, int64_t hw, double* state, cudaStr
   for (int ppc = 4; ppc >= 1; ppc >>= 1) {
     const int64_t cb = (int64_t)ppc * hw * 4;
     if (C % ppc != 0 || cb > kSlotBytesMax) continue;
+    // bulk copies of less than 4 KiB cost more to issue than they move (measured on [1024,512,12,12]: 2.3 KiB
+    // chunks ran 3x slower than the two-launch path, whose chunks are channel-agnostic and fill a ring slot)
+    if (cb < 4096) return false;
     const int cpi = C / ppc;
     int grid = 0;  // largest divisor of cpi that fits the SMs
     for (int g = (cpi < sms ? cpi : sms); g >= 1; --g)

@@ -156,6 +156,36 @@ def adaptive_instance_normalization(content_feat, style_feat, alpha=1.0):
     return out
 
 
+def mse_loss(a, b):
+    """nn.MSELoss()(a, b) (net.py:104): mean of squared differences as a 0-dim tensor; squares in fp32,
+    the sum in fp64 in a fixed order."""
+    assert (a.size() == b.size())
+    a, b = _prep(a, "a"), _prep(b, "b")
+    out = torch.empty((1,), dtype=torch.float32, device=a.device)
+    scratch = torch.empty((1024,), dtype=torch.float64, device=a.device)
+    with _lib.on_device(a.device):
+        _lib.check(_lib.lib().ccst_mse_f32(a.data_ptr(), b.data_ptr(), a.numel(), scratch.data_ptr(), out.data_ptr(),
+                                           _stream(a)))
+    return out[0]
+
+
+def mixstyle_stats(x, eps=1e-6):
+    """The statistics of MixStyle (nets/layers.py:46-49): mu = x.mean(dim=[2,3]), sig = sqrt(x.var(dim=[2,3])
+    + eps) with torch's default unbiased variance and MixStyle's eps = 1e-6 -- calc_mean_std with another eps."""
+    return calc_mean_std(x, eps)
+
+
+def mixstyle(x, lmda, perm, eps=1e-6):
+    """MixStyle's forward given its random draws (nets/layers.py:46-74): statistics of x, mixed with those
+    of x[perm] by lmda [B,1,1,1], re-applied to the normalised x -- one fused statistics + affine pass."""
+    mu, sig = mixstyle_stats(x, eps)
+    lmda = lmda.to(x.device, torch.float32).view(-1, 1, 1, 1)
+    perm = perm.to(x.device)
+    mu_mix = mu * lmda + mu[perm] * (1 - lmda)      # [B,C,1,1]: a few KB of host-side glue
+    sig_mix = sig * lmda + sig[perm] * (1 - lmda)
+    return adain_blend(x, (mu_mix, sig_mix), 1.0, eps)
+
+
 class WelfordState:
     """Device-resident running {count, mean[C], M2[C]} (fp64) of one client's features:
     the numerically safe replacement of `all_feat_sum, all_feat_square_sum, all_count`

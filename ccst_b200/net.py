@@ -96,3 +96,62 @@ def truncate_relu4_1(vgg: nn.Sequential) -> nn.Sequential:
 # default init gives until load_state_dict / ccst_b200.synth.init_* is applied)
 decoder = make_decoder()
 vgg = make_vgg()
+
+
+class Net(nn.Module):
+    """Forward-only drop-in for the reference's training wrapper `Net` (net.py:95-152): `forward(content,
+    style, alpha)` returns (loss_c, loss_s) -- the content loss MSE(relu4_1(g_t), t) and the style loss
+    sum over relu1_1..relu4_1 of MSE(mean) + MSE(std) -- computed by the B200 engine: three encoder passes
+    whose intermediate maps stay in the arena (only their calc_mean_std statistics leave it), the fused
+    AdaIN + alpha blend, the decoder, and the deterministic MSE kernel.  No autograd (inference / evaluation
+    of the losses only): backward is out of scope."""
+
+    def __init__(self, encoder, decoder, precision="fp32"):
+        super().__init__()
+        enc_layers = list(encoder.children())
+        self.encoder = nn.Sequential(*enc_layers[:RELU4_1_CHILDREN])  # input -> relu4_1 (net.py:98-102)
+        self.decoder = decoder
+        self.precision = precision
+
+    def _engine(self, device):
+        from .transfer import engine_for
+
+        return engine_for(self.encoder, self.decoder, device)
+
+    def encode_with_intermediate_stats(self, images):
+        return self._engine(images.device).encode_levels(images, self.precision)
+
+    def encode(self, images):
+        return self._engine(images.device).encode(images, self.precision)
+
+    @staticmethod
+    def calc_content_loss(input, target):
+        from . import function as F_
+
+        assert (input.size() == target.size())
+        return F_.mse_loss(input, target)
+
+    @staticmethod
+    def calc_style_loss_from_stats(input_stats, target_stats):
+        from . import function as F_
+
+        return F_.mse_loss(input_stats[0], target_stats[0]) + F_.mse_loss(input_stats[1], target_stats[1])
+
+    def forward(self, content, style, alpha=1.0):
+        from . import function as F_
+
+        assert 0 <= alpha <= 1
+        eng = self._engine(content.device)
+        style_feat, style_stats = eng.encode_levels(style, self.precision, want_feat=False)
+        content_feat = eng.encode(content, self.precision)
+        assert (content_feat.size()[:2] == style_stats[3][0].size()[:2])  # adain's assert (function.py:17)
+        t = F_.adain_blend(content_feat, style_stats[3], alpha)  # adain + alpha blend (net.py:141-142)
+        g_t = eng.decode(t, self.precision)
+        # calc_style_loss asserts input.size() == target.size() on every level (net.py:131): same image size
+        assert (g_t.size() == style.size())
+        g_feat, g_stats = eng.encode_levels(g_t, self.precision)
+        loss_c = self.calc_content_loss(g_feat, t)
+        loss_s = self.calc_style_loss_from_stats(g_stats[0], style_stats[0])
+        for i in range(1, 4):
+            loss_s = loss_s + self.calc_style_loss_from_stats(g_stats[i], style_stats[i])
+        return loss_c, loss_s

@@ -142,6 +142,22 @@ class Engine:
                                                    PRECISIONS[precision], self._stream()))
         return out
 
+    def encode_levels(self, images, precision=DEFAULT_PRECISION, eps=F_.EPS, want_feat=True):
+        """Net.encode_with_intermediate + calc_mean_std per level (net.py:112-136), forward only:
+        returns (relu4_1 [N,512,h,w] or None, [(mean, std)] for relu1_1, relu2_1, relu3_1, relu4_1, each
+        [N,C_l,1,1]).  The intermediate maps never leave the arena; only their statistics do."""
+        x = self._img(images, "images")
+        n, _, h, w = x.shape
+        fh, fw = _lib.feature_hw(h, w)
+        feat = torch.empty((n, 512, fh, fw), dtype=torch.float32, device=self.device) if want_feat else None
+        means = [torch.empty((n, c, 1, 1), dtype=torch.float32, device=self.device) for c in (64, 128, 256, 512)]
+        stds = [torch.empty_like(m) for m in means]
+        with _lib.on_device(self.device):
+            _lib.check(_lib.lib().ccst_encoder_levels(
+                self._h, x.data_ptr(), n, h, w, feat.data_ptr() if want_feat else None, _ptr_array(means),
+                _ptr_array(stds), float(eps), PRECISIONS[precision], self._stream()))
+        return feat, list(zip(means, stds))
+
     def decode(self, feat, precision=DEFAULT_PRECISION):
         """decoder(feat): [N,512,h,w] -> [N,3,8h,8w] fp32."""
         x = F_._prep(feat, "feat")
@@ -319,6 +335,28 @@ def save_image_quantize(images: torch.Tensor) -> torch.Tensor:
     with _lib.on_device(x.device):
         _lib.check(_lib.lib().ccst_quantize_u8(x.data_ptr(), n, c, h, w, out.data_ptr(),
                                                torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
+def resize_input_u8(images_u8: torch.Tensor, size) -> torch.Tensor:
+    """The loader's `transforms.Resize((S, S))` (cjm_util/data_helper.py:45-49) on a uint8 HWC batch
+    [N,H,W,C] on the device: Pillow's 8-bit bilinear resample, bit-exact -> [N,S,S,C] uint8.  `size` is an
+    int (square, as the reference's `(image_size, image_size)`) or (h, w)."""
+    x = images_u8
+    if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype != torch.uint8 or x.dim() != 4:
+        raise RuntimeError("images_u8 must be a CUDA uint8 [N,H,W,C] tensor: ccst_b200 has no CPU fallback")
+    x = x.contiguous()
+    n, h, w, c = x.shape
+    oh, ow = (int(size), int(size)) if not isinstance(size, (tuple, list)) else (int(size[0]), int(size[1]))
+    if (oh, ow) == (h, w):
+        return x  # PIL returns a copy of the image; nothing to compute
+    out = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device)
+    nbytes = _lib.lib().ccst_resize_pil_scratch_bytes(n, h, w, c, oh, ow)
+    scratch = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    with _lib.on_device(x.device):
+        _lib.check(_lib.lib().ccst_resize_pil_bilinear_u8(x.data_ptr(), n, h, w, c, oh, ow, out.data_ptr(),
+                                                          scratch.data_ptr(),
+                                                          torch.cuda.current_stream(x.device).cuda_stream))
     return out
 
 

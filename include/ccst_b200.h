@@ -167,12 +167,34 @@ int ccst_u8_to_tensor(const uint8_t* d_img_nhwc, int N, int C, int H, int W, flo
 int ccst_quantize_u8(const float* d_img_nchw, int N, int C, int H, int W, uint8_t* d_out_nhwc,
                      void* stream);
 
+/* The loader's `transforms.Resize((S, S))` on the PIL image  [cjm_util/data_helper.py:45-49]: torchvision
+ * calls Image.resize(BILINEAR), i.e. Pillow's 8-bit two-pass resample (Pillow is an un-vendored dependency of the
+ * reference; restated from src/libImaging/Resample.c of Pillow 12.2.0: 22-bit fixed-point coefficients, horizontal
+ * pass into an 8-bit intermediate, then the vertical pass) -- bit-exact.  d_in [N,H,W,C] uint8 -> d_out
+ * [N,OH,OW,C] uint8, so that a batch can be uploaded at its ORIGINAL size (PACS: 227x227, 5x fewer bytes than
+ * 512x512) and resized on the GPU.  d_scratch: ccst_resize_pil_scratch_bytes(...) bytes of device memory. */
+int64_t ccst_resize_pil_scratch_bytes(int N, int H, int W, int C, int OH, int OW);
+int ccst_resize_pil_bilinear_u8(const uint8_t* d_in, int N, int H, int W, int C, int OH, int OW, uint8_t* d_out,
+                                void* d_scratch, void* stream);
+
 /* `resize = transforms.Resize(args.output_size); output = resize(output)`
  * [CCST_OverallStyleTransfer.py:134-135,154-155] on the device tensor: torchvision's Resize of a float
  * tensor = torch's anti-aliased bilinear interpolation (align_corners = false).  d_in is `planes`
  * contiguous H x W fp32 planes (planes = N*C), d_out `planes` OH x OW planes. */
 int ccst_resize_bilinear_aa_f32(const float* d_in, int64_t planes, int H, int W, int OH, int OW,
                                 float* d_out, void* stream);
+
+/* Net.encode_with_intermediate + the statistics of calc_style_loss  [net.py:112-136], forward only:
+ * encodes d_img and returns calc_mean_std (unbiased variance, sqrt(var + eps)) of relu1_1, relu2_1, relu3_1
+ * and relu4_1 -- d_mean[l] / d_std[l] hold N*C_l floats, C_l = 64, 128, 256, 512 (the arrays of 4 pointers
+ * are HOST arrays of device pointers) -- taken from the arena while encoding; d_feat (may be NULL) receives
+ * relu4_1 as [N,512,h,w] fp32. */
+int ccst_encoder_levels(ccst_handle* h, const float* d_img, int N, int H, int W, float* d_feat,
+                        float* const* d_mean, float* const* d_std, float eps, int precision, void* stream);
+
+/* nn.MSELoss()(a, b)  [net.py:104, calc_content_loss / calc_style_loss]: d_out[0] = mean((a - b)^2) over n
+ * floats; squares in fp32, sums in fp64 in a fixed order (bit-reproducible).  d_scratch: 1024 doubles. */
+int ccst_mse_f32(const float* d_a, const float* d_b, int64_t n, double* d_scratch, float* d_out, void* stream);
 
 /* one iteration of the overall-statistics loop: vgg(data) + calc_sum + accumulate
  * [mean_std_computation_effcientMem.py:121-131], encoder output never leaves the arena. */

@@ -236,3 +236,115 @@ def calc_mean_std_batch(feat: torch.Tensor, eps: float = EPS):
     flat = feat.swapaxes(1, 0).reshape(c, -1)
     var = flat.var(dim=1) + eps
     return flat.mean(dim=1).reshape(1, c, 1, 1), torch.sqrt(var.reshape(1, c, 1, 1))
+
+
+# --------------------------------------------------------------------------
+# SURVEY 8f rank 4 (forward only): the training wrapper's losses and MixStyle's statistics
+# --------------------------------------------------------------------------
+def encode_with_intermediate(vgg, x):
+    """Net.encode_with_intermediate (style_transfer/AdaIN/net.py:112-117): relu1_1, relu2_1, relu3_1, relu4_1
+    (enc_1 = children[:4], enc_2 = [4:11], enc_3 = [11:18], enc_4 = [18:31], net.py:98-102)."""
+    convs = _conv_list(vgg)
+    x = F.conv2d(x, convs[0].weight, convs[0].bias)
+    feats = []
+    idx = 1
+    for bi, reps in enumerate((2, 2, 4, 1)):
+        if bi:
+            x = F.max_pool2d(x, 2, 2, 0, ceil_mode=True)
+        for k in range(reps):
+            x = _rconv(x, convs[idx])
+            idx += 1
+            if k == 0:
+                feats.append(x)  # relu{bi+1}_1
+    return feats
+
+
+def net_forward_losses(vgg, decoder, content, style, alpha=1.0):
+    """Net.forward (net.py:138-152): (loss_c, loss_s), forward values only."""
+    assert 0 <= alpha <= 1
+    mse = torch.nn.functional.mse_loss
+    style_feats = encode_with_intermediate(vgg, style)
+    content_feat = encode_relu4_1(vgg, content)
+    t = adaptive_instance_normalization(content_feat, style_feats[-1])
+    t = alpha * t + (1 - alpha) * content_feat
+    g_t = decode(decoder, t)
+    g_feats = encode_with_intermediate(vgg, g_t)
+    loss_c = mse(g_feats[-1], t)
+    loss_s = 0
+    for gf, sf in zip(g_feats, style_feats):
+        gm, gs = calc_mean_std(gf)
+        sm, ss = calc_mean_std(sf)
+        loss_s = loss_s + mse(gm, sm) + mse(gs, ss)
+    return loss_c, loss_s
+
+
+def mixstyle_forward(x, lmda, perm, eps: float = 1e-6):
+    """MixStyle.forward after its random draws (nets/layers.py:46-74): lmda [B,1,1,1], perm [B]."""
+    mu = x.mean(dim=[2, 3], keepdim=True)
+    var = x.var(dim=[2, 3], keepdim=True)
+    sig = (var + eps).sqrt()
+    x_normed = (x - mu) / sig
+    mu2, sig2 = mu[perm], sig[perm]
+    mu_mix = mu * lmda + mu2 * (1 - lmda)
+    sig_mix = sig * lmda + sig2 * (1 - lmda)
+    return x_normed * sig_mix + mu_mix
+
+
+# --------------------------------------------------------------------------
+# SURVEY 8f rank 2: the loader's Resize((S, S)) on the PIL image (cjm_util/data_helper.py:45-49)
+# --------------------------------------------------------------------------
+def _pil_bilinear_coeffs(in_size: int, out_size: int):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter (un-vendored dependency of
+    the reference: torchvision's Resize calls Image.resize(BILINEAR); restated from Pillow 12.2.0
+    src/libImaging/Resample.c and pinned against the real Pillow in tests/golden/io_u8.npz)."""
+    import math
+
+    prec = 32 - 8 - 2
+    scale = in_size / out_size
+    fscale = max(scale, 1.0)
+    support = 1.0 * fscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    kk = np.zeros((out_size, ksize), np.int64)
+    bounds = np.zeros((out_size, 2), np.int64)
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        ss = 1.0 / fscale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = np.zeros(ksize)
+        ww = 0.0
+        for x in range(xmax):
+            v = abs((x + xmin - center + 0.5) * ss)
+            w[x] = 1.0 - v if v < 1.0 else 0.0
+            ww += w[x]
+        for x in range(xmax):
+            if ww != 0.0:
+                w[x] /= ww
+        for x in range(ksize):
+            kk[xx, x] = int(-0.5 + w[x] * (1 << prec)) if w[x] < 0 else int(0.5 + w[x] * (1 << prec))
+        bounds[xx] = (xmin, xmax)
+    return kk, bounds, prec
+
+
+def _pil_resample_axis(img: np.ndarray, out_size: int, axis: int) -> np.ndarray:
+    a = np.moveaxis(img, axis, 0).astype(np.int64)
+    kk, b, prec = _pil_bilinear_coeffs(a.shape[0], out_size)
+    out = np.zeros((out_size,) + a.shape[1:], np.int64)
+    for xx in range(out_size):
+        xmin, cnt = b[xx]
+        ss = np.full(a.shape[1:], 1 << (prec - 1), np.int64)
+        for x in range(cnt):
+            ss += a[xmin + x] * kk[xx, x]
+        out[xx] = np.clip(ss >> prec, 0, 255)
+    return np.moveaxis(out.astype(np.uint8), 0, axis)
+
+
+def pil_resize_bilinear_u8(images_u8: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+    """transforms.Resize((oh, ow)) on PIL images, for a uint8 [N,H,W,C] batch: horizontal pass into an
+    8-bit intermediate, then the vertical pass (ImagingResample)."""
+    a = images_u8.numpy()
+    if ow != a.shape[2]:
+        a = _pil_resample_axis(a, ow, 2)
+    if oh != a.shape[1]:
+        a = _pil_resample_axis(a, oh, 1)
+    return torch.from_numpy(np.ascontiguousarray(a))

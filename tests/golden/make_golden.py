@@ -286,15 +286,78 @@ def make_io():
         # (input regenerated by the tests from the same seed; only the 96x96 result is stored)
         big = torch.rand((1, 3, 512, 512), generator=torch.Generator().manual_seed(77))
         out["resize_512_to_96"] = transforms.Resize(96)(big).numpy()
+    # the loader's Resize((S, S)) on PIL images (data_helper.py:45-49): REAL torchvision / Pillow, up- and
+    # down-sizing, non-square inputs; smooth-ish inputs so that the archive stays small
+    import hashlib as _hl
+    for tag, (ih, iw, S) in {"up": (37, 53, 64), "down": (150, 100, 48), "pacs": (227, 227, 512)}.items():
+        gg = torch.Generator().manual_seed(600 + ih)
+        base_ = torch.rand((1, ih // 3 + 1, iw // 3 + 1, 3), generator=gg)
+        im_ = torch.nn.functional.interpolate(base_.permute(0, 3, 1, 2), size=(ih, iw), mode="bilinear",
+                                              align_corners=False).permute(0, 2, 3, 1)
+        im_ = ((im_ + 0.2 * torch.rand((1, ih, iw, 3), generator=gg)).clamp(0, 1) * 255).round().to(torch.uint8).numpy()[0]
+        r_ = np.asarray(transforms.Resize((S, S))(Image.fromarray(im_)))
+        out[f"resize_in_{tag}/x"] = im_
+        if tag == "pacs":  # 786 KB: keep a digest and one row
+            out[f"resize_in_{tag}/sha256"] = np.frombuffer(_hl.sha256(r_.tobytes()).hexdigest().encode(), dtype=np.uint8)
+            out[f"resize_in_{tag}/row100"] = r_[100]
+        else:
+            out[f"resize_in_{tag}/y"] = r_
     np.savez_compressed(os.path.join(HERE, "io_u8.npz"), **out)
     print("io_u8", os.path.getsize(os.path.join(HERE, "io_u8.npz")) // 1024, "KiB",
           "a=1 range [%.3f, %.3f]" % (out["out_f32_a1.0"].min(), out["out_f32_a1.0"].max()),
           "clamped lo/hi:", int((out["out_u8_a0.5"] == 0).sum()), int((out["out_u8_a0.5"] == 255).sum()))
 
 
+def make_f4():
+    """SURVEY 8f rank 4, forward only: the REAL `Net` class (net.py:95-152) and the REAL MixStyle module
+    (nets/layers.py) run on seeded inputs -> f4.npz."""
+    import importlib.util
+    import random
+
+    torch.set_num_threads(1)
+    out = {}
+    vgg_full = ref_net.vgg
+    dec = ref_net.decoder
+    synth.init_vgg_(vgg_full, 0)
+    synth.init_decoder_(dec, 0)
+    net = ref_net.Net(torch.nn.Sequential(*list(vgg_full.children())[:31]), dec).eval()
+    out["weights_sha256"] = np.frombuffer(weights_digest(net.enc_1, net.enc_2, net.enc_3, net.enc_4, dec).encode(), dtype=np.uint8)
+    content = synth.images(2, 64, 72, 901)  # calc_style_loss asserts equal feature sizes: same image size
+    style = synth.images(2, 64, 72, 902)
+    with torch.no_grad():
+        for alpha in (1.0, 0.7):
+            lc, ls = net(content, style, alpha)
+            out[f"loss_c_a{alpha}"] = np.float32(lc.item())
+            out[f"loss_s_a{alpha}"] = np.float32(ls.item())
+        feats = net.encode_with_intermediate(style)
+        for i, f in enumerate(feats):
+            m, sd = ref_function.calc_mean_std(f)
+            out[f"style_level{i}_mean"], out[f"style_level{i}_std"] = m.numpy(), sd.numpy()
+    out["content"], out["style"] = content.numpy(), style.numpy()
+    # MixStyle: the real module, its two random draws replayed from the same seeds
+    spec = importlib.util.spec_from_file_location("ref_layers", os.path.join(os.path.dirname(os.path.dirname(REF)), "nets", "layers.py"))
+    layers = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(layers)
+    mix = layers.MixStyle(p=1.0, alpha=0.1, eps=1e-6, mix="random")
+    mix.train()
+    x = synth.features((4, 16, 9, 11), 903)
+    torch.manual_seed(77)
+    random.seed(77)
+    y = mix(x)
+    torch.manual_seed(77)
+    lmda = mix.beta.sample((4, 1, 1, 1))
+    perm = torch.randperm(4)
+    out["mix_x"], out["mix_y"], out["mix_lmda"], out["mix_perm"] = x.numpy(), y.numpy(), lmda.numpy(), perm.numpy()
+    np.savez_compressed(os.path.join(HERE, "f4.npz"), **out)
+    print("f4", os.path.getsize(os.path.join(HERE, "f4.npz")) // 1024, "KiB", {k: float(v) for k, v in out.items() if k.startswith("loss")})
+
+
 if __name__ == "__main__":
-    if "--only-io" in sys.argv:
+    if "--only-f4" in sys.argv:
+        make_f4()
+    elif "--only-io" in sys.argv:
         make_io()
     else:
         main()
         make_io()
+        make_f4()

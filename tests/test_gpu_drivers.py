@@ -206,3 +206,42 @@ def test_single_transfer_per_image_sampling(models, engine):
                     stat = O.single_style_stats(O.encode_relu4_1(vgg, rng.choice(styles)))
                     ref = O.style_transfer(vgg, dec, b[j:j + 1], stat, 1.0)
                     assert (outs[i][j:j + 1] - ref).abs().max().item() < 1e-4
+
+
+def test_input_resize_is_bit_exact_with_pillow(golden, tmp_path):
+    """`transforms.Resize((S, S))` of the loader (data_helper.py:45-49) on the GPU, bit-exact
+    with the real Pillow (golden) and with the oracle at PACS size for a whole batch; then the list reader +
+    host decode + GPU resize path end to end on PNG files."""
+    import hashlib
+    from PIL import Image
+    from ccst_b200 import data
+    g = golden["io_u8"]
+    for tag, S in (("up", 64), ("down", 48), ("pacs", 512)):
+        x = torch.from_numpy(g[f"resize_in_{tag}/x"])[None].to(DEV)
+        y = ccst_b200.resize_input_u8(x, S)[0].cpu().numpy()
+        if tag == "pacs":
+            assert hashlib.sha256(y.tobytes()).hexdigest().encode() == g[f"resize_in_{tag}/sha256"].tobytes()
+        else:
+            assert np.array_equal(y, g[f"resize_in_{tag}/y"])
+    gen = torch.Generator().manual_seed(3)
+    xb = torch.randint(0, 256, (8, 227, 227, 3), generator=gen, dtype=torch.uint8)
+    yb = ccst_b200.resize_input_u8(xb.to(DEV), 512)
+    assert torch.equal(yb.cpu(), O.pil_resize_bilinear_u8(xb, 512, 512))
+    assert ccst_b200.resize_input_u8(xb.to(DEV), 227).shape == xb.shape  # same size: the image itself
+    non_sq = torch.randint(0, 256, (2, 40, 90, 3), generator=gen, dtype=torch.uint8)
+    assert torch.equal(ccst_b200.resize_input_u8(non_sq.to(DEV), (30, 100)).cpu(), O.pil_resize_bilinear_u8(non_sq, 30, 100))
+    # list file -> PIL decode on the host -> upload at the original size -> Resize on the GPU
+    lines = []
+    for i, (h, w) in enumerate(((50, 70), (64, 64), (33, 41))):
+        im = torch.randint(0, 256, (h, w, 3), generator=gen, dtype=torch.uint8).numpy()
+        Image.fromarray(im).save(tmp_path / f"img{i}.png")
+        lines.append(f"img{i}.png {i}\n")
+    (tmp_path / "list.txt").write_text("".join(lines))
+    from torchvision import transforms
+    tr = transforms.Resize((48, 48))
+    got = list(data.list_batches(str(tmp_path / "list.txt"), str(tmp_path), 48, 2, DEV))
+    assert [b.shape[0] for b, _ in got] == [2, 1]
+    flat = torch.cat([b for b, _ in got]).cpu().numpy()
+    for i in range(3):
+        ref = np.asarray(tr(Image.open(tmp_path / f"img{i}.png").convert("RGB")))
+        assert np.array_equal(flat[i], ref)

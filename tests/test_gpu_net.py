@@ -414,3 +414,28 @@ def test_style_transfer_smallest_feature_maps(models, hw):
     assert out32.shape == ref.shape
     assert (out32.cpu() - ref).abs().max().item() < TOL_FP32
     assert (out16.cpu() - ref).abs().max().item() < TOL_TC
+
+
+def test_net_forward_losses_golden(models, golden):
+    """SURVEY 8f rank 4, forward only: `ccst_b200.net.Net.forward` (level statistics taken from the arena,
+    deterministic MSE kernel) against the losses of the reference's real `Net` class (net.py:138-152)."""
+    from ccst_b200 import net as B
+    g = golden["f4"]
+    vgg, dec = models
+    content, style = T(g["content"]).to(DEV), T(g["style"]).to(DEV)
+    for precision, tol in (("fp32", 1e-4), ("fp16", 2e-2)):
+        model = B.Net(vgg, dec, precision=precision)
+        for alpha in (1.0, 0.7):
+            lc, ls = model(content, style, alpha)
+            rc, rs = float(g[f"loss_c_a{alpha}"]), float(g[f"loss_s_a{alpha}"])
+            report(f"Net.forward a={alpha} {precision}", loss_c=lc.item(), ref_c=rc, loss_s=ls.item(), ref_s=rs)
+            assert abs(lc.item() - rc) < tol * rc and abs(ls.item() - rs) < tol * rs
+    # the level statistics themselves (calc_mean_std on relu1_1 .. relu4_1), fp32 engine, 1e-5 of each level's scale
+    eng = ccst_b200.engine_for(vgg, dec, torch.device(DEV))
+    feat, stats = eng.encode_levels(style, "fp32")
+    for i, (m, s) in enumerate(stats):
+        assert _stat_rel(m, T(g[f"style_level{i}_mean"])) < TOL_STATS and _stat_rel(s, T(g[f"style_level{i}_std"])) < TOL_STATS
+    with torch.no_grad():
+        assert (feat.cpu() - O.encode_relu4_1(vgg, style.cpu())).abs().max().item() < TOL_FP32
+    with pytest.raises(AssertionError):  # calc_style_loss's size assert (net.py:131)
+        B.Net(vgg, dec)(content, synth.images(2, 48, 48, 1).to(DEV), 1.0)

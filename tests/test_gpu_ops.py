@@ -191,3 +191,29 @@ def test_calc_mean_std_batch_golden(golden):
     assert tuple(m.shape) == tuple(s.shape) == (1, 24, 1, 1)
     assert torch.allclose(m.cpu().double(), torch.from_numpy(g["batchstat/mean64"]), rtol=1e-5, atol=1e-6)
     assert torch.allclose(s.cpu().double(), torch.from_numpy(g["batchstat/std64"]), rtol=1e-5, atol=1e-6)
+
+
+def test_mixstyle_statistics_and_forward_golden(golden):
+    """MixStyle (nets/layers.py:46-74): mean / sqrt(unbiased var + 1e-6) and the mixed re-normalisation,
+    against the real module's output for the same random draws."""
+    g = golden["f4"]
+    x = T(g["mix_x"]).to(DEV)
+    mu, sig = ccst_b200.mixstyle_stats(x)
+    xr = T(g["mix_x"]).double()
+    assert torch.allclose(mu.cpu().double(), xr.mean(dim=[2, 3], keepdim=True), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(sig.cpu().double(), (xr.var(dim=[2, 3], keepdim=True) + 1e-6).sqrt(), rtol=1e-5, atol=1e-6)
+    y = ccst_b200.mixstyle(x, T(g["mix_lmda"]), T(g["mix_perm"]))
+    ref = T(g["mix_y"])
+    assert (y.cpu() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
+
+
+def test_mse_loss_matches_torch_and_is_deterministic():
+    g = torch.Generator().manual_seed(5)
+    for n in (1, 7, 1000, 3 * 512 * 64 * 64 + 5):
+        a, b = torch.randn((n,), generator=g), torch.randn((n,), generator=g)
+        ref = torch.nn.functional.mse_loss(a.double(), b.double()).item()
+        l1 = ccst_b200.mse_loss(a.to(DEV), b.to(DEV)).item()
+        l2 = ccst_b200.mse_loss(a.to(DEV), b.to(DEV)).item()
+        assert l1 == l2 and abs(l1 - ref) < 1e-6 * max(ref, 1e-6)
+    with pytest.raises(AssertionError):
+        ccst_b200.mse_loss(torch.zeros(3, device=DEV), torch.zeros(4, device=DEV))

@@ -140,3 +140,49 @@ def test_batch_calc_mean_std_matches_reference(golden):
     m, s = O.calc_mean_std_batch(T(g["batchstat/x"]))
     np.testing.assert_array_equal(m.numpy(), g["batchstat/mean"])
     np.testing.assert_array_equal(s.numpy(), g["batchstat/std"])
+
+
+def test_net_forward_losses_and_mixstyle_match_reference(golden, models):
+    """SURVEY 8f rank 4 (forward only): the oracle's restatement of Net.forward (net.py:138-152) and of
+    MixStyle.forward (nets/layers.py:46-74) against outputs of the real classes."""
+    g = golden["f4"]
+    vgg, dec = models
+    content, style = torch.from_numpy(g["content"]), torch.from_numpy(g["style"])
+    with torch.no_grad():
+        for alpha in (1.0, 0.7):
+            lc, ls = O.net_forward_losses(vgg, dec, content, style, alpha)
+            assert abs(lc.item() - float(g[f"loss_c_a{alpha}"])) < 1e-6 * max(1.0, abs(lc.item()))
+            assert abs(ls.item() - float(g[f"loss_s_a{alpha}"])) < 1e-6 * max(1.0, abs(ls.item()))
+        feats = O.encode_with_intermediate(vgg, style)
+        assert [f.shape[1] for f in feats] == [64, 128, 256, 512]
+        for i, f in enumerate(feats):
+            m, s = O.calc_mean_std(f)
+            np.testing.assert_allclose(m.numpy(), g[f"style_level{i}_mean"], rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(s.numpy(), g[f"style_level{i}_std"], rtol=1e-6, atol=1e-7)
+    y = O.mixstyle_forward(torch.from_numpy(g["mix_x"]), torch.from_numpy(g["mix_lmda"]), torch.from_numpy(g["mix_perm"]))
+    np.testing.assert_array_equal(y.numpy(), g["mix_y"])
+
+
+def test_pil_resize_matches_real_pillow(golden):
+    """The loader's Resize((S, S)) (data_helper.py:45-49): the oracle's restatement of Pillow's 8-bit bilinear
+    resample against the real torchvision / Pillow output, bit for bit."""
+    import hashlib
+    g = golden["io_u8"]
+    for tag, S in (("up", 64), ("down", 48), ("pacs", 512)):
+        x = T(g[f"resize_in_{tag}/x"])[None]
+        y = O.pil_resize_bilinear_u8(x, S, S)[0].numpy()
+        if tag == "pacs":
+            assert hashlib.sha256(y.tobytes()).hexdigest().encode() == g[f"resize_in_{tag}/sha256"].tobytes()
+            np.testing.assert_array_equal(y[100], g[f"resize_in_{tag}/row100"])
+        else:
+            np.testing.assert_array_equal(y, g[f"resize_in_{tag}/y"])
+
+
+def test_image_list_reader(tmp_path):
+    """`_dataset_info` (cjm_util/ImageLoader.py:31-42): "<path> <label>" per line."""
+    from ccst_b200 import data
+    p = tmp_path / "art_painting_train.txt"
+    p.write_text("/disk1/pacs/art_painting/dog/pic_001.jpg 1\n/disk1/pacs/art_painting/house/pic_010.jpg 6\n")
+    names, labels = data.dataset_info(str(p))
+    assert names == ["/disk1/pacs/art_painting/dog/pic_001.jpg", "/disk1/pacs/art_painting/house/pic_010.jpg"]
+    assert labels == [1, 6]
