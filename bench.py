@@ -49,6 +49,7 @@ SIZE = 512
 FLOP_PER_IMG = 253.072e9  # SURVEY.md §8d (enc 126.538 + dec 126.534 GFLOP @512^2)
 FLOP_PER_IMG_96 = 8.897e9
 ENC_FLOP_PER_IMG = 126.538e9
+FIRST_FLOP_PER_IMG = 2 * 27 * 64 * 512 * 512  # conv1_1 (+ folded 1x1): CUDA cores in the f16x3 engine
 CLIENT_IMAGES = 2048      # config 2: PACS art_painting-sized client
 
 
@@ -550,8 +551,16 @@ def run_configs(args, torch, dist, dev, rank, world, eng, vgg, dec, stat, peaks,
     c2 = {"workload": f"overall style statistics of a {CLIENT_IMAGES}-image client @512x512, batch 32, images "
                       f"sharded over {world} rank(s), uint8 host batches uploaded in the timed region, one "
                       "all-reduce(sum) of the 1025 fp64 Welford moments + image count"}
-    for prec, n_img in ((precision, CLIENT_IMAGES), ("fp32", min(CLIENT_IMAGES, 64 * world))):
-        if prec == "fp32" and precision == "fp32":
+    # three engines: the drivers' default (f16x3: split f16 operands, promoted fp32 accumulation; meets the
+    # 1e-5 statistics bar) on the whole client, the plain 16-bit tensor-core encoder (does not meet it) and the
+    # fp32 CUDA-core engine on a 64-image-per-rank sample
+    STAT_NOTE = {"fp16x3": "< 1e-5 relative (measured 2e-6, tests/test_gpu_net.py::test_overall_statistics_loop[fp16x3])",
+                 "fp32": "< 1e-5 relative (measured 6e-7, tests/test_gpu_net.py::test_overall_statistics_loop[fp32])"}
+    KEY = {"fp16x3": "f16x3_engine_default", "fp32": "fp32_cuda_core_engine"}
+    for prec, n_img in ((overall.STATS_PRECISION, CLIENT_IMAGES), (precision, CLIENT_IMAGES),
+                        ("fp32", min(CLIENT_IMAGES, 64 * world))):
+        key = KEY.get(prec, "tensor_core_encoder_16bit")
+        if key in c2:
             continue
         b_, e_ = overall.shard_range(n_img, rank, world)
         drivers.overall_statistics(eng, client_batches(b_, min(e_, b_ + BATCH)), prec, group)  # warm-up
@@ -561,13 +570,15 @@ def run_configs(args, torch, dist, dev, rank, world, eng, vgg, dec, stat, peaks,
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         assert seen == n_img, (seen, n_img)
-        key = "tensor_core_encoder" if prec != "fp32" else "fp32_engine_default"
         c2[key] = {"precision": prec, "images": n_img, "value": round(n_img / dt, 1), "unit": UNIT,
                    "seconds": round(dt, 4),
                    "tensor_frac_algorithmic": round(n_img / world * ENC_FLOP_PER_IMG / dt / 1e12 / peaks["tf_burst"], 4)
                    if prec != "fp32" else None,
-                   "statistics_vs_reference": "~1e-3 relative (16-bit encoder)" if prec != "fp32" else
-                   "< 1e-5 relative (tests/test_gpu_net.py::test_overall_statistics_loop)"}
+                   "tensor_frac_executed": round(n_img / world * 4 * (ENC_FLOP_PER_IMG - FIRST_FLOP_PER_IMG) / dt / 1e12
+                                                 / peaks["tf_burst"], 4) if prec == "fp16x3" else None,
+                   "statistics_vs_reference": STAT_NOTE.get(prec, "~1e-3 relative (16-bit encoder): above the 1e-5 bar")}
+    c2["value"] = c2[KEY["fp16x3"]]["value"]
+    c2["unit"] = UNIT
     # the collective on its own: all-reduce of the 1026-double payload, CUDA events, 50 repetitions
     payload = torch.zeros((1026,), dtype=torch.float64, device=dev)
     if dist is not None:

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <set>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -106,6 +107,10 @@ struct ConvLayer {
   // per-(cout, cin) sums over the 9 taps
   float* w_k32 = nullptr;
   float* w_tapsum = nullptr;
+  // f16x3 engine (encoder layers): [cout/64][hi | lo][64][9*cin] f16 halves of w * 2^e; the epilogue multiplies
+  // the accumulator by x3_scale = 2^-e
+  __half* w_x3 = nullptr;
+  float x3_scale = 1.f;
 };
 
 constexpr int kEncLayers = 8;  // conv1_2 .. conv4_1 (conv1_1 is the fused first conv)
@@ -144,6 +149,7 @@ struct ccst_handle {
   float* b_fold = nullptr; // per-image dec1 bias [N][256]
   size_t b_fold_elems = 0;
   unsigned int* sat_count = nullptr;  // f16 stores that hit the +-65504 clamp since the last reset
+  bool split = false;  // the call in flight runs the f16x3 engine (set by check_common from the precision code)
   bool profiling = false;
   int prof_n = 0;
   ProfSlot prof[kMaxProf];
@@ -179,12 +185,13 @@ void free_layer(ConvLayer& L) {
   cudaFree(L.bias);
   cudaFree(L.w_k32);
   cudaFree(L.w_tapsum);
+  cudaFree(L.w_x3);
   L = ConvLayer();
 }
 
 // OIHW fp32 host weights -> device packs
 int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b, bool up_before = false,
-               bool fold_src = false) {
+               bool fold_src = false, bool split_pack = false) {
   free_layer(L);
   L.cin = cin, L.cout = cout;
   L.pad64 = (cout + 63) / 64 * 64;
@@ -214,6 +221,35 @@ int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b, 
   CCST_CUDA(cudaMemcpy(L.w_ffma, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(L.w_umma, wu.data(), wu.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (split_pack && cout % 64 == 0) {
+    // split weights: w * 2^e = hi + lo with hi = f16(w * 2^e), lo = f16(w * 2^e - hi); e puts the largest
+    // |w| just below 2^10, so the low parts (2^-11 relative) of all but vanishing weights are normal f16
+    // numbers and the product of the scale with any activation stays far inside the fp32 range
+    float wmax = 0.f;
+    for (size_t i = 0; i < (size_t)cout * cin * 9; ++i) wmax = fmaxf(wmax, fabsf(w[i]));
+    int e = 0;
+    if (wmax > 0.f && std::isfinite(wmax)) {
+      int ex;
+      frexpf(wmax, &ex);  // wmax = m * 2^ex, m in [0.5, 1)
+      e = 10 - ex;
+    }
+    // rows [tile of 64 output channels][hi | lo][co], K = 9 * cin: the two halves of a tile are the N = 128
+    // rows of one MMA (conv_x3.cuh)
+    std::vector<__half> wx((size_t)2 * cout * K);
+    for (int o = 0; o < cout; ++o)
+      for (int c = 0; c < cin; ++c)
+        for (int t = 0; t < 9; ++t) {
+          const float v = ldexpf(w[((size_t)o * cin + c) * 9 + t], e);
+          const __half hi = __float2half(v);
+          const __half lo = __float2half(v - __half2float(hi));
+          const size_t row_hi = (size_t)(o / 64) * 128 + (o % 64), row_lo = row_hi + 64;
+          wx[row_hi * K + (size_t)t * cin + c] = hi;
+          wx[row_lo * K + (size_t)t * cin + c] = lo;
+        }
+    CCST_CUDA(cudaMalloc(&L.w_x3, wx.size() * sizeof(__half)));
+    CCST_CUDA(cudaMemcpy(L.w_x3, wx.data(), wx.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    L.x3_scale = ldexpf(1.f, -e);
+  }
   if (fold_src) {
     std::vector<float> wk((size_t)cout * K), ws((size_t)cout * cin);
     for (int o = 0; o < cout; ++o)
@@ -394,10 +430,12 @@ struct Pipe {
   float* const* lvl_std = nullptr;
   float lvl_eps = 1e-5f;
 
+  // f16x3 engine: every map holds the [hi | lo] halves of its C logical channels (v.C = 2 * C)
+  bool split() const { return sizeof(T) == 2 && h->split; }
   ActView<T> view(int slot, int N, int H, int W, int C) {
     ActView<T> v;
     v.p = reinterpret_cast<T*>(h->arena[slot]);
-    v.N = N, v.H = H, v.W = W, v.C = C;
+    v.N = N, v.H = H, v.W = W, v.C = split() ? 2 * C : C;
     return v;
   }
 
@@ -416,7 +454,8 @@ struct Pipe {
   // conv (+ fused or separate pool / fused upsample); result becomes `cur`
   int step(const ConvLayer& L, bool pool_after, bool up_after, bool want_stats = false) {
     const int N = cur.N, H = cur.H, W = cur.W;
-    const bool fused_pool = pool_after && h->fuse_pool && sizeof(T) == 2;
+    const bool fused_pool = pool_after && (h->fuse_pool || split()) && sizeof(T) == 2;
+    CCST_CHECK_ARG(!split() || (!up_after && !up_pending && !fold_pending), "the f16x3 engine runs the encoder only");
     // tcgen05 path: a layer followed by `Upsample` stores its low-resolution output with a replicate
     // halo and the NEXT conv consumes it through the phase-decomposed kernel (EPI_UPS): 16 instead of
     // 36 tap-GEMMs per source pixel and no 4x-replicated activation in HBM.
@@ -431,7 +470,7 @@ struct Pipe {
     if (fused_pool) oh = (H + 1) / 2, ow = (W + 1) / 2, epi = EPI_ACT_POOL;
     // relu4_1 statistics in the epilogue of the conv that produces it (tcgen05 path, N = 256 tiles)
     float2* tile_stats = nullptr;
-    if (want_stats && h->fuse_stats && sizeof(T) == 2 && epi == EPI_ACT && halo_edge == 1 &&
+    if (want_stats && h->fuse_stats && sizeof(T) == 2 && !split() && epi == EPI_ACT && halo_edge == 1 &&
         L.cout % 256 == 0 && N <= 65535) {
       if (int e = ensure_raw(h, nhwc_tile_scratch_elems(N, L.cout, H, W))) return e;
       tile_stats = h->raw + 2 * (size_t)N * L.cout;
@@ -443,8 +482,8 @@ struct Pipe {
     {
       // executed FLOPs: the phase form runs 4 phases x 4 taps per SOURCE pixel (= 4 taps per output
       // pixel) where the plain form runs 9 taps per output pixel
-      const double flops = ups ? 2.0 * 16 * L.cin * L.cout * (double)N * H * W
-                               : 2.0 * 9 * L.cin * L.cout * (double)N * H * W;
+      const double flops = (ups ? 2.0 * 16 * L.cin * L.cout * (double)N * H * W
+                                : 2.0 * 9 * L.cin * L.cout * (double)N * H * W) * (split() ? 4.0 : 1.0);
       const double bytes = (double)cur.elems() * sizeof(T) + (double)out.elems() * sizeof(T);
       ProfScope ps(h, st, sizeof(T) == 2 ? 1 : 2, flops, bytes);
       if (int e = conv(L, 1, epi, out, nullptr, halo_edge, tile_stats, per_sample)) return e;
@@ -465,10 +504,11 @@ struct Pipe {
   // statistics of `cur` (one of the four relu*_1 maps) for the style losses
   int level_stats(int level) {
     if (!lvl_mean) return CCST_OK;
-    const int NC = cur.N * cur.C, HW = cur.H * cur.W;
+    const int C = split() ? cur.C / 2 : cur.C;
+    const int NC = cur.N * C, HW = cur.H * cur.W;
     ProfScope ps(h, st, 4, 0, (double)cur.elems() * sizeof(T));
-    if (int e = ensure_raw(h, nhwc_scratch_elems(cur.N, cur.C, HW))) return e;
-    if (int e = launch_stats_nhwc<T>(cur, h->raw, st)) return e;
+    if (int e = ensure_raw(h, nhwc_scratch_elems(cur.N, C, HW))) return e;
+    if (int e = stats_launch()) return e;
     return launch_raw_to_mean_std(h->raw, NC, HW, lvl_eps, 1, lvl_mean[level], lvl_std[level], st);
   }
 
@@ -498,6 +538,10 @@ struct Pipe {
     stats_in_tiles = false;
     return CCST_OK;
   }
+
+  // {mean, M2} per (n, c) of `cur` -> h->raw[0 .. N*C) (scratch already sized)
+  int stats_launch();
+  int to_nchw(float* d_feat);
 
   int fold_rc = CCST_OK;
   bool try_fold(const float* mu_s, const float* sigma_s, int64_t stride, float alpha);
@@ -551,6 +595,23 @@ int Pipe<T>::adain_launch(ActView<T> out, const float* mu_s, const float* sigma_
   return launch_adain_nhwc<T>(cur, out, mu_s, sigma_s, stride, alpha, 1e-5f, h->raw, st);
 }
 
+template <typename T>
+int Pipe<T>::stats_launch() {
+  return launch_stats_nhwc<T>(cur, h->raw, st);
+}
+template <>
+int Pipe<__half>::stats_launch() {
+  return split() ? launch_stats_nhwc_split(cur, h->raw, st) : launch_stats_nhwc<__half>(cur, h->raw, st);
+}
+template <typename T>
+int Pipe<T>::to_nchw(float* d_feat) {
+  return launch_act_to_nchw<T>(cur, d_feat, st);
+}
+template <>
+int Pipe<__half>::to_nchw(float* d_feat) {
+  return split() ? launch_act_to_nchw_split(cur, d_feat, st) : launch_act_to_nchw<__half>(cur, d_feat, st);
+}
+
 template <>
 int Pipe<float>::first_launch(const float* img, int N, int H, int W) {
   return launch_conv_first<float>(img, N, H, W, h->first_w27, h->first_b64, cur, st);
@@ -558,6 +619,12 @@ int Pipe<float>::first_launch(const float* img, int N, int H, int W) {
 template <typename T>
 int Pipe<T>::first_launch(const float* img, int N, int H, int W) {
   return launch_conv_first_umma<T>(img, N, H, W, Weights16<T>::first(h), h->first_b64, cur, st, h->sat_count);
+}
+template <>
+int Pipe<__half>::first_launch(const float* img, int N, int H, int W) {
+  // f16x3 engine: conv1_1 (K = 27, HBM-bound) on the fp32 CUDA-core kernel, stored as [hi | lo]
+  if (split()) return launch_conv_first_split(img, N, H, W, h->first_w27, h->first_b64, cur, st, h->sat_count);
+  return launch_conv_first_umma<__half>(img, N, H, W, Weights16<__half>::first(h), h->first_b64, cur, st, h->sat_count);
 }
 template <>
 int Pipe<float>::conv(const ConvLayer& L, int relu, int epi, ActView<float> out, float* out_nchw, int,
@@ -578,17 +645,26 @@ int Pipe<T>::conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* 
   a.tile_stats = tile_stats;
   a.sat_count = h->sat_count;
   a.per_sample = per_sample;
+  if constexpr (std::is_same<T, __half>::value) {
+    if (split()) {
+      CCST_CHECK_ARG(L.w_x3 != nullptr, "the f16x3 engine has split weights for the encoder layers only");
+      a.split = true, a.wk_x3 = L.w_x3, a.out_scale = L.x3_scale;
+    }
+  }
   return launch_conv_umma<T>(a, st);
 }
 
-int check_common(ccst_handle* h, int precision) {
+int check_common(ccst_handle* h, int precision, bool allow_x3 = false) {
   CCST_CHECK_ARG(h != nullptr, "null handle");
   CCST_CHECK_ARG(precision == CCST_PREC_FP32 || precision == CCST_PREC_BF16 ||
-                     precision == CCST_PREC_FP16,
-                 "bad precision %d", precision);
+                     precision == CCST_PREC_FP16 || (precision == CCST_PREC_FP16X3 && allow_x3),
+                 precision == CCST_PREC_FP16X3 ? "precision %d (f16x3) is available for the encoder entry points only"
+                                               : "bad precision %d",
+                 precision);
   CCST_CUDA(cudaSetDevice(h->device));
   if (int e = require_sm100()) return e;
   h->prof_n = 0;
+  h->split = precision == CCST_PREC_FP16X3;
   return CCST_OK;
 }
 
@@ -647,13 +723,13 @@ int run_encoder(ccst_handle* h, const float* d_img, int N, int H, int W, float* 
                 float lvl_eps = 1e-5f) {
   int fh, fw;
   ccst_feature_hw(H, W, &fh, &fw);
-  if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T), true, false))) return e;
+  if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T) * (h->split ? 2 : 1), true, false))) return e;
   Pipe<T> p{h, st};
   p.lvl_mean = lvl_mean, p.lvl_std = lvl_std, p.lvl_eps = lvl_eps;
   if (int e = p.encoder(d_img, N, H, W)) return e;
   if (d_feat) {
     ProfScope ps(h, st, 5, 0, (double)N * fh * fw * 512 * (4.0 + sizeof(T)));
-    if (int e = launch_act_to_nchw<T>(p.cur, d_feat, st)) return e;
+    if (int e = p.to_nchw(d_feat)) return e;
   }
   if (d_state) {
     ProfScope ps(h, st, 4, 0, (double)N * fh * fw * 512 * sizeof(T));
@@ -661,7 +737,7 @@ int run_encoder(ccst_handle* h, const float* d_img, int N, int H, int W, float* 
       if (int e = launch_stats_from_tiles(N, 512, fh, fw, h->raw, st)) return e;
     } else {
       if (int e = ensure_raw(h, nhwc_scratch_elems(N, 512, fh * fw))) return e;
-      if (int e = launch_stats_nhwc<T>(p.cur, h->raw, st)) return e;
+      if (int e = p.stats_launch()) return e;
     }
     if (int e = merge_raw_into_state(h->raw, N, 512, (int64_t)fh * fw, d_state, st)) return e;
   }
@@ -792,7 +868,8 @@ extern "C" int ccst_set_encoder_weights(ccst_handle* h, const float* const* w,
   CCST_CUDA(cudaMemcpy(h->first_wk_b, wkb.data(), wkb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(h->first_wk_h, wkh.data(), wkh.size() * sizeof(__half), cudaMemcpyHostToDevice));
   for (int i = 0; i < kEncLayers; ++i)
-    if (int e = pack_layer(h->enc[i], kEncCh[i][0], kEncCh[i][1], w[2 + i], b[2 + i])) return e;
+    if (int e = pack_layer(h->enc[i], kEncCh[i][0], kEncCh[i][1], w[2 + i], b[2 + i], false, false, /*split_pack=*/true))
+      return e;
   h->enc_ready = true;
   return CCST_OK;
 }
@@ -817,7 +894,7 @@ extern "C" int ccst_set_decoder_weights(ccst_handle* h, const float* const* w,
     if ((precision) == CCST_PREC_BF16) {                       \
       typedef bf16 T;                                          \
       return call_T;                                           \
-    } else if ((precision) == CCST_PREC_FP16) {                \
+    } else if ((precision) == CCST_PREC_FP16 || (precision) == CCST_PREC_FP16X3) { \
       typedef __half T;                                        \
       return call_T;                                           \
     } else {                                                   \
@@ -836,7 +913,7 @@ extern "C" int ccst_set_decoder_weights(ccst_handle* h, const float* const* w,
 
 extern "C" int ccst_encoder_fwd(ccst_handle* h, const float* d_img, int N, int H, int W,
                                 float* d_feat, int precision, void* stream) {
-  if (int e = check_common(h, precision)) return e;
+  if (int e = check_common(h, precision, /*allow_x3=*/true)) return e;
   CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_fwd: encoder weights not set");
   CCST_CHECK_ARG(d_img && d_feat && N >= 1 && H >= 8 && W >= 8, "ccst_encoder_fwd: bad argument");
   CCST_DISPATCH(precision, run_encoder<T>(h, d_img, N, H, W, d_feat, nullptr, (cudaStream_t)stream));
@@ -845,7 +922,7 @@ extern "C" int ccst_encoder_fwd(ccst_handle* h, const float* d_img, int N, int H
 extern "C" int ccst_encoder_levels(ccst_handle* h, const float* d_img, int N, int H, int W, float* d_feat,
                                    float* const* d_mean, float* const* d_std, float eps, int precision,
                                    void* stream) {
-  if (int e = check_common(h, precision)) return e;
+  if (int e = check_common(h, precision, /*allow_x3=*/true)) return e;
   CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_levels: encoder weights not set");
   CCST_CHECK_ARG(d_img && d_mean && d_std && N >= 1 && H >= 8 && W >= 8, "ccst_encoder_levels: bad argument");
   for (int l = 0; l < 4; ++l)
@@ -862,7 +939,7 @@ extern "C" int ccst_mse_f32(const float* d_a, const float* d_b, int64_t n, doubl
 
 extern "C" int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N, int H, int W,
                                        double* d_state, int precision, void* stream) {
-  if (int e = check_common(h, precision)) return e;
+  if (int e = check_common(h, precision, /*allow_x3=*/true)) return e;
   CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_accumulate: encoder weights not set");
   CCST_CHECK_ARG(d_img && d_state && N >= 1 && H >= 8 && W >= 8,
                  "ccst_encoder_accumulate: bad argument");
@@ -883,7 +960,7 @@ int run_encoder_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W, do
 
 extern "C" int ccst_encoder_accumulate_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W,
                                           double* d_state, int precision, void* stream) {
-  if (int e = check_common(h, precision)) return e;
+  if (int e = check_common(h, precision, /*allow_x3=*/true)) return e;
   CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_accumulate_u8: encoder weights not set");
   CCST_CHECK_ARG(d_img && d_state && N >= 1 && H >= 8 && W >= 8,
                  "ccst_encoder_accumulate_u8: bad argument");

@@ -1,0 +1,360 @@
+// f16x3 engine: fp32-grade 3x3 reflect-pad convolution on the f16 tensor pipe (encoder layers).
+//
+// The reference computes relu4_1 in fp32 (net.py:38-69 under torch defaults) and BASELINE.json asks the style
+// statistics to match it to 1e-5 relative; one f16 rounding per layer is 5e-4.  Here every activation v is
+// stored as hi = f16(v) and lo = f16(v - hi) in the channel ranges [0, C) and [C, 2C) of its map, every weight
+// w (times an exact power of two that keeps its low part out of the f16 subnormals) as w_hi + w_lo, and
+//   a * w = a_hi * w_hi + a_hi * w_lo + a_lo * w_hi + a_lo * w_lo
+// runs as ONE tcgen05 implicit GEMM per 64-channel output tile: K = 9 x 2*Cin over the [a_hi | a_lo] channels,
+// N = 128 = [w_hi rows | w_lo rows] of the tile (N = 64 would be capped at half the tensor rate by the
+// A-operand fetch; the fourth, 2^-22-sized term comes for free).  Operand precision: 22 significand bits.
+//
+// Accumulation.  tcgen05.mma adds into its fp32 TMEM accumulator with truncation, not round-to-nearest
+// (measured: accumulating a whole K = 9 * 3 * Cin reduction in TMEM leaves every positive output 1e-5 low per
+// layer, 7e-5 on relu4_1 -- the effect Ootomo & Yokota describe for earlier tensor cores).  So the
+// accumulator is PROMOTED: the 12 MMAs of one (channel chunk, filter column) step write a fresh partial sum
+// into one of four 128-column TMEM buffers, and the epilogue warps add the partials in registers with
+// round-to-nearest fp32 adds while the next steps' MMAs run (buffers 2g, 2g+1 belong to epilogue group g,
+// which owns the tiles of parity g).  Truncation then only acts inside a 12-MMA partial.
+//
+// Epilogue: v = acc * 2^-k + bias, ReLU, optional 2x2 ceil-mode max-pool (all fp32), split into hi / lo and
+// stored as two TMA tiles at channels co and Cout + co.
+#pragma once
+#include "conv_main.cuh"
+
+namespace ccst {
+namespace {
+
+template <int CG>
+struct X3Cfg {
+  static constexpr int kN = 128;
+  static constexpr int kBRows = kN / CG;
+  static constexpr int kBBytes = kBRows * kBlockK * 2;  // 16 KiB / CG
+  static constexpr int kAStages = CG == 2 ? 5 : 4;
+  static constexpr int kBStages = 6;  // two groups of three filter-row tiles
+  static constexpr int kAOff = 0;
+  static constexpr int kBOff = kAStages * kASlabBytes;
+  static constexpr int kStoreOff = kBOff + kBStages * kBBytes;
+  static constexpr int kBiasOff = kStoreOff + 2 * kStoreBytes;
+  static constexpr int kBiasBytes = 2048;  // up to 512 fp32 biases
+  static constexpr int kBarOff = kBiasOff + kBiasBytes;
+  static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 8;
+  static constexpr int kTmemCols = 512;  // 4 partial buffers x 128 columns
+  static constexpr int kSmemBytes = kBarOff + 8 * kNumBars + 16 + 1024;
+  static_assert(kSmemBytes <= 232448, "shared memory plan exceeds 227 KiB");
+};
+
+template <int EPI, int CG>
+__global__ void __launch_bounds__(kThreadsUmma, 1)
+    conv_x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const __grid_constant__ CUtensorMap tmap_out, ConvParams<__half> p) {
+  static_assert(EPI == EPI_ACT || EPI == EPI_ACT_POOL, "encoder epilogues");
+  using T16 = __half;
+  using Cfg = X3Cfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t store_base = smem_base + Cfg::kStoreOff;
+  const uint32_t bar_base = smem_base + Cfg::kBarOff;
+  float* s_bias = reinterpret_cast<float*>(smem_gen + Cfg::kBiasOff);
+  auto a_smem = [&](int s) { return smem_base + Cfg::kAOff + s * kASlabBytes; };
+  auto b_smem = [&](int s) { return smem_base + Cfg::kBOff + s * Cfg::kBBytes; };
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (Cfg::kAStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * Cfg::kAStages + Cfg::kBStages + s); };
+  constexpr int kBar2 = 2 * Cfg::kAStages + 2 * Cfg::kBStages;
+  auto part_full = [&](int b) { return bar_base + 8u * (kBar2 + b); };       // partial buffer b written
+  auto part_empty = [&](int b) { return bar_base + 8u * (kBar2 + 4 + b); };  // ... and read out again
+  const uint32_t tmem_slot = bar_base + 8u * Cfg::kNumBars;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int klog = p.Cin / kBlockK;  // 64-channel chunks of the logical input
+  const int kchunks = 2 * klog;      // [hi | lo]
+  const int steps = kchunks * 3;     // (chunk, filter column) steps per tile: even
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  auto lead = [&](uint32_t bar) { return CG == 2 ? mapa_rank(bar, 0) : bar; };
+  const int unit_id = CG == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_cnt = CG == 2 ? (int)ncluster_x() : (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kAStages; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < Cfg::kBStages; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(part_full(b), 1);
+      mbar_init(part_empty(b), 4 * CG);  // one arrive per warp of the owning epilogue group (of both CTAs)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_cg<CG, Cfg::kTmemCols>(tmem_slot);
+  for (int i = threadIdx.x; i < p.Cout; i += kThreadsUmma) s_bias[i] = p.bias[i];
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kBarOff + 8 * Cfg::kNumBars);
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    const int b_row0 = (int)cta_rank * Cfg::kBRows;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int unit = unit_id; unit < p.total_tiles; unit += unit_cnt) {
+      const TileCoord t = decode_tile<CG>(p, unit, (int)cta_rank);
+      const int b_row = t.nt * Cfg::kN + b_row0;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        const int kb = kc >= klog ? kc - klog : kc;  // the lo chunks meet the same weights as the hi chunks
+        for (int s = 0; s < 3; ++s) {
+          MBAR_WAIT_RELAXED(a_empty(as), aph ^ 1, 700 + as);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(a_full(as), CG * kASlabBytes);
+            tma_load_4d_cg<CG>(a_smem(as), &tmap_a, lead(a_full(as)), kc * kBlockK, t.x0 + s, t.y0, t.n);
+          }
+          __syncwarp();
+          if (++as == Cfg::kAStages) as = 0, aph ^= 1;
+          MBAR_WAIT_RELAXED(b_empty(bs), bph ^ 1, 720 + bs);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(b_full(bs), CG * 3 * Cfg::kBBytes);
+            const uint32_t bar = lead(b_full(bs));
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              tma_load_2d_cg<CG>(b_smem(bs + r), &tmap_b, bar, (r * 3 + s) * p.Cin + kb * kBlockK, b_row);
+          }
+          __syncwarp();
+          if ((bs += 3) == Cfg::kBStages) bs = 0, bph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: every step starts a fresh partial sum
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc<T16, Cfg::kN, CG>();
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      for (int unit = unit_id; unit < p.total_tiles; unit += unit_cnt, ++it) {
+        const uint32_t use0 = (uint32_t)(it >> 1) * (uint32_t)(steps >> 1);  // uses of this tile parity's buffers so far
+        int j = 0;
+        for (int kc = 0; kc < kchunks; ++kc) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s, ++j) {
+            const int pb = 2 * (it & 1) + (j & 1);
+            const uint32_t use = use0 + (uint32_t)(j >> 1);
+            mbar_wait(a_full(as), aph, 740 + as);
+            mbar_wait(b_full(bs), bph, 750 + bs);
+            if (CG == 2) mbar_wait_cluster(part_empty(pb), (use & 1u) ^ 1u, 760 + pb);
+            else mbar_wait(part_empty(pb), (use & 1u) ^ 1u, 760 + pb);
+            tc_fence_after();
+            const int bs0 = bs;
+            if ((bs += 3) == Cfg::kBStages) bs = 0, bph ^= 1;
+            if (elect_one()) {
+              const uint32_t tmem_d = tmem_base + (uint32_t)(pb * Cfg::kN);
+              const uint64_t adesc0 = make_kmajor_sw128_desc(a_smem(as));
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const uint64_t adesc = adesc0 + (uint64_t)(r * (kTileW * 128 >> 4));
+                const uint64_t bdesc = make_kmajor_sw128_desc(b_smem(bs0 + r));
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_f16_cg<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (r | k) ? 1u : 0u);
+              }
+              umma_commit_cg<CG>(b_empty(bs0));
+              umma_commit_cg<CG>(a_empty(as));
+              umma_commit_cg<CG>(part_full(pb));
+            }
+            __syncwarp();
+            if (++as == Cfg::kAStages) as = 0, aph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue group g: tiles of parity g, partial buffers 2g and 2g + 1
+    const int grp = (warp - kEpiWarp0) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int py = row / kTileW, px = row % kTileW;
+    const bool issuer_warp = (quad == 0);
+    const uint32_t sbuf = store_base + grp * kStoreBytes;
+    SatTracker<T16> sat;
+    for (int it = grp;; it += 2) {
+      const long long unit_ll = (long long)unit_id + (long long)it * unit_cnt;
+      if (unit_ll >= p.total_tiles) break;
+      const TileCoord t = decode_tile<CG>(p, (int)unit_ll, (int)cta_rank);
+      const int y = t.y0 + py, x = t.x0 + px;
+      const bool valid = (y < p.H) && (x < p.W) && (CG == 1 || t.n < p.N);
+      const uint32_t use0 = (uint32_t)(it >> 1) * (uint32_t)(steps >> 1);
+      float acc[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < steps; ++j) {
+        const int pb = 2 * grp + (j & 1);
+        const uint32_t use = use0 + (uint32_t)(j >> 1);
+        mbar_wait(part_full(pb), use & 1u, 780 + pb);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(pb * Cfg::kN);
+        {
+          uint32_t u[32], v[32];
+          tmem_ld32(taddr, u);       // a * w_hi, channels 0..31
+          tmem_ld32(taddr + 64, v);  // a * w_lo
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = (acc[i] + __uint_as_float(u[i])) + __uint_as_float(v[i]);
+        }
+        {
+          uint32_t u[32], v[32];
+          tmem_ld32(taddr + 32, u);
+          tmem_ld32(taddr + 96, v);
+          tmem_ld_wait();
+          // the buffer is in registers: hand it back to the MMA warp before the adds
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(lead(part_empty(pb)));
+            else mbar_arrive(part_empty(pb));
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[32 + i] = (acc[32 + i] + __uint_as_float(u[i])) + __uint_as_float(v[i]);
+        }
+      }
+      // ---- v = acc * 2^-k + bias, ReLU, pooling: all in fp32
+      const int co = t.nt * 64;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        float v = fmaf(acc[i], p.out_scale, s_bias[co + i]);
+        if (p.relu) v = fmaxf(v, 0.f);
+        if (EPI == EPI_ACT_POOL) v = valid ? v : 0.f;  // outside the image: 0, the identity for post-ReLU values
+        acc[i] = v;
+      }
+      if (EPI == EPI_ACT_POOL) {
+        // 2x2 window = lanes {l, l^1, l^16, l^17}
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          float tt[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tt[i] = __shfl_xor_sync(0xffffffffu, acc[h2 * 32 + i], 1);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[h2 * 32 + i] = fmaxf(acc[h2 * 32 + i], tt[i]);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tt[i] = __shfl_xor_sync(0xffffffffu, acc[h2 * 32 + i], 16);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[h2 * 32 + i] = fmaxf(acc[h2 * 32 + i], tt[i]);
+        }
+      }
+      int srow = row;
+      bool writer = true;
+      if (EPI == EPI_ACT_POOL) {
+        writer = !(lane & 1) && lane < 16;  // anchor of a 2x2 window
+        srow = (py >> 1) * (kTileW / 2) + (px >> 1);
+      }
+      // ---- the two halves, one after the other through the group's staging tile
+#pragma unroll 1
+      for (int part = 0; part < 2; ++part) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v0 = acc[2 * i], v1 = acc[2 * i + 1];
+          const uint32_t hi = pack16x2<T16>(v0, v1);
+          if (part == 0) {
+            pk[i] = hi;
+          } else {
+            const float2 hf = unpack16x2<T16>(hi);
+            pk[i] = pack16x2<T16>(v0 - hf.x, v1 - hf.y);
+          }
+        }
+        if (part == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sat.track(pk[i]);
+        }
+        const int cs = co + part * p.Cout;  // channel of this half in the [hi | lo] map
+        if (issuer_warp) bulk_wait_read<0>();
+        epi_barrier(grp);
+        if (writer) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t dst = sbuf + srow * 128 + ((q ^ (srow & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                         "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                         : "memory");
+          }
+        }
+        if (valid) {
+          if (EPI == EPI_ACT) store_aliases(p.out, t.n, y, x, cs, pk, 1);
+          else if (writer) store_aliases(p.out, t.n, y >> 1, x >> 1, cs, pk, 1);
+        }
+        fence_async_smem();
+        epi_barrier(grp);
+        if (issuer_warp && elect_one()) {
+          if (EPI == EPI_ACT_POOL) tma_store_4d(&tmap_out, sbuf, cs, t.x0 >> 1, t.y0 >> 1, t.n);
+          else tma_store_4d(&tmap_out, sbuf, cs, t.x0, t.y0, t.n);
+          bulk_commit();
+        }
+      }
+    }
+    if (issuer_warp) bulk_wait_all();
+    sat.flush(p.sat_count);
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc_cg<CG, Cfg::kTmemCols>(tmem_base);
+}
+
+template <int EPI, int CG>
+int launch_x3_cfg(const CUtensorMap& ma, const __half* wk_x3, ConvParams<__half> p, cudaStream_t st) {
+  using Cfg = X3Cfg<CG>;
+  CUtensorMap mb, mo;
+  // [n_tiles * 128 rows = (tile, hi | lo, co)][9 * Cin]
+  if (int e = make_weight_map(&mb, wk_x3, 9 * p.Cin, 2 * p.Cout, Cfg::kBRows)) return e;
+  if (EPI == EPI_ACT) {
+    if (int e = make_out_map(&mo, p.out, 0, 0, 1, 1, kTileW, kTileH)) return e;
+  } else {
+    if (int e = make_out_map(&mo, p.out, 0, 0, 1, 1, kTileW / 2, kTileH / 2)) return e;
+  }
+  auto kernel = conv_x3_kernel<EPI, CG>;
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(kernel), Cfg::kSmemBytes));
+  const int64_t units = ((int64_t)p.m_tiles + CG - 1) / CG * p.n_tiles;
+  CCST_CHECK_ARG(units < (1ll << 31), "conv_x3: too many tiles");
+  p.total_tiles = (int)units;
+  const int slots = sm_count() / CG;
+  const int grid = (int)(units < slots ? units : slots) * CG;
+  CCST_CUDA(launch_conv(kernel, grid, kThreadsUmma, Cfg::kSmemBytes, st, CG, ma, mb, mo, p));
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+// in: [hi | lo] map of in.C / 2 logical channels; out: [hi | lo] map of Cout logical channels
+inline int launch_x3(const UmmaConvArgs<__half>& a, ConvParams<__half> p, cudaStream_t st) {
+  const ActView<__half>& in = a.in;
+  CCST_CHECK_ARG((a.epi == EPI_ACT || a.epi == EPI_ACT_POOL) && a.halo_edge == 1 && !a.per_sample && a.wk_x3 != nullptr,
+                 "conv_x3: the f16x3 engine runs the plain and the pooled epilogue of the encoder");
+  CCST_CHECK_ARG(in.C % (2 * kBlockK) == 0 && a.CoutPad == a.Cout && a.Cout % 64 == 0 && a.Cout <= 512 &&
+                     a.out.C == 2 * a.Cout,
+                 "conv_x3: Cin=%d/2 and Cout=%d must be multiples of 64 (Cout <= 512)", in.C, a.Cout);
+  p.Cin = in.C / 2;
+  p.out_scale = a.out_scale;
+  p.n_tiles = a.Cout / 64;
+  const int64_t mt = (int64_t)in.N * p.tiles_x * p.tiles_y;
+  CCST_CHECK_ARG(mt * p.n_tiles < (1ll << 30), "conv_x3: too many tiles");
+  p.m_tiles = (int)mt;
+  CUtensorMap ma;
+  if (int e = make_act_map(&ma, in)) return e;
+  if (a.epi == EPI_ACT) return launch_x3_cfg<EPI_ACT, 2>(ma, a.wk_x3, p, st);
+  return launch_x3_cfg<EPI_ACT_POOL, 2>(ma, a.wk_x3, p, st);
+}
+
+}  // namespace
+}  // namespace ccst

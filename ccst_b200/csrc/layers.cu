@@ -165,6 +165,104 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
   });
 }
 
+// The same conv1_1 with 4 consecutive pixels per thread (CTA = 256 pixels of one image row x 64 channels,
+// thread = 4 pixels x 16 channels): every weight vector read from shared memory feeds 4 pixels (64 FMAs per
+// 4 LDS.128 instead of 16), which is what the one-pixel form above is bound by.  Used by the f16x3 engine,
+// whose first layer stays on the CUDA cores in fp32 and is stored as [hi | lo] f16 halves.
+constexpr int kFirst4Tile = 256;
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+    conv_first_px4_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w27,
+                          const float* __restrict__ bias64, ActView<__half> out, unsigned int* sat_count) {
+  __shared__ __align__(16) float sw[27 * 64];
+  __shared__ float sb[64];
+  __shared__ float sin[3][3][kFirst4Tile + 4];  // [ci][row][col]
+  const int tiles_x = (W + kFirst4Tile - 1) / kFirst4Tile;
+  int b = blockIdx.x;
+  const int tx = b % tiles_x;
+  b /= tiles_x;
+  const int y = b % H;
+  const int n = b / H;
+  const int x0 = tx * kFirst4Tile;
+
+  for (int i = threadIdx.x; i < 27 * 64; i += 256) sw[i] = w27[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias64[threadIdx.x];
+  for (int i = threadIdx.x; i < 3 * 3 * (kFirst4Tile + 2); i += 256) {
+    const int col = i % (kFirst4Tile + 2);
+    const int row = (i / (kFirst4Tile + 2)) % 3;
+    const int ci = i / (3 * (kFirst4Tile + 2));
+    const int yy = reflect_idx(y + row - 1, H);
+    int xx = x0 + col - 1;
+    float v = 0.f;
+    if (xx <= W) {  // xx == W is the right halo of the last pixel
+      xx = reflect_idx(xx, W);
+      v = __ldg(img + (((size_t)n * 3 + ci) * H + yy) * W + xx);
+    }
+    sin[ci][row][col] = v;
+  }
+  __syncthreads();
+
+  const int pg = threadIdx.x >> 2;        // group of 4 pixels
+  const int cg = (threadIdx.x & 3) * 16;  // first output channel
+  const int xb = x0 + 4 * pg;
+  if (xb >= W) return;
+  float acc[4][16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[q][j] = sb[cg + j];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      float v[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) v[c] = sin[ci][r][4 * pg + c];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const float4* w4 = reinterpret_cast<const float4*>(&sw[((r * 3 + s) * 3 + ci) * 64 + cg]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 w = w4[k];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[q][k * 4 + 0] = fmaf(v[q + s], w.x, acc[q][k * 4 + 0]);
+            acc[q][k * 4 + 1] = fmaf(v[q + s], w.y, acc[q][k * 4 + 1]);
+            acc[q][k * 4 + 2] = fmaf(v[q + s], w.z, acc[q][k * 4 + 2]);
+            acc[q][k * 4 + 3] = fmaf(v[q + s], w.w, acc[q][k * 4 + 3]);
+          }
+        }
+      }
+    }
+  uint32_t hmax = 0u;  // running maximum of the stored (non-negative) high parts: f16 saturation guard
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int x = xb + q;
+    if (x >= W) break;
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v0 = fmaxf(acc[q][2 * j], 0.f), v1 = fmaxf(acc[q][2 * j + 1], 0.f);
+      hi[j] = pack16x2<__half>(v0, v1);
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
+      lo[j] = pack16x2<__half>(v0 - hf.x, v1 - hf.y);
+      hmax = max16x2<__half>(hmax, hi[j]);
+    }
+    for_each_halo_alias(y, x, H, W, [&](int yy, int xx) {
+      uint4* dst = reinterpret_cast<uint4*>(out.px(n, yy, xx) + cg);
+      dst[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      dst[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      if (SPLIT) {
+        uint4* dl = reinterpret_cast<uint4*>(out.px(n, yy, xx) + 64 + cg);
+        dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
+    });
+  }
+  if (((hmax & 0xffffu) >= 0x7bffu || (hmax >> 16) >= 0x7bffu) && sat_count != nullptr) atomicAdd(sat_count, 1u);
+}
+
 // =====================================================================================
 // fp32 FFMA implicit GEMM: CTA tile = 8x16 pixels x 64 output channels, K chunk = 16 channels
 // (all 9 taps per chunk).  Thread = 8 consecutive pixels of one tile row x 4 output channels.
@@ -362,12 +460,13 @@ __host__ __device__ inline int nhwc_chunks(int HW) { return (HW + kNhwcChunk - 1
 // cancellation in  M2 = sum d^2 - (sum d)^2 / n  scales with the spread of the values, not with
 // their mean; 3 instructions per element instead of a Welford update); pixel lanes are merged
 // through shared memory (Chan).
-template <typename T>
+// SPLIT (f16x3 engine): the map holds [hi | lo] halves of C = in.C / 2 logical channels; value = hi + lo.
+template <typename T, bool SPLIT = false>
 __global__ void __launch_bounds__(256)
     nhwc_stats_partial_kernel(ActView<T> in, float2* __restrict__ part) {
   constexpr int VEC = VecOf<T>::value;
   extern __shared__ float s_part[];  // [PX_LANES][C] mean, [PX_LANES][C] M2, [PX_LANES] count
-  const int C = in.C, ch_lanes = C / VEC, px_lanes = 256 / ch_lanes;
+  const int C = SPLIT ? in.C / 2 : in.C, ch_lanes = C / VEC, px_lanes = 256 / ch_lanes;
   float* s_mean = s_part;
   float* s_m2 = s_part + px_lanes * C;
   float* s_n = s_part + 2 * px_lanes * C;
@@ -381,13 +480,15 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int k = 0; k < VEC; ++k) piv[k] = 0.f, s1[k] = 0.f, s2[k] = 0.f;
   for (int pb = p0 + pl; pb < p1; pb += kNhwcBatch * px_lanes) {
-    Pack<T, VEC> v[kNhwcBatch];
+    Pack<T, VEC> v[kNhwcBatch], v2[SPLIT ? kNhwcBatch : 1];
 #pragma unroll
     for (int i = 0; i < kNhwcBatch; ++i) {  // all loads of the batch first
       const int p = pb + i * px_lanes;
       if (p < p1) {
         const int y = p / in.W, x = p - y * in.W;
-        v[i].v = *reinterpret_cast<const decltype(v[i].v)*>(src0 + (size_t)y * in.pitch_y() + (size_t)x * C);
+        const T* src = src0 + (size_t)y * in.pitch_y() + (size_t)x * in.C;
+        v[i].v = *reinterpret_cast<const decltype(v[i].v)*>(src);
+        if (SPLIT) v2[SPLIT ? i : 0].v = *reinterpret_cast<const decltype(v[i].v)*>(src + C);
       }
     }
 #pragma unroll
@@ -396,6 +497,12 @@ __global__ void __launch_bounds__(256)
       if (p < p1) {
         float f[VEC];
         unpack_vec(v[i], f);
+        if (SPLIT) {
+          float f2[VEC];
+          unpack_vec(v2[SPLIT ? i : 0], f2);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) f[k] += f2[k];
+        }
         if (cnt == 0.f) {
 #pragma unroll
           for (int k = 0; k < VEC; ++k) piv[k] = f[k];
@@ -642,25 +749,27 @@ __global__ void __launch_bounds__(256)
 // =====================================================================================
 // layout converters (32 pixels x 32 channels tiles through shared memory)
 // =====================================================================================
-template <typename T>
+template <typename T, bool SPLIT = false>
 __global__ void __launch_bounds__(256) act_to_nchw_kernel(ActView<T> in, float* __restrict__ out) {
   __shared__ float tile[32][33];
   const int HW = in.H * in.W;
+  const int C = SPLIT ? in.C / 2 : in.C;  // SPLIT: [hi | lo] halves, value = hi + lo
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32, n = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int p = p0 + i, c = c0 + tx;
     float v = 0.f;
-    if (p < HW && c < in.C) {
+    if (p < HW && c < C) {
       const int y = p / in.W, x = p - y * in.W;
       v = to_f32(in.px(n, y, x)[c]);
+      if (SPLIT) v += to_f32(in.px(n, y, x)[C + c]);
     }
     tile[i][tx] = v;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, p = p0 + tx;
-    if (p < HW && c < in.C) out[((size_t)n * in.C + c) * HW + p] = tile[tx][i];
+    if (p < HW && c < C) out[((size_t)n * C + c) * HW + p] = tile[tx][i];
   }
 }
 
@@ -871,6 +980,16 @@ int launch_conv_first(const float* img, int N, int H, int W, const float* w27, c
   const size_t blocks = (size_t)N * H * tiles_x;
   CCST_CHECK_ARG(blocks < (1ull << 31), "conv_first: grid too large");
   conv_first_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(img, N, H, W, w27, bias64, out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+int launch_conv_first_split(const float* img, int N, int H, int W, const float* w27, const float* bias64,
+                            ActView<__half> out, cudaStream_t st, unsigned int* sat_count) {
+  CCST_CHECK_ARG(out.C == 128, "conv_first(f16x3): the output map holds 64 + 64 channels");
+  const int tiles_x = (W + kFirst4Tile - 1) / kFirst4Tile;
+  const size_t blocks = (size_t)N * H * tiles_x;
+  CCST_CHECK_ARG(blocks < (1ull << 31), "conv_first: grid too large");
+  conv_first_px4_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(img, N, H, W, w27, bias64, out, sat_count);
   CCST_LAUNCHED();
   return CCST_OK;
 }
@@ -1105,6 +1224,19 @@ int launch_stats_nhwc(ActView<T> in, float2* scratch, cudaStream_t st) {
   CCST_LAUNCHED();
   return CCST_OK;
 }
+int launch_stats_nhwc_split(ActView<__half> in, float2* scratch, cudaStream_t st) {
+  ActView<__half> logical = in;
+  logical.C = in.C / 2;  // geometry and shared memory follow the logical channel count
+  if (int e = nhwc_geometry_ok(logical, "stats_nhwc(f16x3)")) return e;
+  const int HW = in.H * in.W, chunks = nhwc_chunks(HW);
+  const int NC = in.N * logical.C;
+  dim3 grid(chunks, in.N);
+  nhwc_stats_partial_kernel<__half, true><<<grid, 256, nhwc_stats_smem(logical), st>>>(in, scratch + NC);
+  CCST_LAUNCHED();
+  nhwc_stats_merge_kernel<<<(NC + 255) / 256, 256, 0, st>>>(scratch + NC, scratch, NC, logical.C, HW);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
 template int launch_stats_nhwc<float>(ActView<float>, float2*, cudaStream_t);
 template int launch_stats_nhwc<__nv_bfloat16>(ActView<__nv_bfloat16>, float2*, cudaStream_t);
 template int launch_stats_nhwc<__half>(ActView<__half>, float2*, cudaStream_t);
@@ -1113,6 +1245,12 @@ template <typename T>
 int launch_act_to_nchw(ActView<T> in, float* out_nchw, cudaStream_t st) {
   dim3 grid((in.H * in.W + 31) / 32, (in.C + 31) / 32, in.N);
   act_to_nchw_kernel<T><<<grid, 256, 0, st>>>(in, out_nchw);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+int launch_act_to_nchw_split(ActView<__half> in, float* out_nchw, cudaStream_t st) {
+  dim3 grid((in.H * in.W + 31) / 32, (in.C / 2 + 31) / 32, in.N);
+  act_to_nchw_kernel<__half, true><<<grid, 256, 0, st>>>(in, out_nchw);
   CCST_LAUNCHED();
   return CCST_OK;
 }

@@ -55,6 +55,9 @@ struct ConvParams {
   int w_rows_per_n, bias_per_n;
   int m_tiles_img;  // pixel tiles per image (padded to even for CTA pairs when weights are per sample)
   int contig_units; // s-merged kernel: every CTA takes a contiguous range of work units instead of a strided one
+  // f16x3 engine (conv_x3.cuh): the accumulator is multiplied by `out_scale`, the exact power of two the
+  // split weights were scaled by, before the bias is added
+  float out_scale;
   const float* bias;
   ActView<T16> out;
   float* out_nchw;

@@ -19,11 +19,12 @@ import torch
 from . import function as F_
 from .transfer import Engine
 
-# The statistics drivers default to the fp32 engine: it is the one whose relu4_1 features -- and hence
-# the .npy a user writes for a client -- meet the 1e-5 relative bar of BASELINE.json against the
-# reference.  The 16-bit tensor-core encoder ("fp16"/"bf16", ~25x faster) lands at ~1e-3 relative
-# (tests/test_gpu_net.py prints the measured figures) and must be asked for explicitly.
-STATS_PRECISION = "fp32"
+# The statistics drivers default to the f16x3 engine: the tensor-core encoder with split f16 operands and
+# promoted fp32 accumulation (csrc/conv_x3.cuh).  Its relu4_1 features -- and hence the .npy a user writes for
+# a client -- meet the 1e-5 relative bar of BASELINE.json against the reference (measured 2e-6), like the fp32
+# CUDA-core engine ("fp32", 1e-7, ~8x slower).  The plain 16-bit encoder ("fp16"/"bf16", ~4x faster again)
+# lands at ~1e-3 relative (tests/test_gpu_net.py prints the measured figures) and must be asked for explicitly.
+STATS_PRECISION = "fp16x3"
 
 
 def shard_range(total: int, rank: int, world: int):

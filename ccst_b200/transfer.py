@@ -26,7 +26,9 @@ import torch.nn as nn
 from . import _lib
 from . import function as F_
 
-PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16}
+PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16,
+              # encoder entry points only: split f16 operands (hi + lo), fp32-grade features on the tensor pipe
+              "fp16x3": _lib.PREC_FP16X3}
 # tensor-core path with f16 operands: meets the 1e-2 image tolerance of BASELINE.json; "bf16" runs
 # the same kernels with bf16 operands (wider range, ~7x larger rounding error), "fp32" the FFMA
 # validation mode (1e-4)

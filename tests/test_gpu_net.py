@@ -124,6 +124,23 @@ def test_encoder_decoder_golden_fp32(engine, golden, tag):
 
 
 @pytest.mark.parametrize("tag", ["sq40", "odd37x45", "r96"])
+def test_encoder_golden_f16x3(engine, golden, tag):
+    """Split-operand tensor-core encoder (f16 hi + lo parts, three MMAs per product term): the fp32 mode's
+    1e-4 bar on relu4_1 against the reference's golden features, odd sizes / ragged tiles included."""
+    g = golden["net"]
+    feat = engine.encode(T(g[tag + "/x"]).to(DEV), "fp16x3").cpu().numpy()
+    err = float(np.abs(feat - g[tag + "/feat"]).max())
+    report(f"encoder f16x3 {tag}", max_abs=err, feat_max=float(np.abs(g[tag + "/feat"]).max()))
+    np.testing.assert_allclose(feat, g[tag + "/feat"], rtol=0, atol=1e-4)
+
+
+def test_f16x3_is_encoder_only(engine, golden):
+    g = golden["net"]
+    with pytest.raises(RuntimeError, match="f16x3"):
+        engine.decode(T(g["sq40/feat"]).to(DEV), "fp16x3")
+
+
+@pytest.mark.parametrize("tag", ["sq40", "odd37x45", "r96"])
 def test_encoder_decoder_golden_tensor_core(engine, golden, tag):
     """tcgen05 path per stage (catches halo / border errors that a loose image tolerance hides): f16
     operands within 4e-3 of each stage's range; the bf16 figures are printed, not asserted (the image-
@@ -260,7 +277,7 @@ def _stat_rel(a, b):
     return ((a.cpu().double().flatten() - b).abs().max() / b.abs().max()).item()
 
 
-@pytest.mark.parametrize("precision", ["fp32", pytest.param("fp16", marks=STATS16_MISS),
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", pytest.param("fp16", marks=STATS16_MISS),
                                        pytest.param("bf16", marks=STATS16_MISS)])
 def test_overall_statistics_loop(models, precision):
     """mean_std_computation_effcientMem.py:117-137 on 3 batches of images against the reference formula
@@ -282,18 +299,18 @@ def test_overall_statistics_loop(models, precision):
 
 
 def test_overall_statistics_default_engine_and_identical_features(models):
-    """The statistics drivers default to the engine that meets 1e-5 (fp32); and given identical
-    features the accumulator itself meets the bar per element."""
+    """The statistics drivers default to an engine that meets 1e-5 (f16x3: split f16 operands on the tensor
+    pipe); and given identical features the accumulator itself meets the bar per element."""
     from ccst_b200 import overall
     vgg, dec = models
-    assert overall.STATS_PRECISION == "fp32"
+    assert overall.STATS_PRECISION == "fp16x3"
     batches = [synth.images(n, 64, 64, 50 + i) for i, n in enumerate((3, 3, 2))]
     with torch.no_grad():
         feats = [O.encode_relu4_1(vgg, b) for b in batches]
     mean64, std64, count, imgs = O.overall_style_stats(feats, dtype=torch.float64)
     eng = ccst_b200.engine_for(vgg, dec, torch.device(DEV))
     acc = OverallStyleAccumulator(eng)
-    assert acc.precision == "fp32"
+    assert acc.precision == "fp16x3"
     for f in feats:
         acc.add_features(f.to(DEV))
     mean, std = acc.finalize()

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--precision", default="fp16")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--encoder", action="store_true", help="the statistics loop's step (encode + Welford fold) instead of style_transfer")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     vgg, dec = synth.make_models(0)
@@ -31,12 +32,14 @@ def main():
     x = synth.images(a.batch, a.size, a.size, 1).to(dev)
     g = torch.Generator().manual_seed(7)
     stat = [torch.randn((1, 512, 1, 1), generator=g).abs().to(dev), (torch.rand((1, 512, 1, 1), generator=g) + 0.1).to(dev)]
+    state = ccst_b200.function.WelfordState(512, dev)
+    step = (lambda: eng.accumulate(x, state, a.precision)) if a.encoder else (lambda: eng.transfer(x, stat, 1.0, a.precision))
     for _ in range(3):
-        eng.transfer(x, stat, 1.0, a.precision)
+        step()
     eng.profile(True)
     acc = None
     for _ in range(a.iters):
-        eng.transfer(x, stat, 1.0, a.precision)
+        step()
         recs = eng.profile_read()
         if acc is None:
             acc = recs
@@ -45,7 +48,7 @@ def main():
                 r["ms"] += q["ms"]
     eng.profile(False)
     tot = sum(r["ms"] for r in acc) / a.iters
-    names = NAMES if len(acc) == len(NAMES) else [f"L{i}" for i in range(len(acc))]
+    names = NAMES if len(acc) == len(NAMES) else (NAMES[:9] + ["stats"] if len(acc) == 10 else [f"L{i}" for i in range(len(acc))])
     print(f"precision={a.precision} batch={a.batch} size={a.size}: {tot:.3f} ms/step, {a.batch / tot * 1e3:.1f} img/s")
     print(f"{'layer':10s} {'kind':12s} {'ms':>8s} {'share':>6s} {'TFLOP/s':>9s} {'GB/s':>8s}")
     for nm, r in zip(names, acc):
