@@ -19,11 +19,12 @@ tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3}
 res = {}
 for r in data:
     name = r[ik]
-    if "plane_bulk_kernel<(int)0" in name:
+    flat = name.replace("(int)", "").replace(" ", "")
+    if "plane_bulk_kernel<0," in flat:
         key = "calc_mean_std"
-    elif "plane_bulk_kernel<(int)2" in name:
+    elif "plane_bulk_kernel<2," in flat:
         key = "adain_stat"
-    elif "welford_bulk_kernel" in name or "plane_bulk_kernel<(int)1" in name:
+    elif "welford_bulk_kernel" in flat or "plane_bulk_kernel<1," in flat:
         key = "welford_accumulate"
     else:
         continue
