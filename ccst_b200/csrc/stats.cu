@@ -11,6 +11,8 @@
 // local (count, mean, M2) triple, the triples are merged with Chan's formula by warp shuffles and
 // (for CTA groups) a shared-memory combine.  Planes that do not fit in registers, or whose size /
 // alignment rules out 128-bit access, take a streaming variant of the same algorithm.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ccst {
@@ -271,35 +273,56 @@ __device__ __forceinline__ void bump_count_last_block(double* state, int C, doub
   if (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1) state[0] = old_count + add;
 }
 
+// Block = 8 channels x 32 batch lanes (thread t: channel t & 7, lane t >> 3): a warp reads 4 batch rows x 8
+// adjacent channels (64 contiguous bytes per row) per step, every thread Chan-merges N / 32 planes, the 32
+// lanes of a channel are combined through shared memory in fixed order.  (One warp per channel with a
+// 32-long dependent fp64 chain per lane and 4 KiB-strided loads took 20 us at [1024,512]; this form is
+// bound by the loads.)
 __global__ void __launch_bounds__(256) merge_planes_kernel(const float2* __restrict__ raw, int N,
                                                             int C, double hw,
                                                             double* __restrict__ state) {
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  __shared__ double s_n[8][8], s_mean[8][8], s_m2[8][8];
+  const int ch = threadIdx.x & 7, nl = threadIdx.x >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 8 + ch;
   const double old_count = state[0];
+  double n = 0.0, mean = 0.0, m2 = 0.0;
   if (c < C) {
-    double n = 0.0, mean = 0.0, m2 = 0.0;
-    for (int i = lane; i < N; i += 32) {
+    int i = nl;
+    for (; i + 96 < N; i += 128) {  // four independent loads in flight
+      const float2 r0 = raw[(size_t)i * C + c], r1 = raw[(size_t)(i + 32) * C + c];
+      const float2 r2 = raw[(size_t)(i + 64) * C + c], r3 = raw[(size_t)(i + 96) * C + c];
+      chan_merge(n, mean, m2, hw, (double)r0.x, (double)r0.y);
+      chan_merge(n, mean, m2, hw, (double)r1.x, (double)r1.y);
+      chan_merge(n, mean, m2, hw, (double)r2.x, (double)r2.y);
+      chan_merge(n, mean, m2, hw, (double)r3.x, (double)r3.y);
+    }
+    for (; i < N; i += 32) {
       const float2 r = raw[(size_t)i * C + c];
       chan_merge(n, mean, m2, hw, (double)r.x, (double)r.y);
     }
+  }
+  // the warp's four batch lanes of a channel (lanes ch, ch + 8, ch + 16, ch + 24): butterfly in which both
+  // partners compute (lower lane) <- (upper lane), so the result does not depend on who keeps it
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const double nb = __shfl_xor_sync(0xffffffffu, n, off);
-      const double mb = __shfl_xor_sync(0xffffffffu, mean, off);
-      const double qb = __shfl_xor_sync(0xffffffffu, m2, off);
-      // both partners must compute the same bits: merge (lower lane's value) <- (upper lane's value)
-      double an = n, am = mean, aq = m2, bn = nb, bm = mb, bq = qb;
-      if (lane & off) an = nb, am = mb, aq = qb, bn = n, bm = mean, bq = m2;
-      chan_merge(an, am, aq, bn, bm, bq);
-      n = an, mean = am, m2 = aq;
-    }
-    if (lane == 0) {
-      double sn = old_count, sm = state[1 + c], sq = state[1 + C + c];
-      chan_merge(sn, sm, sq, n, mean, m2);
-      state[1 + c] = sm;
-      state[1 + C + c] = sq;
-    }
+  for (int off = 8; off < 32; off <<= 1) {
+    const double nb = __shfl_xor_sync(0xffffffffu, n, off);
+    const double mb = __shfl_xor_sync(0xffffffffu, mean, off);
+    const double qb = __shfl_xor_sync(0xffffffffu, m2, off);
+    double an = n, am = mean, aq = m2, bn = nb, bm = mb, bq = qb;
+    if (lane & off) an = nb, am = mb, aq = qb, bn = n, bm = mean, bq = m2;
+    chan_merge(an, am, aq, bn, bm, bq);
+    n = an, mean = am, m2 = aq;
+  }
+  if (lane < 8) s_n[warp][ch] = n, s_mean[warp][ch] = mean, s_m2[warp][ch] = m2;
+  __syncthreads();
+  if (threadIdx.x < 8 && c < C) {
+    double an = s_n[0][ch], am = s_mean[0][ch], aq = s_m2[0][ch];
+    for (int l = 1; l < 8; ++l) chan_merge(an, am, aq, s_n[l][ch], s_mean[l][ch], s_m2[l][ch]);
+    double sn = old_count, sm = state[1 + c], sq = state[1 + C + c];
+    chan_merge(sn, sm, sq, an, am, aq);
+    state[1 + c] = sm;
+    state[1 + C + c] = sq;
   }
   __syncthreads();
   if (threadIdx.x == 0) bump_count_last_block(state, C, old_count, hw * (double)N);
@@ -347,16 +370,22 @@ __global__ void from_moments_kernel(const double* __restrict__ mom, int C,
 }
 
 // =====================================================================================
-// Bulk-staged variant (the fast path): planes are contiguous in memory, so a CTA streams 16 KiB
-// chunks of consecutive planes into a shared-memory ring with 1-D TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx), 8 chunks = 128 KiB in flight per SM, issued by one
-// producer lane far ahead of the consumers.  Each of the 8 consumer warps owns one ring slot and
-// reduces its chunk from shared memory with an exact two-pass (sum, then sum of squared deviations;
+// Bulk-staged variant (the fast path): planes are contiguous in memory, so a CTA streams chunks of
+// consecutive planes (4 .. 16 KiB) into a shared-memory ring with 1-D TMA bulk copies (cp.async.bulk +
+// mbarrier complete_tx), 128 .. 200 KiB in flight per SM.  Each consumer warp owns its ring slots and
+// reduces a chunk from shared memory with an exact two-pass (sum, then sum of squared deviations;
 // warp shuffles combine the lanes of a plane), then -- for AdaIN -- makes a third pass that applies
 // the affine and writes 128-bit coalesced stores.  HBM sees exactly one read (+ one write).
 // =====================================================================================
-constexpr int kRingBytes = 131072;
+constexpr int kRingBytes = 131072;     // ring of the one-launch accumulation (welford_bulk_kernel)
 constexpr int kSlotBytesMax = 16384;
+// plane_bulk_kernel sizes its ring at launch: what bounds the statistics kernels on small inputs is the number
+// of bytes in flight per SM (ncu on [64,512,28,28] with a 16 x 8 KiB ring, 77 % filled: the consumer warps
+// spend 44 % of their samples waiting for a full slot, DRAM at 49 %), so the ring takes all the shared
+// memory an SM has and its slots are whole multiples of the plane size.
+constexpr int kRingBudget = 225 * 1024;
+constexpr int kMaxSlots = 32;
+constexpr int kMaxConsumers = 16;
 
 struct BulkArgs {
   const float* x;
@@ -364,6 +393,8 @@ struct BulkArgs {
   int64_t planes;
   int hw;          // elements per plane, hw % 4 == 0, hw * 4 <= kSlotBytesMax
   int ppc;         // planes per chunk
+  int slots;       // ring slots of ppc * hw * 4 bytes (<= kMaxSlots)
+  int warps;       // consumer warps (<= kMaxConsumers): warp w takes the CTA's chunks w, w + warps, ...
   int64_t chunks;
   float eps;
   int unbiased;
@@ -411,57 +442,79 @@ __device__ __forceinline__ float group_sum(float v) {
 }
 
 // MODE 0: mean/std, 1: raw {mean, M2}, 2: AdaIN
-// SLOTS ring slots of kRingBytes / SLOTS bytes, one consumer warp per slot: 8 x 16 KiB by default,
-// 16 x 8 KiB for planes <= 1 KiB (the per-plane latency chain -- two shared-memory passes, shuffles,
-// sqrt -- bounds small planes, so twice the warps are put on it)
-template <int MODE, int G, int SLOTS>
-__global__ void __launch_bounds__(32 * (1 + SLOTS), 1) plane_bulk_kernel(BulkArgs a) {
-  constexpr int kSlots = SLOTS, kSlotBytes = kRingBytes / SLOTS;
-  extern __shared__ __align__(128) uint8_t ring[];  // kSlots * kSlotBytes, then the barriers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kSlots * kSlotBytes);
+// Ring of a.slots slots of a.ppc planes, a.warps consumer warps; the CTA's chunks are blockIdx.x,
+// blockIdx.x + gridDim.x, ..., consumer warp w takes every a.warps-th of them and owns the slots
+// w * depth .. w * depth + depth - 1 (depth = slots / warps), so a slot is always read by the same warp.
+//   PROD = false (statistics): self-service -- every warp issues the bulk copies of its first `depth` chunks
+//     itself and, after reducing a chunk, the copy of the chunk that reuses the slot.  A single producer lane
+//     was the bound of the read-only modes on every shape with chunks below 16 KiB (ncu on [64,512,28,28]:
+//     consumers 44 % of their samples waiting for a full slot, DRAM at 49 %); with the issue work spread
+//     over 16 warps [1024,512,12,12] went from 4.9 to 6.0 TB/s, [64,512,28,28] from 3.7 to 4.5.
+//   PROD = true (AdaIN): warp 0 is a dedicated producer running ahead through empty barriers; the consumers
+//     spend most of their time storing, and loads issued only when a warp gets around to it leave the read
+//     side idle (measured 5 .. 8 % slower on the 28^2 / 32^2 shapes).
+// Small planes are bound by the per-plane latency chain (two shared-memory passes, shuffles, sqrt): they get
+// 16 warps and few lanes per plane.
+template <int MODE, int G, bool PROD>
+__global__ void __launch_bounds__(32 * (kMaxConsumers + (PROD ? 1 : 0)), 1) plane_bulk_kernel(BulkArgs a) {
+  extern __shared__ __align__(128) uint8_t ring[];  // slots * slot_bytes, then the barriers (full, empty)
+  const int kSlots = a.slots, W = a.warps;
+  const int kDepth = kSlots / W;  // slots (chunks in flight) per consumer warp
+  const int kSlotBytes = a.ppc * a.hw * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)kSlots * kSlotBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSlots; ++s) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[s])));           // full
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[kSlots + s])));  // empty
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[s])));  // full
+      if (PROD) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[kSlots + s])));  // empty
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int64_t plane_bytes = (int64_t)a.hw * 4;
-  // this CTA's chunks: blockIdx.x, blockIdx.x + gridDim.x, ...; its i-th chunk uses slot i % kSlots
-  if (warp == 0) {
+  // bulk copy of chunk c into `slot` (one lane)
+  auto issue = [&](int64_t c, int slot) {
+    const int64_t p0 = c * a.ppc;
+    const int64_t np = (a.planes - p0) < a.ppc ? (a.planes - p0) : a.ppc;
+    const uint32_t bytes = (uint32_t)(np * plane_bytes);
+    const uint32_t full = smem_addr(&bars[slot]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_addr(ring + (size_t)slot * kSlotBytes)),
+        "l"(a.x + p0 * a.hw), "r"(bytes), "r"(full)
+        : "memory");
+  };
+  const int64_t cstep = (int64_t)W * gridDim.x;
+  if (PROD && warp == 0) {
+    // the CTA's i-th chunk belongs to warp i % W, round i / W: slot (i % W) * depth + (i / W) % depth
     if (lane == 0) {
-      int64_t i = 0;
-      for (int64_t c = blockIdx.x; c < a.chunks; c += gridDim.x, ++i) {
-        const int slot = (int)(i % kSlots);
-        const uint32_t use = (uint32_t)(i / kSlots);
-        bar_wait(smem_addr(&bars[kSlots + slot]), (use & 1) ^ 1);
-        const int64_t p0 = c * a.ppc;
-        const int64_t np = (a.planes - p0) < a.ppc ? (a.planes - p0) : a.ppc;
-        const uint32_t bytes = (uint32_t)(np * plane_bytes);
-        const uint32_t full = smem_addr(&bars[slot]);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes)
-                     : "memory");
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                smem_addr(ring + slot * kSlotBytes)),
-            "l"(a.x + p0 * a.hw), "r"(bytes), "r"(full)
-            : "memory");
+      int cw = 0, round = 0;
+      for (int64_t c = blockIdx.x; c < a.chunks; c += gridDim.x) {
+        const int slot = cw * kDepth + round % kDepth;
+        bar_wait(smem_addr(&bars[kSlots + slot]), (((uint32_t)(round / kDepth)) & 1) ^ 1);
+        issue(c, slot);
+        if (++cw == W) cw = 0, ++round;
       }
     }
     return;
   }
-  // ---- consumer warp w owns slot w: the CTA's chunks i = w, w + 8, ...
-  const int slot = warp - 1;
-  const float4* buf = reinterpret_cast<const float4*>(ring + slot * kSlotBytes);
+  const int w = warp - (PROD ? 1 : 0);
+  const int64_t c_first = (int64_t)blockIdx.x + (int64_t)w * gridDim.x;
+  if (!PROD) {
+    if (lane == 0)
+      for (int d0 = 0; d0 < kDepth; ++d0)
+        if (c_first + d0 * cstep < a.chunks) issue(c_first + d0 * cstep, w * kDepth + d0);
+    __syncwarp();
+  }
   const int n4 = a.hw >> 2;              // float4 per plane
   constexpr int kGroups = 32 / G;        // planes processed concurrently by the warp
   const int grp = lane / G, sub = lane % G;
-  int64_t i = slot;
-  for (int64_t c = (int64_t)blockIdx.x + (int64_t)slot * gridDim.x; c < a.chunks;
-       c += (int64_t)kSlots * gridDim.x, i += kSlots) {
-    const uint32_t use = (uint32_t)(i / kSlots);
+  int d = 0;          // slot of this warp the current chunk sits in
+  uint32_t use = 0;   // how often the warp has been around its slots
+  for (int64_t c = c_first; c < a.chunks; c += cstep) {
+    const int slot = w * kDepth + d;
+    const float4* buf = reinterpret_cast<const float4*>(ring + (size_t)slot * kSlotBytes);
     bar_wait(smem_addr(&bars[slot]), use & 1);
     const int64_t p0 = c * a.ppc;
     const int np = (int)((a.planes - p0) < a.ppc ? (a.planes - p0) : a.ppc);
@@ -541,12 +594,14 @@ __global__ void __launch_bounds__(32 * (1 + SLOTS), 1) plane_bulk_kernel(BulkArg
         }
       }
     }
-    // generic-proxy reads of the slot -> ordered before the producer's next bulk copy (async proxy)
+    // every lane's generic-proxy reads of the slot -> ordered before the bulk copy (async proxy) that refills it
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    if (lane == 0)
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bars[kSlots + slot]))
-                   : "memory");
+    if (lane == 0) {
+      if (PROD) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bars[kSlots + slot])) : "memory");
+      else if (c + kDepth * cstep < a.chunks) issue(c + kDepth * cstep, slot);
+    }
+    if (++d == kDepth) d = 0, ++use;
   }
 }
 
@@ -570,23 +625,24 @@ struct AccArgs {
   const float* x;
   int N, C, hw;
   int J;        // chunk classes per CTA
+  int slots;    // ring slots of one chunk (PPC planes) each, <= kMaxSlots
+  int warps;    // consumer warps, <= kMaxConsumers, a multiple of J
   double* state;
 };
 
-template <int PPC, int NSLOTS>
-__global__ void __launch_bounds__(32 * (1 + (NSLOTS < 16 ? NSLOTS : 16)), 1) welford_bulk_kernel(AccArgs a) {
-  constexpr int kSlotBytes = kRingBytes / NSLOTS;
-  constexpr int W = NSLOTS < 16 ? NSLOTS : 16;
+template <int PPC>
+__global__ void __launch_bounds__(32 * kMaxConsumers, 1) welford_bulk_kernel(AccArgs a) {
+  const int NSLOTS = a.slots, W = a.warps;
+  const int kDepth = NSLOTS / W;  // slots (chunks in flight) per warp: warp w owns slots w * kDepth ..
+  const int kSlotBytes = PPC * a.hw * 4;
   constexpr int G = 32 / PPC;
   extern __shared__ __align__(128) uint8_t ring[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kRingBytes);
-  double* s_part = reinterpret_cast<double*>(ring + kRingBytes + 2 * 32 * 8);  // [W][PPC][3]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)NSLOTS * kSlotBytes);
+  double* s_part = reinterpret_cast<double*>(bars + 2 * kMaxSlots);  // [W][PPC][3]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSLOTS; ++s) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[s])));           // full
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[NSLOTS + s])));  // empty
-    }
+    for (int s = 0; s < NSLOTS; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[s])));  // full
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -599,33 +655,31 @@ __global__ void __launch_bounds__(32 * (1 + (NSLOTS < 16 ? NSLOTS : 16)), 1) wel
     const int j = b + (int)(i % a.J) * grid;
     return a.x + ((n * cpi + j) * PPC) * (int64_t)a.hw;
   };
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int64_t i = 0; i < chunks; ++i) {
-        const int slot = (int)(i % NSLOTS);
-        const uint32_t use = (uint32_t)(i / NSLOTS);
-        bar_wait(smem_addr(&bars[NSLOTS + slot]), (use & 1) ^ 1);
-        const uint32_t full = smem_addr(&bars[slot]);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(chunk_bytes)
-                     : "memory");
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                smem_addr(ring + slot * kSlotBytes)),
-            "l"(chunk_src(i)), "r"(chunk_bytes), "r"(full)
-            : "memory");
-      }
-    }
-    return;
-  }
+  // self-service ring (see plane_bulk_kernel): every warp issues the bulk copies of its own chunks
+  auto issue = [&](int64_t i, int slot) {
+    const uint32_t full = smem_addr(&bars[slot]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(chunk_bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_addr(ring + (size_t)slot * kSlotBytes)),
+        "l"(chunk_src(i)), "r"(chunk_bytes), "r"(full)
+        : "memory");
+  };
+  const int w = warp;
+  if (lane == 0)
+    for (int d0 = 0; d0 < kDepth; ++d0)
+      if (w + (int64_t)d0 * W < chunks) issue(w + (int64_t)d0 * W, w * kDepth + d0);
+  __syncwarp();
   const double old_count = a.state[0];
-  const int w = warp - 1;
   const int grp = lane / G, sub = lane % G;  // plane of the chunk, lane inside the plane's group
   const int n4 = a.hw >> 2;
   double rn = 0.0, rmean = 0.0, rm2 = 0.0;   // running state of channel (class of this warp, plane grp); lane sub == 0
+  int d = 0;
+  uint32_t use = 0;
   for (int64_t i = w; i < chunks; i += W) {
-    const int slot = (int)(i % NSLOTS);
-    bar_wait(smem_addr(&bars[slot]), (uint32_t)(i / NSLOTS) & 1);
-    const float4* src = reinterpret_cast<const float4*>(ring + slot * kSlotBytes) + (size_t)grp * n4;
+    const int slot = w * kDepth + d;
+    bar_wait(smem_addr(&bars[slot]), use & 1);
+    const float4* src = reinterpret_cast<const float4*>(ring + (size_t)slot * kSlotBytes) + (size_t)grp * n4;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int k = sub;
     for (; k + 3 * G < n4; k += 4 * G) {
@@ -655,11 +709,11 @@ __global__ void __launch_bounds__(32 * (1 + (NSLOTS < 16 ? NSLOTS : 16)), 1) wel
     }
     for (; k < n4; k += G) q0 += sq(src[k]);
     const float q = group_sum<G>((q0 + q1) + (q2 + q3));
-    // generic-proxy reads of the slot -> ordered before the producer's next bulk copy (async proxy)
+    // every lane's generic-proxy reads of the slot -> ordered before the bulk copy (async proxy) that refills it
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    if (lane == 0)
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bars[NSLOTS + slot])) : "memory");
+    if (lane == 0 && i + (int64_t)kDepth * W < chunks) issue(i + (int64_t)kDepth * W, slot);
+    if (++d == kDepth) d = 0, ++use;
     if (sub == 0) chan_merge(rn, rmean, rm2, (double)a.hw, (double)mean, (double)q);
   }
   // warps of the CTA -> shared memory -> fixed-order merge per channel -> global state
@@ -667,7 +721,7 @@ __global__ void __launch_bounds__(32 * (1 + (NSLOTS < 16 ? NSLOTS : 16)), 1) wel
     double* d = s_part + ((size_t)w * PPC + grp) * 3;
     d[0] = rn, d[1] = rmean, d[2] = rm2;
   }
-  asm volatile("bar.sync 1, %0;" ::"r"(32 * W) : "memory");  // consumer warps only (the producer warp has left)
+  __syncthreads();
   if (w == 0) {
     if (lane < a.J * PPC) {
       const int jj = lane / PPC, pl = lane % PPC;
@@ -687,22 +741,34 @@ __global__ void __launch_bounds__(32 * (1 + (NSLOTS < 16 ? NSLOTS : 16)), 1) wel
   }
 }
 
-constexpr int kAccSmem = kRingBytes + 2 * 32 * 8 + 16 * 8 * 3 * 8;
+// (slots, consumer warps) of a ring.  A slot must always be consumed by the SAME warp -- a parity wait may run
+// at most one phase ahead of the barrier, which only program order inside one warp guarantees -- so warps | slots.
+struct RingPlan {
+  int slots = 0, warps = 0;
+};
 
-template <int PPC, int NSLOTS>
+constexpr int kAccTail = 2 * kMaxSlots * 8 + kMaxConsumers * 4 * 3 * 8;  // barriers + [W][PPC <= 4][3] doubles
+
+template <int PPC>
 int launch_acc_cfg(const AccArgs& a, int grid, cudaStream_t st) {
-  constexpr int W = NSLOTS < 16 ? NSLOTS : 16;
-  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(welford_bulk_kernel<PPC, NSLOTS>), kAccSmem));
-  welford_bulk_kernel<PPC, NSLOTS><<<grid, 32 * (1 + W), kAccSmem, st>>>(a);
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(welford_bulk_kernel<PPC>), kRingBudget + kAccTail));
+  const int smem = a.slots * PPC * a.hw * 4 + kAccTail;
+  welford_bulk_kernel<PPC><<<grid, 32 * a.warps, smem, st>>>(a);
   CCST_LAUNCHED();
   return CCST_OK;
 }
 
-// Picks (PPC, NSLOTS, grid) for the one-launch accumulation, or returns false (-> two-launch path).
+// Picks (PPC, slots, warps, grid) for the one-launch accumulation, or returns false (-> two-launch path).
 bool launch_acc(const float* x, int N, int C, int64_t hw, double* state, cudaStream_t st, int* rc) {
   if (!bulk_ok(x, hw) || C % 4 != 0) return false;
   const int sms = sm_count();
+  int force_ppc = 0, force_slots = 0, force_warps = 0;
+#ifdef CCST_DEV
+  if (const char* e = getenv("CCST_ACC_PLAN"))  // "ppc,slots,warps" (tools/bulk_sweep.sh)
+    if (sscanf(e, "%d,%d,%d", &force_ppc, &force_slots, &force_warps) != 3) force_ppc = 0;
+#endif
   for (int ppc = 4; ppc >= 1; ppc >>= 1) {
+    if (force_ppc && ppc != force_ppc) continue;
     const int64_t cb = (int64_t)ppc * hw * 4;
     if (C % ppc != 0 || cb > kSlotBytesMax) continue;
     // bulk copies of less than 4 KiB cost more to issue than they move (measured on [1024,512,12,12]: 2.3 KiB
@@ -716,41 +782,81 @@ bool launch_acc(const float* x, int N, int C, int64_t hw, double* state, cudaStr
         break;
       }
     const int J = cpi / grid;
-    const int nslots = cb <= 4096 ? 32 : (cb <= 8192 ? 16 : 8);
-    const int W = nslots < 16 ? nslots : 16;
+    // one chunk in flight per warp; measured (tools/acc_sweep.sh, profiles/r02_bulk_sweep.txt): 16 warps when 16
+    // chunks fit the ring, else 12 for the J = 4 layout of 16 KiB planes, else 8 -- the kernel is insensitive to
+    // the ring beyond that (its small-input floor is the 128-CTA grid, the fp64 merges and the launch)
+    RingPlan rp;
+    for (int wc : {16, 12, 8, 4, 2, 1})
+      if ((int64_t)wc * cb <= kRingBudget && wc % J == 0 && (wc != 12 || J == 4)) {
+        rp.slots = rp.warps = wc;
+        break;
+      }
+    if (force_ppc && force_slots >= 1 && force_slots <= kMaxSlots && force_warps >= 1 && force_warps <= kMaxConsumers &&
+        force_slots % force_warps == 0 && force_warps % J == 0 && (int64_t)force_slots * cb <= kRingBudget)
+      rp.slots = force_slots, rp.warps = force_warps;
     // enough CTAs to pull the HBM bandwidth, classes a warp can own, one lane per channel in the final merge
-    if (grid * 4 < sms * 3 || W % J != 0 || J * ppc > 32) continue;
-    AccArgs a{x, N, C, (int)hw, J, state};
-    if (ppc == 4) *rc = nslots == 32 ? launch_acc_cfg<4, 32>(a, grid, st) : (nslots == 16 ? launch_acc_cfg<4, 16>(a, grid, st) : launch_acc_cfg<4, 8>(a, grid, st));
-    else if (ppc == 2) *rc = nslots == 32 ? launch_acc_cfg<2, 32>(a, grid, st) : (nslots == 16 ? launch_acc_cfg<2, 16>(a, grid, st) : launch_acc_cfg<2, 8>(a, grid, st));
-    else *rc = nslots == 32 ? launch_acc_cfg<1, 32>(a, grid, st) : (nslots == 16 ? launch_acc_cfg<1, 16>(a, grid, st) : launch_acc_cfg<1, 8>(a, grid, st));
+    if (grid * 4 < sms * 3 || rp.warps < 1 || J * ppc > 32) continue;
+    AccArgs a{x, N, C, (int)hw, J, rp.slots, rp.warps, state};
+    if (ppc == 4) *rc = launch_acc_cfg<4>(a, grid, st);
+    else if (ppc == 2) *rc = launch_acc_cfg<2>(a, grid, st);
+    else *rc = launch_acc_cfg<1>(a, grid, st);
     return true;
   }
   return false;
 }
 
-constexpr int kBulkSmem = kRingBytes + 2 * 16 * 8;
-
-template <int MODE, int G, int SLOTS>
+template <int MODE, int G>
 int launch_bulk_cfg(BulkArgs a, cudaStream_t st) {
-  a.ppc = (int)((kRingBytes / SLOTS) / ((int64_t)a.hw * 4));
-  CCST_CHECK_ARG(a.ppc >= 1, "plane_bulk: a plane of %d floats does not fit a %d-byte ring slot", a.hw,
-                 kRingBytes / SLOTS);
+  constexpr bool PROD = (MODE == 2);
+  constexpr int kGroups = 32 / G;
+  const int64_t plane_bytes = (int64_t)a.hw * 4;
+  const int sms = sm_count();
+  // measured geometries (tools/bulk_sweep.sh, profiles/r02_bulk_sweep.txt)
+  if (PROD) {
+    // AdaIN: 16 x 8 KiB slots / 16 warps up to 4 KiB planes, 8 x 16 KiB / 8 warps above
+    const int slot_max = G == 32 ? 16384 : 8192;
+    a.ppc = (int)(slot_max / plane_bytes);
+    a.slots = a.warps = G == 32 ? 8 : 16;
+  } else if (G == 32) {
+    // one plane (<= 16 KiB) per chunk; inputs with few chunks per CTA ramp up faster on more warps
+    a.ppc = 1;
+    const int64_t per_cta = ceil_div64(a.planes, sms);
+    const int fit = (int)(kRingBudget / plane_bytes);
+    a.slots = a.warps = per_cta < 48 ? (fit < 12 ? fit : 12) : 8;
+  } else {
+    // chunk = the planes one warp works on at a time (32 / G), repeated up to >= 4 KiB; two chunks in
+    // flight per warp when the ring has room for 32 of them
+    const int64_t unit = kGroups * plane_bytes;
+    a.ppc = kGroups * (int)ceil_div64(4096, unit);
+    a.warps = 16;
+    a.slots = 32 * a.ppc * plane_bytes <= kRingBudget ? 32 : 16;
+  }
+  CCST_CHECK_ARG(a.ppc >= 1 && (int64_t)a.slots * a.ppc * plane_bytes <= kRingBudget,
+                 "plane_bulk: a plane of %d floats does not fit the ring", a.hw);
+#ifdef CCST_DEV
+  if (const char* e = getenv("CCST_BULK_PLAN")) {  // "slots,warps,ppc" (tools/bulk_sweep.sh)
+    int sl = 0, w = 0, pp = 0;
+    if (sscanf(e, "%d,%d,%d", &sl, &w, &pp) == 3 && sl >= 1 && sl <= kMaxSlots && w >= 1 && w <= kMaxConsumers &&
+        sl % w == 0 && pp >= 1 && (int64_t)sl * pp * plane_bytes <= kRingBudget)
+      a.slots = sl, a.warps = w, a.ppc = pp;
+  }
+#endif
   a.chunks = ceil_div64(a.planes, a.ppc);
-  const int grid = (int)(a.chunks < sm_count() ? a.chunks : sm_count());
-  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(plane_bulk_kernel<MODE, G, SLOTS>), kBulkSmem));
-  plane_bulk_kernel<MODE, G, SLOTS><<<grid, 32 * (1 + SLOTS), kBulkSmem, st>>>(a);
+  const int grid = (int)(a.chunks < sms ? a.chunks : sms);
+  const int smem = (int)((int64_t)a.slots * a.ppc * plane_bytes) + 2 * kMaxSlots * 8;
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(plane_bulk_kernel<MODE, G, PROD>), kRingBudget + 2 * kMaxSlots * 8));
+  plane_bulk_kernel<MODE, G, PROD><<<grid, 32 * (a.warps + (PROD ? 1 : 0)), smem, st>>>(a);
   CCST_LAUNCHED();
   return CCST_OK;
 }
 
 template <int MODE>
 int launch_bulk(BulkArgs a, cudaStream_t st) {
-  if (a.hw <= 256)  // up to 1 KiB planes (12x12 .. 16x16): 4 lanes per plane, 16 warps
-    return launch_bulk_cfg<MODE, 4, 16>(a, st);
-  if (a.hw <= 1024)  // up to 4 KiB planes: 16 lanes per plane, 16 warps
-    return launch_bulk_cfg<MODE, 16, 16>(a, st);
-  return launch_bulk_cfg<MODE, 32, 8>(a, st);
+  if (a.hw <= 256)  // up to 1 KiB planes (12x12 .. 16x16): 4 lanes per plane
+    return launch_bulk_cfg<MODE, 4>(a, st);
+  if (a.hw <= 1024)  // up to 4 KiB planes: 16 lanes per plane
+    return launch_bulk_cfg<MODE, 16>(a, st);
+  return launch_bulk_cfg<MODE, 32>(a, st);
 }
 
 int grid_for(int64_t groups) {

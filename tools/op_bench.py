@@ -36,13 +36,18 @@ def timeit(fn, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--shapes", default="", help="e.g. 64x512x28x28,32x512x32x32 (default: the five profile shapes)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     L = _lib.lib()
     _lib.check(L.ccst_set_device(0))
     st = torch.cuda.current_stream().cuda_stream
     rows = []
-    for (n, c, h, w) in [(32, 512, 64, 64), (6, 512, 64, 64), (1024, 512, 12, 12), (64, 512, 28, 28), (32, 512, 32, 32)]:
+    shapes = [(32, 512, 64, 64), (6, 512, 64, 64), (1024, 512, 12, 12), (64, 512, 28, 28), (32, 512, 32, 32),
+              (128, 512, 32, 32)]  # the last: the reference's own default (256x256 images, batch 128)
+    if a.shapes:
+        shapes = [tuple(int(v) for v in sh.split("x")) for sh in a.shapes.split(",")]
+    for (n, c, h, w) in shapes:
         xs = [torch.randn((n, c, h, w), device=dev).relu_() for _ in range(2)]  # alternate buffers
         out = torch.empty_like(xs[0])
         mean = torch.empty((n * c,), device=dev)
