@@ -318,6 +318,35 @@ def run_ours(args, rank, world, local_rank):
     e2e_serial_value = args.batch * args.steps / (time.perf_counter() - t0)
     img_bytes = args.batch * 3 * SIZE * SIZE * 4
 
+    # The box's pinned-copy ceiling: every rank moves one fp32 batch up and one down per iteration, concurrently
+    # on two streams, nothing else running -- what the host side (PCIe switches, memory controllers) allows the
+    # fp32 host-tensor form of the loop above at this rank count, whatever the GPUs do in between.
+    def host_copy_ceiling(iters=12):
+        s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def go(n):
+            for i in range(n):
+                with torch.cuda.stream(s_up):
+                    dev_in[i & 1].copy_(host[i & 1], non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    host_out.copy_(out, non_blocking=True)
+            s_up.synchronize()
+            s_dn.synchronize()
+
+        go(2)
+        barrier()
+        t0 = time.perf_counter()
+        go(iters)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        gbs = world * iters * 2 * img_bytes / dt / 1e9
+        return {"aggregate_GBps_h2d_plus_d2h": round(gbs, 1), "per_gpu_GBps_each_way": round(gbs / world / 2, 1),
+                "images_per_s_ceiling": round(world * iters * args.batch / dt, 1),
+                "how": "all ranks copy one pinned fp32 batch up and one down per iteration (2 x %.0f MB), two streams, "
+                       "no compute; max over ranks" % (img_bytes / 1e6)}
+
+    copy_ceiling = host_copy_ceiling()
+
     # (rank 0, right after the timed regions: the GPU is in the same thermal / power state as for `value`)
     line = None
     if rank == 0:
@@ -484,7 +513,8 @@ def run_ours(args, rank, world, local_rank):
                                           "d2h_bytes_per_step": img_bytes,
                                           "api": "drivers.overall_transfer(engine, pinned fp32 NCHW host batches, "
                                                  "style_stat): data.to(device) -> style_transfer -> output.cpu() "
-                                                 "as in the reference, overlapped"},
+                                                 "as in the reference, overlapped",
+                                          "host_copy_ceiling": copy_ceiling},
                     "serial_per_gpu": round(e2e_serial_value, 2),
                     "serial_api": "x.to(device); ccst_b200.style_transfer(vgg, decoder, x, style_stat, alpha); out.cpu() "
                                   "per step with fp32 tensors, no overlap (rank 0)"},
