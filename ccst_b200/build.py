@@ -20,7 +20,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(PKG, "libccst_b200.so")
 SOURCES = ["api.cu", "stats.cu", "layers.cu", "conv_umma_bf16.cu", "conv_umma_f16.cu"]
 HEADERS = ["common.cuh", "layers.h", "conv_umma_impl.cuh", "umma_common.cuh", "conv_main.cuh", "conv_smerge.cuh",
-           "conv_first.cuh", "conv_ups4.cuh", "conv_last.cuh", os.path.join("..", "..", "include", "ccst_b200.h")]
+           "conv_first.cuh", "conv_ups4.cuh", "conv_last.cuh", "conv_x3.cuh", os.path.join("..", "..", "include", "ccst_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -110,6 +110,7 @@ struct ConvLayer {
   // f16x3 engine (encoder layers): [cout/64][hi | lo][64][9*cin] f16 halves of w * 2^e; the epilogue multiplies
   // the accumulator by x3_scale = 2^-e
   __half* w_x3 = nullptr;
+  bf16* w_x3_b = nullptr;  // the same split with bf16 halves (bf16x3 engine)
   float x3_scale = 1.f;
 };
 
@@ -186,6 +187,7 @@ void free_layer(ConvLayer& L) {
   cudaFree(L.w_k32);
   cudaFree(L.w_tapsum);
   cudaFree(L.w_x3);
+  cudaFree(L.w_x3_b);
   L = ConvLayer();
 }
 
@@ -221,10 +223,12 @@ int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b, 
   CCST_CUDA(cudaMemcpy(L.w_ffma, wf.data(), wf.size() * sizeof(float), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(L.w_umma, wu.data(), wu.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
-  if (split_pack && cout % 64 == 0) {
-    // split weights: w * 2^e = hi + lo with hi = f16(w * 2^e), lo = f16(w * 2^e - hi); e puts the largest
-    // |w| just below 2^10, so the low parts (2^-11 relative) of all but vanishing weights are normal f16
-    // numbers and the product of the scale with any activation stays far inside the fp32 range
+  if (split_pack) {
+    // split weights for the x3 engines: w * 2^e = hi + lo with hi = T16(w * 2^e), lo = T16(w * 2^e - hi); e puts
+    // the largest |w| just below 2^10, so the low parts (2^-11 relative) of all but vanishing weights are normal
+    // f16 numbers and the product of the scale with any activation stays far inside the fp32 range.
+    // Rows [tile of 64 output channels][hi | lo][co], K = 9 * cin: the two halves of a tile are the N = 128
+    // rows of one MMA (conv_x3.cuh); a layer with fewer than 64 output channels is zero-padded to one tile.
     float wmax = 0.f;
     for (size_t i = 0; i < (size_t)cout * cin * 9; ++i) wmax = fmaxf(wmax, fabsf(w[i]));
     int e = 0;
@@ -233,21 +237,26 @@ int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b, 
       frexpf(wmax, &ex);  // wmax = m * 2^ex, m in [0.5, 1)
       e = 10 - ex;
     }
-    // rows [tile of 64 output channels][hi | lo][co], K = 9 * cin: the two halves of a tile are the N = 128
-    // rows of one MMA (conv_x3.cuh)
-    std::vector<__half> wx((size_t)2 * cout * K);
+    const int tiles = (cout + 63) / 64;
+    std::vector<__half> wx((size_t)tiles * 128 * K, __float2half(0.f));
+    std::vector<bf16> wxb((size_t)tiles * 128 * K, __float2bfloat16(0.f));
     for (int o = 0; o < cout; ++o)
       for (int c = 0; c < cin; ++c)
         for (int t = 0; t < 9; ++t) {
           const float v = ldexpf(w[((size_t)o * cin + c) * 9 + t], e);
-          const __half hi = __float2half(v);
-          const __half lo = __float2half(v - __half2float(hi));
           const size_t row_hi = (size_t)(o / 64) * 128 + (o % 64), row_lo = row_hi + 64;
-          wx[row_hi * K + (size_t)t * cin + c] = hi;
-          wx[row_lo * K + (size_t)t * cin + c] = lo;
+          const size_t k = (size_t)t * cin + c;
+          const __half hi = __float2half(v);
+          wx[row_hi * K + k] = hi;
+          wx[row_lo * K + k] = __float2half(v - __half2float(hi));
+          const bf16 hb = __float2bfloat16(v);
+          wxb[row_hi * K + k] = hb;
+          wxb[row_lo * K + k] = __float2bfloat16(v - __bfloat162float(hb));
         }
     CCST_CUDA(cudaMalloc(&L.w_x3, wx.size() * sizeof(__half)));
     CCST_CUDA(cudaMemcpy(L.w_x3, wx.data(), wx.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CCST_CUDA(cudaMalloc(&L.w_x3_b, wxb.size() * sizeof(bf16)));
+    CCST_CUDA(cudaMemcpy(L.w_x3_b, wxb.data(), wxb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
     L.x3_scale = ldexpf(1.f, -e);
   }
   if (fold_src) {
@@ -405,6 +414,7 @@ struct Weights16<bf16> {
   static const bf16* sm(const ConvLayer& L) { return L.w_sm; }
   static const bf16* up(const ConvLayer& L) { return L.w_up; }
   static const bf16* first(const ccst_handle* h) { return h->first_wk_b; }
+  static const bf16* x3(const ConvLayer& L) { return L.w_x3_b; }
 };
 template <>
 struct Weights16<__half> {
@@ -412,6 +422,7 @@ struct Weights16<__half> {
   static const __half* sm(const ConvLayer& L) { return L.w_sm_h; }
   static const __half* up(const ConvLayer& L) { return L.w_up_h; }
   static const __half* first(const ccst_handle* h) { return h->first_wk_h; }
+  static const __half* x3(const ConvLayer& L) { return L.w_x3; }
 };
 
 template <typename T>
@@ -430,7 +441,7 @@ struct Pipe {
   float* const* lvl_std = nullptr;
   float lvl_eps = 1e-5f;
 
-  // f16x3 engine: every map holds the [hi | lo] halves of its C logical channels (v.C = 2 * C)
+  // x3 engines: every map holds the [hi | lo] halves of its C logical channels (v.C = 2 * C)
   bool split() const { return sizeof(T) == 2 && h->split; }
   ActView<T> view(int slot, int N, int H, int W, int C) {
     ActView<T> v;
@@ -455,11 +466,10 @@ struct Pipe {
   int step(const ConvLayer& L, bool pool_after, bool up_after, bool want_stats = false) {
     const int N = cur.N, H = cur.H, W = cur.W;
     const bool fused_pool = pool_after && (h->fuse_pool || split()) && sizeof(T) == 2;
-    CCST_CHECK_ARG(!split() || (!up_after && !up_pending && !fold_pending), "the f16x3 engine runs the encoder only");
     // tcgen05 path: a layer followed by `Upsample` stores its low-resolution output with a replicate
     // halo and the NEXT conv consumes it through the phase-decomposed kernel (EPI_UPS): 16 instead of
     // 36 tap-GEMMs per source pixel and no 4x-replicated activation in HBM.
-    const bool defer_up = up_after && h->fuse_up && sizeof(T) == 2 && !pool_after;
+    const bool defer_up = up_after && h->fuse_up && sizeof(T) == 2 && !pool_after && !split();
     const bool ups = up_pending;
     CCST_CHECK_ARG(!ups || (!pool_after && !up_after && L.w_up != nullptr),
                    "upsample-fused conv cannot pool/upsample itself and needs phase weights");
@@ -531,7 +541,7 @@ struct Pipe {
   // under reflection padding) and the decoder's first conv reads relu4_1 as conv4_1 left it.
   int adain(const float* mu_s, const float* sigma_s, int64_t stride, float alpha) {
     if (try_fold(mu_s, sigma_s, stride, alpha)) return fold_rc;
-    ActView<T> out = view(cur_slot ^ 1, cur.N, cur.H, cur.W, cur.C);
+    ActView<T> out = view(cur_slot ^ 1, cur.N, cur.H, cur.W, split() ? cur.C / 2 : cur.C);
     ProfScope ps(h, st, 4, 0, 2.0 * (double)cur.N * cur.H * cur.W * cur.C * sizeof(T));
     if (int e = adain_launch(out, mu_s, sigma_s, stride, alpha)) return e;
     cur = out, cur_slot ^= 1;
@@ -542,6 +552,12 @@ struct Pipe {
   // {mean, M2} per (n, c) of `cur` -> h->raw[0 .. N*C) (scratch already sized)
   int stats_launch();
   int to_nchw(float* d_feat);
+  int from_nchw(const float* d_feat) {
+    if constexpr (sizeof(T) == 2) {
+      if (split()) return launch_nchw_to_act_split<T>(d_feat, cur, st);
+    }
+    return launch_nchw_to_act<T>(d_feat, cur, st);
+  }
 
   int fold_rc = CCST_OK;
   bool try_fold(const float* mu_s, const float* sigma_s, int64_t stride, float alpha);
@@ -567,7 +583,7 @@ template <typename T>
 bool Pipe<T>::try_fold(const float* mu_s, const float* sigma_s, int64_t stride, float alpha) {
   const ConvLayer& L = h->dec[0];
   const size_t w_bytes = (size_t)cur.N * L.cout * 9 * L.cin * sizeof(T);
-  if (!(stats_in_tiles && h->fuse_adain && h->fuse_up && L.w_k32 && cur.C == L.cin && L.cout == 256 &&
+  if (!(stats_in_tiles && !split() && h->fuse_adain && h->fuse_up && L.w_k32 && cur.C == L.cin && L.cout == 256 &&
         cur.H * cur.W >= kFoldMinHW && w_bytes <= ((size_t)1 << 30)))
     return false;
   fold_rc = CCST_OK;
@@ -589,6 +605,10 @@ int Pipe<float>::adain_launch(ActView<float> out, const float* mu_s, const float
 template <typename T>
 int Pipe<T>::adain_launch(ActView<T> out, const float* mu_s, const float* sigma_s, int64_t stride,
                           float alpha) {
+  if (split()) {
+    if (int e = ensure_raw(h, nhwc_scratch_elems(cur.N, cur.C / 2, cur.H * cur.W))) return e;
+    return launch_adain_nhwc_split<T>(cur, out, mu_s, sigma_s, stride, alpha, 1e-5f, h->raw, st);
+  }
   if (stats_in_tiles)  // statistics already taken by the producing conv's epilogue
     return launch_adain_nhwc_tiles<T>(cur, out, mu_s, sigma_s, stride, alpha, 1e-5f, h->raw, st);
   if (int e = ensure_raw(h, nhwc_scratch_elems(cur.N, cur.C, cur.H * cur.W))) return e;
@@ -597,19 +617,17 @@ int Pipe<T>::adain_launch(ActView<T> out, const float* mu_s, const float* sigma_
 
 template <typename T>
 int Pipe<T>::stats_launch() {
+  if constexpr (sizeof(T) == 2) {
+    if (split()) return launch_stats_nhwc_split<T>(cur, h->raw, st);
+  }
   return launch_stats_nhwc<T>(cur, h->raw, st);
-}
-template <>
-int Pipe<__half>::stats_launch() {
-  return split() ? launch_stats_nhwc_split(cur, h->raw, st) : launch_stats_nhwc<__half>(cur, h->raw, st);
 }
 template <typename T>
 int Pipe<T>::to_nchw(float* d_feat) {
+  if constexpr (sizeof(T) == 2) {
+    if (split()) return launch_act_to_nchw_split<T>(cur, d_feat, st);
+  }
   return launch_act_to_nchw<T>(cur, d_feat, st);
-}
-template <>
-int Pipe<__half>::to_nchw(float* d_feat) {
-  return split() ? launch_act_to_nchw_split(cur, d_feat, st) : launch_act_to_nchw<__half>(cur, d_feat, st);
 }
 
 template <>
@@ -618,13 +636,9 @@ int Pipe<float>::first_launch(const float* img, int N, int H, int W) {
 }
 template <typename T>
 int Pipe<T>::first_launch(const float* img, int N, int H, int W) {
+  // x3 engines: conv1_1 (K = 27, HBM-bound) on the fp32 CUDA-core kernel, stored as [hi | lo]
+  if (split()) return launch_conv_first_split<T>(img, N, H, W, h->first_w27, h->first_b64, cur, st, h->sat_count);
   return launch_conv_first_umma<T>(img, N, H, W, Weights16<T>::first(h), h->first_b64, cur, st, h->sat_count);
-}
-template <>
-int Pipe<__half>::first_launch(const float* img, int N, int H, int W) {
-  // f16x3 engine: conv1_1 (K = 27, HBM-bound) on the fp32 CUDA-core kernel, stored as [hi | lo]
-  if (split()) return launch_conv_first_split(img, N, H, W, h->first_w27, h->first_b64, cur, st, h->sat_count);
-  return launch_conv_first_umma<__half>(img, N, H, W, Weights16<__half>::first(h), h->first_b64, cur, st, h->sat_count);
 }
 template <>
 int Pipe<float>::conv(const ConvLayer& L, int relu, int epi, ActView<float> out, float* out_nchw, int,
@@ -645,26 +659,26 @@ int Pipe<T>::conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* 
   a.tile_stats = tile_stats;
   a.sat_count = h->sat_count;
   a.per_sample = per_sample;
-  if constexpr (std::is_same<T, __half>::value) {
-    if (split()) {
-      CCST_CHECK_ARG(L.w_x3 != nullptr, "the f16x3 engine has split weights for the encoder layers only");
-      a.split = true, a.wk_x3 = L.w_x3, a.out_scale = L.x3_scale;
-    }
+  if (split()) {
+    CCST_CHECK_ARG(Weights16<T>::x3(L) != nullptr, "this layer has no split weights for the x3 engines");
+    a.split = true, a.wk_x3 = Weights16<T>::x3(L), a.out_scale = L.x3_scale;
   }
   return launch_conv_umma<T>(a, st);
 }
 
-int check_common(ccst_handle* h, int precision, bool allow_x3 = false) {
+int check_common(ccst_handle* h, int precision, bool allow_x3 = true) {
   CCST_CHECK_ARG(h != nullptr, "null handle");
   CCST_CHECK_ARG(precision == CCST_PREC_FP32 || precision == CCST_PREC_BF16 ||
-                     precision == CCST_PREC_FP16 || (precision == CCST_PREC_FP16X3 && allow_x3),
-                 precision == CCST_PREC_FP16X3 ? "precision %d (f16x3) is available for the encoder entry points only"
-                                               : "bad precision %d",
+                     precision == CCST_PREC_FP16 ||
+                     ((precision == CCST_PREC_FP16X3 || precision == CCST_PREC_BF16X3) && allow_x3),
+                 (precision == CCST_PREC_FP16X3 || precision == CCST_PREC_BF16X3)
+                     ? "precision %d (an x3 engine) is not available for this entry point"
+                     : "bad precision %d",
                  precision);
   CCST_CUDA(cudaSetDevice(h->device));
   if (int e = require_sm100()) return e;
   h->prof_n = 0;
-  h->split = precision == CCST_PREC_FP16X3;
+  h->split = precision == CCST_PREC_FP16X3 || precision == CCST_PREC_BF16X3;
   return CCST_OK;
 }
 
@@ -682,7 +696,7 @@ int run_style_transfer(ccst_handle* h, const float* d_img, int N, int H, int W, 
                        const float* sg, int64_t stride, float alpha, float* d_out, cudaStream_t st) {
   int fh, fw;
   ccst_feature_hw(H, W, &fh, &fw);
-  if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T), true, true))) return e;
+  if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T) * (h->split ? 2 : 1), true, true))) return e;
   Pipe<T> p{h, st};
   if (int e = p.encoder(d_img, N, H, W)) return e;
   if (int e = p.adain(mu, sg, stride, alpha)) return e;
@@ -699,7 +713,7 @@ int run_style_transfer_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, in
   const size_t in_elems = (size_t)N * 3 * H * W, out_elems = (size_t)N * 3 * (8 * fh) * (8 * fw);
   const bool fused_store = sizeof(T) == 2;  // tcgen05 path: quantisation fused into the last conv
   if (int e = ensure_io(h, in_elems + (fused_store ? 0 : out_elems))) return e;
-  if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T), true, true))) return e;
+  if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T) * (h->split ? 2 : 1), true, true))) return e;
   {
     ProfScope ps(h, st, 5, 0, (double)in_elems * 5.0);
     if (int e = launch_u8_nhwc_to_f32_nchw(d_img, N, 3, H, W, h->io_f32, st)) return e;
@@ -747,13 +761,13 @@ int run_encoder(ccst_handle* h, const float* d_img, int N, int H, int W, float* 
 template <typename T>
 int run_decoder(ccst_handle* h, const float* d_feat, int N, int fh, int fw, float* d_img,
                 cudaStream_t st) {
-  if (int e = ensure_arena(h, plan_bytes(N, 0, 0, fh, fw, sizeof(T), false, true))) return e;
+  if (int e = ensure_arena(h, plan_bytes(N, 0, 0, fh, fw, sizeof(T) * (h->split ? 2 : 1), false, true))) return e;
   Pipe<T> p{h, st};
   p.cur_slot = 0;
   p.cur = p.view(0, N, fh, fw, 512);
   {
     ProfScope ps(h, st, 5, 0, (double)N * fh * fw * 512 * (4.0 + sizeof(T)));
-    if (int e = launch_nchw_to_act<T>(d_feat, p.cur, st)) return e;
+    if (int e = p.from_nchw(d_feat)) return e;
   }
   return p.decoder(d_img);
 }
@@ -881,7 +895,7 @@ extern "C" int ccst_set_decoder_weights(ccst_handle* h, const float* const* w,
   for (int i = 0; i < kDecLayers; ++i) {
     CCST_CHECK_ARG(w[i] && b[i], "ccst_set_decoder_weights: null tensor %d", i);
     if (int e = pack_layer(h->dec[i], kDecCh[i][0], kDecCh[i][1], w[i], b[i], i > 0 && kDecUpAfter[i - 1],
-                           /*fold_src=*/i == 0))
+                           /*fold_src=*/i == 0, /*split_pack=*/true))
       return e;
   }
   h->dec_ready = true;
@@ -891,7 +905,7 @@ extern "C" int ccst_set_decoder_weights(ccst_handle* h, const float* const* w,
 // expands `call` for the activation type selected by `precision`
 #define CCST_DISPATCH(precision, call_T)                       \
   do {                                                         \
-    if ((precision) == CCST_PREC_BF16) {                       \
+    if ((precision) == CCST_PREC_BF16 || (precision) == CCST_PREC_BF16X3) { \
       typedef bf16 T;                                          \
       return call_T;                                           \
     } else if ((precision) == CCST_PREC_FP16 || (precision) == CCST_PREC_FP16X3) { \
@@ -913,7 +927,7 @@ extern "C" int ccst_set_decoder_weights(ccst_handle* h, const float* const* w,
 
 extern "C" int ccst_encoder_fwd(ccst_handle* h, const float* d_img, int N, int H, int W,
                                 float* d_feat, int precision, void* stream) {
-  if (int e = check_common(h, precision, /*allow_x3=*/true)) return e;
+  if (int e = check_common(h, precision)) return e;
   CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_fwd: encoder weights not set");
   CCST_CHECK_ARG(d_img && d_feat && N >= 1 && H >= 8 && W >= 8, "ccst_encoder_fwd: bad argument");
   CCST_DISPATCH(precision, run_encoder<T>(h, d_img, N, H, W, d_feat, nullptr, (cudaStream_t)stream));
@@ -922,7 +936,7 @@ extern "C" int ccst_encoder_fwd(ccst_handle* h, const float* d_img, int N, int H
 extern "C" int ccst_encoder_levels(ccst_handle* h, const float* d_img, int N, int H, int W, float* d_feat,
                                    float* const* d_mean, float* const* d_std, float eps, int precision,
                                    void* stream) {
-  if (int e = check_common(h, precision, /*allow_x3=*/true)) return e;
+  if (int e = check_common(h, precision)) return e;
   CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_levels: encoder weights not set");
   CCST_CHECK_ARG(d_img && d_mean && d_std && N >= 1 && H >= 8 && W >= 8, "ccst_encoder_levels: bad argument");
   for (int l = 0; l < 4; ++l)
@@ -939,7 +953,7 @@ extern "C" int ccst_mse_f32(const float* d_a, const float* d_b, int64_t n, doubl
 
 extern "C" int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N, int H, int W,
                                        double* d_state, int precision, void* stream) {
-  if (int e = check_common(h, precision, /*allow_x3=*/true)) return e;
+  if (int e = check_common(h, precision)) return e;
   CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_accumulate: encoder weights not set");
   CCST_CHECK_ARG(d_img && d_state && N >= 1 && H >= 8 && W >= 8,
                  "ccst_encoder_accumulate: bad argument");
@@ -960,7 +974,7 @@ int run_encoder_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W, do
 
 extern "C" int ccst_encoder_accumulate_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W,
                                           double* d_state, int precision, void* stream) {
-  if (int e = check_common(h, precision, /*allow_x3=*/true)) return e;
+  if (int e = check_common(h, precision)) return e;
   CCST_REQUIRE_STATE(h->enc_ready, "ccst_encoder_accumulate_u8: encoder weights not set");
   CCST_CHECK_ARG(d_img && d_state && N >= 1 && H >= 8 && W >= 8,
                  "ccst_encoder_accumulate_u8: bad argument");
@@ -1200,7 +1214,7 @@ int debug_conv(ccst_handle* h, const float* d_in, int N, int H, int W, int Cin, 
 extern "C" int ccst_debug_conv3x3(ccst_handle* h, const float* d_in, int N, int H, int W, int Cin,
                                   int Cout, const float* h_weight, const float* h_bias, int relu,
                                   int mode, float* d_out, int precision, void* stream) {
-  if (int e = check_common(h, precision)) return e;
+  if (int e = check_common(h, precision, /*allow_x3=*/false)) return e;
   CCST_CHECK_ARG(d_in && d_out && h_weight && h_bias, "ccst_debug_conv3x3: null pointer");
   CCST_CHECK_ARG(N >= 1 && H >= 2 && W >= 2 && Cin % 64 == 0 && mode >= 0 && mode <= 4,
                  "ccst_debug_conv3x3: bad shape/mode");

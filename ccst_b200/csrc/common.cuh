@@ -196,4 +196,16 @@ __device__ __forceinline__ uint32_t pack16x2_relu<__half>(float lo, float hi) {
   return r;
 }
 
+// packed pair -> two fp32
+template <typename T16>
+__device__ __forceinline__ float2 unpack16x2(uint32_t w);
+template <>
+__device__ __forceinline__ float2 unpack16x2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+template <>
+__device__ __forceinline__ float2 unpack16x2<__nv_bfloat16>(uint32_t w) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+
 }  // namespace ccst

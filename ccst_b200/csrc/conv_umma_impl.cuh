@@ -52,14 +52,7 @@ int launch_conv_umma(const UmmaConvArgs<T16>& a, cudaStream_t st) {
   CCST_CHECK_ARG(a.out_u8 == nullptr || epi == EPI_NCHW_F32, "conv_umma: uint8 store is the last conv's");
   CCST_CHECK_ARG(a.halo_edge == 1 || (a.halo_edge == 0 && epi == EPI_ACT),
                  "conv_umma: a replicate halo is only written by the plain epilogue");
-  if (a.split) {
-    if constexpr (std::is_same<T16, __half>::value) {
-      return launch_x3(a, p, st);
-    } else {
-      set_error("conv_umma: the f16x3 engine takes f16 operands");
-      return CCST_EINVAL;
-    }
-  }
+  if (a.split) return launch_x3<T16>(a, p, st);  // x3 engines: split operands (conv_x3.cuh)
   if (epi == EPI_NCHW_F32) {
     // the last decoder conv (64 -> 3): filter rows by operand shifts, filter columns in N + two shuffles
     CCST_CHECK_ARG(a.CoutPad == 16 && Cout <= 3 && in.C == kBlockK && !a.per_sample,

@@ -1,4 +1,4 @@
-// f16x3 engine: fp32-grade 3x3 reflect-pad convolution on the f16 tensor pipe (encoder layers).
+// x3 engines ("fp16x3", "bf16x3"): 3x3 reflect-pad convolution with SPLIT 16-bit operands on the tensor pipe.
 //
 // The reference computes relu4_1 in fp32 (net.py:38-69 under torch defaults) and BASELINE.json asks the style
 // statistics to match it to 1e-5 relative; one f16 rounding per layer is 5e-4.  Here every activation v is
@@ -18,7 +18,13 @@
 // which owns the tiles of parity g).  Truncation then only acts inside a 12-MMA partial.
 //
 // Epilogue: v = acc * 2^-k + bias, ReLU, optional 2x2 ceil-mode max-pool (all fp32), split into hi / lo and
-// stored as two TMA tiles at channels co and Cout + co.
+// stored as two TMA tiles at channels co and Cout + co (EPI_ACT, EPI_ACT_POOL; EPI_ACT_UP2 stores every pixel
+// at its four nearest-x2 replicas), or written as fp32 NCHW / save_image-quantised uint8 NHWC (EPI_NCHW_F32:
+// the last decoder conv, whose <= 3 output channels ride in a zero-padded 64-channel tile).
+//
+// With T16 = __nv_bfloat16 the same kernel gives 16 significand bits at the fp32 exponent range ("bf16x3"):
+// the tensor-core path for weights whose activations leave the f16 range, meeting the image bar that single
+// bf16 operands miss.
 #pragma once
 #include "conv_main.cuh"
 
@@ -44,12 +50,11 @@ struct X3Cfg {
   static_assert(kSmemBytes <= 232448, "shared memory plan exceeds 227 KiB");
 };
 
-template <int EPI, int CG>
+template <typename T16, int EPI, int CG>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const __grid_constant__ CUtensorMap tmap_out, ConvParams<__half> p) {
-  static_assert(EPI == EPI_ACT || EPI == EPI_ACT_POOL, "encoder epilogues");
-  using T16 = __half;
+                   const __grid_constant__ OutMaps tmap_out, ConvParams<T16> p) {
+  static_assert(EPI == EPI_ACT || EPI == EPI_ACT_POOL || EPI == EPI_ACT_UP2 || EPI == EPI_NCHW_F32, "x3 epilogues");
   using Cfg = X3Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
-    prefetch_tmap(&tmap_out);
+    prefetch_tmap(&tmap_out.m[0]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kAStages; ++s) {
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_cg<CG, Cfg::kTmemCols>(tmem_slot);
-  for (int i = threadIdx.x; i < p.Cout; i += kThreadsUmma) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.n_tiles * 64; i += kThreadsUmma) s_bias[i] = i < p.Cout ? p.bias[i] : 0.f;
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -253,6 +258,23 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           for (int i = 0; i < 32; ++i) acc[h2 * 32 + i] = fmaxf(acc[h2 * 32 + i], tt[i]);
         }
       }
+      if (EPI == EPI_NCHW_F32) {
+        // last conv: the first p.Cout (<= 3) channels of the tile go to the caller's tensor, fp32 NCHW or
+        // quantised like save_image as uint8 NHWC; a tile row = 16 consecutive pixels of one image row
+        if (valid && t.nt == 0) {
+          if (p.out_u8 != nullptr) {
+            uint8_t* dst = p.out_u8 + (((size_t)t.n * p.H + y) * p.W + x) * p.Cout;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < p.Cout) dst[c] = quantize_u8(acc[c]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < p.Cout) p.out_nchw[(((size_t)t.n * p.Cout + c) * p.H + y) * p.W + x] = acc[c];
+          }
+        }
+        continue;
+      }
       int srow = row;
       bool writer = true;
       if (EPI == EPI_ACT_POOL) {
@@ -291,14 +313,30 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
           }
         }
         if (valid) {
-          if (EPI == EPI_ACT) store_aliases(p.out, t.n, y, x, cs, pk, 1);
-          else if (writer) store_aliases(p.out, t.n, y >> 1, x >> 1, cs, pk, 1);
+          if (EPI == EPI_ACT) {
+            store_aliases(p.out, t.n, y, x, cs, pk, 1);
+          } else if (EPI == EPI_ACT_UP2) {
+#pragma unroll
+            for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+              for (int bb = 0; bb < 2; ++bb) store_aliases(p.out, t.n, 2 * y + aa, 2 * x + bb, cs, pk, 1);
+          } else if (writer) {
+            store_aliases(p.out, t.n, y >> 1, x >> 1, cs, pk, 1);
+          }
         }
         fence_async_smem();
         epi_barrier(grp);
         if (issuer_warp && elect_one()) {
-          if (EPI == EPI_ACT_POOL) tma_store_4d(&tmap_out, sbuf, cs, t.x0 >> 1, t.y0 >> 1, t.n);
-          else tma_store_4d(&tmap_out, sbuf, cs, t.x0, t.y0, t.n);
+          if (EPI == EPI_ACT_POOL) {
+            tma_store_4d(&tmap_out.m[0], sbuf, cs, t.x0 >> 1, t.y0 >> 1, t.n);
+          } else {
+            tma_store_4d(&tmap_out.m[0], sbuf, cs, t.x0, t.y0, t.n);
+            if (EPI == EPI_ACT_UP2) {
+              tma_store_4d(&tmap_out.m[1], sbuf, cs, t.x0, t.y0, t.n);
+              tma_store_4d(&tmap_out.m[2], sbuf, cs, t.x0, t.y0, t.n);
+              tma_store_4d(&tmap_out.m[3], sbuf, cs, t.x0, t.y0, t.n);
+            }
+          }
           bulk_commit();
         }
       }
@@ -313,18 +351,24 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   if (warp == 2) tmem_dealloc_cg<CG, Cfg::kTmemCols>(tmem_base);
 }
 
-template <int EPI, int CG>
-int launch_x3_cfg(const CUtensorMap& ma, const __half* wk_x3, ConvParams<__half> p, cudaStream_t st) {
+template <typename T16, int EPI, int CG>
+int launch_x3_cfg(const CUtensorMap& ma, const T16* wk_x3, ConvParams<T16> p, cudaStream_t st) {
   using Cfg = X3Cfg<CG>;
-  CUtensorMap mb, mo;
+  CUtensorMap mb;
   // [n_tiles * 128 rows = (tile, hi | lo, co)][9 * Cin]
-  if (int e = make_weight_map(&mb, wk_x3, 9 * p.Cin, 2 * p.Cout, Cfg::kBRows)) return e;
+  if (int e = make_weight_map(&mb, wk_x3, 9 * p.Cin, p.n_tiles * Cfg::kN, Cfg::kBRows)) return e;
+  OutMaps mo;
+  memset(&mo, 0, sizeof(mo));
   if (EPI == EPI_ACT) {
-    if (int e = make_out_map(&mo, p.out, 0, 0, 1, 1, kTileW, kTileH)) return e;
-  } else {
-    if (int e = make_out_map(&mo, p.out, 0, 0, 1, 1, kTileW / 2, kTileH / 2)) return e;
+    if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kTileW, kTileH)) return e;
+  } else if (EPI == EPI_ACT_POOL) {
+    if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kTileW / 2, kTileH / 2)) return e;
+  } else if (EPI == EPI_ACT_UP2) {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, kTileW, kTileH)) return e;
   }
-  auto kernel = conv_x3_kernel<EPI, CG>;
+  auto kernel = conv_x3_kernel<T16, EPI, CG>;
   CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(kernel), Cfg::kSmemBytes));
   const int64_t units = ((int64_t)p.m_tiles + CG - 1) / CG * p.n_tiles;
   CCST_CHECK_ARG(units < (1ll << 31), "conv_x3: too many tiles");
@@ -336,24 +380,37 @@ int launch_x3_cfg(const CUtensorMap& ma, const __half* wk_x3, ConvParams<__half>
   return CCST_OK;
 }
 
-// in: [hi | lo] map of in.C / 2 logical channels; out: [hi | lo] map of Cout logical channels
-inline int launch_x3(const UmmaConvArgs<__half>& a, ConvParams<__half> p, cudaStream_t st) {
-  const ActView<__half>& in = a.in;
-  CCST_CHECK_ARG((a.epi == EPI_ACT || a.epi == EPI_ACT_POOL) && a.halo_edge == 1 && !a.per_sample && a.wk_x3 != nullptr,
-                 "conv_x3: the f16x3 engine runs the plain and the pooled epilogue of the encoder");
-  CCST_CHECK_ARG(in.C % (2 * kBlockK) == 0 && a.CoutPad == a.Cout && a.Cout % 64 == 0 && a.Cout <= 512 &&
-                     a.out.C == 2 * a.Cout,
-                 "conv_x3: Cin=%d/2 and Cout=%d must be multiples of 64 (Cout <= 512)", in.C, a.Cout);
+// in: [hi | lo] map of in.C / 2 logical channels; out: [hi | lo] map of Cout logical channels (or the caller's
+// NCHW fp32 / NHWC uint8 tensor for EPI_NCHW_F32)
+template <typename T16>
+int launch_x3(const UmmaConvArgs<T16>& a, ConvParams<T16> p, cudaStream_t st) {
+  const ActView<T16>& in = a.in;
+  const bool last = a.epi == EPI_NCHW_F32;
+  CCST_CHECK_ARG((a.epi == EPI_ACT || a.epi == EPI_ACT_POOL || a.epi == EPI_ACT_UP2 || last) && a.halo_edge == 1 &&
+                     !a.per_sample && a.wk_x3 != nullptr,
+                 "conv_x3: epilogue %d is not available on the x3 engines", a.epi);
+  CCST_CHECK_ARG(in.C % (2 * kBlockK) == 0, "conv_x3: Cin=%d/2 must be a multiple of 64", in.C);
+  if (last) {
+    CCST_CHECK_ARG(a.Cout >= 1 && a.Cout <= 4 && (a.out_nchw != nullptr || a.out_u8 != nullptr),
+                   "conv_x3: the NCHW epilogue is the (<= 4)-channel last conv");
+  } else {
+    CCST_CHECK_ARG(a.Cout % 64 == 0 && a.Cout <= 512 && a.out.C == 2 * a.Cout,
+                   "conv_x3: Cout=%d must be a multiple of 64 (<= 512)", a.Cout);
+  }
   p.Cin = in.C / 2;
   p.out_scale = a.out_scale;
-  p.n_tiles = a.Cout / 64;
+  p.n_tiles = (a.Cout + 63) / 64;
   const int64_t mt = (int64_t)in.N * p.tiles_x * p.tiles_y;
   CCST_CHECK_ARG(mt * p.n_tiles < (1ll << 30), "conv_x3: too many tiles");
   p.m_tiles = (int)mt;
   CUtensorMap ma;
   if (int e = make_act_map(&ma, in)) return e;
-  if (a.epi == EPI_ACT) return launch_x3_cfg<EPI_ACT, 2>(ma, a.wk_x3, p, st);
-  return launch_x3_cfg<EPI_ACT_POOL, 2>(ma, a.wk_x3, p, st);
+  switch (a.epi) {
+    case EPI_ACT: return launch_x3_cfg<T16, EPI_ACT, 2>(ma, a.wk_x3, p, st);
+    case EPI_ACT_POOL: return launch_x3_cfg<T16, EPI_ACT_POOL, 2>(ma, a.wk_x3, p, st);
+    case EPI_ACT_UP2: return launch_x3_cfg<T16, EPI_ACT_UP2, 2>(ma, a.wk_x3, p, st);
+    default: return launch_x3_cfg<T16, EPI_NCHW_F32, 2>(ma, a.wk_x3, p, st);
+  }
 }
 
 }  // namespace

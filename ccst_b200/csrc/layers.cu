@@ -171,10 +171,10 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 // whose first layer stays on the CUDA cores in fp32 and is stored as [hi | lo] f16 halves.
 constexpr int kFirst4Tile = 256;
 
-template <bool SPLIT>
+template <typename T16, bool SPLIT>
 __global__ void __launch_bounds__(256)
     conv_first_px4_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w27,
-                          const float* __restrict__ bias64, ActView<__half> out, unsigned int* sat_count) {
+                          const float* __restrict__ bias64, ActView<T16> out, unsigned int* sat_count) {
   __shared__ __align__(16) float sw[27 * 64];
   __shared__ float sb[64];
   __shared__ float sin[3][3][kFirst4Tile + 4];  // [ci][row][col]
@@ -244,10 +244,10 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float v0 = fmaxf(acc[q][2 * j], 0.f), v1 = fmaxf(acc[q][2 * j + 1], 0.f);
-      hi[j] = pack16x2<__half>(v0, v1);
-      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
-      lo[j] = pack16x2<__half>(v0 - hf.x, v1 - hf.y);
-      hmax = max16x2<__half>(hmax, hi[j]);
+      hi[j] = pack16x2<T16>(v0, v1);
+      const float2 hf = unpack16x2<T16>(hi[j]);
+      lo[j] = pack16x2<T16>(v0 - hf.x, v1 - hf.y);
+      hmax = max16x2<T16>(hmax, hi[j]);
     }
     for_each_halo_alias(y, x, H, W, [&](int yy, int xx) {
       uint4* dst = reinterpret_cast<uint4*>(out.px(n, yy, xx) + cg);
@@ -260,7 +260,9 @@ __global__ void __launch_bounds__(256)
       }
     });
   }
-  if (((hmax & 0xffffu) >= 0x7bffu || (hmax >> 16) >= 0x7bffu) && sat_count != nullptr) atomicAdd(sat_count, 1u);
+  if (std::is_same<T16, __half>::value && ((hmax & 0xffffu) >= 0x7bffu || (hmax >> 16) >= 0x7bffu) &&
+      sat_count != nullptr)
+    atomicAdd(sat_count, 1u);
 }
 
 // =====================================================================================
@@ -773,24 +775,29 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(ActView<T> in, float* 
   }
 }
 
-template <typename T>
+template <typename T, bool SPLIT = false>
 __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restrict__ in,
                                                           ActView<T> out) {
   __shared__ float tile[32][33];
   const int HW = out.H * out.W;
+  const int C = SPLIT ? out.C / 2 : out.C;  // SPLIT: the map holds [hi | lo] halves of C logical channels
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32, n = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, p = p0 + tx;
-    tile[i][tx] = (p < HW && c < out.C) ? in[((size_t)n * out.C + c) * HW + p] : 0.f;
+    tile[i][tx] = (p < HW && c < C) ? in[((size_t)n * C + c) * HW + p] : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int p = p0 + i, c = c0 + tx;
-    if (p < HW && c < out.C) {
+    if (p < HW && c < C) {
       const int y = p / out.W, x = p - y * out.W;
       const T v = from_f32<T>(tile[tx][i]);
-      for_each_halo_alias(y, x, out.H, out.W, [&](int yy, int xx) { out.px(n, yy, xx)[c] = v; });
+      const T lo = SPLIT ? from_f32<T>(tile[tx][i] - to_f32(v)) : v;
+      for_each_halo_alias(y, x, out.H, out.W, [&](int yy, int xx) {
+        out.px(n, yy, xx)[c] = v;
+        if (SPLIT) out.px(n, yy, xx)[C + c] = lo;
+      });
     }
   }
 }
@@ -983,16 +990,21 @@ int launch_conv_first(const float* img, int N, int H, int W, const float* w27, c
   CCST_LAUNCHED();
   return CCST_OK;
 }
+template <typename T16>
 int launch_conv_first_split(const float* img, int N, int H, int W, const float* w27, const float* bias64,
-                            ActView<__half> out, cudaStream_t st, unsigned int* sat_count) {
+                            ActView<T16> out, cudaStream_t st, unsigned int* sat_count) {
   CCST_CHECK_ARG(out.C == 128, "conv_first(f16x3): the output map holds 64 + 64 channels");
   const int tiles_x = (W + kFirst4Tile - 1) / kFirst4Tile;
   const size_t blocks = (size_t)N * H * tiles_x;
   CCST_CHECK_ARG(blocks < (1ull << 31), "conv_first: grid too large");
-  conv_first_px4_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(img, N, H, W, w27, bias64, out, sat_count);
+  conv_first_px4_kernel<T16, true><<<(unsigned)blocks, 256, 0, st>>>(img, N, H, W, w27, bias64, out, sat_count);
   CCST_LAUNCHED();
   return CCST_OK;
 }
+template int launch_conv_first_split<__half>(const float*, int, int, int, const float*, const float*, ActView<__half>,
+                                             cudaStream_t, unsigned int*);
+template int launch_conv_first_split<__nv_bfloat16>(const float*, int, int, int, const float*, const float*,
+                                                    ActView<__nv_bfloat16>, cudaStream_t, unsigned int*);
 template int launch_conv_first<float>(const float*, int, int, int, const float*, const float*,
                                       ActView<float>, cudaStream_t);
 template int launch_conv_first<__nv_bfloat16>(const float*, int, int, int, const float*,
@@ -1081,6 +1093,70 @@ template int launch_adain_nhwc<__nv_bfloat16>(ActView<__nv_bfloat16>, ActView<__
                                               float2*, cudaStream_t);
 template int launch_adain_nhwc<__half>(ActView<__half>, ActView<__half>, const float*, const float*,
                                        int64_t, float, float, float2*, cudaStream_t);
+
+// x3 engines: the affine on a [hi | lo] map of C = in.C / 2 logical channels; x = hi + lo, result split again.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    adain_nhwc_apply_split_kernel(ActView<T> in, ActView<T> out, const float4* __restrict__ coef) {
+  constexpr int VEC = VecOf<T>::value;
+  const int C = in.C / 2, ch_lanes = C / VEC, px_lanes = 256 / ch_lanes;
+  const int chunk = blockIdx.x, n = blockIdx.y;
+  const int HW = in.H * in.W;
+  const int p0 = chunk * kNhwcChunk, p1 = min(HW, p0 + kNhwcChunk);
+  const int cl = threadIdx.x % ch_lanes, pl = threadIdx.x / ch_lanes;
+  const size_t coff = (size_t)cl * VEC;
+  float A[VEC], B[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const float4 q = coef[(size_t)n * C + coff + k];
+    A[k] = q.y, B[k] = fmaf(-q.x, q.y, q.z);
+  }
+  for (int p = p0 + pl; p < p1; p += px_lanes) {
+    const int y = p / in.W, x = p - y * in.W;
+    Pack<T, VEC> vh, vl;
+    vh.v = *reinterpret_cast<const decltype(vh.v)*>(in.px(n, y, x) + coff);
+    vl.v = *reinterpret_cast<const decltype(vl.v)*>(in.px(n, y, x) + C + coff);
+    float fh[VEC], fl[VEC];
+    unpack_vec(vh, fh);
+    unpack_vec(vl, fl);
+    Pack<T, VEC> oh, ol;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float v = fmaf(fh[k] + fl[k], A[k], B[k]);
+      oh.set(k, v);
+      ol.set(k, v - oh.get(k));
+    }
+    for_each_halo_alias(y, x, in.H, in.W, [&](int yy, int xx) {
+      *reinterpret_cast<decltype(oh.v)*>(out.px(n, yy, xx) + coff) = oh.v;
+      *reinterpret_cast<decltype(ol.v)*>(out.px(n, yy, xx) + C + coff) = ol.v;
+    });
+  }
+}
+
+template <typename T16>
+int launch_adain_nhwc_split(ActView<T16> in, ActView<T16> out, const float* mu_s, const float* sigma_s,
+                            int64_t stat_batch_stride, float alpha, float eps, float2* scratch, cudaStream_t st) {
+  ActView<T16> logical = in;
+  logical.C = in.C / 2;
+  if (int e = nhwc_geometry_ok(logical, "adain_nhwc(x3)")) return e;
+  const int chunks = nhwc_chunks(in.H * in.W);
+  dim3 grid(chunks, in.N);
+  const int NC = in.N * logical.C;
+  float4* coef = reinterpret_cast<float4*>(scratch);  // NC float4 = 2 NC float2
+  float2* part = scratch + 2 * (size_t)NC;            // NC * chunks float2
+  nhwc_stats_partial_kernel<T16, true><<<grid, 256, nhwc_stats_smem(logical), st>>>(in, part);
+  CCST_LAUNCHED();
+  adain_nhwc_coef_kernel<<<(NC + 255) / 256, 256, 0, st>>>(part, coef, NC, logical.C, in.H * in.W, mu_s, sigma_s,
+                                                           stat_batch_stride, alpha, eps);
+  CCST_LAUNCHED();
+  adain_nhwc_apply_split_kernel<T16><<<grid, 256, 0, st>>>(in, out, coef);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_adain_nhwc_split<__half>(ActView<__half>, ActView<__half>, const float*, const float*, int64_t,
+                                             float, float, float2*, cudaStream_t);
+template int launch_adain_nhwc_split<__nv_bfloat16>(ActView<__nv_bfloat16>, ActView<__nv_bfloat16>, const float*,
+                                                    const float*, int64_t, float, float, float2*, cudaStream_t);
 
 // Row-wise apply: CTA = (image n, row y), thread = (VEC channels, every PX_LANES-th pixel of the row).
 // No per-pixel index arithmetic, the row's halo aliases are decided once per CTA / per x.
@@ -1224,19 +1300,22 @@ int launch_stats_nhwc(ActView<T> in, float2* scratch, cudaStream_t st) {
   CCST_LAUNCHED();
   return CCST_OK;
 }
-int launch_stats_nhwc_split(ActView<__half> in, float2* scratch, cudaStream_t st) {
-  ActView<__half> logical = in;
+template <typename T16>
+int launch_stats_nhwc_split(ActView<T16> in, float2* scratch, cudaStream_t st) {
+  ActView<T16> logical = in;
   logical.C = in.C / 2;  // geometry and shared memory follow the logical channel count
   if (int e = nhwc_geometry_ok(logical, "stats_nhwc(f16x3)")) return e;
   const int HW = in.H * in.W, chunks = nhwc_chunks(HW);
   const int NC = in.N * logical.C;
   dim3 grid(chunks, in.N);
-  nhwc_stats_partial_kernel<__half, true><<<grid, 256, nhwc_stats_smem(logical), st>>>(in, scratch + NC);
+  nhwc_stats_partial_kernel<T16, true><<<grid, 256, nhwc_stats_smem(logical), st>>>(in, scratch + NC);
   CCST_LAUNCHED();
   nhwc_stats_merge_kernel<<<(NC + 255) / 256, 256, 0, st>>>(scratch + NC, scratch, NC, logical.C, HW);
   CCST_LAUNCHED();
   return CCST_OK;
 }
+template int launch_stats_nhwc_split<__half>(ActView<__half>, float2*, cudaStream_t);
+template int launch_stats_nhwc_split<__nv_bfloat16>(ActView<__nv_bfloat16>, float2*, cudaStream_t);
 template int launch_stats_nhwc<float>(ActView<float>, float2*, cudaStream_t);
 template int launch_stats_nhwc<__nv_bfloat16>(ActView<__nv_bfloat16>, float2*, cudaStream_t);
 template int launch_stats_nhwc<__half>(ActView<__half>, float2*, cudaStream_t);
@@ -1248,12 +1327,15 @@ int launch_act_to_nchw(ActView<T> in, float* out_nchw, cudaStream_t st) {
   CCST_LAUNCHED();
   return CCST_OK;
 }
-int launch_act_to_nchw_split(ActView<__half> in, float* out_nchw, cudaStream_t st) {
+template <typename T16>
+int launch_act_to_nchw_split(ActView<T16> in, float* out_nchw, cudaStream_t st) {
   dim3 grid((in.H * in.W + 31) / 32, (in.C / 2 + 31) / 32, in.N);
-  act_to_nchw_kernel<__half, true><<<grid, 256, 0, st>>>(in, out_nchw);
+  act_to_nchw_kernel<T16, true><<<grid, 256, 0, st>>>(in, out_nchw);
   CCST_LAUNCHED();
   return CCST_OK;
 }
+template int launch_act_to_nchw_split<__half>(ActView<__half>, float*, cudaStream_t);
+template int launch_act_to_nchw_split<__nv_bfloat16>(ActView<__nv_bfloat16>, float*, cudaStream_t);
 template int launch_act_to_nchw<float>(ActView<float>, float*, cudaStream_t);
 template int launch_act_to_nchw<__nv_bfloat16>(ActView<__nv_bfloat16>, float*, cudaStream_t);
 template int launch_act_to_nchw<__half>(ActView<__half>, float*, cudaStream_t);
@@ -1265,6 +1347,15 @@ int launch_nchw_to_act(const float* in_nchw, ActView<T> out, cudaStream_t st) {
   CCST_LAUNCHED();
   return CCST_OK;
 }
+template <typename T16>
+int launch_nchw_to_act_split(const float* in_nchw, ActView<T16> out, cudaStream_t st) {
+  dim3 grid((out.H * out.W + 31) / 32, (out.C / 2 + 31) / 32, out.N);
+  nchw_to_act_kernel<T16, true><<<grid, 256, 0, st>>>(in_nchw, out);
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+template int launch_nchw_to_act_split<__half>(const float*, ActView<__half>, cudaStream_t);
+template int launch_nchw_to_act_split<__nv_bfloat16>(const float*, ActView<__nv_bfloat16>, cudaStream_t);
 template int launch_nchw_to_act<float>(const float*, ActView<float>, cudaStream_t);
 template int launch_nchw_to_act<__nv_bfloat16>(const float*, ActView<__nv_bfloat16>, cudaStream_t);
 template int launch_nchw_to_act<__half>(const float*, ActView<__half>, cudaStream_t);

@@ -23,9 +23,10 @@ enum Epilogue {
 template <typename T>
 int launch_conv_first(const float* img, int N, int H, int W, const float* w27, const float* bias64,
                       ActView<T> out, cudaStream_t st);
-// f16x3 engine: the same fp32 FFMA conv1_1, result stored as [hi | lo] f16 halves (out.C == 128)
+// x3 engines: the same fp32 FFMA conv1_1, result stored as [hi | lo] 16-bit halves (out.C == 128)
+template <typename T16>
 int launch_conv_first_split(const float* img, int N, int H, int W, const float* w27, const float* bias64,
-                            ActView<__half> out, cudaStream_t st, unsigned int* sat_count = nullptr);
+                            ActView<T16> out, cudaStream_t st, unsigned int* sat_count = nullptr);
 
 // fp32 FFMA implicit GEMM.  w: [9][Cin][CoutPad64] fp32, bias [CoutPad64].
 int launch_conv_ffma(ActView<float> in, const float* w, const float* bias, int Cout, int CoutPad,
@@ -65,9 +66,17 @@ int launch_adain_fold(int N, int C, int H, int W, int Cout, float2* scratch, con
 // per-(n,c) {mean, M2} of an activation -> scratch[0 .. N*C)
 template <typename T>
 int launch_stats_nhwc(ActView<T> in, float2* scratch, cudaStream_t st);
-// f16x3 engine: `in` holds [hi | lo] halves of in.C / 2 logical channels; statistics of hi + lo
-int launch_stats_nhwc_split(ActView<__half> in, float2* scratch, cudaStream_t st);
-int launch_act_to_nchw_split(ActView<__half> in, float* out_nchw, cudaStream_t st);
+// x3 engines: the maps hold [hi | lo] halves of C / 2 logical channels; value = hi + lo
+template <typename T16>
+int launch_stats_nhwc_split(ActView<T16> in, float2* scratch, cudaStream_t st);
+template <typename T16>
+int launch_act_to_nchw_split(ActView<T16> in, float* out_nchw, cudaStream_t st);
+template <typename T16>
+int launch_nchw_to_act_split(const float* in_nchw, ActView<T16> out, cudaStream_t st);
+// calc_mean_std + AdaIN + alpha blend on a [hi | lo] map (scratch: nhwc_scratch_elems of the logical channels)
+template <typename T16>
+int launch_adain_nhwc_split(ActView<T16> in, ActView<T16> out, const float* mu_s, const float* sigma_s,
+                            int64_t stat_batch_stride, float alpha, float eps, float2* scratch, cudaStream_t st);
 
 // raw[i] = {mean, M2} of a plane of `hw` values -> mean[i], std[i] = sqrt(M2 / (hw - unbiased) + eps)
 int launch_raw_to_mean_std(const float2* raw, int planes, int64_t hw, float eps, int unbiased, float* mean,
@@ -119,8 +128,8 @@ struct UmmaConvArgs {
   float2* tile_stats = nullptr;       // EPI_ACT_STATS
   unsigned int* sat_count = nullptr;  // device counter of f16 stores that hit the +-65504 clamp (may be NULL)
   bool per_sample = false;     // image n uses weights wk[n] / bias[n] (AdaIN folded into dec1)
-  // f16x3 engine (T16 = __half, EPI_ACT / EPI_ACT_POOL, conv_x3.cuh): `in` and `out` hold [hi | lo] halves (2 x
-  // the logical channel counts), wk_x3 = [Cout/64 tiles][hi | lo][64 co][9 * Cin] K-major (k = tap * Cin + c)
+  // x3 engines (conv_x3.cuh; EPI_ACT / _POOL / _UP2 / NCHW_F32): `in` and `out` hold [hi | lo] halves (2 x the
+  // logical channel counts), wk_x3 = [ceil(Cout/64) tiles][hi | lo][64 co][9 * Cin] K-major (k = tap * Cin + c)
   // with hi + lo = w * 2^k, out_scale = 2^-k
   bool split = false;
   const T16* wk_x3 = nullptr;

@@ -216,17 +216,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-template <typename T16>
-__device__ __forceinline__ float2 unpack16x2(uint32_t w);
-template <>
-__device__ __forceinline__ float2 unpack16x2<__half>(uint32_t w) {
-  return __half22float2(*reinterpret_cast<const __half2*>(&w));
-}
-template <>
-__device__ __forceinline__ float2 unpack16x2<__nv_bfloat16>(uint32_t w) {
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-}
-
 // Programmatic dependent launch: the conv kernels of a step are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the CTAs of layer i+1 may be scheduled on an
 // SM as soon as layer i's CTA there has exited and run their prologue (barrier init, TMEM allocation,

@@ -27,8 +27,9 @@ from . import _lib
 from . import function as F_
 
 PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "fp16": _lib.PREC_FP16,
-              # encoder entry points only: split f16 operands (hi + lo), fp32-grade features on the tensor pipe
-              "fp16x3": _lib.PREC_FP16X3}
+              # x3 engines: split operands (hi + lo halves) on the tensor pipe.  "fp16x3" = 22 significand bits
+              # (fp32-grade: statistics 1e-5, images 1e-4), "bf16x3" = 16 bits at the fp32 exponent range
+              "fp16x3": _lib.PREC_FP16X3, "bf16x3": _lib.PREC_BF16X3}
 # tensor-core path with f16 operands: meets the 1e-2 image tolerance of BASELINE.json; "bf16" runs
 # the same kernels with bf16 operands (wider range, ~7x larger rounding error), "fp32" the FFMA
 # validation mode (1e-4)

@@ -43,12 +43,16 @@ extern "C" {
 #define CCST_PREC_FP32 0 /* fp32 activations + fp32 FFMA implicit GEMM (validation mode, 1e-4) */
 #define CCST_PREC_BF16 1 /* bf16 activations + tcgen05/TMEM implicit GEMM fed by TMA (fp32 accum) */
 #define CCST_PREC_FP16 2 /* same kernels with f16 operands (11-bit significand, saturating stores) */
-/* ENCODER entry points only (ccst_encoder_fwd / _levels / _accumulate / _accumulate_u8): fp32-grade results on
- * the f16 tensor pipe.  Activations and weights are split into f16 high and low parts (22 significand bits)
- * and a * w = a_hi*w_hi + a_lo*w_hi + a_hi*w_lo runs as one tcgen05 implicit GEMM over 3x the channels with
- * fp32 accumulation; relu4_1 statistics meet the 1e-5 bar of the fp32 reference at ~10x the rate of
- * CCST_PREC_FP32.  Other entry points return CCST_EINVAL for it. */
+/* x3 engines: fp32-grade results on the 16-bit tensor pipe, every entry point.  Activations and weights are split
+ * into 16-bit high and low parts and a * w = (a_hi + a_lo) * (w_hi + w_lo) runs as one tcgen05 implicit GEMM over
+ * 2x the channels and 2x the filter rows with fp32 accumulation (partial sums promoted to registers every 12 MMAs).
+ * FP16X3: f16 halves, 22 significand bits -- relu4_1 statistics meet the 1e-5 bar of the fp32 reference and the
+ * stylised image its 1e-4 bar at ~8x the rate of CCST_PREC_FP32; activations must stay inside the f16 range (the
+ * saturation counter applies).  BF16X3: bf16 halves, 16 significand bits at the fp32 exponent range -- the
+ * tensor-core mode for weights whose activations leave the f16 range; meets the 1e-2 image bar that single bf16
+ * operands (CCST_PREC_BF16) miss. */
 #define CCST_PREC_FP16X3 3
+#define CCST_PREC_BF16X3 4
 
 typedef struct ccst_handle ccst_handle;
 
