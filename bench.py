@@ -441,10 +441,15 @@ def run_ours(args, rank, world, local_rank):
 
         # ---------------- same step with the other operand type (single GPU, informative) ----------
         other = {}
-        for alt in ("bf16", "fp16"):
+        ACCURACY = {"bf16": "1.3e-2 .. 1.6e-2 max-abs (misses the 1e-2 bar; strict xfail in the tests)",
+                    "fp16": "2e-3 max-abs (bar 1e-2)",
+                    "fp16x3": "2.5e-6 max-abs vs the fp32 reference (fp32 mode's bar 1e-4): split f16 operands, 4x the MMAs",
+                    "bf16x3": "3e-5 max-abs (fp32 mode's bar 1e-4): split bf16 operands, fp32 exponent range, 4x the MMAs"}
+        for alt in ("bf16", "fp16", "fp16x3", "bf16x3"):
             if alt != precision and precision != "fp32":
-                ms_alt = timed_steps(alt, args.steps)
-                other[alt] = {"ms_per_step": round(ms_alt, 4), "images_per_s_per_gpu": round(args.batch / ms_alt * 1e3, 2)}
+                ms_alt = timed_steps(alt, args.steps if len(alt) == 4 else max(3, args.steps // 4))
+                other[alt] = {"ms_per_step": round(ms_alt, 4), "images_per_s_per_gpu": round(args.batch / ms_alt * 1e3, 2),
+                              "image_error": ACCURACY[alt]}
 
     barrier()
 

@@ -133,6 +133,9 @@ struct ccst_handle {
   float* first_b64 = nullptr;
   bf16* first_wk_b = nullptr;   // same, [64][32] K-major bf16 / f16 (tcgen05 path)
   __half* first_wk_h = nullptr;
+  bf16* first_x3_b = nullptr;   // x3 engines: [128 = hi | lo][64 = 2 x 32 k] halves of w * 2^e (conv_first_x3_ws_kernel)
+  __half* first_x3_h = nullptr;
+  float first_x3_scale = 1.f;   // 2^-e
   ConvLayer enc[kEncLayers];
   ConvLayer dec[kDecLayers];
   void* arena[2] = {nullptr, nullptr};
@@ -414,6 +417,7 @@ struct Weights16<bf16> {
   static const bf16* sm(const ConvLayer& L) { return L.w_sm; }
   static const bf16* up(const ConvLayer& L) { return L.w_up; }
   static const bf16* first(const ccst_handle* h) { return h->first_wk_b; }
+  static const bf16* first_x3(const ccst_handle* h) { return h->first_x3_b; }
   static const bf16* x3(const ConvLayer& L) { return L.w_x3_b; }
 };
 template <>
@@ -422,6 +426,7 @@ struct Weights16<__half> {
   static const __half* sm(const ConvLayer& L) { return L.w_sm_h; }
   static const __half* up(const ConvLayer& L) { return L.w_up_h; }
   static const __half* first(const ccst_handle* h) { return h->first_wk_h; }
+  static const __half* first_x3(const ccst_handle* h) { return h->first_x3_h; }
   static const __half* x3(const ConvLayer& L) { return L.w_x3; }
 };
 
@@ -636,8 +641,14 @@ int Pipe<float>::first_launch(const float* img, int N, int H, int W) {
 }
 template <typename T>
 int Pipe<T>::first_launch(const float* img, int N, int H, int W) {
-  // x3 engines: conv1_1 (K = 27, HBM-bound) on the fp32 CUDA-core kernel, stored as [hi | lo]
-  if (split()) return launch_conv_first_split<T>(img, N, H, W, h->first_w27, h->first_b64, cur, st, h->sat_count);
+  if (split()) {
+    // x3 engines: split im2col rows on the tensor pipe when TMA can fetch the image rows, else the fp32
+    // CUDA-core kernel; both store [hi | lo]
+    if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0)
+      return launch_conv_first_x3<T>(img, N, H, W, Weights16<T>::first_x3(h), h->first_x3_scale, h->first_b64, cur, st,
+                                     h->sat_count);
+    return launch_conv_first_split<T>(img, N, H, W, h->first_w27, h->first_b64, cur, st, h->sat_count);
+  }
   return launch_conv_first_umma<T>(img, N, H, W, Weights16<T>::first(h), h->first_b64, cur, st, h->sat_count);
 }
 template <>
@@ -826,6 +837,8 @@ extern "C" void ccst_destroy(ccst_handle* h) {
   cudaFree(h->first_b64);
   cudaFree(h->first_wk_b);
   cudaFree(h->first_wk_h);
+  cudaFree(h->first_x3_b);
+  cudaFree(h->first_x3_h);
   for (auto& L : h->enc) free_layer(L);
   for (auto& L : h->dec) free_layer(L);
   cudaFree(h->arena[0]);
@@ -881,6 +894,36 @@ extern "C" int ccst_set_encoder_weights(ccst_handle* h, const float* const* w,
   if (!h->first_wk_h) CCST_CUDA(cudaMalloc(&h->first_wk_h, wkh.size() * sizeof(__half)));
   CCST_CUDA(cudaMemcpy(h->first_wk_b, wkb.data(), wkb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   CCST_CUDA(cudaMemcpy(h->first_wk_h, wkh.data(), wkh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  {
+    // x3 engines: w * 2^e = hi + lo (e puts the largest |w| just below 2^10, see pack_layer); row o holds the 27
+    // hi halves of channel o under k = 0..26 AND k = 32..58 (the [a_hi | a_lo] halves of the im2col row meet the
+    // same weights), row 64 + o the lo halves
+    float wmax = 0.f;
+    for (float v : w27) wmax = fmaxf(wmax, fabsf(v));
+    int e = 0;
+    if (wmax > 0.f) {
+      int ex;
+      frexpf(wmax, &ex);
+      e = 10 - ex;
+    }
+    std::vector<bf16> xb(128 * 64, __float2bfloat16(0.f));
+    std::vector<__half> xh(128 * 64, __float2half(0.f));
+    for (int o = 0; o < 64; ++o)
+      for (int k = 0; k < 27; ++k) {
+        const float v = ldexpf(w27[(size_t)k * 64 + o], e);
+        const __half hh = __float2half(v), hl = __float2half(v - __half2float(hh));
+        const bf16 bh = __float2bfloat16(v), bl = __float2bfloat16(v - __bfloat162float(bh));
+        for (int half = 0; half < 2; ++half) {
+          xh[(size_t)o * 64 + half * 32 + k] = hh, xh[(size_t)(64 + o) * 64 + half * 32 + k] = hl;
+          xb[(size_t)o * 64 + half * 32 + k] = bh, xb[(size_t)(64 + o) * 64 + half * 32 + k] = bl;
+        }
+      }
+    if (!h->first_x3_b) CCST_CUDA(cudaMalloc(&h->first_x3_b, xb.size() * sizeof(bf16)));
+    if (!h->first_x3_h) CCST_CUDA(cudaMalloc(&h->first_x3_h, xh.size() * sizeof(__half)));
+    CCST_CUDA(cudaMemcpy(h->first_x3_b, xb.data(), xb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    CCST_CUDA(cudaMemcpy(h->first_x3_h, xh.data(), xh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    h->first_x3_scale = ldexpf(1.f, -e);
+  }
   for (int i = 0; i < kEncLayers; ++i)
     if (int e = pack_layer(h->enc[i], kEncCh[i][0], kEncCh[i][1], w[2 + i], b[2 + i], false, false, /*split_pack=*/true))
       return e;

@@ -444,5 +444,250 @@ __global__ void __launch_bounds__(kF2Threads, 2)
   if (warp == 5) tmem_dealloc<128>(tmem_base);
 }
 
+// =====================================================================================
+// conv1_1 of the x3 engines (split operands, conv_x3.cuh) on the tensor pipe: the warp-specialised kernel
+// above with 64-wide im2col rows [a_hi (27, padded to 32) | a_lo (27, padded to 32)] and a 128-row weight
+// tile [w_hi | w_lo] whose rows repeat the same 27 weights under both halves of K, so that
+//   D[:, 0..63] = (a_hi + a_lo) * w_hi,   D[:, 64..127] = (a_hi + a_lo) * w_lo      (4 MMAs of K = 16, N = 128).
+// Four MMAs per accumulator: the truncating TMEM accumulation that forces the promoted partial sums of the
+// deeper layers is negligible here.  Epilogue: v = (D_hi + D_lo) * 2^-e + bias, ReLU, split into hi / lo, two
+// TMA stores per warp (channels 0..63 and 64..127 of the [hi | lo] map).  HBM-bound on its 256 B per pixel.
+// One CTA per SM (two staging tiles per accumulator stage).
+// =====================================================================================
+constexpr int kF3OffA = 0;                                     // 2 A tiles (128 rows x 128 B, all 64 k used)
+constexpr int kF3OffOut = 2 * kF2ABytes;                       // 2 stages x {hi, lo} staging tiles
+constexpr int kF3OffB = 6 * kF2ABytes;                         // weights 128 x 128 B
+constexpr int kF3OffWin = kF3OffB + 128 * 128;
+constexpr int kF3OffBias = kF3OffWin + kF2WinStages * kF2WinBytes;
+constexpr int kF3OffBar = kF3OffBias + 256;
+constexpr int kF3Smem = 1024 + kF3OffBar + 8 * kF2NumBars + 16;
+
+constexpr int kF3Threads = 448;  // producer, 4 builder warps, MMA issuer, 2 epilogue groups of 4 warps
+
+template <typename T16>
+__global__ void __launch_bounds__(kF3Threads, 1)
+    conv_first_x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_img,
+                            const __grid_constant__ CUtensorMap tmap_out, FirstParams<T16> p, float out_scale) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + kF3OffBar;
+  auto win_full = [&](int s) { return bar0 + 8u * s; };
+  auto win_empty = [&](int s) { return bar0 + 8u * (kF2WinStages + s); };
+  auto a_full = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + s); };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + 2 + s); };
+  auto t_full = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + 4 + s); };
+  auto t_empty = [&](int s) { return bar0 + 8u * (2 * kF2WinStages + 6 + s); };
+  const uint32_t tmem_slot = bar0 + 8u * kF2NumBars;
+  float* sbias = reinterpret_cast<float*>(gen + kF3OffBias);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // one-time: weights [128 rows = hi | lo][64 k] -> swizzled K-major B tile, bias, barriers, TMEM (2 x 128 columns)
+  for (int i = tid; i < 128 * 8; i += kF3Threads) {
+    const int o = i >> 3, j = i & 7;
+    const uint4 v = reinterpret_cast<const uint4*>(p.wk)[o * 8 + j];
+    *reinterpret_cast<uint4*>(gen + kF3OffB + o * 128 + ((j ^ (o & 7)) << 4)) = v;
+  }
+  if (tid < 64) sbias[tid] = p.bias[tid];
+  if (tid == 0) {
+    for (int s = 0; s < kF2WinStages; ++s) {
+      mbar_init(win_full(s), 1);
+      mbar_init(win_empty(s), 128);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_full(s), 128);
+      mbar_init(a_empty(s), 1);
+      mbar_init(t_full(s), 1);
+      mbar_init(t_empty(s), 4);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tmap_img);
+    prefetch_tmap(&tmap_out);
+  }
+  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + kF3OffBar + 8 * kF2NumBars);
+
+  auto tile_coord = [&](int tile, int& n, int& y, int& x0) {
+    x0 = (tile % p.tiles_x) * kFirstPx;
+    const int b = tile / p.tiles_x;
+    y = b % p.H;
+    n = b / p.H;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int ws = it % kF2WinStages;
+      const uint32_t ph = (it / kF2WinStages) & 1;
+      int n, y, x0;
+      tile_coord(tile, n, y, x0);
+      mbar_wait(win_empty(ws), ph ^ 1, 960);
+      if (elect_one()) {
+        mbar_expect_tx(win_full(ws), kF2WinTx);
+        tma_load_4d(base + kF3OffWin + ws * kF2WinBytes, &tmap_img, win_full(ws), x0 - kF2WinX0, y - 1, 0, n);
+      }
+      __syncwarp();
+    }
+  } else if (warp <= 4) {
+    // ===================== builders: split im2col row of pixel px
+    const int px = tid - 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int ws = it % kF2WinStages, as = it & 1;
+      int n, y, x0;
+      tile_coord(tile, n, y, x0);
+      int ridx[3] = {0, 1, 2};
+      if (y == 0) ridx[0] = 2;
+      if (y == p.H - 1) ridx[2] = 0;
+      int cidx[3];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        int xx = x0 + px + s - 1;
+        xx = xx < 0 ? -xx : (xx >= p.W ? 2 * p.W - 2 - xx : xx);
+        int c = xx - (x0 - kF2WinX0);
+        cidx[s] = c < 0 ? 0 : (c > kF2WinCols - 1 ? kF2WinCols - 1 : c);
+      }
+      mbar_wait(win_full(ws), (it / kF2WinStages) & 1, 961);
+      const float* win = reinterpret_cast<const float*>(gen + kF3OffWin + ws * kF2WinBytes);
+      float v[28];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        const int tap = k / 3, ci = k - 3 * tap;
+        const int r = tap / 3, s = tap - 3 * r;
+        v[k] = win[(ci * 3 + ridx[r]) * kF2WinCols + cidx[s]];
+      }
+      v[27] = 0.f;
+      fence_async_smem();  // (see conv_first_umma_ws_kernel: generic reads before the async-proxy rewrite)
+      mbar_arrive(win_empty(ws));
+      uint32_t pk[32];
+#pragma unroll
+      for (int k2 = 0; k2 < 14; ++k2) {
+        pk[k2] = pack16x2<T16>(v[2 * k2], v[2 * k2 + 1]);
+        const float2 hf = unpack16x2<T16>(pk[k2]);
+        pk[16 + k2] = pack16x2<T16>(v[2 * k2] - hf.x, v[2 * k2 + 1] - hf.y);
+      }
+      pk[14] = 0u, pk[15] = 0u, pk[30] = 0u, pk[31] = 0u;
+      MBAR_WAIT_RELAXED(a_empty(as), ((it >> 1) & 1) ^ 1, 962);
+      const uint32_t sA = base + kF3OffA + as * kF2ABytes;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t dst = sA + px * 128 + ((j ^ (px & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                     "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                     : "memory");
+      }
+      fence_async_smem();
+      mbar_arrive(a_full(as));
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer: K = 64 = [hi | lo] in four steps, N = 128 = [w_hi | w_lo]
+    constexpr uint32_t idesc = make_idesc<T16, 128>();
+    const uint64_t bdesc = make_kmajor_sw128_desc(base + kF3OffB);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(t_empty(as), ph ^ 1, 963);
+      mbar_wait(a_full(as), ph, 964);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = make_kmajor_sw128_desc(base + kF3OffA + as * kF2ABytes);
+        const uint32_t d = tmem_base + (uint32_t)(as * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
+        umma_commit(a_empty(as));
+        umma_commit(t_full(as));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: group g = tiles of parity g, accumulator stage g, staging pair g; warp q of a
+    // group owns TMEM lanes 32q..32q+31 = pixels 32q.. of the tile
+    const int grp = (warp - 6) >> 2;
+    const int q = warp & 3;
+    const int px = q * 32 + lane;
+    SatTracker<T16> sat;
+    const uint32_t sHi = base + kF3OffOut + (2 * grp) * kF2ABytes, sLo = sHi + kF2ABytes;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 128);
+    int it = grp;
+    for (long long tile = (long long)blockIdx.x + (long long)grp * gridDim.x; tile < p.total_tiles;
+         tile += 2ll * gridDim.x, it += 2) {
+      int n, y, x0;
+      tile_coord((int)tile, n, y, x0);
+      const int x = x0 + px;
+      MBAR_WAIT_RELAXED(t_full(grp), (it >> 1) & 1, 965);
+      tc_fence_after();
+      // the group's staging pair: the stores of its previous tile must have read it
+      bulk_wait_read<0>();
+      __syncwarp();
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t u[32], w[32];
+        tmem_ld32(taddr + h2 * 32, u);       // a * w_hi, channels 32 h2 ..
+        tmem_ld32(taddr + 64 + h2 * 32, w);  // a * w_lo
+        tmem_ld_wait();
+        if (h2 == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty(grp));
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float v0 = fmaxf(fmaf(__uint_as_float(u[2 * j]) + __uint_as_float(w[2 * j]), out_scale,
+                                      sbias[h2 * 32 + 2 * j]), 0.f);
+          const float v1 = fmaxf(fmaf(__uint_as_float(u[2 * j + 1]) + __uint_as_float(w[2 * j + 1]), out_scale,
+                                      sbias[h2 * 32 + 2 * j + 1]), 0.f);
+          hi[j] = pack16x2<T16>(v0, v1);
+          const float2 hf = unpack16x2<T16>(hi[j]);
+          lo[j] = pack16x2<T16>(v0 - hf.x, v1 - hf.y);
+          sat.track_nonneg(hi[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = px * 128 + (((h2 * 4 + j) ^ (px & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sHi + off), "r"(hi[4 * j]),
+                       "r"(hi[4 * j + 1]), "r"(hi[4 * j + 2]), "r"(hi[4 * j + 3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sLo + off), "r"(lo[4 * j]),
+                       "r"(lo[4 * j + 1]), "r"(lo[4 * j + 2]), "r"(lo[4 * j + 3])
+                       : "memory");
+        }
+        // reflection-halo aliases of a border pixel (the pixel itself goes out through the TMA store)
+        if (x < p.W && (y == 1 || y == p.H - 2 || x == 1 || x == p.W - 2)) {
+          for_each_halo_alias(y, x, p.H, p.W, [&](int yy, int xx) {
+            if (yy == y && xx == x) return;
+            uint4* dh = reinterpret_cast<uint4*>(p.out.px(n, yy, xx) + h2 * 32);
+            uint4* dl = reinterpret_cast<uint4*>(p.out.px(n, yy, xx) + 64 + h2 * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          });
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        tma_store_4d(&tmap_out, sHi + q * (32 * 128), 0, x0 + q * 32, y, n);  // clipped at W
+        tma_store_4d(&tmap_out, sLo + q * (32 * 128), 64, x0 + q * 32, y, n);
+        bulk_commit();
+      }
+      __syncwarp();
+    }
+    bulk_wait_all();
+    sat.flush(p.sat_count);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<256>(tmem_base);
+}
+
 }  // namespace
 }  // namespace ccst

@@ -145,6 +145,55 @@ int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk,
   CCST_LAUNCHED();
   return CCST_OK;
 }
+// conv1_1 of the x3 engines on the tensor pipe (conv_first_x3_ws_kernel): wk_x3 = [128 rows = hi | lo][64 k], the 27
+// weights * 2^e repeated under k = 0..31 and k = 32..63; out = [hi | lo] map of 64 logical channels.  Needs TMA-
+// fetchable image rows (W % 4 == 0, 16-byte aligned base); returns CCST_EINVAL otherwise (the caller falls back to
+// the CUDA-core kernel).
+template <typename T16>
+int launch_conv_first_x3(const float* img, int N, int H, int W, const T16* wk_x3, float out_scale, const float* bias,
+                         ActView<T16> out, cudaStream_t st, unsigned int* sat_count) {
+  CCST_CHECK_ARG(out.C == 128 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0,
+                 "conv_first_x3: needs a [hi | lo] map of 64 channels and 16-byte aligned image rows");
+  FirstParams<T16> p;
+  p.img = img, p.N = N, p.H = H, p.W = W, p.wk = wk_x3, p.bias = bias, p.out = out;
+  p.sat_count = sat_count;
+  p.tiles_x = (W + kFirstPx - 1) / kFirstPx;
+  const int64_t total = (int64_t)N * H * p.tiles_x;
+  CCST_CHECK_ARG(total < (1ll << 31), "conv_first_x3: too many tiles");
+  p.total_tiles = (int)total;
+  CUtensorMap mo, mi;
+  if (int e = make_out_map(&mo, out, 0, 0, 1, 1, 32, 1)) return e;  // one warp's quarter, 64 of the 128 channels
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return CCST_ECUDA;
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+  const cuuint32_t box[4] = {kF2WinCols, 3, 3, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&mi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)img, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(image %dx3x%dx%d) failed: CUresult %d", N, H, W, (int)r);
+    return CCST_ECUDA;
+  }
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_first_x3_ws_kernel<T16>), kF3Smem));
+  const int grid = (int)(total < sm_count() ? total : sm_count());
+  CCST_CUDA(launch_conv(conv_first_x3_ws_kernel<T16>, grid, kF3Threads, kF3Smem, st, 1, mi, mo, p, out_scale));
+  CCST_LAUNCHED();
+  return CCST_OK;
+}
+#if CCST_INST_BF16
+template int launch_conv_first_x3<__nv_bfloat16>(const float*, int, int, int, const __nv_bfloat16*, float, const float*,
+                                                 ActView<__nv_bfloat16>, cudaStream_t, unsigned int*);
+#endif
+#if CCST_INST_F16
+template int launch_conv_first_x3<__half>(const float*, int, int, int, const __half*, float, const float*,
+                                          ActView<__half>, cudaStream_t, unsigned int*);
+#endif
+
 #if CCST_INST_BF16
 template int launch_conv_first_umma<__nv_bfloat16>(const float*, int, int, int,
                                                    const __nv_bfloat16*, const float*,

@@ -143,5 +143,10 @@ int launch_conv_umma(const UmmaConvArgs<T16>& a, cudaStream_t st);
 template <typename T16>
 int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk, const float* bias,
                            ActView<T16> out, cudaStream_t st, unsigned int* sat_count = nullptr);
+// conv1_1 of the x3 engines on tcgen05: wk_x3 [128 = hi | lo rows][64 = 2 x (27 padded to 32) k] of w * 2^e,
+// out_scale = 2^-e, out = [hi | lo] map (C == 128).  W % 4 == 0 and a 16-byte aligned image only.
+template <typename T16>
+int launch_conv_first_x3(const float* img, int N, int H, int W, const T16* wk_x3, float out_scale, const float* bias,
+                         ActView<T16> out, cudaStream_t st, unsigned int* sat_count = nullptr);
 
 }  // namespace ccst
