@@ -17,7 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "ccst_b200.h")
 OK, EINVAL, EARCH, ECUDA, ESTATE = 0, -1, -2, -3, -4
 PREC_FP32, PREC_BF16, PREC_FP16, PREC_FP16X3, PREC_BF16X3 = 0, 1, 2, 3, 4
 ABI_VERSION = 2
-FUSE_POOL, FUSE_UPSAMPLE, FUSE_STATS, FUSE_ADAIN, FUSE_ALL = 1, 2, 4, 8, 15
+FUSE_POOL, FUSE_UPSAMPLE, FUSE_STATS, FUSE_ADAIN, FUSE_TOTENSOR, FUSE_ALL = 1, 2, 4, 8, 16, 31
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _pp = C.POINTER(C.c_void_p)

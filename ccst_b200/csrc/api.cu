@@ -148,6 +148,7 @@ struct ccst_handle {
   bool fuse_up = true;  // nearest-x2 upsample folded into the NEXT conv (EPI_UPS) instead of the store
   bool fuse_stats = true;  // relu4_1 statistics taken in conv4_1's epilogue (EPI_ACT_STATS)
   bool fuse_adain = true;  // AdaIN folded into dec1's weights / bias per image (maps >= kFoldMinHW pixels)
+  bool fuse_totensor = true;  // uint8 entry points: conv1_1's window loader reads the uint8 HWC batch itself
   void* w_fold = nullptr;  // per-image dec1 weights [N][256][9*512] (16-bit) of the folded AdaIN
   size_t w_fold_bytes = 0;
   float* b_fold = nullptr; // per-image dec1 bias [N][256]
@@ -445,6 +446,8 @@ struct Pipe {
   float* const* lvl_mean = nullptr;
   float* const* lvl_std = nullptr;
   float lvl_eps = 1e-5f;
+  // the batch as the loader holds it (uint8 HWC): conv1_1 of the tcgen05 engines reads it directly, `img` is unused
+  const uint8_t* img_u8 = nullptr;
 
   // x3 engines: every map holds the [hi | lo] halves of its C logical channels (v.C = 2 * C)
   bool split() const { return sizeof(T) == 2 && h->split; }
@@ -644,12 +647,12 @@ int Pipe<T>::first_launch(const float* img, int N, int H, int W) {
   if (split()) {
     // x3 engines: split im2col rows on the tensor pipe when TMA can fetch the image rows, else the fp32
     // CUDA-core kernel; both store [hi | lo]
-    if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0)
+    if (img_u8 || (W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0))
       return launch_conv_first_x3<T>(img, N, H, W, Weights16<T>::first_x3(h), h->first_x3_scale, h->first_b64, cur, st,
-                                     h->sat_count);
+                                     h->sat_count, img_u8);
     return launch_conv_first_split<T>(img, N, H, W, h->first_w27, h->first_b64, cur, st, h->sat_count);
   }
-  return launch_conv_first_umma<T>(img, N, H, W, Weights16<T>::first(h), h->first_b64, cur, st, h->sat_count);
+  return launch_conv_first_umma<T>(img, N, H, W, Weights16<T>::first(h), h->first_b64, cur, st, h->sat_count, img_u8);
 }
 template <>
 int Pipe<float>::conv(const ConvLayer& L, int relu, int epi, ActView<float> out, float* out_nchw, int,
@@ -723,13 +726,17 @@ int run_style_transfer_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, in
   ccst_feature_hw(H, W, &fh, &fw);
   const size_t in_elems = (size_t)N * 3 * H * W, out_elems = (size_t)N * 3 * (8 * fh) * (8 * fw);
   const bool fused_store = sizeof(T) == 2;  // tcgen05 path: quantisation fused into the last conv
-  if (int e = ensure_io(h, in_elems + (fused_store ? 0 : out_elems))) return e;
+  // ... and ToTensor into conv1_1's window loader when TMA can fetch the uint8 rows
+  const bool fused_load = sizeof(T) == 2 && h->fuse_totensor && first_u8_ok(d_img, W);
+  if (int e = ensure_io(h, (fused_load ? 0 : in_elems) + (fused_store ? 0 : out_elems))) return e;
   if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T) * (h->split ? 2 : 1), true, true))) return e;
-  {
+  Pipe<T> p{h, st};
+  if (fused_load) {
+    p.img_u8 = d_img;
+  } else {
     ProfScope ps(h, st, 5, 0, (double)in_elems * 5.0);
     if (int e = launch_u8_nhwc_to_f32_nchw(d_img, N, 3, H, W, h->io_f32, st)) return e;
   }
-  Pipe<T> p{h, st};
   if (int e = p.encoder(h->io_f32, N, H, W)) return e;
   if (int e = p.adain(mu, sg, stride, alpha)) return e;
   if (fused_store) {
@@ -745,12 +752,13 @@ int run_style_transfer_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, in
 template <typename T>
 int run_encoder(ccst_handle* h, const float* d_img, int N, int H, int W, float* d_feat,
                 double* d_state, cudaStream_t st, float* const* lvl_mean = nullptr, float* const* lvl_std = nullptr,
-                float lvl_eps = 1e-5f) {
+                float lvl_eps = 1e-5f, const uint8_t* d_img_u8 = nullptr) {
   int fh, fw;
   ccst_feature_hw(H, W, &fh, &fw);
   if (int e = ensure_arena(h, plan_bytes(N, H, W, fh, fw, sizeof(T) * (h->split ? 2 : 1), true, false))) return e;
   Pipe<T> p{h, st};
   p.lvl_mean = lvl_mean, p.lvl_std = lvl_std, p.lvl_eps = lvl_eps;
+  p.img_u8 = d_img_u8;
   if (int e = p.encoder(d_img, N, H, W)) return e;
   if (d_feat) {
     ProfScope ps(h, st, 5, 0, (double)N * fh * fw * 512 * (4.0 + sizeof(T)));
@@ -1006,6 +1014,8 @@ extern "C" int ccst_encoder_accumulate(ccst_handle* h, const float* d_img, int N
 namespace {
 template <typename T>
 int run_encoder_u8(ccst_handle* h, const uint8_t* d_img, int N, int H, int W, double* d_state, cudaStream_t st) {
+  if (sizeof(T) == 2 && h->fuse_totensor && first_u8_ok(d_img, W))  // conv1_1 reads the uint8 batch itself
+    return run_encoder<T>(h, nullptr, N, H, W, nullptr, d_state, st, nullptr, nullptr, 1e-5f, d_img);
   if (int e = ensure_io(h, (size_t)N * 3 * H * W)) return e;
   {
     ProfScope ps(h, st, 5, 0, (double)N * 3 * H * W * 5.0);
@@ -1095,6 +1105,7 @@ extern "C" int ccst_set_fusion(ccst_handle* h, int mask) {
   h->fuse_up = (mask & CCST_FUSE_UPSAMPLE) != 0;
   h->fuse_stats = (mask & CCST_FUSE_STATS) != 0;
   h->fuse_adain = (mask & CCST_FUSE_ADAIN) != 0;
+  h->fuse_totensor = (mask & CCST_FUSE_TOTENSOR) != 0;
   return CCST_OK;
 }
 

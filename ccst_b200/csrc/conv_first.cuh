@@ -238,11 +238,48 @@ constexpr int kF2OffOut = 2 * kF2ABytes;                       // 2 staging tile
 constexpr int kF2OffB = 4 * kF2ABytes;                         // weights 64 x 128 B
 constexpr int kF2OffWin = kF2OffB + 64 * 128;
 constexpr int kF2OffBias = kF2OffWin + kF2WinStages * kF2WinBytes;
-constexpr int kF2OffBar = kF2OffBias + 256;
+constexpr int kF2OffLut = kF2OffBias + 256;  // 256 table words (U8 only)
+constexpr int kF2OffBar = kF2OffLut + 1024;
 constexpr int kF2NumBars = 2 * kF2WinStages + 8;
 constexpr int kF2Smem = 1024 + kF2OffBar + 8 * kF2NumBars + 16;
 
+// U8 = true: the window is fetched from the loader's uint8 HWC batch [N,H,W,3] itself (ToTensor fused into the
+// builders, cjm_util/data_helper.py:45): TMA box {104 x 4 bytes, 3 rows} = bytes x0*3 - 16 .. x0*3 + 399 of rows
+// y-1..y+1 (needs 3 W % 16 == 0), and float(b) / 255 rounded to T16 comes from a 256-entry table (low half: the
+// T16 value, high half: the T16 remainder for the x3 engines) -- the same values as ccst_u8_to_tensor + pack.
+constexpr int kU8RowBytes = 416;  // 16 + 130 pixels x 3, rounded up to 16
+constexpr int kU8WinX0 = 16;      // window byte of pixel x0, channel 0
+constexpr int kU8WinTx = 3 * kU8RowBytes;
+static_assert(kU8WinTx <= kF2WinBytes, "the uint8 window fits the fp32 window's slot");
+
 template <typename T16>
+__device__ __forceinline__ uint32_t u8_lut_word(int b) {
+  const float v = __fdiv_rn((float)b, 255.f);  // ToTensor: IEEE division, as torch's div
+  const uint32_t hi = pack16x2<T16>(v, 0.f) & 0xffffu;
+  const uint32_t lo = pack16x2<T16>(v - unpack16x2<T16>(hi).x, 0.f) & 0xffffu;
+  return hi | (lo << 16);
+}
+// the 27 taps of pixel px as table words (k = (r*3+s)*3 + ci)
+__device__ __forceinline__ void u8_gather27(const uint8_t* win, const uint32_t* lut, const int (&ridx)[3], int x0, int px,
+                                            int W, uint32_t (&wv)[28]) {
+  int cidx[3];
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    int xx = x0 + px + s - 1;
+    xx = xx < 0 ? -xx : (xx >= W ? 2 * W - 2 - xx : xx);
+    const int c = kU8WinX0 + (xx - x0) * 3;
+    cidx[s] = c < 0 ? 0 : (c > kU8RowBytes - 3 ? kU8RowBytes - 3 : c);  // only for pixels past W
+  }
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    const int tap = k / 3, ci = k - 3 * tap;
+    const int r = tap / 3, s = tap - 3 * r;
+    wv[k] = lut[win[ridx[r] * kU8RowBytes + cidx[s] + ci]];
+  }
+  wv[27] = 0u;
+}
+
+template <typename T16, bool U8 = false>
 __global__ void __launch_bounds__(kF2Threads, 2)
     conv_first_umma_ws_kernel(const __grid_constant__ CUtensorMap tmap_img,
                               const __grid_constant__ CUtensorMap tmap_out, FirstParams<T16> p) {
@@ -267,6 +304,8 @@ __global__ void __launch_bounds__(kF2Threads, 2)
     *reinterpret_cast<uint4*>(gen + kF2OffB + o * 128 + ((j ^ (o & 7)) << 4)) = v;
   }
   if (tid < 64) sbias[tid] = p.bias[tid];
+  uint32_t* lut = reinterpret_cast<uint32_t*>(gen + kF2OffLut);
+  if (U8 && tid < 256) lut[tid] = u8_lut_word<T16>(tid);
   if (tid == 0) {
     for (int s = 0; s < kF2WinStages; ++s) {
       mbar_init(win_full(s), 1);
@@ -308,8 +347,9 @@ __global__ void __launch_bounds__(kF2Threads, 2)
       tile_coord(tile, n, y, x0);
       mbar_wait(win_empty(ws), ph ^ 1, 910);
       if (elect_one()) {
-        mbar_expect_tx(win_full(ws), kF2WinTx);
-        tma_load_4d(base + kF2OffWin + ws * kF2WinBytes, &tmap_img, win_full(ws), x0 - kF2WinX0, y - 1, 0, n);
+        mbar_expect_tx(win_full(ws), U8 ? kU8WinTx : kF2WinTx);
+        tma_load_4d(base + kF2OffWin + ws * kF2WinBytes, &tmap_img, win_full(ws),
+                    U8 ? (x0 * 3 - kU8WinX0) >> 2 : x0 - kF2WinX0, y - 1, 0, n);
       }
       __syncwarp();
     }
@@ -334,23 +374,32 @@ __global__ void __launch_bounds__(kF2Threads, 2)
         cidx[s] = c < 0 ? 0 : (c > kF2WinCols - 1 ? kF2WinCols - 1 : c);  // only for pixels past W
       }
       mbar_wait(win_full(ws), (it / kF2WinStages) & 1, 920);
-      const float* win = reinterpret_cast<const float*>(gen + kF2OffWin + ws * kF2WinBytes);
-      float v[28];
-#pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        const int tap = k / 3, ci = k - 3 * tap;
-        const int r = tap / 3, s = tap - 3 * r;
-        v[k] = win[(ci * 3 + ridx[r]) * kF2WinCols + cidx[s]];
-      }
-      v[27] = 0.f;
-      // The window is rewritten by TMA (async proxy): this thread's generic-proxy reads must be
-      // ordered before that write, which takes a proxy fence before the release (without it a
-      // 32-pixel quarter of a tile came out wrong about once per 10^5 tiles).
-      fence_async_smem();
-      mbar_arrive(win_empty(ws));
       uint32_t pk[16];
+      if (U8) {
+        uint32_t wv[28];
+        u8_gather27(gen + kF2OffWin + ws * kF2WinBytes, lut, ridx, x0, px, p.W, wv);
+        fence_async_smem();  // (as below)
+        mbar_arrive(win_empty(ws));
 #pragma unroll
-      for (int k2 = 0; k2 < 14; ++k2) pk[k2] = pack16x2<T16>(v[2 * k2], v[2 * k2 + 1]);
+        for (int k2 = 0; k2 < 14; ++k2) pk[k2] = __byte_perm(wv[2 * k2], wv[2 * k2 + 1], 0x5410);
+      } else {
+        const float* win = reinterpret_cast<const float*>(gen + kF2OffWin + ws * kF2WinBytes);
+        float v[28];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+          const int tap = k / 3, ci = k - 3 * tap;
+          const int r = tap / 3, s = tap - 3 * r;
+          v[k] = win[(ci * 3 + ridx[r]) * kF2WinCols + cidx[s]];
+        }
+        v[27] = 0.f;
+        // The window is rewritten by TMA (async proxy): this thread's generic-proxy reads must be
+        // ordered before that write, which takes a proxy fence before the release (without it a
+        // 32-pixel quarter of a tile came out wrong about once per 10^5 tiles).
+        fence_async_smem();
+        mbar_arrive(win_empty(ws));
+#pragma unroll
+        for (int k2 = 0; k2 < 14; ++k2) pk[k2] = pack16x2<T16>(v[2 * k2], v[2 * k2 + 1]);
+      }
       pk[14] = 0u, pk[15] = 0u;
       MBAR_WAIT_RELAXED(a_empty(as), ((it >> 1) & 1) ^ 1, 930);
       const uint32_t sA = base + kF2OffA + as * kF2ABytes;
@@ -459,12 +508,13 @@ constexpr int kF3OffOut = 2 * kF2ABytes;                       // 2 stages x {hi
 constexpr int kF3OffB = 6 * kF2ABytes;                         // weights 128 x 128 B
 constexpr int kF3OffWin = kF3OffB + 128 * 128;
 constexpr int kF3OffBias = kF3OffWin + kF2WinStages * kF2WinBytes;
-constexpr int kF3OffBar = kF3OffBias + 256;
+constexpr int kF3OffLut = kF3OffBias + 256;
+constexpr int kF3OffBar = kF3OffLut + 1024;
 constexpr int kF3Smem = 1024 + kF3OffBar + 8 * kF2NumBars + 16;
 
 constexpr int kF3Threads = 448;  // producer, 4 builder warps, MMA issuer, 2 epilogue groups of 4 warps
 
-template <typename T16>
+template <typename T16, bool U8 = false>
 __global__ void __launch_bounds__(kF3Threads, 1)
     conv_first_x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_img,
                             const __grid_constant__ CUtensorMap tmap_out, FirstParams<T16> p, float out_scale) {
@@ -489,6 +539,8 @@ __global__ void __launch_bounds__(kF3Threads, 1)
     *reinterpret_cast<uint4*>(gen + kF3OffB + o * 128 + ((j ^ (o & 7)) << 4)) = v;
   }
   if (tid < 64) sbias[tid] = p.bias[tid];
+  uint32_t* lut = reinterpret_cast<uint32_t*>(gen + kF3OffLut);
+  if (U8 && tid < 256) lut[tid] = u8_lut_word<T16>(tid);
   if (tid == 0) {
     for (int s = 0; s < kF2WinStages; ++s) {
       mbar_init(win_full(s), 1);
@@ -528,8 +580,9 @@ __global__ void __launch_bounds__(kF3Threads, 1)
       tile_coord(tile, n, y, x0);
       mbar_wait(win_empty(ws), ph ^ 1, 960);
       if (elect_one()) {
-        mbar_expect_tx(win_full(ws), kF2WinTx);
-        tma_load_4d(base + kF3OffWin + ws * kF2WinBytes, &tmap_img, win_full(ws), x0 - kF2WinX0, y - 1, 0, n);
+        mbar_expect_tx(win_full(ws), U8 ? kU8WinTx : kF2WinTx);
+        tma_load_4d(base + kF3OffWin + ws * kF2WinBytes, &tmap_img, win_full(ws),
+                    U8 ? (x0 * 3 - kU8WinX0) >> 2 : x0 - kF2WinX0, y - 1, 0, n);
       }
       __syncwarp();
     }
@@ -553,23 +606,35 @@ __global__ void __launch_bounds__(kF3Threads, 1)
         cidx[s] = c < 0 ? 0 : (c > kF2WinCols - 1 ? kF2WinCols - 1 : c);
       }
       mbar_wait(win_full(ws), (it / kF2WinStages) & 1, 961);
-      const float* win = reinterpret_cast<const float*>(gen + kF3OffWin + ws * kF2WinBytes);
-      float v[28];
-#pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        const int tap = k / 3, ci = k - 3 * tap;
-        const int r = tap / 3, s = tap - 3 * r;
-        v[k] = win[(ci * 3 + ridx[r]) * kF2WinCols + cidx[s]];
-      }
-      v[27] = 0.f;
-      fence_async_smem();  // (see conv_first_umma_ws_kernel: generic reads before the async-proxy rewrite)
-      mbar_arrive(win_empty(ws));
       uint32_t pk[32];
+      if (U8) {
+        uint32_t wv[28];
+        u8_gather27(gen + kF3OffWin + ws * kF2WinBytes, lut, ridx, x0, px, p.W, wv);
+        fence_async_smem();
+        mbar_arrive(win_empty(ws));
 #pragma unroll
-      for (int k2 = 0; k2 < 14; ++k2) {
-        pk[k2] = pack16x2<T16>(v[2 * k2], v[2 * k2 + 1]);
-        const float2 hf = unpack16x2<T16>(pk[k2]);
-        pk[16 + k2] = pack16x2<T16>(v[2 * k2] - hf.x, v[2 * k2 + 1] - hf.y);
+        for (int k2 = 0; k2 < 14; ++k2) {
+          pk[k2] = __byte_perm(wv[2 * k2], wv[2 * k2 + 1], 0x5410);       // hi halves
+          pk[16 + k2] = __byte_perm(wv[2 * k2], wv[2 * k2 + 1], 0x7632);  // lo halves
+        }
+      } else {
+        const float* win = reinterpret_cast<const float*>(gen + kF3OffWin + ws * kF2WinBytes);
+        float v[28];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) {
+          const int tap = k / 3, ci = k - 3 * tap;
+          const int r = tap / 3, s = tap - 3 * r;
+          v[k] = win[(ci * 3 + ridx[r]) * kF2WinCols + cidx[s]];
+        }
+        v[27] = 0.f;
+        fence_async_smem();  // (see conv_first_umma_ws_kernel: generic reads before the async-proxy rewrite)
+        mbar_arrive(win_empty(ws));
+#pragma unroll
+        for (int k2 = 0; k2 < 14; ++k2) {
+          pk[k2] = pack16x2<T16>(v[2 * k2], v[2 * k2 + 1]);
+          const float2 hf = unpack16x2<T16>(pk[k2]);
+          pk[16 + k2] = pack16x2<T16>(v[2 * k2] - hf.x, v[2 * k2 + 1] - hf.y);
+        }
       }
       pk[14] = 0u, pk[15] = 0u, pk[30] = 0u, pk[31] = 0u;
       MBAR_WAIT_RELAXED(a_empty(as), ((it >> 1) & 1) ^ 1, 962);

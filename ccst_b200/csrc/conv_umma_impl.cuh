@@ -99,9 +99,41 @@ template int launch_conv_umma<__nv_bfloat16>(const UmmaConvArgs<__nv_bfloat16>&,
 template int launch_conv_umma<__half>(const UmmaConvArgs<__half>&, cudaStream_t);
 #endif
 
+// TMA map of the input image for the warp-specialised conv1_1 kernels: the fp32 NCHW tensor (box {136 col, 3 row,
+// 3 ch}) or, u8 != nullptr, the loader's uint8 HWC batch as rows of 3 W / 4 four-byte words (box {104 words, 3 rows})
+inline int make_image_map(CUtensorMap* mi, const float* img, const uint8_t* u8, int N, int H, int W) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return CCST_ECUDA;
+  }
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r;
+  if (u8) {
+    const cuuint64_t row = (cuuint64_t)W * 3;
+    const cuuint64_t dims[4] = {row / 4, (cuuint64_t)H, 1, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {row, row * H, row * H};
+    const cuuint32_t box[4] = {kU8RowBytes / 4, 3, 1, 1};
+    r = enc(mi, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void*)u8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+    const cuuint32_t box[4] = {kF2WinCols, 3, 3, 1};
+    r = enc(mi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(image %dx3x%dx%d%s) failed: CUresult %d", N, H, W, u8 ? ", uint8 HWC" : "", (int)r);
+    return CCST_ECUDA;
+  }
+  return CCST_OK;
+}
+
+// img: fp32 NCHW image, or (img_u8 != nullptr) the uint8 HWC batch read directly -- ccst_first_u8_ok() must hold
 template <typename T16>
 int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk, const float* bias,
-                           ActView<T16> out, cudaStream_t st, unsigned int* sat_count) {
+                           ActView<T16> out, cudaStream_t st, unsigned int* sat_count, const uint8_t* img_u8) {
   FirstParams<T16> p;
   p.img = img, p.N = N, p.H = H, p.W = W, p.wk = wk, p.bias = bias, p.out = out;
   p.sat_count = sat_count;
@@ -111,29 +143,20 @@ int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk,
   p.total_tiles = (int)total;
   CUtensorMap mo;
   if (int e = make_out_map(&mo, out, 0, 0, 1, 1, 32, 1)) return e;  // one warp's quarter
-  if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0) {
+  CCST_CHECK_ARG(img_u8 == nullptr || first_u8_ok(img_u8, W), "conv_first_umma: uint8 rows must be 16-byte aligned");
+  if (img_u8 || (W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0)) {
     // rows are 16-byte aligned: TMA-fed warp-specialised kernel
-    PFN_encodeTiled enc = get_encode_fn();
-    if (!enc) {
-      set_error("cuTensorMapEncodeTiled entry point not available");
-      return CCST_ECUDA;
-    }
     CUtensorMap mi;
-    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)N};
-    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
-    const cuuint32_t box[4] = {kF2WinCols, 3, 3, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&mi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)img, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled(image %dx3x%dx%d) failed: CUresult %d", N, H, W, (int)r);
-      return CCST_ECUDA;
-    }
-    CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_first_umma_ws_kernel<T16>), kF2Smem));
+    if (int e = make_image_map(&mi, img, img_u8, N, H, W)) return e;
     const int64_t cap2 = (int64_t)sm_count() * 2;
     const int grid2 = (int)(total < cap2 ? total : cap2);
-    CCST_CUDA(launch_conv(conv_first_umma_ws_kernel<T16>, grid2, kF2Threads, kF2Smem, st, 1, mi, mo, p));
+    if (img_u8) {
+      CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_first_umma_ws_kernel<T16, true>), kF2Smem));
+      CCST_CUDA(launch_conv(conv_first_umma_ws_kernel<T16, true>, grid2, kF2Threads, kF2Smem, st, 1, mi, mo, p));
+    } else {
+      CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_first_umma_ws_kernel<T16, false>), kF2Smem));
+      CCST_CUDA(launch_conv(conv_first_umma_ws_kernel<T16, false>, grid2, kF2Threads, kF2Smem, st, 1, mi, mo, p));
+    }
     CCST_LAUNCHED();
     return CCST_OK;
   }
@@ -145,14 +168,16 @@ int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk,
   CCST_LAUNCHED();
   return CCST_OK;
 }
+
 // conv1_1 of the x3 engines on the tensor pipe (conv_first_x3_ws_kernel): wk_x3 = [128 rows = hi | lo][64 k], the 27
 // weights * 2^e repeated under k = 0..31 and k = 32..63; out = [hi | lo] map of 64 logical channels.  Needs TMA-
-// fetchable image rows (W % 4 == 0, 16-byte aligned base); returns CCST_EINVAL otherwise (the caller falls back to
-// the CUDA-core kernel).
+// fetchable image rows (fp32: W % 4 == 0 and a 16-byte aligned base; uint8: first_u8_ok), CCST_EINVAL otherwise
+// (the caller falls back to the CUDA-core kernel).
 template <typename T16>
 int launch_conv_first_x3(const float* img, int N, int H, int W, const T16* wk_x3, float out_scale, const float* bias,
-                         ActView<T16> out, cudaStream_t st, unsigned int* sat_count) {
-  CCST_CHECK_ARG(out.C == 128 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0,
+                         ActView<T16> out, cudaStream_t st, unsigned int* sat_count, const uint8_t* img_u8) {
+  CCST_CHECK_ARG(out.C == 128 && (img_u8 ? first_u8_ok(img_u8, W)
+                                         : (W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0)),
                  "conv_first_x3: needs a [hi | lo] map of 64 channels and 16-byte aligned image rows");
   FirstParams<T16> p;
   p.img = img, p.N = N, p.H = H, p.W = W, p.wk = wk_x3, p.bias = bias, p.out = out;
@@ -163,45 +188,35 @@ int launch_conv_first_x3(const float* img, int N, int H, int W, const T16* wk_x3
   p.total_tiles = (int)total;
   CUtensorMap mo, mi;
   if (int e = make_out_map(&mo, out, 0, 0, 1, 1, 32, 1)) return e;  // one warp's quarter, 64 of the 128 channels
-  PFN_encodeTiled enc = get_encode_fn();
-  if (!enc) {
-    set_error("cuTensorMapEncodeTiled entry point not available");
-    return CCST_ECUDA;
-  }
-  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)N};
-  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
-  const cuuint32_t box[4] = {kF2WinCols, 3, 3, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&mi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)img, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(image %dx3x%dx%d) failed: CUresult %d", N, H, W, (int)r);
-    return CCST_ECUDA;
-  }
-  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_first_x3_ws_kernel<T16>), kF3Smem));
+  if (int e = make_image_map(&mi, img, img_u8, N, H, W)) return e;
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  CCST_CUDA(launch_conv(conv_first_x3_ws_kernel<T16>, grid, kF3Threads, kF3Smem, st, 1, mi, mo, p, out_scale));
+  if (img_u8) {
+    CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_first_x3_ws_kernel<T16, true>), kF3Smem));
+    CCST_CUDA(launch_conv(conv_first_x3_ws_kernel<T16, true>, grid, kF3Threads, kF3Smem, st, 1, mi, mo, p, out_scale));
+  } else {
+    CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_first_x3_ws_kernel<T16, false>), kF3Smem));
+    CCST_CUDA(launch_conv(conv_first_x3_ws_kernel<T16, false>, grid, kF3Threads, kF3Smem, st, 1, mi, mo, p, out_scale));
+  }
   CCST_LAUNCHED();
   return CCST_OK;
 }
 #if CCST_INST_BF16
 template int launch_conv_first_x3<__nv_bfloat16>(const float*, int, int, int, const __nv_bfloat16*, float, const float*,
-                                                 ActView<__nv_bfloat16>, cudaStream_t, unsigned int*);
+                                                 ActView<__nv_bfloat16>, cudaStream_t, unsigned int*, const uint8_t*);
 #endif
 #if CCST_INST_F16
 template int launch_conv_first_x3<__half>(const float*, int, int, int, const __half*, float, const float*,
-                                          ActView<__half>, cudaStream_t, unsigned int*);
+                                          ActView<__half>, cudaStream_t, unsigned int*, const uint8_t*);
 #endif
 
 #if CCST_INST_BF16
 template int launch_conv_first_umma<__nv_bfloat16>(const float*, int, int, int,
                                                    const __nv_bfloat16*, const float*,
-                                                   ActView<__nv_bfloat16>, cudaStream_t, unsigned int*);
+                                                   ActView<__nv_bfloat16>, cudaStream_t, unsigned int*, const uint8_t*);
 #endif
 #if CCST_INST_F16
 template int launch_conv_first_umma<__half>(const float*, int, int, int, const __half*,
-                                            const float*, ActView<__half>, cudaStream_t, unsigned int*);
+                                            const float*, ActView<__half>, cudaStream_t, unsigned int*, const uint8_t*);
 #endif
 
 }  // namespace ccst

@@ -139,14 +139,21 @@ template <typename T16>
 int launch_conv_umma(const UmmaConvArgs<T16>& a, cudaStream_t st);
 
 // conv1_1 (+ folded 1x1) on tcgen05: thread-built im2col rows (K = 27 padded to 32).
-// wk: [64][32] T16 K-major, bias fp32 [64].
+// wk: [64][32] T16 K-major, bias fp32 [64].  img_u8 != nullptr: the window is read from the loader's uint8 HWC batch
+// [N,H,W,3] itself (ToTensor fused into the loader; first_u8_ok(img_u8, W) must hold) and `img` is unused.
 template <typename T16>
 int launch_conv_first_umma(const float* img, int N, int H, int W, const T16* wk, const float* bias,
-                           ActView<T16> out, cudaStream_t st, unsigned int* sat_count = nullptr);
+                           ActView<T16> out, cudaStream_t st, unsigned int* sat_count = nullptr,
+                           const uint8_t* img_u8 = nullptr);
 // conv1_1 of the x3 engines on tcgen05: wk_x3 [128 = hi | lo rows][64 = 2 x (27 padded to 32) k] of w * 2^e,
-// out_scale = 2^-e, out = [hi | lo] map (C == 128).  W % 4 == 0 and a 16-byte aligned image only.
+// out_scale = 2^-e, out = [hi | lo] map (C == 128).  fp32 image: W % 4 == 0 and a 16-byte aligned base only.
 template <typename T16>
 int launch_conv_first_x3(const float* img, int N, int H, int W, const T16* wk_x3, float out_scale, const float* bias,
-                         ActView<T16> out, cudaStream_t st, unsigned int* sat_count = nullptr);
+                         ActView<T16> out, cudaStream_t st, unsigned int* sat_count = nullptr,
+                         const uint8_t* img_u8 = nullptr);
+// uint8 HWC rows that TMA can fetch as 4-byte words: 3 W bytes per row a multiple of 16, 16-byte aligned base
+inline bool first_u8_ok(const uint8_t* img_u8, int W) {
+  return W % 16 == 0 && (reinterpret_cast<uintptr_t>(img_u8) & 15) == 0;
+}
 
 }  // namespace ccst

@@ -251,7 +251,8 @@ int ccst_debug_conv3x3(ccst_handle* h, const float* d_in, int N, int H, int W, i
 #define CCST_FUSE_UPSAMPLE 2  /* nearest x2 upsample folded into the NEXT conv (4 phase convolutions) */
 #define CCST_FUSE_STATS 4     /* relu4_1 statistics taken in conv4_1's epilogue                      */
 #define CCST_FUSE_ADAIN 8     /* AdaIN folded into dec1's per-image weights / bias (maps >= 2048 px)  */
-#define CCST_FUSE_ALL 15
+#define CCST_FUSE_TOTENSOR 16 /* uint8 entry points: conv1_1 reads the uint8 HWC batch itself (W % 16 == 0)      */
+#define CCST_FUSE_ALL 31
 int ccst_set_fusion(ccst_handle* h, int mask);
 
 /* Per-launch device timing of the encoder/decoder entry points (CUDA events recorded on the

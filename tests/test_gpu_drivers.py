@@ -139,6 +139,35 @@ def test_style_transfer_u8_equals_float_path_quantised(models):
         assert torch.equal(a.cpu(), O.save_image_batch_u8(f.cpu()))
 
 
+@pytest.mark.parametrize("hw", [(48, 64), (40, 144), (24, 256), (16, 400)])
+def test_fused_totensor_equals_conversion_pass(models, engine, hw):
+    """ToTensor fused into conv1_1's window loader (the uint8 HWC rows fetched by TMA, float(b)/255 from a table) ==
+    the separate conversion pass, bit for bit, for every tensor-core engine; widths with one partial 128-pixel
+    tile, several tiles, and a ragged last tile (W % 16 == 0 is what the fused loader needs)."""
+    from ccst_b200 import _lib
+    vgg, dec = models
+    h, w = hw
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    x_u8 = torch.randint(0, 256, (3, h, w, 3), generator=g, dtype=torch.uint8).to(DEV)
+    x_u8[0, :, :, :] = 255  # the table's last entry
+    x_u8[1, 0, :, 0] = 0
+    stat = [torch.randn((1, 512, 1, 1), generator=g).abs().to(DEV), (torch.rand((1, 512, 1, 1), generator=g) + 0.2).to(DEV)]
+    try:
+        for prec in ("fp16", "bf16", "fp16x3", "bf16x3"):
+            engine.set_fusion(_lib.FUSE_ALL)
+            a = ccst_b200.style_transfer_u8(vgg, dec, x_u8, stat, 0.9, precision=prec)
+            st_a = ccst_b200.function.WelfordState(512, torch.device(DEV))
+            engine.accumulate_u8(x_u8, st_a, prec)
+            engine.set_fusion(_lib.FUSE_ALL & ~_lib.FUSE_TOTENSOR)
+            b = ccst_b200.style_transfer_u8(vgg, dec, x_u8, stat, 0.9, precision=prec)
+            st_b = ccst_b200.function.WelfordState(512, torch.device(DEV))
+            engine.accumulate_u8(x_u8, st_b, prec)
+            assert torch.equal(a, b), (prec, hw, (a.int() - b.int()).abs().max().item())
+            assert torch.equal(st_a.buf, st_b.buf), (prec, hw)
+    finally:
+        engine.set_fusion(_lib.FUSE_ALL)
+
+
 def test_overall_transfer_u8_pipeline(models, engine):
     """The overlapped batch loop with uint8 batches equals per-batch calls."""
     vgg, dec = models
