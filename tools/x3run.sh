@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_drivers.py -q -m gpu --timeout 600 -rxXs -x > gpurun_out/tests_u8_r02o.log 2>&1; echo tests rc=$?; tail -15 gpurun_out/tests_u8_r02o.log
+python tools/layer_report.py --batch 1024 --size 96 > gpurun_out/layers_96_r02p.log 2>&1; cat gpurun_out/layers_96_r02p.log
