@@ -26,6 +26,7 @@
 // the tensor-core path for weights whose activations leave the f16 range, meeting the image bar that single
 // bf16 operands miss.
 #pragma once
+#include "conv_last.cuh"
 #include "conv_main.cuh"
 
 namespace ccst {
@@ -399,6 +400,8 @@ int launch_x3(const UmmaConvArgs<T16>& a, ConvParams<T16> p, cudaStream_t st) {
   }
   p.Cin = in.C / 2;
   p.out_scale = a.out_scale;
+  // the decoder's 64 -> 3 last conv: filter columns in N, two slabs per tile (conv_last_rows_x3_kernel)
+  if (last && a.Cout <= 3 && in.C == 2 * kBlockK) return launch_last_rows_x3<T16>(in, a.wk_x3, p, st);
   p.n_tiles = (a.Cout + 63) / 64;
   const int64_t mt = (int64_t)in.N * p.tiles_x * p.tiles_y;
   CCST_CHECK_ARG(mt * p.n_tiles < (1ll << 30), "conv_x3: too many tiles");
