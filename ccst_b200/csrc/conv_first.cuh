@@ -243,6 +243,31 @@ constexpr int kF2OffBar = kF2OffLut + 1024;
 constexpr int kF2NumBars = 2 * kF2WinStages + 8;
 constexpr int kF2Smem = 1024 + kF2OffBar + 8 * kF2NumBars + 16;
 
+// (n, y, x tile) of the tiles blockIdx.x, + stride, + 2 stride ... kept by additions: the plain decode costs two
+// integer divisions and two remainders (~80 instructions) per tile in EVERY warp, a third of the instructions the
+// warp-specialised first-layer kernels issued per tile (ncu: issue slots 59 % busy at 3.8 TB/s).
+struct FirstTileIter {
+  int tx, y, n;
+  int step_tx, step_y, step_n, tiles_x, H;
+  __device__ __forceinline__ void init(int tiles_x_, int H_, int tile0, int stride) {
+    tiles_x = tiles_x_, H = H_;
+    tx = tile0 % tiles_x;
+    const int row0 = tile0 / tiles_x;
+    y = row0 % H, n = row0 / H;
+    step_tx = stride % tiles_x;
+    const int rows = stride / tiles_x;
+    step_y = rows % H, step_n = rows / H;
+  }
+  __device__ __forceinline__ void next() {
+    tx += step_tx;
+    int carry = 0;
+    if (tx >= tiles_x) tx -= tiles_x, carry = 1;
+    y += step_y + carry;  // < 2 H
+    if (y >= H) y -= H, ++n;
+    n += step_n;
+  }
+};
+
 // U8 = true: the window is fetched from the loader's uint8 HWC batch [N,H,W,3] itself (ToTensor fused into the
 // builders, cjm_util/data_helper.py:45): TMA box {104 x 4 bytes, 3 rows} = bytes x0*3 - 16 .. x0*3 + 399 of rows
 // y-1..y+1 (needs 3 W % 16 == 0), and float(b) / 255 rounded to T16 comes from a 256-entry table (low half: the
@@ -330,21 +355,16 @@ __global__ void __launch_bounds__(kF2Threads, 2)
   pdl_launch_dependents();
   pdl_wait();
 
-  auto tile_coord = [&](int tile, int& n, int& y, int& x0) {
-    x0 = (tile % p.tiles_x) * kFirstPx;
-    const int b = tile / p.tiles_x;
-    y = b % p.H;
-    n = b / p.H;
-  };
+  FirstTileIter ti;  // this thread's walk over the CTA's tiles
+  ti.init(p.tiles_x, p.H, blockIdx.x, gridDim.x);
 
   if (warp == 0) {
     // ===================== TMA producer
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, ti.next()) {
       const int ws = it % kF2WinStages;
       const uint32_t ph = (it / kF2WinStages) & 1;
-      int n, y, x0;
-      tile_coord(tile, n, y, x0);
+      const int n = ti.n, y = ti.y, x0 = ti.tx * kFirstPx;
       mbar_wait(win_empty(ws), ph ^ 1, 910);
       if (elect_one()) {
         mbar_expect_tx(win_full(ws), U8 ? kU8WinTx : kF2WinTx);
@@ -357,10 +377,9 @@ __global__ void __launch_bounds__(kF2Threads, 2)
     // ===================== builders: im2col row of pixel px of the tile
     const int px = tid - 32;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, ti.next()) {
       const int ws = it % kF2WinStages, as = it & 1;
-      int n, y, x0;
-      tile_coord(tile, n, y, x0);
+      const int y = ti.y, x0 = ti.tx * kFirstPx;
       // reflection = index remap inside the window (rows y-1..y+1 at 0..2, columns from x0-4)
       int ridx[3] = {0, 1, 2};
       if (y == 0) ridx[0] = 2;
@@ -440,10 +459,9 @@ __global__ void __launch_bounds__(kF2Threads, 2)
     const int px = q * 32 + lane;
     int it = 0;
     SatTracker<T16> sat;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, ti.next()) {
       const int as = it & 1;
-      int n, y, x0;
-      tile_coord(tile, n, y, x0);
+      const int n = ti.n, y = ti.y, x0 = ti.tx * kFirstPx;
       MBAR_WAIT_RELAXED(t_full(as), (it >> 1) & 1, 950);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 64);
@@ -457,12 +475,15 @@ __global__ void __launch_bounds__(kF2Threads, 2)
       uint32_t pk[32];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        pk[j] = pack16x2_relu<T16>(__uint_as_float(r0[2 * j]) + sbias[2 * j],
-                                   __uint_as_float(r0[2 * j + 1]) + sbias[2 * j + 1]);
-        pk[16 + j] = pack16x2_relu<T16>(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j],
-                                        __uint_as_float(r1[2 * j + 1]) + sbias[33 + 2 * j]);
-        sat.track(pk[j]);
-        sat.track(pk[16 + j]);
+        // packed fp32 adds (each half rounds like a scalar add)
+        const float2 a0 = add2_f32(make_float2(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1])),
+                                   *reinterpret_cast<const float2*>(&sbias[2 * j]));
+        const float2 a1 = add2_f32(make_float2(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1])),
+                                   *reinterpret_cast<const float2*>(&sbias[32 + 2 * j]));
+        pk[j] = pack16x2_relu<T16>(a0.x, a0.y);
+        pk[16 + j] = pack16x2_relu<T16>(a1.x, a1.y);
+        sat.track_nonneg(pk[j]);
+        sat.track_nonneg(pk[16 + j]);
       }
       // per-warp staging (two buffers): the store issued two tiles ago must have read its buffer
       bulk_wait_read<1>();
@@ -563,21 +584,16 @@ __global__ void __launch_bounds__(kF3Threads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + kF3OffBar + 8 * kF2NumBars);
 
-  auto tile_coord = [&](int tile, int& n, int& y, int& x0) {
-    x0 = (tile % p.tiles_x) * kFirstPx;
-    const int b = tile / p.tiles_x;
-    y = b % p.H;
-    n = b / p.H;
-  };
+  FirstTileIter ti;  // this thread's walk over the CTA's tiles
+  ti.init(p.tiles_x, p.H, blockIdx.x, gridDim.x);
 
   if (warp == 0) {
     // ===================== TMA producer
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, ti.next()) {
       const int ws = it % kF2WinStages;
       const uint32_t ph = (it / kF2WinStages) & 1;
-      int n, y, x0;
-      tile_coord(tile, n, y, x0);
+      const int n = ti.n, y = ti.y, x0 = ti.tx * kFirstPx;
       mbar_wait(win_empty(ws), ph ^ 1, 960);
       if (elect_one()) {
         mbar_expect_tx(win_full(ws), U8 ? kU8WinTx : kF2WinTx);
@@ -590,10 +606,9 @@ __global__ void __launch_bounds__(kF3Threads, 1)
     // ===================== builders: split im2col row of pixel px
     const int px = tid - 32;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it, ti.next()) {
       const int ws = it % kF2WinStages, as = it & 1;
-      int n, y, x0;
-      tile_coord(tile, n, y, x0);
+      const int y = ti.y, x0 = ti.tx * kFirstPx;
       int ridx[3] = {0, 1, 2};
       if (y == 0) ridx[0] = 2;
       if (y == p.H - 1) ridx[2] = 0;
@@ -680,10 +695,11 @@ __global__ void __launch_bounds__(kF3Threads, 1)
     const uint32_t sHi = base + kF3OffOut + (2 * grp) * kF2ABytes, sLo = sHi + kF2ABytes;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 128);
     int it = grp;
+    if ((long long)blockIdx.x + (long long)grp * gridDim.x < p.total_tiles)
+      ti.init(p.tiles_x, p.H, blockIdx.x + grp * gridDim.x, 2 * gridDim.x);
     for (long long tile = (long long)blockIdx.x + (long long)grp * gridDim.x; tile < p.total_tiles;
-         tile += 2ll * gridDim.x, it += 2) {
-      int n, y, x0;
-      tile_coord((int)tile, n, y, x0);
+         tile += 2ll * gridDim.x, it += 2, ti.next()) {
+      const int n = ti.n, y = ti.y, x0 = ti.tx * kFirstPx;
       const int x = x0 + px;
       MBAR_WAIT_RELAXED(t_full(grp), (it >> 1) & 1, 965);
       tc_fence_after();

@@ -24,7 +24,11 @@ constexpr int kROffBar = kROffB + 3 * 2048 + 1024;        // (+ slack: the last 
 constexpr int kRNumBars = 2 * kRStages + 4;
 constexpr int kRSmem = 1024 + kROffBar + 8 * kRNumBars + 16;
 
-template <typename T16>
+// CG = 2: a CTA pair runs two consecutive tiles as ONE M = 256 MMA (cta_group::2).  At N = 16 a single-CTA
+// tcgen05.mma is bound by the fetch of its A operand (64 cycles per MMA for 8 cycles of math), and the 12 MMAs of
+// a tile took 0.20 ms of the kernel's 0.26 at batch 32 @512^2 -- above its HBM time; in the pair each SM fetches
+// only its own tile's slab, so the MMA time per tile halves.  B: each CTA holds 8 of the 16 (s, co) rows.
+template <typename T16, int CG>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_last_rows_kernel(const __grid_constant__ CUtensorMap tmap_a, const T16* __restrict__ wk,
                           ConvParams<T16> p) {
@@ -38,7 +42,20 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   auto t_empty = [&](int s) { return bar0 + 8u * (2 * kRStages + 2 + s); };
   const uint32_t tmem_slot = bar0 + 8u * kRNumBars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  auto tile_of = [&](int tile, int& n, int& y0, int& x0) {
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  auto lead = [&](uint32_t bar) { return CG == 2 ? mapa_rank(bar, 0) : bar; };
+  const int unit_id = CG == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_cnt = CG == 2 ? (int)ncluster_x() : (int)gridDim.x;
+  const int units = (p.total_tiles + CG - 1) / CG;
+  // tile of this CTA in work unit `unit`; the second tile of an odd last pair is a dummy at image n = N (its TMA
+  // box is out of bounds = zero fill, its stores are masked)
+  auto tile_of = [&](int unit, int& n, int& y0, int& x0) {
+    int tile = unit * CG + (int)cta_rank;
+    if (tile >= p.total_tiles) {
+      n = p.N, y0 = 0, x0 = 0;
+      return;
+    }
     x0 = (tile % p.tiles_x) * kROutW;
     tile /= p.tiles_x;
     y0 = (tile % p.tiles_y) * kRRows;
@@ -46,14 +63,16 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   };
 
   // B_r[n = s*4 + co][k = c] = W[co][c][r][s] from the packed weights wk[co][(r*3+s)*64 + c]; K-major
-  // rows of 128 B with the 128-byte swizzle; unused rows are zero
-  for (int i = threadIdx.x; i < 3 * 16 * 8; i += kThreadsUmma) {
-    const int r = i / 128, n = (i >> 3) & 15, j = i & 7;
+  // rows of 128 B with the 128-byte swizzle; unused rows are zero.  A pair: this CTA keeps rows 8 rank .. 8 rank + 7.
+  constexpr int kRowsB = 16 / CG;
+  for (int i = threadIdx.x; i < 3 * kRowsB * 8; i += kThreadsUmma) {
+    const int r = i / (kRowsB * 8), nl = (i >> 3) % kRowsB, j = i & 7;
+    const int n = nl + (int)cta_rank * kRowsB;
     const int sc = n >> 2, co = n & 3;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (sc < 3 && co < p.Cout && co < 3)
       v = *reinterpret_cast<const uint4*>(wk + (size_t)co * (9 * kBlockK) + (r * 3 + sc) * kBlockK + j * 8);
-    *reinterpret_cast<uint4*>(gen + kROffB + r * 2048 + n * 128 + ((j ^ (n & 7)) << 4)) = v;
+    *reinterpret_cast<uint4*>(gen + kROffB + r * 2048 + nl * 128 + ((j ^ (nl & 7)) << 4)) = v;
   }
   if (warp == 0 && lane == 0) prefetch_tmap(&tmap_a);
   if (warp == 1 && lane == 0) {
@@ -63,59 +82,62 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(t_full(s), 1);
-      mbar_init(t_empty(s), 4);
+      mbar_init(t_empty(s), 4 * CG);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<32>(tmem_slot);
+  if (warp == 2) tmem_alloc_cg<CG, 32>(tmem_slot);
   fence_async_smem();
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + kROffBar + 8 * kRNumBars);
   pdl_launch_dependents();
   pdl_wait();
 
   if (warp == 0) {
-    // ===================== TMA producer: one slab per tile
+    // ===================== TMA producer: one slab per tile; the leader's "full" barrier counts both CTAs' bytes
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int unit = unit_id; unit < units; unit += unit_cnt) {
       int n, y0, x0;
-      tile_of(tile, n, y0, x0);
+      tile_of(unit, n, y0, x0);
       MBAR_WAIT_RELAXED(a_empty(s), ph ^ 1, 800 + s);
       if (elect_one()) {
-        mbar_expect_tx(a_full(s), kRSlabBytes);
-        tma_load_4d(base + s * kRSlabBytes, &tmap_a, a_full(s), 0, x0, y0, n);
+        if (leader) mbar_expect_tx(a_full(s), CG * kRSlabBytes);
+        tma_load_4d_cg<CG>(base + s * kRSlabBytes, &tmap_a, lead(a_full(s)), 0, x0, y0, n);
       }
       __syncwarp();
       if (++s == kRStages) s = 0, ph ^= 1;
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: 3 filter rows x 4 K steps, M = 128, N = 16
-    constexpr uint32_t idesc = make_idesc<T16, 16>();
-    const uint64_t bdesc0 = make_kmajor_sw128_desc(base + kROffB);
-    int s = 0, it = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int acs = it & 1;
-      mbar_wait(t_empty(acs), ((it >> 1) & 1) ^ 1, 810 + acs);
-      mbar_wait(a_full(s), ph, 820 + s);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t adesc0 = make_kmajor_sw128_desc(base + s * kRSlabBytes);
-        const uint32_t d = tmem_base + (uint32_t)(acs * 16);
+    // ===================== MMA issuer (leader): 3 filter rows x 4 K steps, M = 128 CG, N = 16
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc<T16, 16, CG>();
+      const uint64_t bdesc0 = make_kmajor_sw128_desc(base + kROffB);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int unit = unit_id; unit < units; unit += unit_cnt, ++it) {
+        const int acs = it & 1;
+        if (CG == 2) mbar_wait_cluster(t_empty(acs), ((it >> 1) & 1) ^ 1, 810 + acs);
+        else mbar_wait(t_empty(acs), ((it >> 1) & 1) ^ 1, 810 + acs);
+        mbar_wait(a_full(s), ph, 820 + s);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc0 = make_kmajor_sw128_desc(base + s * kRSlabBytes);
+          const uint32_t d = tmem_base + (uint32_t)(acs * 16);
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(d, adesc0 + (uint64_t)(r * (kRBoxW * 128 >> 4) + 2 * k), bdesc0 + (uint64_t)(r * (2048 >> 4) + 2 * k),
-                      idesc, (r | k) ? 1u : 0u);
-        umma_commit(a_empty(s));
-        umma_commit(t_full(acs));
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16_cg<CG>(d, adesc0 + (uint64_t)(r * (kRBoxW * 128 >> 4) + 2 * k),
+                              bdesc0 + (uint64_t)(r * (2048 >> 4) + 2 * k), idesc, (r | k) ? 1u : 0u);
+          umma_commit_cg<CG>(a_empty(s));
+          umma_commit_cg<CG>(t_full(acs));
+        }
+        __syncwarp();
+        if (++s == kRStages) s = 0, ph ^= 1;
       }
-      __syncwarp();
-      if (++s == kRStages) s = 0, ph ^= 1;
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue: group g takes tiles g, g+2, ...; warp <-> tile row, lane <-> column
@@ -125,10 +147,10 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
 #pragma unroll
     for (int c = 0; c < 3; ++c) bias[c] = c < p.Cout ? p.bias[c] : 0.f;
     for (int it = grp;; it += 2) {
-      const long long tile_ll = (long long)blockIdx.x + (long long)it * gridDim.x;
-      if (tile_ll >= p.total_tiles) break;
+      const long long unit_ll = (long long)unit_id + (long long)it * unit_cnt;
+      if (unit_ll >= units) break;
       int n, y0, x0;
-      tile_of((int)tile_ll, n, y0, x0);
+      tile_of((int)unit_ll, n, y0, x0);
       const int acs = it & 1;
       MBAR_WAIT_RELAXED(t_full(acs), (it >> 1) & 1, 830 + acs);
       tc_fence_after();
@@ -137,9 +159,12 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty(acs));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(lead(t_empty(acs)));
+        else mbar_arrive(t_empty(acs));
+      }
       const int y = y0 + quad, x = x0 + lane;
-      const bool ok = lane < kROutW && y < p.H && x < p.W;
+      const bool ok = lane < kROutW && y < p.H && x < p.W && n < p.N;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float p1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[4 + c]), 1);
@@ -155,22 +180,26 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   }
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<32>(tmem_base);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc_cg<CG, 32>(tmem_base);
 }
 
 template <typename T16>
 int launch_last_rows(ActView<T16> in, const T16* wk, ConvParams<T16> p, cudaStream_t st) {
+  constexpr int CG = 2;
   CUtensorMap mr;
   if (int e = make_act_map(&mr, in, kRBoxW, kRRows + 2)) return e;
-  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_last_rows_kernel<T16>), kRSmem));
+  auto kernel = conv_last_rows_kernel<T16, CG>;
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(kernel), kRSmem));
   p.tiles_x = (in.W + kROutW - 1) / kROutW;
   p.tiles_y = (in.H + kRRows - 1) / kRRows;
   const int64_t tiles = (int64_t)in.N * p.tiles_x * p.tiles_y;
-  CCST_CHECK_ARG(tiles < (1ll << 31), "conv_last_rows: too many tiles");
+  CCST_CHECK_ARG(tiles < (1ll << 31) - 2, "conv_last_rows: too many tiles");
   p.m_tiles = p.total_tiles = (int)tiles;
-  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  CCST_CUDA(launch_conv(conv_last_rows_kernel<T16>, grid, kThreadsUmma, kRSmem, st, 1, mr, wk, p));
+  const int64_t units = (tiles + CG - 1) / CG;
+  const int slots = sm_count() / CG;
+  const int grid = (int)(units < slots ? units : slots) * CG;
+  CCST_CUDA(launch_conv(kernel, grid, kThreadsUmma, kRSmem, st, CG, mr, wk, p));
   CCST_LAUNCHED();
   return CCST_OK;
 }

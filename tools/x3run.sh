@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_net.py tests/test_gpu_drivers.py -q -m gpu --timeout 600 -rxXs -s -k "x3 or u8" > gpurun_out/tests_x3_r02q.log 2>&1; echo tests rc=$?; grep "measured\|passed\|failed\|FAILED\|Error" gpurun_out/tests_x3_r02q.log | grep -i "decoder\|config\|u8\|passed\|failed\|error" | tail -30
-python tools/layer_report.py --precision fp16x3 > gpurun_out/layers_fp16x3_r02q.log 2>&1; tail -21 gpurun_out/layers_fp16x3_r02q.log
+timeout 900 python -m pytest tests/test_gpu_net.py tests/test_gpu_drivers.py -q -m gpu --timeout 600 -x -k "golden or u8 or totensor or reproducible or deterministic or config1" > gpurun_out/tests_r02s.log 2>&1; echo tests rc=$?; tail -3 gpurun_out/tests_r02s.log
+python tools/layer_report.py > gpurun_out/layers_r02s.log 2>&1; head -4 gpurun_out/layers_r02s.log
+python tools/layer_report.py --precision fp16x3 --encoder > gpurun_out/layers_enc_x3_r02s.log 2>&1; head -4 gpurun_out/layers_enc_x3_r02s.log
