@@ -221,7 +221,7 @@ constexpr int kR3NumBars = 2 * kR3Stages + 4;
 constexpr int kR3Smem = 1024 + kR3OffBar + 8 * kR3NumBars + 16;
 static_assert(kR3Smem <= 232448, "conv_last_rows_x3: shared memory plan exceeds 227 KiB");
 
-template <typename T16>
+template <typename T16, int CG>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_last_rows_x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const T16* __restrict__ wk_x3,
                              ConvParams<T16> p) {
@@ -235,21 +235,36 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   auto t_empty = [&](int s) { return bar0 + 8u * (2 * kR3Stages + 2 + s); };
   const uint32_t tmem_slot = bar0 + 8u * kR3NumBars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  auto tile_of = [&](int tile, int& n, int& y0, int& x0) {
+  // CTA pairs as in conv_last_rows_kernel (24 MMAs of N = 32 per tile are A-fetch-bound at twice its cost)
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  auto lead = [&](uint32_t bar) { return CG == 2 ? mapa_rank(bar, 0) : bar; };
+  const int unit_id = CG == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_cnt = CG == 2 ? (int)ncluster_x() : (int)gridDim.x;
+  const int units = (p.total_tiles + CG - 1) / CG;
+  auto tile_of = [&](int unit, int& n, int& y0, int& x0) {
+    int tile = unit * CG + (int)cta_rank;
+    if (tile >= p.total_tiles) {  // dummy second tile of an odd last pair
+      n = p.N, y0 = 0, x0 = 0;
+      return;
+    }
     x0 = (tile % p.tiles_x) * kROutW;
     tile /= p.tiles_x;
     y0 = (tile % p.tiles_y) * kRRows;
     n = tile / p.tiles_y;
   };
 
-  // B_r[n = half*16 + s*4 + co][k = c] = W_half[co][c][r][s]; K-major rows of 128 B, 128-byte swizzle, unused rows zero
-  for (int i = threadIdx.x; i < 3 * 32 * 8; i += kThreadsUmma) {
-    const int r = i / 256, n = (i >> 3) & 31, j = i & 7;
+  // B_r[n = half*16 + s*4 + co][k = c] = W_half[co][c][r][s]; K-major rows of 128 B, 128-byte swizzle, unused rows
+  // zero.  A pair: rank 0 keeps the w_hi rows (n < 16), rank 1 the w_lo rows.
+  constexpr int kRowsB = 32 / CG;
+  for (int i = threadIdx.x; i < 3 * kRowsB * 8; i += kThreadsUmma) {
+    const int r = i / (kRowsB * 8), nl = (i >> 3) % kRowsB, j = i & 7;
+    const int n = nl + (int)cta_rank * kRowsB;
     const int half = n >> 4, sc = (n >> 2) & 3, co = n & 3;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (sc < 3 && co < p.Cout && co < 3)
       v = *reinterpret_cast<const uint4*>(wk_x3 + (size_t)(half * 64 + co) * (9 * kBlockK) + (r * 3 + sc) * kBlockK + j * 8);
-    *reinterpret_cast<uint4*>(gen + kR3OffB + r * 4096 + n * 128 + ((j ^ (n & 7)) << 4)) = v;
+    *reinterpret_cast<uint4*>(gen + kR3OffB + r * 4096 + nl * 128 + ((j ^ (nl & 7)) << 4)) = v;
   }
   if (warp == 0 && lane == 0) prefetch_tmap(&tmap_a);
   if (warp == 1 && lane == 0) {
@@ -259,14 +274,14 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(t_full(s), 1);
-      mbar_init(t_empty(s), 4);
+      mbar_init(t_empty(s), 4 * CG);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<128>(tmem_slot);
+  if (warp == 2) tmem_alloc_cg<CG, 128>(tmem_slot);
   fence_async_smem();
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + kR3OffBar + 8 * kR3NumBars);
 
@@ -274,46 +289,49 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     // ===================== TMA producer: the hi and the lo slab of a tile under one barrier
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int unit = unit_id; unit < units; unit += unit_cnt) {
       int n, y0, x0;
-      tile_of(tile, n, y0, x0);
+      tile_of(unit, n, y0, x0);
       MBAR_WAIT_RELAXED(a_empty(s), ph ^ 1, 840 + s);
       if (elect_one()) {
-        mbar_expect_tx(a_full(s), 2 * kRSlabBytes);
-        tma_load_4d(base + (2 * s) * kRSlabBytes, &tmap_a, a_full(s), 0, x0, y0, n);
-        tma_load_4d(base + (2 * s + 1) * kRSlabBytes, &tmap_a, a_full(s), kBlockK, x0, y0, n);
+        if (leader) mbar_expect_tx(a_full(s), CG * 2 * kRSlabBytes);
+        tma_load_4d_cg<CG>(base + (2 * s) * kRSlabBytes, &tmap_a, lead(a_full(s)), 0, x0, y0, n);
+        tma_load_4d_cg<CG>(base + (2 * s + 1) * kRSlabBytes, &tmap_a, lead(a_full(s)), kBlockK, x0, y0, n);
       }
       __syncwarp();
       if (++s == kR3Stages) s = 0, ph ^= 1;
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: per slab 3 filter rows x 4 K steps, M = 128, N = 32
-    constexpr uint32_t idesc = make_idesc<T16, 32>();
-    const uint64_t bdesc0 = make_kmajor_sw128_desc(base + kR3OffB);
-    int s = 0, it = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int acs = it & 1;
-      mbar_wait(t_empty(acs), ((it >> 1) & 1) ^ 1, 850 + acs);
-      mbar_wait(a_full(s), ph, 860 + s);
-      tc_fence_after();
-      if (elect_one()) {
+    // ===================== MMA issuer (leader): per slab 3 filter rows x 4 K steps, M = 128 CG, N = 32
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc<T16, 32, CG>();
+      const uint64_t bdesc0 = make_kmajor_sw128_desc(base + kR3OffB);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int unit = unit_id; unit < units; unit += unit_cnt, ++it) {
+        const int acs = it & 1;
+        if (CG == 2) mbar_wait_cluster(t_empty(acs), ((it >> 1) & 1) ^ 1, 850 + acs);
+        else mbar_wait(t_empty(acs), ((it >> 1) & 1) ^ 1, 850 + acs);
+        mbar_wait(a_full(s), ph, 860 + s);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const uint64_t adesc0 = make_kmajor_sw128_desc(base + (2 * s + h2) * kRSlabBytes);
-          const uint32_t d = tmem_base + (uint32_t)(acs * 64 + h2 * 32);
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const uint64_t adesc0 = make_kmajor_sw128_desc(base + (2 * s + h2) * kRSlabBytes);
+            const uint32_t d = tmem_base + (uint32_t)(acs * 64 + h2 * 32);
 #pragma unroll
-          for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16(d, adesc0 + (uint64_t)(r * (kRBoxW * 128 >> 4) + 2 * k), bdesc0 + (uint64_t)(r * (4096 >> 4) + 2 * k),
-                        idesc, (r | k) ? 1u : 0u);
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16_cg<CG>(d, adesc0 + (uint64_t)(r * (kRBoxW * 128 >> 4) + 2 * k),
+                                bdesc0 + (uint64_t)(r * (4096 >> 4) + 2 * k), idesc, (r | k) ? 1u : 0u);
+          }
+          umma_commit_cg<CG>(a_empty(s));
+          umma_commit_cg<CG>(t_full(acs));
         }
-        umma_commit(a_empty(s));
-        umma_commit(t_full(acs));
+        __syncwarp();
+        if (++s == kR3Stages) s = 0, ph ^= 1;
       }
-      __syncwarp();
-      if (++s == kR3Stages) s = 0, ph ^= 1;
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue: group g takes tiles g, g+2, ...; warp <-> tile row, lane <-> column
@@ -323,10 +341,10 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
 #pragma unroll
     for (int c = 0; c < 3; ++c) bias[c] = c < p.Cout ? p.bias[c] : 0.f;
     for (int it = grp;; it += 2) {
-      const long long tile_ll = (long long)blockIdx.x + (long long)it * gridDim.x;
-      if (tile_ll >= p.total_tiles) break;
+      const long long unit_ll = (long long)unit_id + (long long)it * unit_cnt;
+      if (unit_ll >= units) break;
       int n, y0, x0;
-      tile_of((int)tile_ll, n, y0, x0);
+      tile_of((int)unit_ll, n, y0, x0);
       const int acs = it & 1;
       MBAR_WAIT_RELAXED(t_full(acs), (it >> 1) & 1, 870 + acs);
       tc_fence_after();
@@ -337,9 +355,12 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty(acs));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(lead(t_empty(acs)));
+        else mbar_arrive(t_empty(acs));
+      }
       const int y = y0 + quad, x = x0 + lane;
-      const bool ok = lane < kROutW && y < p.H && x < p.W;
+      const bool ok = lane < kROutW && y < p.H && x < p.W && n < p.N;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float q[3];
@@ -362,23 +383,27 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   }
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<128>(tmem_base);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc_cg<CG, 128>(tmem_base);
 }
 
 // in: [hi | lo] map (in.C == 128); p carries bias, out_scale, out_nchw / out_u8, relu, Cout <= 3
 template <typename T16>
 int launch_last_rows_x3(ActView<T16> in, const T16* wk_x3, ConvParams<T16> p, cudaStream_t st) {
+  constexpr int CG = 2;
   CUtensorMap mr;
   if (int e = make_act_map(&mr, in, kRBoxW, kRRows + 2)) return e;
-  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(conv_last_rows_x3_kernel<T16>), kR3Smem));
+  auto kernel = conv_last_rows_x3_kernel<T16, CG>;
+  CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(kernel), kR3Smem));
   p.tiles_x = (in.W + kROutW - 1) / kROutW;
   p.tiles_y = (in.H + kRRows - 1) / kRRows;
   const int64_t tiles = (int64_t)in.N * p.tiles_x * p.tiles_y;
-  CCST_CHECK_ARG(tiles < (1ll << 31), "conv_last_rows_x3: too many tiles");
+  CCST_CHECK_ARG(tiles < (1ll << 31) - 2, "conv_last_rows_x3: too many tiles");
   p.m_tiles = p.total_tiles = (int)tiles;
-  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  CCST_CUDA(launch_conv(conv_last_rows_x3_kernel<T16>, grid, kThreadsUmma, kR3Smem, st, 1, mr, wk_x3, p));
+  const int64_t units = (tiles + CG - 1) / CG;
+  const int slots = sm_count() / CG;
+  const int grid = (int)(units < slots ? units : slots) * CG;
+  CCST_CUDA(launch_conv(kernel, grid, kThreadsUmma, kR3Smem, st, CG, mr, wk_x3, p));
   CCST_LAUNCHED();
   return CCST_OK;
 }

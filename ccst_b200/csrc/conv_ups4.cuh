@@ -19,11 +19,22 @@ namespace {
 // =====================================================================================
 constexpr int kU4BoxW = 32, kU4Rows = 4, kU4OutW = kU4BoxW - 2;
 constexpr int kU4SlabBytes = (kU4Rows + 2) * kU4BoxW * 128;  // 24576
-constexpr int kU4AStages = 2;
-constexpr int kU4OffB = kU4AStages * kU4SlabBytes;           // 16 tiles x 8 KiB
-constexpr int kU4OffStore = kU4OffB + 16 * 8192;
+// The kernel runs as CTA PAIRS (cta_group::2, two consecutive tiles per M = 256 MMA): every SM fetches only its
+// own tile's A operand, each CTA keeps HALF of every stacked weight block (64 KiB instead of 128), and the freed
+// shared memory holds a third slab stage and a second staging tile per epilogue group.  Measured at batch 32
+// @512^2: 0.302 ms against 0.298-0.308 for the single-CTA form -- no gain, although the same change took the
+// last conv from 0.26 to 0.21 ms: here the MMA side (1.47 us of A-operand fetch per 2.4 us tile) was not the
+// bound.  Per tile the SM moves ~420 KB through shared memory (10 operand views x 4 K steps x 4 KB of A, the
+// weights, the slab write, 64 KB of staged output written and read back by the TMA store) at 128 B/clk --
+// 70 % of the tile time -- beside 67 % of the HBM rate (1.07 GB of output per launch) and an epilogue that issues
+// ~560 instructions per warp and tile; ncu: l1/smem 63 %, dram 52-56 %, tensor 58 %, issue slots 38 %.
+constexpr int kU4CG = 2;
+constexpr int kU4AStages = 3;
+constexpr int kU4OffB = kU4AStages * kU4SlabBytes;           // 16 half-tiles of 32 rows x 128 B per CTA
+constexpr int kU4BBytes = 16 * 4096;
+constexpr int kU4OffStore = kU4OffB + kU4BBytes;
 constexpr int kU4StoreBytes = 16384;                          // 120 rows x 128 B, rounded
-constexpr int kU4OffBias = kU4OffStore + 2 * kU4StoreBytes;
+constexpr int kU4OffBias = kU4OffStore + 4 * kU4StoreBytes;   // 2 groups x 2 staging tiles
 constexpr int kU4OffBar = kU4OffBias + 256;
 constexpr int kU4NumBars = 2 * kU4AStages + 4 + 1;
 constexpr int kU4Smem = 1024 + kU4OffBar + 8 * kU4NumBars + 16;
@@ -45,6 +56,7 @@ template <typename T16>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_ups4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ OutMaps tmap_out, ConvParams<T16> p) {
+  constexpr int CG = kU4CG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -57,7 +69,19 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   const uint32_t bres_bar = bar0 + 8u * (2 * kU4AStages + 4);
   const uint32_t tmem_slot = bar0 + 8u * kU4NumBars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  auto tile_of = [&](int tile, int& n, int& y0, int& x0) {
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  auto lead = [&](uint32_t bar) { return mapa_rank(bar, 0); };
+  const int unit_id = (int)cluster_id_x(), unit_cnt = (int)ncluster_x();
+  const int units = (p.total_tiles + CG - 1) / CG;
+  // tile of this CTA in work unit `unit`; the second tile of an odd last pair is a dummy at image n = N (TMA
+  // loads out of bounds = zero fill, TMA stores clipped away, alias stores masked)
+  auto tile_of = [&](int unit, int& n, int& y0, int& x0) {
+    int tile = unit * CG + (int)cta_rank;
+    if (tile >= p.total_tiles) {
+      n = p.N, y0 = 0, x0 = 0;
+      return;
+    }
     x0 = (tile % p.tiles_x) * kU4OutW;
     tile /= p.tiles_x;
     y0 = (tile % p.tiles_y) * kU4Rows;
@@ -76,101 +100,117 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(t_full(s), 1);
-      mbar_init(t_empty(s), 4);
+      mbar_init(t_empty(s), 4 * CG);  // one arrive per epilogue warp of both CTAs
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) tmem_alloc_cg<CG, 512>(tmem_slot);
   if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias[threadIdx.x];
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + kU4OffBar + 8 * kU4NumBars);
   pdl_launch_dependents();
   if (warp != 0) pdl_wait();
 
   if (warp == 0) {
-    // ===================== TMA producer: resident phase weights once, then one slab per tile
+    // ===================== TMA producer: this CTA's half of every stacked weight block once (the operand view of
+    // kU4Ops[o] multiplies ntiles x 64 stacked rows; rank r keeps rows r N/2 .. (r+1) N/2 - 1 of them, as 32-row
+    // boxes in issue order), then one slab per tile
     if (elect_one()) {
-      mbar_expect_tx(bres_bar, 16 * 8192);
+      if (leader) mbar_expect_tx(bres_bar, CG * kU4BBytes);
+      const uint32_t bar = lead(bres_bar);
+      int blk = 0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        tma_load_2d(base + kU4OffB + i * 8192, &tmap_b, bres_bar, kU4TileTap[i] * kBlockK, kU4TilePh[i] * 64);
+      for (int o = 0; o < 10; ++o) {
+#pragma unroll
+        for (int j = 0; j < kU4Ops[o].ntiles; ++j, ++blk) {
+          const int row = (int)cta_rank * 32 * kU4Ops[o].ntiles + 32 * j;  // stacked row of the view's weight block
+          const int t = kU4Ops[o].first + (row >> 6);
+          tma_load_2d_cg<CG>(base + kU4OffB + blk * 4096, &tmap_b, bar, kU4TileTap[t] * kBlockK,
+                             kU4TilePh[t] * 64 + (row & 32));
+        }
+      }
     }
     __syncwarp();
     pdl_wait();
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int unit = unit_id; unit < units; unit += unit_cnt) {
       int n, y0, x0;
-      tile_of(tile, n, y0, x0);
+      tile_of(unit, n, y0, x0);
       MBAR_WAIT_RELAXED(a_empty(s), ph ^ 1, 900 + s);
       if (elect_one()) {
-        mbar_expect_tx(a_full(s), kU4SlabBytes);
+        if (leader) mbar_expect_tx(a_full(s), CG * kU4SlabBytes);
         // slab position (jy, jx) = padded pixel (y0 + jy, x0 + jx) = source (y0 - 1 + jy, x0 - 1 + jx)
-        tma_load_4d(base + s * kU4SlabBytes, &tmap_a, a_full(s), 0, x0, y0, n);
+        tma_load_4d_cg<CG>(base + s * kU4SlabBytes, &tmap_a, lead(a_full(s)), 0, x0, y0, n);
       }
       __syncwarp();
       if (++s == kU4AStages) s = 0, ph ^= 1;
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: 10 operand views x 4 K steps per tile
-    mbar_wait(bres_bar, 0, 905);
-    tc_fence_after();
-    int s = 0, it = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int acs = it & 1;
-      mbar_wait(t_empty(acs), ((it >> 1) & 1) ^ 1, 910 + acs);
-      mbar_wait(a_full(s), ph, 920 + s);
+    // ===================== MMA issuer (leader): 10 operand views x 4 K steps per PAIR of tiles
+    if (leader) {
+      mbar_wait(bres_bar, 0, 905);
       tc_fence_after();
-      if (elect_one()) {
-        const uint64_t adesc0 = make_kmajor_sw128_desc(base + s * kU4SlabBytes);
-        const uint64_t bdesc0 = make_kmajor_sw128_desc(base + kU4OffB);
-        const uint32_t d0 = tmem_base + (uint32_t)(acs * 256);
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      for (int unit = unit_id; unit < units; unit += unit_cnt, ++it) {
+        const int acs = it & 1;
+        mbar_wait_cluster(t_empty(acs), ((it >> 1) & 1) ^ 1, 910 + acs);
+        mbar_wait(a_full(s), ph, 920 + s);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc0 = make_kmajor_sw128_desc(base + s * kU4SlabBytes);
+          const uint64_t bdesc0 = make_kmajor_sw128_desc(base + kU4OffB);
+          const uint32_t d0 = tmem_base + (uint32_t)(acs * 256);
+          int blk = 0;
 #pragma unroll
-        for (int o = 0; o < 10; ++o) {
-          const uint64_t adesc = adesc0 + (uint64_t)((kU4Ops[o].R * kU4BoxW + kU4Ops[o].S) * 128 >> 4);
-          const uint64_t bdesc = bdesc0 + (uint64_t)(kU4Ops[o].first * (8192 >> 4));
-          const uint32_t d = d0 + (uint32_t)(kU4Ops[o].slot * 64);
+          for (int o = 0; o < 10; ++o) {
+            const uint64_t adesc = adesc0 + (uint64_t)((kU4Ops[o].R * kU4BoxW + kU4Ops[o].S) * 128 >> 4);
+            const uint64_t bdesc = bdesc0 + (uint64_t)(blk * (4096 >> 4));
+            const uint32_t d = d0 + (uint32_t)(kU4Ops[o].slot * 64);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint32_t acc = (o | k) ? 1u : 0u;
-            if (kU4Ops[o].ntiles == 4) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 256>(), acc);
-            else if (kU4Ops[o].ntiles == 2) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 128>(), acc);
-            else umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 64>(), acc);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint32_t acc = (o | k) ? 1u : 0u;
+              if (kU4Ops[o].ntiles == 4) umma_f16_cg<CG>(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 256, CG>(), acc);
+              else if (kU4Ops[o].ntiles == 2) umma_f16_cg<CG>(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 128, CG>(), acc);
+              else umma_f16_cg<CG>(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 64, CG>(), acc);
+            }
+            blk += kU4Ops[o].ntiles;
           }
+          umma_commit_cg<CG>(a_empty(s));
+          umma_commit_cg<CG>(t_full(acs));
         }
-        umma_commit(a_empty(s));
-        umma_commit(t_full(acs));
+        __syncwarp();
+        if (++s == kU4AStages) s = 0, ph ^= 1;
       }
-      __syncwarp();
-      if (++s == kU4AStages) s = 0, ph ^= 1;
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue: group g drains accumulator stage g; warp <-> tile row, lane <-> column
     const int grp = (warp - kEpiWarp0) >> 2;
     const int quad = warp & 3;
     const bool issuer_warp = (quad == 0);
-    const uint32_t sbuf = base + kU4OffStore + grp * kU4StoreBytes;
+    const uint32_t sbuf0 = base + kU4OffStore + grp * 2 * kU4StoreBytes;  // two staging tiles, used in turn
     const int srow = quad * kU4OutW + lane;
     SatTracker<T16> sat;
     for (int it = grp;; it += 2) {
-      const long long tile_ll = (long long)blockIdx.x + (long long)it * gridDim.x;
-      if (tile_ll >= p.total_tiles) break;
+      const long long unit_ll = (long long)unit_id + (long long)it * unit_cnt;
+      if (unit_ll >= units) break;
       int n, y0, x0;
-      tile_of((int)tile_ll, n, y0, x0);
+      tile_of((int)unit_ll, n, y0, x0);
       const int acs = it & 1;
       const int y = y0 + quad, x = x0 + lane;
       const bool col_ok = lane < kU4OutW;
-      const bool valid = col_ok && y < p.H && x < p.W;
+      const bool valid = col_ok && y < p.H && x < p.W && n < p.N;
       MBAR_WAIT_RELAXED(t_full(acs), (it >> 1) & 1, 930 + acs);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acs * 256);
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         const int phs = kU4SlotPh[ch], a = phs >> 1, b = phs & 1;
+        const uint32_t sbuf = sbuf0 + (ch & 1) * kU4StoreBytes;
         uint32_t r[64];
         {
           uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
@@ -182,17 +222,18 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         if (ch == 3) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty(acs));
+          if (lane == 0) mbar_arrive_cluster(lead(t_empty(acs)));
         }
         uint32_t pk[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float v0 = __uint_as_float(r[2 * j]) + s_bias[2 * j];
-          const float v1 = __uint_as_float(r[2 * j + 1]) + s_bias[2 * j + 1];
-          pk[j] = p.relu ? pack16x2_relu<T16>(v0, v1) : pack16x2<T16>(v0, v1);
+          const float2 v = add2_f32(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])),
+                                    *reinterpret_cast<const float2*>(&s_bias[2 * j]));
+          pk[j] = p.relu ? pack16x2_relu<T16>(v.x, v.y) : pack16x2<T16>(v.x, v.y);
           sat.track(pk[j]);
         }
-        if (issuer_warp) bulk_wait_read<0>();  // the staging buffer has been read out by its TMA store
+        // the staging tile used two chunks ago has been read out by its TMA store
+        if (issuer_warp) bulk_wait_read<1>();
         epi_barrier(grp);
         if (col_ok) {
 #pragma unroll
@@ -217,15 +258,16 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   }
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_cg<CG, 512>(tmem_base);
 }
 
 template <typename T16>
 int launch_ups4(ActView<T16> in, const T16* wk_up, ConvParams<T16> p, cudaStream_t st) {
+  constexpr int CG = kU4CG;
   CUtensorMap m4, mb;
   if (int e = make_act_map(&m4, in, kU4BoxW, kU4Rows + 2)) return e;
-  if (int e = make_weight_map(&mb, wk_up, 4 * in.C, 4 * p.Cout, 64)) return e;
+  if (int e = make_weight_map(&mb, wk_up, 4 * in.C, 4 * p.Cout, 32)) return e;  // half-tile boxes of 32 rows
   OutMaps mo;
   memset(&mo, 0, sizeof(mo));
   for (int a = 0; a < 2; ++a)
@@ -235,10 +277,12 @@ int launch_ups4(ActView<T16> in, const T16* wk_up, ConvParams<T16> p, cudaStream
   p.tiles_x = (in.W + kU4OutW - 1) / kU4OutW;
   p.tiles_y = (in.H + kU4Rows - 1) / kU4Rows;
   const int64_t tiles = (int64_t)in.N * p.tiles_x * p.tiles_y;
-  CCST_CHECK_ARG(tiles < (1ll << 31), "conv_ups4: too many tiles");
+  CCST_CHECK_ARG(tiles < (1ll << 31) - 2, "conv_ups4: too many tiles");
   p.m_tiles = p.total_tiles = (int)tiles;
-  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  CCST_CUDA(launch_conv(conv_ups4_kernel<T16>, grid, kThreadsUmma, kU4Smem, st, 1, m4, mb, mo, p));
+  const int64_t units = (tiles + CG - 1) / CG;
+  const int slots = sm_count() / CG;
+  const int grid = (int)(units < slots ? units : slots) * CG;
+  CCST_CUDA(launch_conv(conv_ups4_kernel<T16>, grid, kThreadsUmma, kU4Smem, st, CG, m4, mb, mo, p));
   CCST_LAUNCHED();
   return CCST_OK;
 }
