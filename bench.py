@@ -377,7 +377,7 @@ def run_ours(args, rank, world, local_rank):
             traffic_src = td["source"]
         roofline = {
             "kernel": "tcgen05.mma + TMA implicit-GEMM 3x3 convs (conv_umma_kernel / conv_smerge_kernel / "
-                      "conv_ups4_kernel / conv_last_rows_kernel, 18 launches/step)"
+                      "conv_ups4_kernel / conv_last_rows_kernel, %d launches/step)" % round(conv["n"] / psteps)
             if precision != "fp32" else "conv_ffma_kernel (fp32 validation mode)",
             "bound": "tensor", "achieved": round(conv_tflops, 2), "peak": peaks["tf_burst"], "unit": "TFLOP/s",
             "frac": round(conv_tflops / peaks["tf_burst"], 4),

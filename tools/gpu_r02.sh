@@ -51,7 +51,9 @@ for s in $STAGES; do
             # style_transfer per engine
       TAILN=12 run san_ops 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_ops.py -q -m gpu -x --timeout 800
       TAILN=12 run san_net32 600 compute-sanitizer --tool memcheck --error-exitcode 3 python tools/san_small.py fp32
-      TAILN=12 run san_net16 600 compute-sanitizer --tool memcheck --error-exitcode 3 python tools/san_small.py fp16 ;;
+      TAILN=12 run san_net16 600 compute-sanitizer --tool memcheck --error-exitcode 3 python tools/san_small.py fp16
+      TAILN=12 run san_net16x3 600 compute-sanitizer --tool memcheck --error-exitcode 3 python tools/san_small.py fp16x3
+      TAILN=12 run san_netb16x3 600 compute-sanitizer --tool memcheck --error-exitcode 3 python tools/san_small.py bf16x3 ;;
   esac
 done
 du -sh gpurun_out

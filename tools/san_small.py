@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """One small style_transfer (2 x 3 x 64 x 64) through one engine, for compute-sanitizer runs.
-usage: compute-sanitizer --tool memcheck python tools/san_small.py fp32|fp16|bf16"""
+usage: compute-sanitizer --tool memcheck python tools/san_small.py fp32|fp16|bf16|fp16x3|bf16x3
+(the tensor-core engines also run the uint8 entry point: ToTensor fused into conv1_1, quantised store in the last conv)"""
 import os
 import sys
 
@@ -19,3 +20,10 @@ stat = [torch.randn((1, 512, 1, 1), generator=g).abs().to(dev), (torch.rand((1, 
 out = ccst_b200.style_transfer(vgg, dec, x, stat, 1.0, precision=prec)
 torch.cuda.synchronize()
 print(prec, "ok", tuple(out.shape), float(out.mean()))
+if prec != "fp32":
+    x_u8 = (x.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous()
+    o8 = ccst_b200.style_transfer_u8(vgg, dec, x_u8, stat, 1.0, precision=prec)
+    st = ccst_b200.function.WelfordState(512, dev)
+    ccst_b200.engine_for(vgg, dec, dev).accumulate_u8(x_u8, st, prec)
+    torch.cuda.synchronize()
+    print(prec, "u8 ok", tuple(o8.shape), float(o8.float().mean()), float(st.buf[0]))
