@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-bash tools/gpu_r02.sh r02v san ncu_all ncu_list
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_8gpu_r02x.log 2> gpurun_out/bench_8gpu_r02x.err; echo rc=$?; tail -c 1500 gpurun_out/bench_8gpu_r02x.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 tools/multi_gpu_check.py --images 256 --size 256 --batch 16 --precision fp16x3 --oracle > gpurun_out/multi_gpu_check_8gpu_r02x.log 2>&1; echo rc=$?; tail -3 gpurun_out/multi_gpu_check_8gpu_r02x.log
