@@ -21,20 +21,21 @@ constexpr int kU4BoxW = 32, kU4Rows = 4, kU4OutW = kU4BoxW - 2;
 constexpr int kU4SlabBytes = (kU4Rows + 2) * kU4BoxW * 128;  // 24576
 // The kernel runs as CTA PAIRS (cta_group::2, two consecutive tiles per M = 256 MMA): every SM fetches only its
 // own tile's A operand, each CTA keeps HALF of every stacked weight block (64 KiB instead of 128), and the freed
-// shared memory holds a third slab stage and a second staging tile per epilogue group.  Measured at batch 32
-// @512^2: 0.302 ms against 0.298-0.308 for the single-CTA form -- no gain, although the same change took the
-// last conv from 0.26 to 0.21 ms: here the MMA side (1.47 us of A-operand fetch per 2.4 us tile) was not the
-// bound.  Per tile the SM moves ~420 KB through shared memory (10 operand views x 4 K steps x 4 KB of A, the
-// weights, the slab write, 64 KB of staged output written and read back by the TMA store) at 128 B/clk --
-// 70 % of the tile time -- beside 67 % of the HBM rate (1.07 GB of output per launch) and an epilogue that issues
-// ~560 instructions per warp and tile; ncu: l1/smem 63 %, dram 52-56 %, tensor 58 %, issue slots 38 %.
+// shared memory holds a third slab stage and one staging tile per epilogue group.  Measured at batch 32 @512^2
+// (same box, interleaved, profiles/r02z_ab_ups4_2_vs_4_groups.txt): pairs alone changed nothing (0.302 ms against
+// 0.298-0.308 for the single-CTA form); with FOUR epilogue groups (below) 0.307 -> 0.278 ms.  The following
+// last conv then takes 0.013 ms longer (0.222 -> 0.236): it starts while ~100 MB of this kernel's output are
+// still being written back from L2 -- together the two kernels move 2.5 GB in 0.51 ms = 4.9 TB/s, and that HBM
+// round trip of the 64-channel 512^2 map, not either kernel, is what is left.
 constexpr int kU4CG = 2;
+constexpr int kU4EpiGroups = 4;                              // one 4-warp epilogue group per output phase
+constexpr int kU4Threads = 32 * (kEpiWarp0 + 4 * kU4EpiGroups);  // 640
 constexpr int kU4AStages = 3;
 constexpr int kU4OffB = kU4AStages * kU4SlabBytes;           // 16 half-tiles of 32 rows x 128 B per CTA
 constexpr int kU4BBytes = 16 * 4096;
 constexpr int kU4OffStore = kU4OffB + kU4BBytes;
 constexpr int kU4StoreBytes = 16384;                          // 120 rows x 128 B, rounded
-constexpr int kU4OffBias = kU4OffStore + 4 * kU4StoreBytes;   // 2 groups x 2 staging tiles
+constexpr int kU4OffBias = kU4OffStore + kU4EpiGroups * kU4StoreBytes;   // one staging tile per epilogue group
 constexpr int kU4OffBar = kU4OffBias + 256;
 constexpr int kU4NumBars = 2 * kU4AStages + 4 + 1;
 constexpr int kU4Smem = 1024 + kU4OffBar + 8 * kU4NumBars + 16;
@@ -53,7 +54,7 @@ __device__ constexpr int kU4TileTap[16] = {0, 1, 0, 1, 0, 2, 1, 3, 2, 0, 3, 1, 2
 __device__ constexpr int kU4SlotPh[4] = {2, 0, 1, 3};  // accumulator column slot -> phase
 
 template <typename T16>
-__global__ void __launch_bounds__(kThreadsUmma, 1)
+__global__ void __launch_bounds__(kU4Threads, 1)
     conv_ups4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ OutMaps tmap_out, ConvParams<T16> p) {
   constexpr int CG = kU4CG;
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(t_full(s), 1);
-      mbar_init(t_empty(s), 4 * CG);  // one arrive per epilogue warp of both CTAs
+      mbar_init(t_empty(s), 4 * kU4EpiGroups * CG);  // one arrive per epilogue warp of both CTAs
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
               const uint32_t acc = (o | k) ? 1u : 0u;
+              if (CCST_ABLATE_BITS(p) & 2) continue;  // (CCST_DEV builds: measurement only)
               if (kU4Ops[o].ntiles == 4) umma_f16_cg<CG>(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 256, CG>(), acc);
               else if (kU4Ops[o].ntiles == 2) umma_f16_cg<CG>(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 128, CG>(), acc);
               else umma_f16_cg<CG>(d, adesc + 2 * k, bdesc + 2 * k, make_idesc<T16, 64, CG>(), acc);
@@ -188,69 +190,78 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ===================== epilogue: group g drains accumulator stage g; warp <-> tile row, lane <-> column
+    // ===================== epilogue: FOUR groups of 4 warps, group g drains output phase slot g (64 accumulator
+    // columns) of EVERY tile; warp <-> tile row, lane <-> column.  Stage ablation (CCST_DEV build,
+    // tools/ablate_ups4.sh, batch 32 @512^2): MMAs + loads alone 0.18 ms, the two-group epilogue alone 0.26 ms
+    // (tcgen05.ld + math 0.13, staging 0.06, TMA store 0.07 -- one serial chain per chunk, four chunks per tile,
+    // two warps per scheduler at ~0.2 instructions per clock each): the epilogue was the bound and it was a
+    // LATENCY bound, so it gets twice the warps and a quarter of the chain per tile.  (Prefetching the next
+    // 32-column half into a second register buffer with two groups was measured first: slower, 0.32 ms.)
     const int grp = (warp - kEpiWarp0) >> 2;
     const int quad = warp & 3;
     const bool issuer_warp = (quad == 0);
-    const uint32_t sbuf0 = base + kU4OffStore + grp * 2 * kU4StoreBytes;  // two staging tiles, used in turn
+    const uint32_t sbuf = base + kU4OffStore + grp * kU4StoreBytes;
     const int srow = quad * kU4OutW + lane;
+    const int phs = kU4SlotPh[grp], a = phs >> 1, b = phs & 1;
     SatTracker<T16> sat;
-    for (int it = grp;; it += 2) {
-      const long long unit_ll = (long long)unit_id + (long long)it * unit_cnt;
-      if (unit_ll >= units) break;
+    int it = 0;
+    for (int unit = unit_id; unit < units; unit += unit_cnt, ++it) {
       int n, y0, x0;
-      tile_of((int)unit_ll, n, y0, x0);
+      tile_of(unit, n, y0, x0);
       const int acs = it & 1;
       const int y = y0 + quad, x = x0 + lane;
       const bool col_ok = lane < kU4OutW;
       const bool valid = col_ok && y < p.H && x < p.W && n < p.N;
       MBAR_WAIT_RELAXED(t_full(acs), (it >> 1) & 1, 930 + acs);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acs * 256);
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        const int phs = kU4SlotPh[ch], a = phs >> 1, b = phs & 1;
-        const uint32_t sbuf = sbuf0 + (ch & 1) * kU4StoreBytes;
-        uint32_t r[64];
-        {
-          uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-          uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-          tmem_ld32(taddr + ch * 64, r0);
-          tmem_ld32(taddr + ch * 64 + 32, r1);
-        }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acs * 256 + grp * 64);
+      if (CCST_ABLATE_BITS(p) & 1) {  // (CCST_DEV builds: measurement only) hand the accumulator back untouched
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead(t_empty(acs)));
+        continue;
+      }
+      uint32_t pk[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld32(taddr + half * 32, r);
         tmem_ld_wait();
-        if (ch == 3) {
+        if (half == 1) {
+          // this group's columns are in registers: hand them back (the stage is free once all 16 warps have)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(lead(t_empty(acs)));
         }
-        uint32_t pk[32];
+        uint32_t m[4] = {0u, 0u, 0u, 0u};  // four independent maxima: no 16-deep HMNMX2 chain
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const float2 v = add2_f32(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])),
-                                    *reinterpret_cast<const float2*>(&s_bias[2 * j]));
-          pk[j] = p.relu ? pack16x2_relu<T16>(v.x, v.y) : pack16x2<T16>(v.x, v.y);
-          sat.track(pk[j]);
+                                    *reinterpret_cast<const float2*>(&s_bias[half * 32 + 2 * j]));
+          const uint32_t w = p.relu ? pack16x2_relu<T16>(v.x, v.y) : pack16x2<T16>(v.x, v.y);
+          pk[half * 16 + j] = w;
+          m[j & 3] = max16x2<T16>(m[j & 3], w & 0x7fff7fffu);
         }
-        // the staging tile used two chunks ago has been read out by its TMA store
-        if (issuer_warp) bulk_wait_read<1>();
-        epi_barrier(grp);
-        if (col_ok) {
+        sat.track_nonneg(max16x2<T16>(max16x2<T16>(m[0], m[1]), max16x2<T16>(m[2], m[3])));
+      }
+      // the group's staging tile has been read out by the TMA store of its previous tile
+      if (issuer_warp) bulk_wait_read<0>();
+      epi_barrier(grp);
+      if (col_ok) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t dst = sbuf + srow * 128 + ((j ^ (srow & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
-                         "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                         : "memory");
-          }
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = sbuf + srow * 128 + ((j ^ (srow & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * j]),
+                       "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                       : "memory");
         }
-        if (valid) store_aliases(p.out, n, 2 * y + a, 2 * x + b, 0, pk);
-        fence_async_smem();
-        epi_barrier(grp);
-        if (issuer_warp && elect_one()) {
-          tma_store_4d(&tmap_out.m[phs], sbuf, 0, x0, y0, n);
-          bulk_commit();
-        }
+      }
+      if (valid) store_aliases(p.out, n, 2 * y + a, 2 * x + b, 0, pk);
+      fence_async_smem();
+      epi_barrier(grp);
+      if (issuer_warp && elect_one() && !(CCST_ABLATE_BITS(p) & 16)) {
+        tma_store_4d(&tmap_out.m[phs], sbuf, 0, x0, y0, n);
+        bulk_commit();
       }
     }
     if (issuer_warp) bulk_wait_all();
@@ -282,7 +293,7 @@ int launch_ups4(ActView<T16> in, const T16* wk_up, ConvParams<T16> p, cudaStream
   const int64_t units = (tiles + CG - 1) / CG;
   const int slots = sm_count() / CG;
   const int grid = (int)(units < slots ? units : slots) * CG;
-  CCST_CUDA(launch_conv(conv_ups4_kernel<T16>, grid, kThreadsUmma, kU4Smem, st, CG, m4, mb, mo, p));
+  CCST_CUDA(launch_conv(conv_ups4_kernel<T16>, grid, kU4Threads, kU4Smem, st, CG, m4, mb, mo, p));
   CCST_LAUNCHED();
   return CCST_OK;
 }

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_8gpu_r02x.log 2> gpurun_out/bench_8gpu_r02x.err; echo rc=$?; tail -c 1500 gpurun_out/bench_8gpu_r02x.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 tools/multi_gpu_check.py --images 256 --size 256 --batch 16 --precision fp16x3 --oracle > gpurun_out/multi_gpu_check_8gpu_r02x.log 2>&1; echo rc=$?; tail -3 gpurun_out/multi_gpu_check_8gpu_r02x.log
+timeout 900 python -m pytest tests/test_gpu_net.py tests/test_gpu_drivers.py -q -m gpu --timeout 600 -x -k "single_conv or golden or u8 or reproducible or deterministic or config1 or smallest or upsample or saturation" > gpurun_out/tests_r02z.log 2>&1; echo tests rc=$?; tail -3 gpurun_out/tests_r02z.log
+python tools/layer_report.py > gpurun_out/layers_r02z.log 2>&1; sed -n '1p;18,21p' gpurun_out/layers_r02z.log
+python tools/layer_report.py > gpurun_out/layers_r02z2.log 2>&1; sed -n '1p;18,21p' gpurun_out/layers_r02z2.log
