@@ -80,8 +80,12 @@ CONV_CASES = [
     (1, 9, 11, 256, 256, True, 2),
     (2, 16, 24, 64, 3, False, 3),     # last decoder conv: 3 channels, NCHW fp32 store
     (1, 5, 7, 64, 3, False, 3),
+    (1, 12, 20, 64, 3, False, 3),     # 3 tiles: the CTA-pair kernel's last pair has a dummy second tile
+    (3, 20, 61, 64, 3, True, 3),      # 45 tiles (odd), three tile columns, ReLU variant
     # mode 4: nearest x2 BEFORE the conv, fused as four 2x2 phase convolutions (tcgen05 path only)
     (1, 8, 16, 64, 64, True, 4),      # dec8 shape class: resident phase weights, one tile
+    (1, 12, 16, 64, 64, True, 4),     # 3 tiles: odd count for the CTA-pair form (dummy second tile)
+    (1, 20, 70, 64, 64, False, 4),    # 15 tiles, three tile columns, no ReLU
     (2, 13, 19, 64, 64, True, 4),     # ragged, several tiles per phase
     (1, 2, 2, 64, 64, False, 4),      # smallest map: every pixel is a corner
     (2, 10, 14, 128, 128, True, 4),   # dec6 class (CTA pairs, odd tile count)
