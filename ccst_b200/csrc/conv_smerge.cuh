@@ -316,6 +316,10 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       // scoreboard).  So each quarter is written in phases: all 32 neighbour shuffles, then all adds and
       // packs, then the 8 + 8 pooling shuffles.
       auto quarter = [&](int cq, const uint32_t (&a)[16], const uint32_t (&b)[16], const uint32_t (&c)[16]) {
+        if (CCST_ABLATE_BITS(p) & 8) {  // (CCST_DEV builds: measurement only) TMEM loads without the math / staging
+          if ((a[0] ^ b[3] ^ c[7]) == 0x12345678u && p.sat_count != nullptr) atomicAdd(p.sat_count, 1u);
+          return;
+        }
         uint32_t pk[8];
         float lft[16], rgt[16];
 #pragma unroll
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       }
       fence_async_smem();
       epi_barrier(grp);
-      if (issuer_warp && elect_one()) {
+      if (issuer_warp && elect_one() && !(CCST_ABLATE_BITS(p) & 24)) {
         if (EPI == EPI_ACT_POOL) {
           tma_store_4d(&tmap_out.m[0], sbuf, 0, x0 >> 1, y0 >> 1, tn);
         } else {
