@@ -111,6 +111,9 @@ struct ConvLayer {
   // the accumulator by x3_scale = 2^-e
   __half* w_x3 = nullptr;
   bf16* w_x3_b = nullptr;  // the same split with bf16 halves (bf16x3 engine)
+  // x3 engines, layer after an upsample: phase weights (w_up) split the same way, [4 phases][cout/64][hi | lo][64][4*cin]
+  __half* w_up_x3 = nullptr;
+  bf16* w_up_x3_b = nullptr;
   float x3_scale = 1.f;
 };
 
@@ -192,6 +195,8 @@ void free_layer(ConvLayer& L) {
   cudaFree(L.w_tapsum);
   cudaFree(L.w_x3);
   cudaFree(L.w_x3_b);
+  cudaFree(L.w_up_x3);
+  cudaFree(L.w_up_x3_b);
   L = ConvLayer();
 }
 
@@ -326,6 +331,40 @@ int pack_layer(ConvLayer& L, int cin, int cout, const float* w, const float* b, 
     CCST_CUDA(cudaMalloc(&L.w_up_h, uh.size() * sizeof(__half)));
     CCST_CUDA(cudaMemcpy(L.w_up, ub.data(), ub.size() * sizeof(bf16), cudaMemcpyHostToDevice));
     CCST_CUDA(cudaMemcpy(L.w_up_h, uh.data(), uh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    if (split_pack) {
+      // x3 engines: the same phase sums (in double) times the layer's 2^e, split into hi + lo; rows
+      // [phase][tile of 64 output channels][hi | lo][co].  A phase weight sums at most 4 taps: |w| 2^e < 2^12.
+      int ex;
+      frexpf(L.x3_scale, &ex);  // x3_scale = 2^-e = 0.5 * 2^ex
+      const int e = 1 - ex;
+      const int tiles = cout / 64;
+      std::vector<__half> xh((size_t)4 * tiles * 128 * K4);
+      std::vector<bf16> xb((size_t)4 * tiles * 128 * K4);
+      for (int a = 0; a < 2; ++a)
+        for (int bb = 0; bb < 2; ++bb)
+          for (int o = 0; o < cout; ++o)
+            for (int dy = 0; dy < 2; ++dy)
+              for (int dx = 0; dx < 2; ++dx)
+                for (int c = 0; c < cin; ++c) {
+                  double acc = 0;
+                  for (int r = lo[a][dy]; r <= hi[a][dy]; ++r)
+                    for (int sc = lo[bb][dx]; sc <= hi[bb][dx]; ++sc)
+                      acc += (double)w[((size_t)o * cin + c) * 9 + r * 3 + sc];
+                  const float v = (float)ldexp(acc, e);
+                  const size_t row_hi = ((size_t)(a * 2 + bb) * tiles + o / 64) * 128 + (o % 64), row_lo = row_hi + 64;
+                  const size_t k = (size_t)(dy * 2 + dx) * cin + c;
+                  const __half hh = __float2half(v);
+                  xh[row_hi * K4 + k] = hh;
+                  xh[row_lo * K4 + k] = __float2half(v - __half2float(hh));
+                  const bf16 hb = __float2bfloat16(v);
+                  xb[row_hi * K4 + k] = hb;
+                  xb[row_lo * K4 + k] = __float2bfloat16(v - __bfloat162float(hb));
+                }
+      CCST_CUDA(cudaMalloc(&L.w_up_x3, xh.size() * sizeof(__half)));
+      CCST_CUDA(cudaMalloc(&L.w_up_x3_b, xb.size() * sizeof(bf16)));
+      CCST_CUDA(cudaMemcpy(L.w_up_x3, xh.data(), xh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+      CCST_CUDA(cudaMemcpy(L.w_up_x3_b, xb.data(), xb.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    }
   }
   return CCST_OK;
 }
@@ -420,6 +459,7 @@ struct Weights16<bf16> {
   static const bf16* first(const ccst_handle* h) { return h->first_wk_b; }
   static const bf16* first_x3(const ccst_handle* h) { return h->first_x3_b; }
   static const bf16* x3(const ConvLayer& L) { return L.w_x3_b; }
+  static const bf16* x3_up(const ConvLayer& L) { return L.w_up_x3_b; }
 };
 template <>
 struct Weights16<__half> {
@@ -429,6 +469,7 @@ struct Weights16<__half> {
   static const __half* first(const ccst_handle* h) { return h->first_wk_h; }
   static const __half* first_x3(const ccst_handle* h) { return h->first_x3_h; }
   static const __half* x3(const ConvLayer& L) { return L.w_x3; }
+  static const __half* x3_up(const ConvLayer& L) { return L.w_up_x3; }
 };
 
 template <typename T>
@@ -477,7 +518,7 @@ struct Pipe {
     // tcgen05 path: a layer followed by `Upsample` stores its low-resolution output with a replicate
     // halo and the NEXT conv consumes it through the phase-decomposed kernel (EPI_UPS): 16 instead of
     // 36 tap-GEMMs per source pixel and no 4x-replicated activation in HBM.
-    const bool defer_up = up_after && h->fuse_up && sizeof(T) == 2 && !pool_after && !split();
+    const bool defer_up = up_after && h->fuse_up && sizeof(T) == 2 && !pool_after;
     const bool ups = up_pending;
     CCST_CHECK_ARG(!ups || (!pool_after && !up_after && L.w_up != nullptr),
                    "upsample-fused conv cannot pool/upsample itself and needs phase weights");
@@ -675,7 +716,7 @@ int Pipe<T>::conv(const ConvLayer& L, int relu, int epi, ActView<T> out, float* 
   a.per_sample = per_sample;
   if (split()) {
     CCST_CHECK_ARG(Weights16<T>::x3(L) != nullptr, "this layer has no split weights for the x3 engines");
-    a.split = true, a.wk_x3 = Weights16<T>::x3(L), a.out_scale = L.x3_scale;
+    a.split = true, a.wk_x3 = Weights16<T>::x3(L), a.wk_x3_up = Weights16<T>::x3_up(L), a.out_scale = L.x3_scale;
   }
   return launch_conv_umma<T>(a, st);
 }

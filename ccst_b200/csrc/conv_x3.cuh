@@ -55,7 +55,12 @@ template <typename T16, int EPI, int CG>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_x3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const __grid_constant__ OutMaps tmap_out, ConvParams<T16> p) {
-  static_assert(EPI == EPI_ACT || EPI == EPI_ACT_POOL || EPI == EPI_ACT_UP2 || EPI == EPI_NCHW_F32, "x3 epilogues");
+  static_assert(EPI == EPI_ACT || EPI == EPI_ACT_POOL || EPI == EPI_ACT_UP2 || EPI == EPI_NCHW_F32 || EPI == EPI_UPS,
+                "x3 epilogues");
+  // EPI_UPS: nearest-x2 upsample folded into this conv as four 2x2 phase convolutions over the low-resolution
+  // input (conv_main.cuh): unit = (pixel tile, phase), 2 x 2 taps, phase weights split like the rest
+  constexpr bool UPS = (EPI == EPI_UPS);
+  constexpr int kTR = UPS ? 2 : 3, kTS = UPS ? 2 : 3;
   using Cfg = X3Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int klog = p.Cin / kBlockK;  // 64-channel chunks of the logical input
   const int kchunks = 2 * klog;      // [hi | lo]
-  const int steps = kchunks * 3;     // (chunk, filter column) steps per tile: even
+  const int steps = kchunks * kTS;   // (chunk, filter column) steps per tile: even
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   auto lead = [&](uint32_t bar) { return CG == 2 ? mapa_rank(bar, 0) : bar; };
@@ -117,28 +122,29 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     for (int unit = unit_id; unit < p.total_tiles; unit += unit_cnt) {
-      const TileCoord t = decode_tile<CG>(p, unit, (int)cta_rank);
-      const int b_row = t.nt * Cfg::kN + b_row0;
+      const TileCoord t = decode_tile<CG, UPS>(p, unit, (int)cta_rank);
+      const int xs0 = t.x0 + (UPS ? (t.ph & 1) : 0);
+      const int b_row = (UPS ? t.ph * p.n_tiles * Cfg::kN : 0) + t.nt * Cfg::kN + b_row0;
       for (int kc = 0; kc < kchunks; ++kc) {
         const int kb = kc >= klog ? kc - klog : kc;  // the lo chunks meet the same weights as the hi chunks
-        for (int s = 0; s < 3; ++s) {
+        for (int s = 0; s < kTS; ++s) {
           MBAR_WAIT_RELAXED(a_empty(as), aph ^ 1, 700 + as);
           if (elect_one()) {
             if (leader) mbar_expect_tx(a_full(as), CG * kASlabBytes);
-            tma_load_4d_cg<CG>(a_smem(as), &tmap_a, lead(a_full(as)), kc * kBlockK, t.x0 + s, t.y0, t.n);
+            tma_load_4d_cg<CG>(a_smem(as), &tmap_a, lead(a_full(as)), kc * kBlockK, xs0 + s, t.y0, t.n);
           }
           __syncwarp();
           if (++as == Cfg::kAStages) as = 0, aph ^= 1;
           MBAR_WAIT_RELAXED(b_empty(bs), bph ^ 1, 720 + bs);
           if (elect_one()) {
-            if (leader) mbar_expect_tx(b_full(bs), CG * 3 * Cfg::kBBytes);
+            if (leader) mbar_expect_tx(b_full(bs), CG * kTR * Cfg::kBBytes);
             const uint32_t bar = lead(b_full(bs));
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
-              tma_load_2d_cg<CG>(b_smem(bs + r), &tmap_b, bar, (r * 3 + s) * p.Cin + kb * kBlockK, b_row);
+            for (int r = 0; r < kTR; ++r)
+              tma_load_2d_cg<CG>(b_smem(bs + r), &tmap_b, bar, (r * kTS + s) * p.Cin + kb * kBlockK, b_row);
           }
           __syncwarp();
-          if ((bs += 3) == Cfg::kBStages) bs = 0, bph ^= 1;
+          if ((bs += kTR) == Cfg::kBStages) bs = 0, bph ^= 1;
         }
       }
     }
@@ -151,10 +157,12 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       int it = 0;
       for (int unit = unit_id; unit < p.total_tiles; unit += unit_cnt, ++it) {
         const uint32_t use0 = (uint32_t)(it >> 1) * (uint32_t)(steps >> 1);  // uses of this tile parity's buffers so far
+        // UPS: row phase a of this unit shifts the slab rows of the two taps to a + r
+        const int row_shift = UPS ? (((unit / p.n_tiles) & 3) >> 1) : 0;
         int j = 0;
         for (int kc = 0; kc < kchunks; ++kc) {
 #pragma unroll
-          for (int s = 0; s < 3; ++s, ++j) {
+          for (int s = 0; s < kTS; ++s, ++j) {
             const int pb = 2 * (it & 1) + (j & 1);
             const uint32_t use = use0 + (uint32_t)(j >> 1);
             mbar_wait(a_full(as), aph, 740 + as);
@@ -163,12 +171,12 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
             else mbar_wait(part_empty(pb), (use & 1u) ^ 1u, 760 + pb);
             tc_fence_after();
             const int bs0 = bs;
-            if ((bs += 3) == Cfg::kBStages) bs = 0, bph ^= 1;
+            if ((bs += kTR) == Cfg::kBStages) bs = 0, bph ^= 1;
             if (elect_one()) {
               const uint32_t tmem_d = tmem_base + (uint32_t)(pb * Cfg::kN);
-              const uint64_t adesc0 = make_kmajor_sw128_desc(a_smem(as));
+              const uint64_t adesc0 = make_kmajor_sw128_desc(a_smem(as) + (uint32_t)(row_shift * kTileW) * 128u);
 #pragma unroll
-              for (int r = 0; r < 3; ++r) {
+              for (int r = 0; r < kTR; ++r) {
                 const uint64_t adesc = adesc0 + (uint64_t)(r * (kTileW * 128 >> 4));
                 const uint64_t bdesc = make_kmajor_sw128_desc(b_smem(bs0 + r));
 #pragma unroll
@@ -197,7 +205,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     for (int it = grp;; it += 2) {
       const long long unit_ll = (long long)unit_id + (long long)it * unit_cnt;
       if (unit_ll >= p.total_tiles) break;
-      const TileCoord t = decode_tile<CG>(p, (int)unit_ll, (int)cta_rank);
+      const TileCoord t = decode_tile<CG, UPS>(p, (int)unit_ll, (int)cta_rank);
       const int y = t.y0 + py, x = t.x0 + px;
       const bool valid = (y < p.H) && (x < p.W) && (CG == 1 || t.n < p.N);
       const uint32_t use0 = (uint32_t)(it >> 1) * (uint32_t)(steps >> 1);
@@ -315,7 +323,9 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         }
         if (valid) {
           if (EPI == EPI_ACT) {
-            store_aliases(p.out, t.n, y, x, cs, pk, 1);
+            store_aliases(p.out, t.n, y, x, cs, pk, p.halo_edge);
+          } else if (EPI == EPI_UPS) {
+            store_aliases(p.out, t.n, 2 * y + (t.ph >> 1), 2 * x + (t.ph & 1), cs, pk, 1);
           } else if (EPI == EPI_ACT_UP2) {
 #pragma unroll
             for (int aa = 0; aa < 2; ++aa)
@@ -330,6 +340,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
         if (issuer_warp && elect_one()) {
           if (EPI == EPI_ACT_POOL) {
             tma_store_4d(&tmap_out.m[0], sbuf, cs, t.x0 >> 1, t.y0 >> 1, t.n);
+          } else if (EPI == EPI_UPS) {
+            tma_store_4d(&tmap_out.m[t.ph], sbuf, cs, t.x0, t.y0, t.n);
           } else {
             tma_store_4d(&tmap_out.m[0], sbuf, cs, t.x0, t.y0, t.n);
             if (EPI == EPI_ACT_UP2) {
@@ -355,23 +367,24 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
 template <typename T16, int EPI, int CG>
 int launch_x3_cfg(const CUtensorMap& ma, const T16* wk_x3, ConvParams<T16> p, cudaStream_t st) {
   using Cfg = X3Cfg<CG>;
+  constexpr bool UPS = (EPI == EPI_UPS);
   CUtensorMap mb;
-  // [n_tiles * 128 rows = (tile, hi | lo, co)][9 * Cin]
-  if (int e = make_weight_map(&mb, wk_x3, 9 * p.Cin, p.n_tiles * Cfg::kN, Cfg::kBRows)) return e;
+  // [n_tiles * 128 rows = (tile, hi | lo, co)][9 * Cin]; UPS: [4 phases x n_tiles * 128 rows][4 * Cin]
+  if (int e = make_weight_map(&mb, wk_x3, (UPS ? 4 : 9) * p.Cin, (UPS ? 4 : 1) * p.n_tiles * Cfg::kN, Cfg::kBRows)) return e;
   OutMaps mo;
   memset(&mo, 0, sizeof(mo));
   if (EPI == EPI_ACT) {
     if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kTileW, kTileH)) return e;
   } else if (EPI == EPI_ACT_POOL) {
     if (int e = make_out_map(&mo.m[0], p.out, 0, 0, 1, 1, kTileW / 2, kTileH / 2)) return e;
-  } else if (EPI == EPI_ACT_UP2) {
+  } else if (EPI == EPI_ACT_UP2 || EPI == EPI_UPS) {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
         if (int e = make_out_map(&mo.m[a * 2 + b], p.out, a, b, 2, 2, kTileW, kTileH)) return e;
   }
   auto kernel = conv_x3_kernel<T16, EPI, CG>;
   CCST_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(kernel), Cfg::kSmemBytes));
-  const int64_t units = ((int64_t)p.m_tiles + CG - 1) / CG * p.n_tiles;
+  const int64_t units = ((int64_t)p.m_tiles + CG - 1) / CG * p.n_tiles * (UPS ? 4 : 1);
   CCST_CHECK_ARG(units < (1ll << 31), "conv_x3: too many tiles");
   p.total_tiles = (int)units;
   const int slots = sm_count() / CG;
@@ -386,10 +399,12 @@ int launch_x3_cfg(const CUtensorMap& ma, const T16* wk_x3, ConvParams<T16> p, cu
 template <typename T16>
 int launch_x3(const UmmaConvArgs<T16>& a, ConvParams<T16> p, cudaStream_t st) {
   const ActView<T16>& in = a.in;
-  const bool last = a.epi == EPI_NCHW_F32;
-  CCST_CHECK_ARG((a.epi == EPI_ACT || a.epi == EPI_ACT_POOL || a.epi == EPI_ACT_UP2 || last) && a.halo_edge == 1 &&
-                     !a.per_sample && a.wk_x3 != nullptr,
+  const bool last = a.epi == EPI_NCHW_F32, ups = a.epi == EPI_UPS;
+  CCST_CHECK_ARG((a.epi == EPI_ACT || a.epi == EPI_ACT_POOL || a.epi == EPI_ACT_UP2 || last || ups) &&
+                     (a.halo_edge == 1 || a.epi == EPI_ACT) && !a.per_sample && a.wk_x3 != nullptr,
                  "conv_x3: epilogue %d is not available on the x3 engines", a.epi);
+  CCST_CHECK_ARG(!ups || (a.wk_x3_up != nullptr && a.out.H == 2 * in.H && a.out.W == 2 * in.W),
+                 "conv_x3: EPI_UPS needs the split phase weights and an output twice the input's size");
   CCST_CHECK_ARG(in.C % (2 * kBlockK) == 0, "conv_x3: Cin=%d/2 must be a multiple of 64", in.C);
   if (last) {
     CCST_CHECK_ARG(a.Cout >= 1 && a.Cout <= 4 && (a.out_nchw != nullptr || a.out_u8 != nullptr),
@@ -412,6 +427,7 @@ int launch_x3(const UmmaConvArgs<T16>& a, ConvParams<T16> p, cudaStream_t st) {
     case EPI_ACT: return launch_x3_cfg<T16, EPI_ACT, 2>(ma, a.wk_x3, p, st);
     case EPI_ACT_POOL: return launch_x3_cfg<T16, EPI_ACT_POOL, 2>(ma, a.wk_x3, p, st);
     case EPI_ACT_UP2: return launch_x3_cfg<T16, EPI_ACT_UP2, 2>(ma, a.wk_x3, p, st);
+    case EPI_UPS: return launch_x3_cfg<T16, EPI_UPS, 2>(ma, a.wk_x3_up, p, st);
     default: return launch_x3_cfg<T16, EPI_NCHW_F32, 2>(ma, a.wk_x3, p, st);
   }
 }

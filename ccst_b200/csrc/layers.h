@@ -133,6 +133,7 @@ struct UmmaConvArgs {
   // with hi + lo = w * 2^k, out_scale = 2^-k
   bool split = false;
   const T16* wk_x3 = nullptr;
+  const T16* wk_x3_up = nullptr;  // EPI_UPS on the x3 engines: [4 phases][tiles][hi | lo][64][4 * Cin]
   float out_scale = 1.f;
 };
 template <typename T16>
