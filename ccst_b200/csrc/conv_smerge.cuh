@@ -38,7 +38,9 @@ __device__ __forceinline__ void store_aliases_q(const ActView<T16>& out, int n, 
 // Two 4-warp epilogue groups (tile i is drained by group i % 2 from accumulator stage i % 2).  A third
 // group was measured to buy nothing: the epilogue alone gets faster (0.50 -> 0.41 ms on conv1_2) but
 // not the kernel (0.59 ms), see DESIGN.md.
-template <bool BRES, int CG>
+// BRES = number of 64-channel input chunks whose weights stay RESIDENT in shared memory (0 = streamed per tile):
+// Cin = 64 (conv1_2, dec8 un-fused) and, as pairs, Cin = 128 (dec7: 6 tiles of 12 KiB per CTA).
+template <int BRES, int CG>
 struct SmergeCfg {
   static constexpr int kASlabBytes = (kTileH + 2) * kTileW * 128;  // 20480
   static constexpr int kBRows = kSmN / CG;
@@ -46,7 +48,7 @@ struct SmergeCfg {
   // streamed weights: the 3 filter-row tiles of a chunk travel as one group (one barrier pair, one
   // wait per chunk in the producer and the MMA warp); two groups in flight
   static constexpr int kAStages = BRES ? 5 : (CG == 2 ? 4 : 2);
-  static constexpr int kBStages = BRES ? 3 : 6;                    // resident: 3 filter rows x (Cin == 64)
+  static constexpr int kBStages = BRES ? 3 * BRES : 6;             // resident: 3 filter rows x BRES chunks
   static constexpr int kAOff = 0;
   static constexpr int kBOff = kAStages * kASlabBytes;
   static constexpr int kStoreOff = kBOff + kBStages * kBBytes;
@@ -77,7 +79,7 @@ __device__ __forceinline__ TileCoord decode_tile_sm(const P& p, int unit, int ra
   return t;
 }
 
-template <typename T16, int EPI, bool BRES, int CG>
+template <typename T16, int EPI, int BRES, int CG>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
     conv_smerge_kernel(const __grid_constant__ CUtensorMap tmap_a,
                        const __grid_constant__ CUtensorMap tmap_b,
@@ -152,9 +154,11 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
     const int b_row0 = (int)cta_rank * Cfg::kBRows;
     if (BRES) {
       if (elect_one()) {
-        if (leader) mbar_expect_tx(bres_bar, CG * 3 * Cfg::kBBytes);
+        if (leader) mbar_expect_tx(bres_bar, CG * 3 * BRES * Cfg::kBBytes);
         const uint32_t bar = lead(bres_bar);
-        for (int r = 0; r < 3; ++r) tma_load_2d_cg<CG>(b_smem(r), &tmap_b, bar, r * p.Cin, b_row0);
+        for (int kc = 0; kc < BRES; ++kc)
+          for (int r = 0; r < 3; ++r)
+            tma_load_2d_cg<CG>(b_smem(kc * 3 + r), &tmap_b, bar, r * p.Cin + kc * kBlockK, b_row0);
       }
       __syncwarp();
     }
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
               const uint64_t adesc = adesc0 + (uint64_t)(r * (kTileW * 128 >> 4));
-              const uint64_t bdesc = make_kmajor_sw128_desc(BRES ? b_smem(r) : b_smem(bs0 + r));
+              const uint64_t bdesc = make_kmajor_sw128_desc(BRES ? b_smem(kc * 3 + r) : b_smem(bs0 + r));
               if (!(CCST_ABLATE_BITS(p) & 2)) {
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k)
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   if (warp == 2) tmem_dealloc_cg<CG, Cfg::kTmemCols>(tmem_base);
 }
 
-template <typename T16, int EPI, bool BRES, int CG>
+template <typename T16, int EPI, int BRES, int CG>
 int launch_smerge_cfg(const CUtensorMap& ma, const T16* wk_sm, ConvParams<T16> p, cudaStream_t st) {
   using Cfg = SmergeCfg<BRES, CG>;
   CUtensorMap mb;
@@ -487,21 +491,20 @@ int launch_smerge_cfg(const CUtensorMap& ma, const T16* wk_sm, ConvParams<T16> p
 }
 
 // CTA pairs everywhere (dec7: 0.30 -> 0.26 ms, conv1_2 0.635 -> 0.58: each CTA stages half of every
-// weight tile); Cin == 64 keeps its three weight tiles resident.
+// weight tile); Cin == 64 keeps its three weight tiles resident, Cin == 128 its six.
+template <typename T16, int EPI>
+int launch_smerge_epi(const CUtensorMap& ma, const T16* wk_sm, const ConvParams<T16>& p, cudaStream_t st) {
+  if (p.Cin == kBlockK) return launch_smerge_cfg<T16, EPI, 1, 2>(ma, wk_sm, p, st);
+  if (p.Cin == 2 * kBlockK) return launch_smerge_cfg<T16, EPI, 2, 2>(ma, wk_sm, p, st);
+  return launch_smerge_cfg<T16, EPI, 0, 2>(ma, wk_sm, p, st);
+}
 template <typename T16>
 int launch_smerge(const CUtensorMap& ma, const T16* wk_sm, const ConvParams<T16>& p, int epi,
                   cudaStream_t st) {
-  const bool res = p.Cin == kBlockK;
   switch (epi) {
-    case EPI_ACT:
-      return res ? launch_smerge_cfg<T16, EPI_ACT, true, 2>(ma, wk_sm, p, st)
-                 : launch_smerge_cfg<T16, EPI_ACT, false, 2>(ma, wk_sm, p, st);
-    case EPI_ACT_UP2:
-      return res ? launch_smerge_cfg<T16, EPI_ACT_UP2, true, 2>(ma, wk_sm, p, st)
-                 : launch_smerge_cfg<T16, EPI_ACT_UP2, false, 2>(ma, wk_sm, p, st);
-    case EPI_ACT_POOL:
-      return res ? launch_smerge_cfg<T16, EPI_ACT_POOL, true, 2>(ma, wk_sm, p, st)
-                 : launch_smerge_cfg<T16, EPI_ACT_POOL, false, 2>(ma, wk_sm, p, st);
+    case EPI_ACT: return launch_smerge_epi<T16, EPI_ACT>(ma, wk_sm, p, st);
+    case EPI_ACT_UP2: return launch_smerge_epi<T16, EPI_ACT_UP2>(ma, wk_sm, p, st);
+    case EPI_ACT_POOL: return launch_smerge_epi<T16, EPI_ACT_POOL>(ma, wk_sm, p, st);
     default:
       set_error("conv_smerge: epilogue %d not available", epi);
       return CCST_EINVAL;

@@ -75,6 +75,8 @@ CONV_CASES = [
     (1, 16, 16, 256, 512, True, 0),   # two N tiles, K = 2304
     (1, 12, 12, 512, 256, True, 1),   # Camelyon-sized map, fused nearest x2
     (2, 10, 14, 128, 64, False, 1),
+    (2, 24, 40, 128, 64, True, 0),    # dec7 shape class: s-merged kernel with six resident weight tiles (Cin = 128)
+    (3, 9, 33, 128, 64, True, 0),     # odd tile count, ragged in x and y
     (1, 16, 32, 64, 64, True, 2),     # fused ceil-mode max-pool
     (1, 15, 21, 128, 128, True, 2),   # odd sizes: partial pooling windows
     (1, 9, 11, 256, 256, True, 2),
