@@ -77,12 +77,37 @@ class TransferPipeline:
                 "precision='bf16' (same speed, wider range) or 'fp32'")
         return j, self._host[hslot]
 
+    @classmethod
+    def for_engine(cls, engine: Engine, precision: str = DEFAULT_PRECISION, u8: bool = False) -> "TransferPipeline":
+        """The engine's pipeline for (precision, u8), kept across calls: its device slots and pinned host buffers
+        (3 x 100 MB for fp32 batches of 32 @512^2 -- cudaHostAlloc costs ~50 ms each) are allocated once per
+        engine instead of once per loop.  A pipeline whose previous loop has not been exhausted is not reused."""
+        cache = engine.__dict__.setdefault("_pipelines", {})
+        pipe = cache.get((precision, u8))
+        if pipe is None or pipe._busy:
+            pipe = cls(engine, precision, u8=u8)
+            cache[(precision, u8)] = pipe
+        return pipe
+
+    _busy = False
+
     def run(self, host_batches: Iterable[torch.Tensor],
             style_for_batch: Callable[[int, torch.Tensor], Sequence[torch.Tensor]],
             alpha: float = 1.0) -> Iterator[Tuple[int, torch.Tensor]]:
+        self._busy = True
+        try:
+            yield from self._run(host_batches, style_for_batch, alpha)
+        finally:
+            self._busy = False
+
+    def _run(self, host_batches: Iterable[torch.Tensor],
+             style_for_batch: Callable[[int, torch.Tensor], Sequence[torch.Tensor]],
+             alpha: float = 1.0) -> Iterator[Tuple[int, torch.Tensor]]:
         """Yields (batch index, stylised batch as a pinned host tensor).  The yielded tensor is a
         pipeline buffer that stays valid until the NEXT result has been requested and handed out
-        (there is one more host buffer than batches in flight); copy it to keep it longer.
+        (there is one more host buffer than batches in flight); copy it to keep it longer.  The drivers
+        keep one pipeline per engine (`for_engine`), so the next loop on the same engine reuses -- and
+        overwrites -- these buffers too.
 
         `style_for_batch(i, device_batch)` returns the `[mean, std]` to use for batch i (called on
         the compute stream, so it may itself run GPU work, e.g. encode a style image)."""
@@ -134,7 +159,7 @@ def overall_transfer(engine: Engine, host_batches: Iterable[torch.Tensor], style
                      precision: str = DEFAULT_PRECISION, u8: bool = False):
     """Inner loop of CCST_OverallStyleTransfer.py:149-167 for one (content domain, style) pair.
     u8 = True: uint8 HWC batches in and out (ToTensor / save_image's quantisation on the GPU)."""
-    pipe = TransferPipeline(engine, precision, u8=u8)
+    pipe = TransferPipeline.for_engine(engine, precision, u8=u8)
     stat = [t.to(engine.device) for t in style_stat]
     return pipe.run(host_batches, lambda i, x: stat, alpha)
 
@@ -180,7 +205,7 @@ def single_transfer(engine: Engine, host_batches: Iterable[torch.Tensor], style_
     python's `random.choice` (seeded like the reference, `:22-26`), its statistics computed on the
     GPU, then the transfer."""
     rng = random.Random(seed)
-    pipe = TransferPipeline(engine, precision)
+    pipe = TransferPipeline.for_engine(engine, precision)
     styles = _StyleSet(engine, style_images)
 
     def stat_for(i, x):
@@ -199,7 +224,7 @@ def single_transfer_per_image(engine: Engine, host_batches: Iterable[torch.Tenso
     one batch, their per-image statistics (:199-203, biased variance) come from one pass of the
     statistics kernel, and AdaIN takes them as [N,512,1,1] (`stat_batch_stride = C`)."""
     rng = random.Random(seed)
-    pipe = TransferPipeline(engine, precision)
+    pipe = TransferPipeline.for_engine(engine, precision)
     styles = _StyleSet(engine, style_images)
 
     def stat_for(i, x):
