@@ -35,6 +35,7 @@ PROTOTYPES = {
     "ccst_welford_to_sums": (_i, [_vp, _i, _vp, _vp, _vp]),
     "ccst_welford_to_moments": (_i, [_vp, _i, _vp, _vp]),
     "ccst_welford_from_moments": (_i, [_vp, _i, _vp, _vp]),
+    "ccst_allreduce_moments": (_i, [_vp, _vp, _i64, _vp]),
     "ccst_adain_stat_nchw_f32": (_i, [_vp, _i, _i, _i64, _vp, _vp, _i64, _f, _f, _vp, _vp]),
     "ccst_adain_feat_nchw_f32": (_i, [_vp, _vp, _i, _i, _i64, _i64, _f, _f, _vp, _vp, _vp]),
     "ccst_create": (_vp, [_i]),

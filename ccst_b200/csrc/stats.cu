@@ -12,6 +12,7 @@
 // (for CTA groups) a shared-memory combine.  Planes that do not fit in registers, or whose size /
 // alignment rules out 128-bit access, take a streaming variant of the same algorithm.
 #include <cstdlib>
+#include <dlfcn.h>
 
 #include "common.cuh"
 
@@ -999,6 +1000,43 @@ extern "C" int ccst_welford_from_moments(const double* d_moments, int C, double*
   if (int e = require_sm100()) return e;
   from_moments_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_moments, C, d_state);
   CCST_LAUNCHED();
+  return CCST_OK;
+}
+
+// ncclAllReduce through a run-time binding: int ncclAllReduce(const void*, void*, size_t, int dtype, int op, void* comm,
+// cudaStream_t); ncclFloat64 = 8, ncclSum = 0 (nccl.h, stable since NCCL 2.0)
+namespace {
+typedef int (*PFN_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*PFN_ncclGetErrorString)(int);
+PFN_ncclAllReduce g_nccl_allreduce = nullptr;
+PFN_ncclGetErrorString g_nccl_errstr = nullptr;
+bool bind_nccl() {
+  if (g_nccl_allreduce) return true;
+  void* lib = nullptr;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    lib = dlopen(name, RTLD_NOW | RTLD_NOLOAD);  // the copy the process already uses (e.g. torch's)
+    if (!lib) lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) return false;
+  g_nccl_allreduce = reinterpret_cast<PFN_ncclAllReduce>(dlsym(lib, "ncclAllReduce"));
+  g_nccl_errstr = reinterpret_cast<PFN_ncclGetErrorString>(dlsym(lib, "ncclGetErrorString"));
+  return g_nccl_allreduce != nullptr;
+}
+}  // namespace
+
+extern "C" int ccst_allreduce_moments(void* nccl_comm, double* d_moments, int64_t count, void* stream) {
+  CCST_CHECK_ARG(nccl_comm && d_moments && count >= 1, "ccst_allreduce_moments: bad argument");
+  if (!bind_nccl()) {
+    set_error("ccst_allreduce_moments: no NCCL in the process or on the loader path (libnccl.so.2)");
+    return CCST_ESTATE;
+  }
+  const int rc = g_nccl_allreduce(d_moments, d_moments, (size_t)count, /*ncclFloat64=*/8, /*ncclSum=*/0, nccl_comm,
+                                  (cudaStream_t)stream);
+  if (rc != 0) {
+    set_error("ccst_allreduce_moments: ncclAllReduce failed: %s", g_nccl_errstr ? g_nccl_errstr(rc) : "?");
+    return CCST_ECUDA;
+  }
   return CCST_OK;
 }
 

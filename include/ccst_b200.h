@@ -107,6 +107,12 @@ int ccst_welford_to_sums(const double* d_state, int C, float* d_sum, float* d_sq
  * single all-reduce(sum) that merges the per-GPU partials of one client. */
 int ccst_welford_to_moments(const double* d_state, int C, double* d_moments, void* stream);
 int ccst_welford_from_moments(const double* d_moments, int C, double* d_state, void* stream);
+/* The collective itself for a host without torch.distributed (the reference's processes
+ * only meet on disk, README.md:28-37): in-place ncclAllReduce(sum, fp64) of `count` doubles (1 + 2 C moments, plus
+ * whatever counters the caller appends) over the caller's communicator `nccl_comm` (an ncclComm_t) on `stream`.
+ * NCCL is resolved at run time (the copy already loaded into the process, else libnccl.so.2 on the loader path):
+ * the library has no link-time dependency on it.  CCST_ESTATE if no NCCL can be found. */
+int ccst_allreduce_moments(void* nccl_comm, double* d_moments, int64_t count, void* stream);
 
 /* ------------------------------------------------------------------------
  * AdaIN

@@ -217,3 +217,22 @@ def test_mse_loss_matches_torch_and_is_deterministic():
         assert l1 == l2 and abs(l1 - ref) < 1e-6 * max(ref, 1e-6)
     with pytest.raises(AssertionError):
         ccst_b200.mse_loss(torch.zeros(3, device=DEV), torch.zeros(4, device=DEV))
+
+
+def test_c_abi_allreduce_single_rank_communicator():
+    """ccst_allreduce_moments binds NCCL at run time and reduces in place over the caller's ncclComm_t; with one rank
+    the sum is the identity (the multi-rank comparison with torch.distributed is tools/multi_gpu_check.py)."""
+    from ccst_b200 import _lib, nccl_raw
+    torch.cuda.set_device(0)
+    comm = nccl_raw.comm_init(1, 0, nccl_raw.unique_id())
+    try:
+        x = torch.arange(1026, dtype=torch.float64, device="cuda:0") * 0.5 - 7.0
+        ref = x.clone()
+        st = torch.cuda.current_stream()
+        _lib.check(_lib.lib().ccst_allreduce_moments(comm, x.data_ptr(), x.numel(), st.cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(x, ref)
+        with pytest.raises(RuntimeError):
+            _lib.check(_lib.lib().ccst_allreduce_moments(None, x.data_ptr(), x.numel(), st.cuda_stream))
+    finally:
+        nccl_raw.comm_destroy(comm)

@@ -58,6 +58,32 @@ def main():
     dt = time.perf_counter() - t0
     res = {"world": world, "images": a.images, "size": a.size, "precision": a.precision, "seen": seen,
            "sharded_s": round(dt, 3)}
+
+    # the same merge through the C ABI alone (ccst_allreduce_moments on a raw ncclComm_t): what a host without
+    # torch.distributed does; torch.distributed is used here only to ship the 128-byte NCCL id to the ranks
+    from ccst_b200 import _lib, nccl_raw
+    from ccst_b200 import function as F_
+
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(nccl_raw.unique_id()), dtype=torch.uint8).clone()
+    if world > 1:
+        uid_d = uid.to(dev)
+        dist.broadcast(uid_d, 0)
+        uid = uid_d.cpu()
+    comm = nccl_raw.comm_init(world, rank, bytes(uid.numpy().tobytes()))
+    acc = overall.OverallStyleAccumulator(eng, a.precision)
+    for b0 in range(begin, end, a.batch):
+        acc.add_images(batch_of(b0, min(a.batch, end - b0)).to(dev))
+    payload = torch.cat([acc.state.moments(), torch.tensor([float(acc.img_count)], dtype=torch.float64, device=dev)])
+    st = torch.cuda.current_stream(dev)
+    _lib.check(_lib.lib().ccst_allreduce_moments(comm, payload.data_ptr(), payload.numel(), st.cuda_stream))
+    merged = F_.WelfordState(512, dev).load_moments(payload[:-1])
+    mean_c, std_c = merged.finalize()
+    torch.cuda.synchronize()
+    res["c_abi_allreduce_equals_torch_distributed"] = bool(torch.equal(mean_c, mean) and torch.equal(std_c, std)
+                                                           and int(round(payload[-1].item())) == seen)
+    nccl_raw.comm_destroy(comm)
     if rank == 0:
         m1, s1, n1 = run(0, a.images, False)
         res["single_gpu_seen"] = n1
@@ -72,7 +98,8 @@ def main():
             m64, s64, _, _ = O.overall_style_stats(feats, dtype=torch.float64)
             res["mean_rel_vs_oracle64"] = ((mean.cpu().double() - m64).abs().max() / m64.abs().max()).item()
             res["std_rel_vs_oracle64"] = ((std.cpu().double() - s64).abs().max() / s64.abs().max()).item()
-        ok = seen == a.images and res["mean_rel_vs_single"] < 1e-5 and res["std_rel_vs_single"] < 1e-5
+        ok = (seen == a.images and res["mean_rel_vs_single"] < 1e-5 and res["std_rel_vs_single"] < 1e-5
+              and res["c_abi_allreduce_equals_torch_distributed"])
         res["ok"] = bool(ok)
         print(json.dumps(res), flush=True)
     if world > 1:

@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-bash tools/gpu_r02.sh r03g bench tests smoke layers layers6 ops
-python tools/layer_report.py --precision fp16x3 > gpurun_out/layers_x3_r03g.log 2>&1
-python tools/layer_report.py --batch 1024 --size 96 > gpurun_out/layers_96_r03g.log 2>&1
-python tools/fuzz_shapes.py 60 2 > gpurun_out/fuzz_r03g.log 2>&1; tail -1 gpurun_out/fuzz_r03g.log
+timeout 600 python -m pytest tests/test_gpu_ops.py -q -m gpu --timeout 300 -x -k "allreduce" > gpurun_out/tests_r03h.log 2>&1; echo tests rc=$?; tail -3 gpurun_out/tests_r03h.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/multi_gpu_check.py --images 64 --size 128 --batch 8 --precision fp16x3 --oracle > gpurun_out/multi_gpu_check_2gpu_r03h.log 2>&1; echo rc=$?; tail -2 gpurun_out/multi_gpu_check_2gpu_r03h.log
