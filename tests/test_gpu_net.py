@@ -438,6 +438,19 @@ def test_pipelines_are_bit_reproducible_over_many_runs(models):
         assert all(torch.equal(f, feats[0]) for f in feats[1:]), precision
         imgs = [eng.decode(feats[0], precision).clone() for _ in range(20)]
         assert all(torch.equal(f, imgs[0]) for f in imgs[1:]), precision
+    # the x3 engines (promoted partial sums handed between the MMA warp and two epilogue groups, conv1_1's builder /
+    # epilogue-group rings) and the uint8 entry point (window ring fed from the uint8 rows, table look-ups)
+    x_u8 = (x.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous()
+    g = torch.Generator().manual_seed(3)
+    stat = [torch.randn((1, 512, 1, 1), generator=g).abs().to(DEV), (torch.rand((1, 512, 1, 1), generator=g) + 0.2).to(DEV)]
+    for precision in ("fp16x3", "bf16x3"):
+        feats = [eng.encode(x, precision).clone() for _ in range(12)]
+        assert all(torch.equal(f, feats[0]) for f in feats[1:]), precision
+        imgs = [eng.decode(feats[0], precision).clone() for _ in range(8)]
+        assert all(torch.equal(f, imgs[0]) for f in imgs[1:]), precision
+    for precision in ("fp16", "fp16x3"):
+        outs = [eng.transfer_u8(x_u8, stat, 1.0, precision).clone() for _ in range(12)]
+        assert all(torch.equal(o, outs[0]) for o in outs[1:]), precision
 
 
 @pytest.mark.parametrize("hw", [(24, 24), (17, 40), (16, 16)])
