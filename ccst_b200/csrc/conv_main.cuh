@@ -292,6 +292,11 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue: two groups of 4 warps, group g drains accumulator stage g
     // (tiles it = g, g+2, ...), so each group has two tile-times to finish one tile ==========
+    // (Four groups -- one 64-column chunk of every tile per group at BN = 256, (tile parity, chunk) at BN = 128,
+    // 640 threads, one staging tile per group and one slab stage less -- were measured on every layer of the step,
+    // interleaved with this form on one box: slower everywhere, 5.11 -> 5.27 ms per step, dec6 0.19 -> 0.23 ms
+    // (profiles/r03l_ab_main_kernel_4_epilogue_groups.txt).  Here the MMA side is the bound and the epilogue has
+    // slack; on dec8, whose epilogue was the bound, the same change paid: conv_ups4.cuh.)
     const int grp = (warp - kEpiWarp0) >> 2;
     const int quad = warp & 3;           // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;    // accumulator row = pixel inside the tile
