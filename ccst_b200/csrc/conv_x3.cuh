@@ -15,7 +15,10 @@
 // accumulator is PROMOTED: the 12 MMAs of one (channel chunk, filter column) step write a fresh partial sum
 // into one of four 128-column TMEM buffers, and the epilogue warps add the partials in registers with
 // round-to-nearest fp32 adds while the next steps' MMAs run (buffers 2g, 2g+1 belong to epilogue group g,
-// which owns the tiles of parity g).  Truncation then only acts inside a 12-MMA partial.
+// which owns the tiles of parity g).  Truncation then only acts inside a 12-MMA partial.  (Two steps = 24 MMAs per
+// partial were measured: 1.6 % faster, relu4_1 statistics 2.2e-6 -> 4.3e-6 relative, encoder max-abs 1.2e-5 ->
+// 2.2e-5 -- not taken; profiles/r03n_ab_x3_two_steps_per_partial.txt.  ncu: tensor pipe 74-80 % active on the
+// large layers, profiles/r03m_ncu_x3_summary.txt.)
 //
 // Epilogue: v = acc * 2^-k + bias, ReLU, optional 2x2 ceil-mode max-pool (all fp32), split into hi / lo and
 // stored as two TMA tiles at channels co and Cout + co (EPI_ACT, EPI_ACT_POOL; EPI_ACT_UP2 stores every pixel
