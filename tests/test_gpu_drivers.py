@@ -124,6 +124,27 @@ def test_pipeline_result_survives_one_more_step(models, engine):
         prev = (i, out)
 
 
+def test_pipeline_is_kept_per_engine_and_reusable(models, engine):
+    """The drivers keep one pipeline per (engine, precision, u8): a second loop reuses its device slots and pinned
+    buffers (also with another batch shape) and gives the same results; a loop that is still open gets its own."""
+    vgg, dec = models
+    g = torch.Generator().manual_seed(12)
+    stat = [torch.randn((1, 512, 1, 1), generator=g).abs(), torch.rand((1, 512, 1, 1), generator=g) + 0.2]
+    sd = [t.to(DEV) for t in stat]
+    a = [synth.images(2, 48, 64, 950 + i).pin_memory() for i in range(3)]
+    b = [synth.images(3, 32, 80, 960 + i).pin_memory() for i in range(2)]
+    p0 = drivers.TransferPipeline.for_engine(engine, drivers.DEFAULT_PRECISION)
+    for batches in (a, b, a):
+        refs = [ccst_b200.style_transfer(vgg, dec, x.to(DEV), sd, 1.0).cpu() for x in batches]
+        for i, out in drivers.overall_transfer(engine, iter(batches), stat, 1.0):
+            assert torch.equal(out, refs[i])
+        assert drivers.TransferPipeline.for_engine(engine, drivers.DEFAULT_PRECISION) is p0
+    it = drivers.overall_transfer(engine, iter(a), stat, 1.0)
+    next(it)  # open loop: the cached pipeline is busy
+    assert drivers.TransferPipeline.for_engine(engine, drivers.DEFAULT_PRECISION) is not p0
+    it.close()
+
+
 def test_style_transfer_u8_equals_float_path_quantised(models):
     """Integer work is bit-exact: the fused uint8 path == ToTensor -> style_transfer -> quantise,
     all on the same engine, for every precision, on a ragged non-multiple-of-8 size."""
