@@ -2,7 +2,7 @@
 """Random-shape sweep of style_transfer / style_transfer_u8 / encoder statistics: every tensor-core engine against the
 fp32 CUDA-core engine of the same library (itself pinned to the oracle by the tests), on ragged sizes that exercise
 partial tiles, odd tile counts of the CTA-pair kernels, 1-pixel-wide remainders, the TMA / cp.async forms of conv1_1
-and the fused uint8 loader.  usage: python tools/fuzz_shapes.py [cases] [seed]"""
+and the fused uint8 loader.  usage: python tools/fuzz_shapes.py [cases] [seed] [big]"""
 import os
 import random
 import sys
@@ -14,6 +14,7 @@ import ccst_b200
 from ccst_b200 import drivers, synth  # noqa: F401
 
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+big = len(sys.argv) > 3 and sys.argv[3] == "big"  # sizes up to 640 (several tile rows / columns of every kernel)
 rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 dev = torch.device("cuda:0")
 vgg, dec = synth.make_models(0)
@@ -28,7 +29,12 @@ bad = 0
 for i in range(cases):
     n = rng.choice([1, 1, 2, 3, 5])
     h = rng.choice([rng.randint(16, 40), rng.randint(16, 200), 16 * rng.randint(1, 12)])
+    if big:
+        h = rng.choice([rng.randint(200, 640), 8 * rng.randint(30, 80)])
     w = rng.choice([rng.randint(16, 40), rng.randint(16, 300), 16 * rng.randint(1, 18), 128, 144, 256])
+    if big:
+        w = rng.choice([rng.randint(200, 640), 16 * rng.randint(13, 40), 512])
+        n = rng.choice([1, 2])
     alpha = rng.choice([1.0, 0.5])
     x = synth.images(n, h, w, 100 + i).to(dev)
     ref = ccst_b200.style_transfer(vgg, dec, x, stat, alpha, precision="fp32")
