@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(kFirstPx)
                                  __uint_as_float(r0[2 * j + 1]) + sbias[2 * j + 1]);
       pk[16 + j] = pack16x2_relu<T16>(__uint_as_float(r1[2 * j]) + sbias[32 + 2 * j],
                                       __uint_as_float(r1[2 * j + 1]) + sbias[33 + 2 * j]);
-      sat.track(pk[j]);
-      sat.track(pk[16 + j]);
+      sat.track_nonneg(pk[j]);  // (packed with ReLU)
+      sat.track_nonneg(pk[16 + j]);
     }
     // TMEM reads are complete (wait::ld); every thread passes two more block barriers before warp 0
     // overwrites the accumulator with the next tile

@@ -383,8 +383,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) pk[j] = max16x2<T16>(pk[j], t[j]);
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sat.track(pk[j]);
+        sat.track_block(pk, p.relu != 0);
         // the staging buffer about to be rewritten must have been read out by its TMA store (waited
         // for only now, so that the bias / ReLU / pack work above overlaps that read-out)
         if (issuer_warp) bulk_wait_read<0>();

@@ -233,17 +233,14 @@ __global__ void __launch_bounds__(kU4Threads, 1)
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(lead(t_empty(acs)));
         }
-        uint32_t m[4] = {0u, 0u, 0u, 0u};  // four independent maxima: no 16-deep HMNMX2 chain
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float2 v = add2_f32(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])),
                                     *reinterpret_cast<const float2*>(&s_bias[half * 32 + 2 * j]));
-          const uint32_t w = p.relu ? pack16x2_relu<T16>(v.x, v.y) : pack16x2<T16>(v.x, v.y);
-          pk[half * 16 + j] = w;
-          m[j & 3] = max16x2<T16>(m[j & 3], w & 0x7fff7fffu);
+          pk[half * 16 + j] = p.relu ? pack16x2_relu<T16>(v.x, v.y) : pack16x2<T16>(v.x, v.y);
         }
-        sat.track_nonneg(max16x2<T16>(max16x2<T16>(m[0], m[1]), max16x2<T16>(m[2], m[3])));
       }
+      sat.track_block(pk, p.relu != 0);
       // the group's staging tile has been read out by the TMA store of its previous tile
       if (issuer_warp) bulk_wait_read<0>();
       epi_barrier(grp);

@@ -308,10 +308,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
             pk[i] = pack16x2<T16>(v0 - hf.x, v1 - hf.y);
           }
         }
-        if (part == 0) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sat.track(pk[i]);
-        }
+        if (part == 0) sat.track_block(pk, p.relu != 0);
         const int cs = co + part * p.Cout;  // channel of this half in the [hi | lo] map
         if (issuer_warp) bulk_wait_read<0>();
         epi_barrier(grp);

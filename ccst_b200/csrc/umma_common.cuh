@@ -396,6 +396,8 @@ template <typename T16>
 struct SatTracker {
   __device__ __forceinline__ void track(uint32_t) {}
   __device__ __forceinline__ void track_nonneg(uint32_t) {}
+  template <int N>
+  __device__ __forceinline__ void track_block(const uint32_t (&)[N], bool) {}
   __device__ __forceinline__ void flush(unsigned int*) {}
 };
 template <>
@@ -404,6 +406,20 @@ struct SatTracker<__half> {
   __device__ __forceinline__ void track(uint32_t w) { m = max16x2<__half>(m, w & 0x7fff7fffu); }
   // values known to be >= 0 (packed with ReLU): one instruction
   __device__ __forceinline__ void track_nonneg(uint32_t w) { m = max16x2<__half>(m, w); }
+  // a block of N packed words: four independent chains instead of one N-deep HMNMX2 chain, and the sign mask only
+  // when the values may be negative (`nonneg` is warp-uniform: one branch per block, not one LOP3 per word)
+  template <int N>
+  __device__ __forceinline__ void track_block(const uint32_t (&w)[N], bool nonneg) {
+    uint32_t a[4] = {0u, 0u, 0u, 0u};
+    if (nonneg) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) a[j & 3] = max16x2<__half>(a[j & 3], w[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) a[j & 3] = max16x2<__half>(a[j & 3], w[j] & 0x7fff7fffu);
+    }
+    m = max16x2<__half>(max16x2<__half>(m, a[0]), max16x2<__half>(max16x2<__half>(a[1], a[2]), a[3]));
+  }
   __device__ __forceinline__ void flush(unsigned int* counter) {
     // bit patterns of non-negative halves order like the values; 0x7bff = 65504, above = inf / NaN
     const bool hit = (m & 0xffffu) >= 0x7bffu || (m >> 16) >= 0x7bffu;
